@@ -1,0 +1,38 @@
+# Builds the B200-native aligner in-tree (the .so travels to the GPU box with gpurun).
+#   make            -> aim_b200/libaim_b200.so, build/host, oracle/libaim_oracle.so
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Iinclude -Iaim_b200/csrc -Xcompiler -fPIC,-Wall,-Wextra -cudart static
+CSRC      := aim_b200/csrc
+OBJDIR    := build/obj
+CU_SRCS   := $(CSRC)/aim_wfa.cu $(CSRC)/aim_dp.cu $(CSRC)/aim_dispatch.cu
+CXX_SRCS  := $(CSRC)/aim_host.cpp
+OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CXX_SRCS))
+HDRS      := include/aim_b200.h $(CSRC)/aim_internal.h
+
+all: aim_b200/libaim_b200.so build/host oracle/libaim_oracle.so
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -Wextra -Iinclude -I$(CSRC) -c $< -o $@
+
+aim_b200/libaim_b200.so: $(OBJS)
+	$(NVCC) -shared $(ARCH) -cudart static -o $@ $(OBJS) -lpthread
+
+build/host: tools/host.cpp aim_b200/libaim_b200.so include/aim_b200.h
+	@mkdir -p build
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude tools/host.cpp -o $@ -Laim_b200 -laim_b200 -Wl,-rpath,'$$ORIGIN/../aim_b200' -lpthread -ldl
+
+oracle/libaim_oracle.so: oracle/aim_oracle.c
+	$(CC) -O2 -std=gnu11 -fPIC -shared -Wall -o $@ $< -lpthread
+
+clean:
+	rm -rf build aim_b200/libaim_b200.so oracle/libaim_oracle.so
+
+.PHONY: all clean

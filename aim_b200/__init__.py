@@ -1,0 +1,9 @@
+"""aim_b200 — B200-native batched pairwise aligner (NW, SWG, WFA, WFA-adaptive), a drop-in for the
+path safaad/aim offloads to UPMEM DPUs.  Thin Python over the C ABI in include/aim_b200.h."""
+from .api import (ALGO_NW, ALGO_SWG, ALGO_WFA, RESULT_DTYPE, AimError, AlignParams, PinnedArray, align_batch,
+                  align_device, cigar_strings, count_pairs, derive_knobs, device_count, generate_pairs,
+                  pairs_to_process, read_pairs, shutdown, write_pairs, write_results)
+
+__all__ = ["ALGO_NW", "ALGO_SWG", "ALGO_WFA", "RESULT_DTYPE", "AimError", "AlignParams", "PinnedArray",
+           "align_batch", "align_device", "cigar_strings", "count_pairs", "derive_knobs", "device_count",
+           "generate_pairs", "pairs_to_process", "read_pairs", "shutdown", "write_pairs", "write_results"]

@@ -1,0 +1,198 @@
+"""Python face of the C ABI: numpy in, numpy out.  All compute happens in libaim_b200.so on the GPU.
+
+Mirrors the reference's surface for the offloaded path: the knobs of */run-*-pim-*.py and
+*/common/common.h as an `AlignParams`, the `>pattern / <text` pair files, the `idx, score, ` +
+CIGAR output (reference: WFA/DPU-MRAM/host/host.c:91-134, 332-353).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import AimParams, AimResult, lib
+
+ALGO_NW, ALGO_SWG, ALGO_WFA = 0, 1, 2
+_ALGO = {"nw": ALGO_NW, "swg": ALGO_SWG, "wfa": ALGO_WFA}
+
+RESULT_DTYPE = np.dtype([("max_operations", "<i4"), ("begin_offset", "<i4"), ("end_offset", "<i4"),
+                         ("score", "<i4"), ("status", "<i4"), ("idx", "<u4")])
+assert RESULT_DTYPE.itemsize == C.sizeof(AimResult)
+
+
+class AimError(RuntimeError):
+    def __init__(self, code: int):
+        self.code = code
+        super().__init__(f"aim_b200 error {code} ({lib.aim_strerror(code).decode()}): {lib.aim_last_error().decode()}")
+
+
+@dataclass
+class AlignParams:
+    """Runtime form of the reference's -D knobs (run-wfa-pim-mram.py:133-139)."""
+    algo: str = "wfa"
+    match: int = 0
+    mismatch: int = 3
+    gap_open: int = 4      # NW: the single linear gap (GAP_I = GAP_D)
+    gap_ext: int = 1
+    max_score: int = 250
+    read_size: int = 112
+    backtrace: bool = False
+    reduce: bool = False
+    ngpus: int = 1
+    device: int = 0
+    arena_mb: int = 0
+
+    def to_c(self) -> AimParams:
+        p = AimParams()
+        p.algo = _ALGO[self.algo]
+        p.match, p.mismatch, p.gap_open, p.gap_ext = self.match, self.mismatch, self.gap_open, self.gap_ext
+        p.max_score, p.read_size = self.max_score, self.read_size
+        p.backtrace, p.reduce = int(self.backtrace), int(self.reduce)
+        p.ngpus, p.device, p.arena_mb = self.ngpus, self.device, self.arena_mb
+        return p
+
+
+def derive_knobs(algo: str, read_length: int, error: float, mismatch: int = 3, gap_open: int = 4,
+                 gap_ext: int = 1) -> tuple[int, int]:
+    """(MAX_SCORE, READ_SIZE) as run-*-pim-*.py derives them (run-wfa-pim-mram.py:58-67)."""
+    ms, rs = C.c_int32(), C.c_int32()
+    rc = lib.aim_derive_knobs(_ALGO[algo], read_length, float(error), mismatch, gap_open, gap_ext, C.byref(ms), C.byref(rs))
+    if rc != 0:
+        raise AimError(rc)
+    return ms.value, rs.value
+
+
+def pairs_to_process(pairs_in_file: int, n_arg: int, nr_dpus: int = 1) -> int:
+    return int(lib.aim_pairs_to_process(pairs_in_file, n_arg, nr_dpus))
+
+
+class PinnedArray:
+    """A numpy view over cudaHostAlloc'ed memory (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(shape)) * self.dtype.itemsize
+        self.ptr = lib.aim_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise MemoryError(f"aim_host_alloc({self.nbytes}) failed: {lib.aim_last_error().decode()}")
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            self.array = None
+            lib.aim_host_free(ptr)
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def count_pairs(path: str | os.PathLike) -> int:
+    n = lib.aim_count_pairs(os.fsencode(path))
+    if n < 0:
+        raise AimError(int(n))
+    return int(n)
+
+
+def read_pairs(path: str | os.PathLike, read_size: int, max_pairs: int | None = None):
+    """get_reads (host.c:91-134) -> (plen, tlen, patterns[n, read_size], texts[n, read_size])."""
+    total = count_pairs(path)
+    want = total if max_pairs is None else min(total, max_pairs)
+    plen = np.zeros(want, np.int32)
+    tlen = np.zeros(want, np.int32)
+    pats = np.zeros((want, read_size), np.uint8)
+    txts = np.zeros((want, read_size), np.uint8)
+    n = lib.aim_read_pairs(os.fsencode(path), want, read_size, _ptr(plen), _ptr(tlen), _ptr(pats), _ptr(txts))
+    if n < 0:
+        raise AimError(int(n))
+    return plen[:n], tlen[:n], pats[:n], txts[:n]
+
+
+def generate_pairs(seed: int, n: int, length: int, error: float, read_size: int, first_pair: int = 0,
+                   nthreads: int = 0, out=None):
+    """Synthetic pairs (generate_dataset semantics, Datasets/README.md:19-25)."""
+    if out is None:
+        plen, tlen = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        pats, txts = np.zeros((n, read_size), np.uint8), np.zeros((n, read_size), np.uint8)
+    else:
+        plen, tlen, pats, txts = out
+    nthreads = nthreads or (os.cpu_count() or 1)
+    rc = lib.aim_generate_pairs(seed, first_pair, n, length, float(error), read_size,
+                                _ptr(plen), _ptr(tlen), _ptr(pats), _ptr(txts), nthreads)
+    if rc != 0:
+        raise AimError(rc)
+    return plen, tlen, pats, txts
+
+
+def write_pairs(path, plen, tlen, pats, txts) -> None:
+    rc = lib.aim_write_pairs(os.fsencode(path), len(plen), pats.shape[1], _ptr(plen), _ptr(tlen), _ptr(pats), _ptr(txts))
+    if rc != 0:
+        raise AimError(rc)
+
+
+def align_batch(params: AlignParams, plen, tlen, patterns, texts, idx_base: int = 0, results=None, ops=None):
+    """aim_align_batch on host arrays -> (results[RESULT_DTYPE], ops[n, 2*read_size] | None, phase_ms[3])."""
+    n = len(plen)
+    rs = params.read_size
+    plen = np.ascontiguousarray(plen, np.int32)
+    tlen = np.ascontiguousarray(tlen, np.int32)
+    patterns = np.ascontiguousarray(patterns, np.uint8)
+    texts = np.ascontiguousarray(texts, np.uint8)
+    if n and (patterns.shape != (n, rs) or texts.shape != (n, rs)):
+        raise ValueError(f"patterns/texts must be [n, read_size={rs}]")
+    if results is None:
+        results = np.zeros(n, RESULT_DTYPE)
+    if ops is None and params.backtrace:
+        ops = np.zeros((n, 2 * rs), np.uint8)
+    phase = (C.c_double * 3)()
+    p = params.to_c()
+    rc = lib.aim_align_batch(C.byref(p), n, idx_base, _ptr(plen), _ptr(tlen), _ptr(patterns), _ptr(texts),
+                             _ptr(results), _ptr(ops) if params.backtrace else None, phase)
+    if rc != 0:
+        raise AimError(rc)
+    return results, (ops if params.backtrace else None), list(phase)
+
+
+def align_device(params: AlignParams, n: int, d_plen: int, d_tlen: int, d_patterns: int, d_texts: int,
+                 d_results: int, d_ops: int | None, stream: int = 0, device: int = 0, timed: bool = True):
+    """aim_align_device on raw device addresses -> (kernel_ms | None, launches)."""
+    p = params.to_c()
+    ms = C.c_float(0.0)
+    nl = C.c_int32(0)
+    rc = lib.aim_align_device(C.byref(p), device, n, 0, d_plen, d_tlen, d_patterns, d_texts, d_results,
+                              d_ops if params.backtrace else None, stream or None,
+                              C.byref(ms) if timed else None, C.byref(nl))
+    if rc != 0:
+        raise AimError(rc)
+    return (ms.value if timed else None), nl.value
+
+
+def cigar_strings(results: np.ndarray, ops: np.ndarray) -> list[str]:
+    """RLE CIGARs as edit_cigar_print writes them (host.c:69-89)."""
+    out = []
+    buf = C.create_string_buffer(ops.shape[1] * 12 + 16)
+    for i in range(len(results)):
+        ln = lib.aim_cigar_rle(_ptr(ops[i]), int(results["begin_offset"][i]), int(results["end_offset"][i]), buf, len(buf))
+        if ln < 0:
+            raise AimError(-5)
+        out.append(buf.raw[:ln].decode())
+    return out
+
+
+def write_results(path, results: np.ndarray, ops: np.ndarray | None, read_size: int, backtrace: bool) -> None:
+    rc = lib.aim_write_results(os.fsencode(path), len(results), read_size, int(backtrace), _ptr(results),
+                               _ptr(ops) if backtrace else None)
+    if rc != 0:
+        raise AimError(rc)
+
+
+def device_count() -> int:
+    return int(lib.aim_device_count())
+
+
+def shutdown() -> None:
+    lib.aim_shutdown()

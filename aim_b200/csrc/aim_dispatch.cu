@@ -1,0 +1,383 @@
+// The device boundary: C-ABI entry points, per-GPU contexts, pinned double-buffered transfers.
+//
+// Replaces the dpu_alloc / dpu_prepare_xfer / dpu_push_xfer / dpu_launch sequence of the
+// reference host (WFA/DPU-MRAM/host/host.c:186-330): the four input pushes (:246-268), the
+// synchronous launch (:289) and the two result pulls (:316-326) become, per GPU, a chunked
+// pipeline on two CUDA streams so that chunk c+1's upload, chunk c's alignment and chunk c-1's
+// CIGAR download overlap.  Pairs shard contiguously over GPUs exactly as the reference shards
+// them over DPUs (host.c:201-209); no collective is involved.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "aim_internal.h"
+
+namespace aim {
+
+namespace {
+
+#define AIM_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                    \
+            return AIM_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+struct ChunkBuf {
+    // device
+    int32_t *d_plen = nullptr, *d_tlen = nullptr;
+    char *d_pat = nullptr, *d_txt = nullptr, *d_ops = nullptr;
+    aim_result *d_res = nullptr;
+    // pinned staging (used only for caller buffers that are not pinned)
+    int32_t *h_plen = nullptr, *h_tlen = nullptr;
+    char *h_pat = nullptr, *h_txt = nullptr, *h_ops = nullptr;
+    aim_result *h_res = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, h2d done, kernel done, d2h done
+    uint32_t pairs_cap = 0;
+    int32_t read_size = 0;
+    bool has_ops = false, has_staging = false;
+};
+
+struct DeviceCtx {
+    int device = -1;
+    bool ready = false;
+    Scratch scratch;
+    ChunkBuf chunk[2];
+    std::mutex mu;
+};
+
+std::mutex g_mu;
+std::vector<DeviceCtx *> g_ctx;
+
+int get_ctx(int device, DeviceCtx **out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                  " (aim_b200 has no CPU fallback)");
+        return AIM_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) { set_error("device ordinal out of range"); return AIM_ERR_ARG; }
+    if ((int)g_ctx.size() < count) g_ctx.resize((size_t)count, nullptr);
+    if (!g_ctx[(size_t)device]) {
+        DeviceCtx *c = new DeviceCtx();
+        c->device = device;
+        cudaDeviceProp prop;
+        AIM_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) {
+            set_error("device is not sm_100 class; this library carries sm_100a code only");
+            delete c;
+            return AIM_ERR_NO_DEVICE;
+        }
+        c->scratch.sm_count = prop.multiProcessorCount;
+        c->scratch.device = device;
+        c->ready = true;
+        g_ctx[(size_t)device] = c;
+    }
+    *out = g_ctx[(size_t)device];
+    return AIM_OK;
+}
+
+void free_chunk(ChunkBuf &b)
+{
+    cudaFree(b.d_plen); cudaFree(b.d_tlen); cudaFree(b.d_pat); cudaFree(b.d_txt); cudaFree(b.d_ops); cudaFree(b.d_res);
+    cudaFreeHost(b.h_plen); cudaFreeHost(b.h_tlen); cudaFreeHost(b.h_pat); cudaFreeHost(b.h_txt);
+    cudaFreeHost(b.h_ops); cudaFreeHost(b.h_res);
+    if (b.stream) cudaStreamDestroy(b.stream);
+    for (auto &e : b.ev) if (e) cudaEventDestroy(e);
+    b = ChunkBuf();
+}
+
+int ensure_chunk(ChunkBuf &b, uint32_t pairs, int32_t read_size, bool ops, bool staging)
+{
+    if (b.pairs_cap >= pairs && b.read_size == read_size && (b.has_ops || !ops) && (b.has_staging || !staging)) return AIM_OK;
+    free_chunk(b);
+    const size_t rs = (size_t)read_size;
+    AIM_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+    for (auto &e : b.ev) AIM_CUDA(cudaEventCreate(&e));
+    AIM_CUDA(cudaMalloc(&b.d_plen, pairs * sizeof(int32_t)));
+    AIM_CUDA(cudaMalloc(&b.d_tlen, pairs * sizeof(int32_t)));
+    AIM_CUDA(cudaMalloc(&b.d_pat, pairs * rs));
+    AIM_CUDA(cudaMalloc(&b.d_txt, pairs * rs));
+    AIM_CUDA(cudaMalloc(&b.d_res, pairs * sizeof(aim_result)));
+    if (ops) AIM_CUDA(cudaMalloc(&b.d_ops, pairs * 2 * rs));
+    if (staging) {
+        AIM_CUDA(cudaHostAlloc(&b.h_plen, pairs * sizeof(int32_t), cudaHostAllocDefault));
+        AIM_CUDA(cudaHostAlloc(&b.h_tlen, pairs * sizeof(int32_t), cudaHostAllocDefault));
+        AIM_CUDA(cudaHostAlloc(&b.h_pat, pairs * rs, cudaHostAllocDefault));
+        AIM_CUDA(cudaHostAlloc(&b.h_txt, pairs * rs, cudaHostAllocDefault));
+        AIM_CUDA(cudaHostAlloc(&b.h_res, pairs * sizeof(aim_result), cudaHostAllocDefault));
+        if (ops) AIM_CUDA(cudaHostAlloc(&b.h_ops, pairs * 2 * rs, cudaHostAllocDefault));
+    }
+    b.pairs_cap = pairs;
+    b.read_size = read_size;
+    b.has_ops = ops;
+    b.has_staging = staging;
+    return AIM_OK;
+}
+
+bool is_pinned(const void *p)
+{
+    if (!p) return true;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int validate(const aim_params *p, bool need_ops, const void *ops)
+{
+    if (!p) { set_error("params is NULL"); return AIM_ERR_ARG; }
+    if (p->algo < AIM_ALGO_NW || p->algo > AIM_ALGO_WFA) { set_error("unknown algo"); return AIM_ERR_ARG; }
+    if (p->read_size <= 0 || (p->read_size % 8) != 0) { set_error("read_size must be a positive multiple of 8"); return AIM_ERR_ARG; }
+    // the run scripts' penalty validation (run-wfa-pim-mram.py:44-46; NW has no gap_ext)
+    if (p->match > 0 || p->mismatch <= 0 || p->gap_open <= 0 || (p->algo != AIM_ALGO_NW && p->gap_ext <= 0)) {
+        set_error("Wrong affine gap penalties must be  m <= 0 and g, a, x > 0");
+        return AIM_ERR_ARG;
+    }
+    if (p->max_score < 0) { set_error("max_score must be >= 0"); return AIM_ERR_ARG; }
+    if (need_ops && p->backtrace && !ops) { set_error("ops buffer required when backtrace is set"); return AIM_ERR_ARG; }
+    return AIM_OK;
+}
+
+int launch(const KernelArgs &a, Scratch *s, cudaStream_t stream, int *launches)
+{
+    if (a.p.algo == AIM_ALGO_WFA) return launch_wfa(a, s, stream, launches);
+    return launch_dp(a, s, stream, launches);
+}
+
+// One GPU's share [first, first + n) of a host batch.
+int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint32_t idx_base,
+              const int32_t *plen, const int32_t *tlen, const char *patterns, const char *texts,
+              aim_result *results, char *ops, double phase_ms[3], std::string *err)
+{
+    auto fail = [&](int rc) { if (err) *err = aim_last_error(); return rc; };
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(device, &ctx);
+    if (rc != AIM_OK) return fail(rc);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(AIM_ERR_CUDA); }
+    if (n == 0) return AIM_OK;
+
+    const size_t rs = (size_t)p.read_size;
+    const bool bt = p.backtrace != 0;
+    plen += first; tlen += first;
+    patterns += (size_t)first * rs; texts += (size_t)first * rs;
+    results += first;
+    if (ops) ops += (size_t)first * 2 * rs;
+    const bool pin_in = is_pinned(plen) && is_pinned(tlen) && is_pinned(patterns) && is_pinned(texts);
+    const bool pin_out = is_pinned(results) && (!bt || is_pinned(ops));
+    const bool staging = !(pin_in && pin_out);
+
+    const size_t per_pair = 2 * rs + (bt ? 2 * rs : 0) + sizeof(aim_result) + 8;
+    uint32_t chunk_pairs = (uint32_t)std::max<size_t>(4096, std::min<size_t>((128u << 20) / per_pair, 1u << 20));
+    chunk_pairs = std::min(chunk_pairs, n);
+    const uint32_t nchunks = (n + chunk_pairs - 1) / chunk_pairs;
+    for (int b = 0; b < (nchunks > 1 ? 2 : 1); ++b) {
+        rc = ensure_chunk(ctx->chunk[b], chunk_pairs, p.read_size, bt, staging);
+        if (rc != AIM_OK) return fail(rc);
+    }
+    double ph[3] = {0, 0, 0};
+    std::vector<uint32_t> cn(nchunks);
+
+    auto finish = [&](uint32_t c) -> int {
+        ChunkBuf &B = ctx->chunk[c & 1];
+        const uint32_t off = c * chunk_pairs, m = cn[c];
+        cudaError_t e = cudaEventSynchronize(B.ev[3]);
+        if (e != cudaSuccess) { set_error(std::string("chunk sync: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
+        if (!pin_out) {
+            memcpy(results + off, B.h_res, (size_t)m * sizeof(aim_result));
+            if (bt) memcpy(ops + (size_t)off * 2 * rs, B.h_ops, (size_t)m * 2 * rs);
+        }
+        float t;
+        for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&t, B.ev[k], B.ev[k + 1]); ph[k] += t; }
+        return AIM_OK;
+    };
+
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        ChunkBuf &B = ctx->chunk[c & 1];
+        if (c >= 2) { rc = finish(c - 2); if (rc != AIM_OK) return fail(rc); }
+        const uint32_t off = c * chunk_pairs, m = std::min(chunk_pairs, n - off);
+        cn[c] = m;
+        const int32_t *s_plen = plen + off, *s_tlen = tlen + off;
+        const char *s_pat = patterns + (size_t)off * rs, *s_txt = texts + (size_t)off * rs;
+        if (!pin_in) {
+            memcpy(B.h_plen, s_plen, (size_t)m * 4); memcpy(B.h_tlen, s_tlen, (size_t)m * 4);
+            memcpy(B.h_pat, s_pat, (size_t)m * rs); memcpy(B.h_txt, s_txt, (size_t)m * rs);
+            s_plen = B.h_plen; s_tlen = B.h_tlen; s_pat = B.h_pat; s_txt = B.h_txt;
+        }
+        cudaStream_t st = B.stream;
+        AIM_CUDA(cudaEventRecord(B.ev[0], st));
+        AIM_CUDA(cudaMemcpyAsync(B.d_plen, s_plen, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        AIM_CUDA(cudaMemcpyAsync(B.d_tlen, s_tlen, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        AIM_CUDA(cudaMemcpyAsync(B.d_pat, s_pat, (size_t)m * rs, cudaMemcpyHostToDevice, st));
+        AIM_CUDA(cudaMemcpyAsync(B.d_txt, s_txt, (size_t)m * rs, cudaMemcpyHostToDevice, st));
+        AIM_CUDA(cudaEventRecord(B.ev[1], st));
+        // kernels of consecutive chunks share the per-device scratch: keep them in order
+        if (c >= 1) AIM_CUDA(cudaStreamWaitEvent(st, ctx->chunk[(c - 1) & 1].ev[2], 0));
+        KernelArgs a{p, m, idx_base + first + off, B.d_plen, B.d_tlen, B.d_pat, B.d_txt, B.d_res, bt ? B.d_ops : nullptr};
+        rc = launch(a, &ctx->scratch, st, nullptr);
+        if (rc != AIM_OK) return fail(rc);
+        AIM_CUDA(cudaEventRecord(B.ev[2], st));
+        aim_result *o_res = pin_out ? results + off : B.h_res;
+        AIM_CUDA(cudaMemcpyAsync(o_res, B.d_res, (size_t)m * sizeof(aim_result), cudaMemcpyDeviceToHost, st));
+        if (bt) {
+            char *o_ops = pin_out ? ops + (size_t)off * 2 * rs : B.h_ops;
+            AIM_CUDA(cudaMemcpyAsync(o_ops, B.d_ops, (size_t)m * 2 * rs, cudaMemcpyDeviceToHost, st));
+        }
+        AIM_CUDA(cudaEventRecord(B.ev[3], st));
+    }
+    for (uint32_t c = (nchunks >= 2 ? nchunks - 2 : 0); c < nchunks; ++c) {
+        rc = finish(c);
+        if (rc != AIM_OK) return fail(rc);
+    }
+    if (phase_ms) for (int k = 0; k < 3; ++k) phase_ms[k] = ph[k];
+    return AIM_OK;
+}
+
+}  // namespace
+
+int scratch_reserve(Scratch *s, size_t bytes)
+{
+    if (s->bytes >= bytes) return AIM_OK;
+    // the scratch may still be in use by an earlier launch on another stream
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && s->buf) e = cudaFree(s->buf);
+    s->buf = nullptr;
+    s->bytes = 0;
+    if (e == cudaSuccess) e = cudaMalloc(&s->buf, bytes);
+    if (e != cudaSuccess) {
+        set_error(std::string("scratch allocation of ") + std::to_string(bytes >> 20) + " MiB: " + cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? AIM_ERR_NOMEM : AIM_ERR_CUDA;
+    }
+    s->bytes = bytes;
+    return AIM_OK;
+}
+
+}  // namespace aim
+
+using namespace aim;
+
+extern "C" int aim_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+extern "C" void *aim_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        set_error("cudaHostAlloc failed");
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void aim_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void aim_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (DeviceCtx *c : g_ctx) {
+        if (!c) continue;
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        free_chunk(c->chunk[0]);
+        free_chunk(c->chunk[1]);
+        cudaFree(c->scratch.buf);
+        delete c;
+    }
+    g_ctx.clear();
+}
+
+extern "C" int aim_align_device(const aim_params *params, int device, uint32_t n, uint32_t idx_base,
+                                const int32_t *d_plen, const int32_t *d_tlen, const char *d_patterns,
+                                const char *d_texts, aim_result *d_results, char *d_ops, void *stream,
+                                float *kernel_ms, int32_t *launches)
+{
+    int rc = validate(params, true, d_ops);
+    if (rc != AIM_OK) return rc;
+    if (!d_plen || !d_tlen || !d_patterns || !d_texts || !d_results) { set_error("NULL device buffer"); return AIM_ERR_ARG; }
+    DeviceCtx *ctx = nullptr;
+    rc = get_ctx(device, &ctx);
+    if (rc != AIM_OK) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    AIM_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) {
+        AIM_CUDA(cudaEventCreate(&e0));
+        AIM_CUDA(cudaEventCreate(&e1));
+        AIM_CUDA(cudaEventRecord(e0, st));
+    }
+    KernelArgs a{*params, n, idx_base, d_plen, d_tlen, d_patterns, d_texts, d_results, params->backtrace ? d_ops : nullptr};
+    int nl = 0;
+    rc = launch(a, &ctx->scratch, st, &nl);
+    if (launches) *launches = nl;
+    if (kernel_ms) {
+        if (rc == AIM_OK) {
+            AIM_CUDA(cudaEventRecord(e1, st));
+            AIM_CUDA(cudaEventSynchronize(e1));
+            AIM_CUDA(cudaEventElapsedTime(kernel_ms, e0, e1));
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return rc;
+}
+
+extern "C" int aim_align_batch(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen,
+                               const int32_t *tlen, const char *patterns, const char *texts,
+                               aim_result *results, char *ops, double phase_ms[3])
+{
+    int rc = validate(params, true, ops);
+    if (rc != AIM_OK) return rc;
+    if (n > 0 && (!plen || !tlen || !patterns || !texts || !results)) { set_error("NULL host buffer"); return AIM_ERR_ARG; }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (plen[i] < 0 || tlen[i] < 0) { set_error("negative sequence length"); return AIM_ERR_ARG; }
+        if (plen[i] > params->read_size || tlen[i] > params->read_size) {
+            set_error("READ LENGTH less than length of the input reads");
+            return AIM_ERR_LENGTH;
+        }
+    }
+    if (phase_ms) phase_ms[0] = phase_ms[1] = phase_ms[2] = 0.0;
+    int ndev = aim_device_count();
+    if (ndev == 0) { set_error("no CUDA device (aim_b200 has no CPU fallback)"); return AIM_ERR_NO_DEVICE; }
+    int g = params->ngpus <= 1 ? 1 : params->ngpus;
+    if (params->device < 0 || params->device + g > ndev) { set_error("device range exceeds visible GPUs"); return AIM_ERR_ARG; }
+    if (g == 1) return run_shard(*params, params->device, 0, n, idx_base, plen, tlen, patterns, texts, results, ops, phase_ms, nullptr);
+
+    // contiguous index ranges per GPU, one host thread + stream set each (host.c:201-209 per DPU)
+    const uint32_t per = (n + (uint32_t)g - 1) / (uint32_t)g;
+    std::vector<std::thread> th;
+    std::vector<int> rcs((size_t)g, AIM_OK);
+    std::vector<std::string> errs((size_t)g);
+    std::vector<double> ph((size_t)g * 3, 0.0);
+    for (int d = 0; d < g; ++d) {
+        const uint32_t first = std::min(n, (uint32_t)d * per), cnt = std::min(per, n - first);
+        th.emplace_back([&, d, first, cnt]() {
+            rcs[(size_t)d] = run_shard(*params, params->device + d, first, cnt, idx_base, plen, tlen, patterns, texts,
+                                       results, ops, &ph[(size_t)d * 3], &errs[(size_t)d]);
+            if (rcs[(size_t)d] != AIM_OK && errs[(size_t)d].empty()) errs[(size_t)d] = aim_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < g; ++d) {
+        if (rcs[(size_t)d] != AIM_OK) { set_error("gpu " + std::to_string(params->device + d) + ": " + errs[(size_t)d]); return rcs[(size_t)d]; }
+        if (phase_ms) for (int k = 0; k < 3; ++k) phase_ms[k] = std::max(phase_ms[k], ph[(size_t)d * 3 + k]);
+    }
+    return AIM_OK;
+}

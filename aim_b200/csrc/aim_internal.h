@@ -1,0 +1,57 @@
+// Internal declarations shared by the host logic, the dispatcher and the kernels.
+#ifndef AIM_INTERNAL_H
+#define AIM_INTERNAL_H
+
+#include <stdint.h>
+#include <string>
+
+#include "aim_b200.h"
+
+namespace aim {
+
+void set_error(const std::string &msg);
+
+// Deterministic (data-independent) wavefront schedule of gap-affine WFA for a penalty set:
+// which scores have a wavefront, its [lo,hi] and whether it carries I / D components when no
+// adaptive trimming happens.  Trimming only narrows ranges, so these are upper bounds and size
+// the per-pair history exactly (WFA/DPU-MRAM/dpu/wfa.c:275-354 computes the same ranges at run time).
+struct WfaSchedule {
+    uint32_t hist_slots;   // int16 slots needed for the full history up to max_score
+    uint32_t max_width;    // widest wavefront
+    uint32_t ring_scores;  // scores that must stay live for score-only mode: max(x, o+e) + 1
+};
+WfaSchedule wfa_schedule(int max_score, int mismatch, int gap_open, int gap_ext);
+
+// Everything a kernel launch needs (device pointers).
+struct KernelArgs {
+    aim_params p;
+    uint32_t n;
+    uint32_t idx_base;
+    const int32_t *plen;
+    const int32_t *tlen;
+    const char *patterns;
+    const char *texts;
+    aim_result *results;
+    char *ops;
+};
+
+// Per-device scratch owned by the dispatcher and handed to the launchers.
+struct Scratch {
+    void *buf = nullptr;        // general scratch (WFA global arena / DP rows+flags)
+    size_t bytes = 0;
+    uint32_t *counter = nullptr;  // work-queue counters (device), 4 words
+    int sm_count = 0;
+    int device = 0;
+};
+
+// Ensure scratch->buf holds at least `bytes` (grows, never shrinks).  Returns AIM_OK/AIM_ERR_*.
+int scratch_reserve(Scratch *s, size_t bytes);
+
+// Launchers (aim_wfa.cu / aim_dp.cu).  Enqueue on `stream`; return AIM_OK or AIM_ERR_*;
+// *launches is incremented by the number of kernels enqueued.
+int launch_wfa(const KernelArgs &a, Scratch *s, void *stream, int *launches);
+int launch_dp(const KernelArgs &a, Scratch *s, void *stream, int *launches);
+
+}  // namespace aim
+
+#endif

@@ -1,0 +1,153 @@
+/* aim_b200.h — C ABI of the B200-native batched pairwise aligner (drop-in for the path
+ * safaad/aim offloads to UPMEM DPUs).  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * The reference has no plugin/FFI API: its boundary is (1) the process `host <pairs> <out> <N>`
+ * and (2) the six dpu_push_xfer transfers + dpu_launch inside host main()
+ * (WFA/DPU-MRAM/host/host.c:186-330; the other five hosts are line-for-line equivalent).
+ * aim_align_batch() replaces (2); tools/host.cpp rebuilds (1) on top of it.  All citations are
+ * paths under the reference checkout.
+ */
+#ifndef AIM_B200_H
+#define AIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIM_B200_ABI_VERSION 1
+
+/* Which reference program is being replaced. */
+#define AIM_ALGO_NW 0  /* NW/DPU-{WRAM,MRAM}: linear gap, int16 flat table (NW/DPU-WRAM/dpu/nw.c:109-153)      */
+#define AIM_ALGO_SWG 1 /* SWG/DPU-MRAM: gap-affine, int16 cells, MAX_SCORE borders (SWG/DPU-MRAM/dpu/swg.c:151) */
+#define AIM_ALGO_WFA 2 /* WFA/DPU-{WRAM,MRAM}: gap-affine WFA, +adaptive with reduce=1 (WFA/DPU-MRAM/dpu/wfa.c:356) */
+
+/* Return codes (the reference aborts the process through DPU_ASSERT/exit instead). */
+#define AIM_OK 0
+#define AIM_ERR_ARG (-1)        /* NULL/invalid argument or penalty set                                  */
+#define AIM_ERR_LENGTH (-2)     /* a sequence is longer than read_size (host.c:119-123 exits the process) */
+#define AIM_ERR_CUDA (-3)       /* CUDA runtime failure; aim_last_error() has the text                    */
+#define AIM_ERR_NO_DEVICE (-4)  /* no usable sm_100 device: there is NO CPU fallback                     */
+#define AIM_ERR_IO (-5)         /* file could not be opened / written                                     */
+#define AIM_ERR_NOMEM (-6)
+
+/* Per-pair status (aim_result.status).  0 everywhere in a healthy run. */
+#define AIM_STATUS_OK 0
+#define AIM_STATUS_BACKTRACE 1 /* reference would print "No link found"/"No backtrace operation found" and exit(1) */
+#define AIM_STATUS_ARENA 2     /* wavefront history exceeded the per-pair arena (reference: "Out of memory MRAM") */
+
+/* The compile-time knobs of the reference (-DMAX_SCORE -DREAD_SIZE -DMATCH -DMISMATCH -DGAP_O
+ * -DGAP_E [-DGAP_I -DGAP_D] [-DBACKTRACE] [-DREDUCE]; WFA/DPU-MRAM/run-wfa-pim-mram.py:133-139)
+ * as runtime parameters.  NW uses gap_open as its single linear gap (GAP_I = GAP_D) and ignores
+ * gap_ext, match and max_score; WFA ignores match (assumed 0); reduce is WFA only. */
+typedef struct aim_params {
+    int32_t algo;       /* AIM_ALGO_*                                                  */
+    int32_t match;      /* MATCH    (<= 0)                                             */
+    int32_t mismatch;   /* MISMATCH (> 0)                                              */
+    int32_t gap_open;   /* GAP_O, or GAP_I = GAP_D for NW (> 0)                        */
+    int32_t gap_ext;    /* GAP_E (> 0)                                                 */
+    int32_t max_score;  /* MAX_SCORE: WFA give-up threshold, SWG border value          */
+    int32_t read_size;  /* READ_SIZE: row pitch of patterns/texts; multiple of 8       */
+    int32_t backtrace;  /* BACKTRACE: produce ops / begin_offset                       */
+    int32_t reduce;     /* REDUCE: WFA-adaptive (min length 10, max distance 50)       */
+    int32_t ngpus;      /* <=1: one device; N: shard pairs contiguously over N devices */
+    int32_t device;     /* first device ordinal                                        */
+    int32_t arena_mb;   /* long-read WFA history arena per resident pair in MiB (0 = default) */
+    int32_t reserved[4];
+} aim_params;
+
+/* result_t of the reference (WFA/DPU-MRAM/common/common.h:179-187; NW/DPU-WRAM/common/common.h:122-130)
+ * with the padding word carrying the per-pair status. */
+typedef struct aim_result {
+    int32_t max_operations; /* pattern_len + text_len                                        */
+    int32_t begin_offset;   /* first valid op; ops[begin_offset .. end_offset) is the CIGAR  */
+    int32_t end_offset;     /* == max_operations                                             */
+    int32_t score;
+    int32_t status;         /* AIM_STATUS_*                                                  */
+    uint32_t idx;           /* 0-based pair number                                           */
+} aim_result;
+
+/* ---- the device boundary (replaces host.c:186-330) ----------------------------------------
+ * Align n pairs held in HOST memory.  Layout is the reference host's own (host.c:126-131,
+ * 203-205, 305-311): pair i's pattern at patterns + i*read_size (plen[i] bytes, compared as raw
+ * bytes), its text at texts + i*read_size, its ops at ops + i*2*read_size ('M'-filled, valid span
+ * [begin_offset,end_offset)), its result at results[i] with idx = idx_base + i.
+ * ops may be NULL iff !backtrace.  phase_ms (may be NULL) receives the three phases the reference
+ * prints: [0] "CPU-DPU" (H2D), [1] "DPU Kernel", [2] "DPU-CPU" (D2H), summed over chunks as
+ * measured by CUDA events; chunks are double-buffered so the phases overlap in wall time.
+ * Synchronous; the caller owns every buffer; nothing is retained.  Buffers obtained from
+ * aim_host_alloc() are DMA'd directly, others are staged through pinned chunks.
+ * Thread-safety: one call at a time per process (as the reference). */
+int aim_align_batch(const aim_params *params, uint32_t n, uint32_t idx_base,
+                    const int32_t *plen, const int32_t *tlen,
+                    const char *patterns, const char *texts,
+                    aim_result *results, char *ops, double phase_ms[3]);
+
+/* Same work with every buffer already resident in the HBM of `device` (all pointers are device
+ * pointers; patterns/texts/ops 16-byte aligned).  stream is a cudaStream_t passed as void*
+ * (NULL = default stream).  Asynchronous w.r.t. the host unless kernel_ms != NULL, in which
+ * case the kernels are bracketed by CUDA events on `stream`, synchronised, and the elapsed
+ * device time is returned.  launches (may be NULL) receives the number of kernels launched. */
+int aim_align_device(const aim_params *params, int device, uint32_t n, uint32_t idx_base,
+                     const int32_t *d_plen, const int32_t *d_tlen,
+                     const char *d_patterns, const char *d_texts,
+                     aim_result *d_results, char *d_ops,
+                     void *stream, float *kernel_ms, int32_t *launches);
+
+/* Pinned host memory for zero-staging transfers (cudaHostAlloc / cudaFreeHost). */
+void *aim_host_alloc(size_t bytes);
+void aim_host_free(void *p);
+
+/* Release cached device/pinned buffers and streams. */
+void aim_shutdown(void);
+
+int aim_device_count(void);              /* number of CUDA devices visible, 0 if none                   */
+const char *aim_last_error(void);        /* text of the last error on this thread                       */
+const char *aim_strerror(int code);
+int aim_abi_version(void);
+
+/* ---- host-side logic shared by the CLI and the run-*-pim-*.py wrappers (no GPU needed) ----- */
+
+/* MAX_SCORE / READ_SIZE exactly as the run scripts derive them with Python floats
+ * (WFA/DPU-MRAM/run-wfa-pim-mram.py:58-67, NW/DPU-MRAM/run-nw-pim-mram.py:51-60):
+ *   w = l*e;  MAX_SCORE = ceil(max(w*x, w*(g+a)))   (NW: ceil(w*g));  READ_SIZE = ceil((l+w+7)/8)*8 */
+int aim_derive_knobs(int32_t algo, int32_t read_length, double error, int32_t mismatch,
+                     int32_t gap_open, int32_t gap_ext, int32_t *max_score, int32_t *read_size);
+
+/* How many pairs the reference host aligns: min(pairs in file, nr_dpus*roundup8(N/nr_dpus))
+ * (host.c:191,201-209); N <= nr_dpus is rejected by the caller as in host.c:180-184. */
+uint32_t aim_pairs_to_process(uint32_t pairs_in_file, uint32_t n_arg, uint32_t nr_dpus);
+
+/* get_reads (host.c:91-134): read up to max_pairs pairs of lines (">PATTERN\n" / "<TEXT\n"; the
+ * first and last character of every line are dropped unchecked).  Buffers are n x read_size.
+ * Returns the number of pairs read (>= 0), AIM_ERR_LENGTH if a sequence exceeds read_size,
+ * AIM_ERR_IO if the file cannot be opened. */
+int64_t aim_read_pairs(const char *path, uint32_t max_pairs, int32_t read_size,
+                       int32_t *plen, int32_t *tlen, char *patterns, char *texts);
+/* Count pairs (complete line pairs) in a file; AIM_ERR_IO on failure. */
+int64_t aim_count_pairs(const char *path);
+
+/* The reference's result printer (host.c:332-353 + edit_cigar_print :69-89): per pair
+ * "%d, %d, \n" (idx, score) and, if backtrace, the run-length CIGAR of ops[begin..end) + "\n". */
+int aim_write_results(const char *path, uint32_t n, int32_t read_size, int32_t backtrace,
+                      const aim_result *results, const char *ops);
+/* RLE one pair's ops into out (capacity cap); returns the length written (no NUL) or -1. */
+int aim_cigar_rle(const char *ops, int32_t begin_offset, int32_t end_offset, char *out, size_t cap);
+
+/* Synthetic pairs with WFA `generate_dataset` semantics (Datasets/README.md:19-25): pattern =
+ * `length` i.i.d. uniform ACGT; text = copy with ceil(length*error) edits, each uniformly a
+ * mismatch to a different base / a 1-base deletion / a 1-base insertion at a uniform position.
+ * Deterministic in (seed, first_pair + i) whatever the thread count. */
+int aim_generate_pairs(uint64_t seed, uint64_t first_pair, uint32_t n, int32_t length, double error,
+                       int32_t read_size, int32_t *plen, int32_t *tlen, char *patterns, char *texts,
+                       int32_t nthreads);
+/* Write pairs in the Datasets file format. */
+int aim_write_pairs(const char *path, uint32_t n, int32_t read_size, const int32_t *plen,
+                    const int32_t *tlen, const char *patterns, const char *texts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIM_B200_H */

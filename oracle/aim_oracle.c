@@ -1,0 +1,491 @@
+/* TEST INFRASTRUCTURE — CPU oracle for the aim_b200 parity tests.  NOT part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this file's library; aim_b200/ never links, imports or falls back to it.
+ *
+ * It restates, with RUNTIME parameters, the algorithms the reference (safaad/aim) compiles into
+ * its DPU binaries with -D knobs.  Every function cites the reference file:line it follows
+ * (paths under /root/reference).  Parity pinning: the reference has no tests or golden vectors
+ * (SURVEY.md section 4); this restatement is pinned instead against the reference ITSELF,
+ * compiled natively by oracle/refbuild.py (tests/test_oracle_vs_reference.py, run wherever
+ * /root/reference exists) and against the committed fixtures in tests/golden/ that were
+ * generated from those reference builds (tests/golden/make_golden.py).
+ *
+ * Semantics kept literally: int16 offsets/cells with truncation at the same assignments, the
+ * -10 / NULL(-16384) sentinels, the flat DP array indexed num_cols*h+v with num_cols=text_len+1
+ * (rows alias when pattern_len > text_len), MAX_SCORE as SWG border "infinity", the WFA give-up
+ * at score > MAX_SCORE, and the backtrace tie-break order.
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_ALGO_NW 0
+#define ORC_ALGO_SWG 1
+#define ORC_ALGO_WFA 2
+
+#define ORC_OK 0
+#define ORC_ERR_BACKTRACE 1 /* reference would print "No link found"/"No backtrace operation found" and exit(1) */
+
+typedef struct {
+    int32_t algo, match, mismatch, gap_open, gap_ext, max_score, read_size, backtrace, reduce;
+} orc_params;
+
+typedef struct {
+    int32_t max_operations, begin_offset, end_offset, score, status;
+} orc_result;
+
+#define OFFSET_NULL (INT16_MIN / 2) /* WFA/DPU-MRAM/common/common.h:95 */
+#define MINI(a, b) (((a) <= (b)) ? (a) : (b))
+#define MAXI(a, b) (((a) >= (b)) ? (a) : (b))
+
+/* ------------------------------------------------------------------------------------------
+ * WFA / WFA-adaptive.  One history record per score (WFA/DPU-MRAM/common/common.h:126-138).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int present; /* mramIdx[score] != 0 */
+    int klo, khi, lo_base, hi_base;
+    int m_null, i_null, d_null;
+    int16_t *m, *i, *d; /* indexed by k - lo_base */
+} wf_rec;
+
+static void wf_free(wf_rec *r)
+{
+    free(r->m); free(r->i); free(r->d);
+    memset(r, 0, sizeof(*r));
+}
+
+/* WFA/DPU-MRAM/dpu/wfa.c:143-190 allocate_new_score */
+static void wf_alloc(wf_rec *r, int lo, int hi, int kernel)
+{
+    int len = hi - lo + 1;
+    r->present = 1;
+    r->m = (int16_t *)malloc(sizeof(int16_t) * len);
+    r->d = (kernel == 3 || kernel == 1) ? (int16_t *)malloc(sizeof(int16_t) * len) : NULL;
+    r->i = (kernel == 3 || kernel == 2) ? (int16_t *)malloc(sizeof(int16_t) * len) : NULL;
+    r->d_null = r->d == NULL;
+    r->i_null = r->i == NULL;
+    r->m_null = 0;
+    r->klo = r->lo_base = lo;
+    r->khi = r->hi_base = hi;
+}
+
+#define WM(r, k) ((r)->m[(k) - (r)->lo_base])
+#define WI(r, k) ((r)->i[(k) - (r)->lo_base])
+#define WD(r, k) ((r)->d[(k) - (r)->lo_base])
+
+/* WFA/DPU-MRAM/dpu/wfa.c:193-215 affine_wfa_extend */
+static void wfa_extend(wf_rec *w, const char *pattern, const char *text, int plen, int tlen)
+{
+    if (!w->present || w->m_null) return;
+    for (int k = w->klo; k <= w->khi; ++k) {
+        int moffset = WM(w, k);
+        if (moffset < 0) continue;
+        int v = moffset - k, h = moffset, count = 0;
+        while ((v < plen && h < tlen && v >= 0 && h >= 0) && pattern[v++] == text[h++]) ++count;
+        WM(w, k) = (int16_t)(WM(w, k) + count);
+    }
+}
+
+/* WFA/DPU-MRAM/dpu/wfa.c:70-141 affine_wfa_reduce_wvs (min_wavefront_length 10, max_distance_threshold 50) */
+static void wfa_reduce(wf_rec *w, int plen, int tlen)
+{
+    const int min_wavefront_length = 10, max_distance_threshold = 50;
+    int alignment_k = tlen - plen;
+    if (!w->present || w->m_null) return;
+    if ((w->khi - w->klo + 1) < min_wavefront_length) return;
+    int min_distance = MAXI(plen, tlen);
+    int klo = w->klo, khi = w->khi;
+    for (int k = klo; k <= khi; ++k) {
+        int16_t offset = WM(w, k);
+        int distance = MAXI(plen - (offset - k), tlen - offset);
+        min_distance = MINI(distance, min_distance);
+    }
+    int top_limit = MINI(alignment_k - 1, khi);
+    for (int k = w->klo; k < top_limit; ++k) {
+        int16_t offset = WM(w, k);
+        int distance = MAXI(plen - (offset - k), tlen - offset);
+        if ((distance - min_distance) <= max_distance_threshold) break;
+        w->klo = w->klo + 1;
+    }
+    int bottom_limit = MAXI(alignment_k + 1, w->klo);
+    for (int k = khi; k > bottom_limit; --k) {
+        int16_t offset = WM(w, k);
+        int distance = MAXI(plen - (offset - k), tlen - offset);
+        if (distance - min_distance <= max_distance_threshold) break;
+        w->khi = w->khi - 1;
+    }
+    if (w->klo > w->khi) {
+        w->m_null = w->i_null = w->d_null = 1;
+        w->khi = khi;
+        w->klo = klo;
+    }
+}
+
+/* WFA/DPU-MRAM/dpu/wfa.c:217-237 affine_wfa_end_reached */
+static int wfa_end_reached(const wf_rec *w, int plen, int tlen)
+{
+    if (!w->present || w->m_null) return 0;
+    int alignment_k = tlen - plen;
+    if (w->klo <= alignment_k && w->khi >= alignment_k) {
+        int offset = WM(w, alignment_k);
+        if (offset >= tlen) return 1;
+    }
+    return 0;
+}
+
+/* WFA/DPU-MRAM/dpu/wfa.c:275-354 affine_wfa_compute_next + :238-273 affine_wfa_compute_offsets */
+static void wfa_compute_next(wf_rec *hist, int score, const orc_params *p)
+{
+    int mismatch_score = score - p->mismatch;
+    int o_score = score - p->gap_open - p->gap_ext;
+    int e_score = score - p->gap_ext;
+    const wf_rec *A = (mismatch_score < 0 || !hist[mismatch_score].present) ? NULL : &hist[mismatch_score];
+    const wf_rec *B = (o_score < 0 || !hist[o_score].present) ? NULL : &hist[o_score];
+    const wf_rec *E = (e_score < 0 || !hist[e_score].present) ? NULL : &hist[e_score];
+
+    int m_sub_null = (A == NULL) || A->m_null;
+    int m_o_null = (B == NULL) || B->m_null;
+    int i_e_null = (E == NULL) || E->i_null || E->i == NULL;
+    int d_e_null = (E == NULL) || E->d_null || E->d == NULL;
+    int i_out_null = m_o_null && i_e_null;
+    int d_out_null = m_o_null && d_e_null;
+
+    wf_rec *w = &hist[score];
+    if (m_sub_null && i_out_null && d_out_null) { w->present = 0; return; }
+
+    int m_sub_lo = 1, m_sub_hi = -1, m_o_lo = 1, m_o_hi = -1, e_lo = 1, e_hi = -1;
+    if (!m_sub_null) { m_sub_lo = A->klo; m_sub_hi = A->khi; }
+    if (!m_o_null) { m_o_lo = B->klo; m_o_hi = B->khi; }
+    if (!(i_e_null && d_e_null)) { e_lo = E->klo; e_hi = E->khi; }
+    int lo = MINI(MINI(m_sub_lo, m_o_lo), e_lo) - 1;
+    int hi = MAXI(MAXI(m_sub_hi, m_o_hi), e_hi) + 1;
+    int kernel = ((!i_out_null) << 1) | (!d_out_null);
+    wf_alloc(w, lo, hi, kernel);
+
+    for (int k = lo; k <= hi; ++k) {
+        int16_t ins = -10;
+        if (!m_o_null || !i_e_null) {
+            int16_t ins_g = (!m_o_null && m_o_lo <= k - 1 && k - 1 <= m_o_hi) ? WM(B, k - 1) : OFFSET_NULL;
+            int16_t ins_i = (!i_e_null && e_lo <= k - 1 && k - 1 <= e_hi) ? WI(E, k - 1) : OFFSET_NULL;
+            if (ins_g == OFFSET_NULL && ins_i == OFFSET_NULL) ins = OFFSET_NULL;
+            else ins = (int16_t)(MAXI(ins_g, ins_i) + 1);
+            WI(w, k) = ins;
+        }
+        int16_t del = -10;
+        if (!m_o_null || !d_e_null) {
+            int16_t del_g = (!m_o_null && m_o_lo <= k + 1 && k + 1 <= m_o_hi) ? WM(B, k + 1) : OFFSET_NULL;
+            int16_t del_d = (!d_e_null && e_lo <= k + 1 && k + 1 <= e_hi) ? WD(E, k + 1) : OFFSET_NULL;
+            del = MAXI(del_g, del_d);
+            WD(w, k) = del;
+        }
+        int16_t sub = -10;
+        if (!m_sub_null)
+            sub = (int16_t)((m_sub_lo <= k && k <= m_sub_hi) ? WM(A, k) + 1 : OFFSET_NULL);
+        int16_t nw = MAXI(sub, ins);
+        WM(w, k) = MAXI(del, nw);
+    }
+}
+
+/* WFA/DPU-MRAM/dpu/wfa_backtracing.c:219-375 affine_wavefronts_backtrace (+ getters :73-166).
+ * ops is the 2*READ_SIZE 'M'-filled buffer; returns ORC_ERR_BACKTRACE on "No link found". */
+static int wfa_backtrace(const wf_rec *hist, int alignment_score, int plen, int tlen, const orc_params *p,
+                         char *ops, int ops_cap, int *begin_offset_io)
+{
+    int begin_offset = *begin_offset_io;
+    int alignment_k = tlen - plen;
+    int score = alignment_score, k = alignment_k;
+    int16_t offset = WM(&hist[alignment_score], k);
+    int v = offset - k, h = offset;
+    int valid_location = (v > 0 && v <= plen && h > 0 && h <= tlen);
+    enum { T_M, T_I, T_D } type = T_M;
+#define PUT(c) do { if (begin_offset < 0 || begin_offset >= ops_cap) return ORC_ERR_BACKTRACE; ops[begin_offset--] = (c); } while (0)
+
+    while (v > 0 && h > 0 && score > 0) {
+        if (!valid_location) {
+            valid_location = (v > 0 && v <= plen && h > 0 && h <= tlen);
+            if (valid_location) { /* wfa_backtracing.c:48-69 add_trailing_gap */
+                if (k < alignment_k) { for (int i = k; i < alignment_k; ++i) PUT('I'); }
+                else if (k > alignment_k) { for (int i = alignment_k; i < k; ++i) PUT('D'); }
+            }
+        }
+        int gap_open_score = score - p->gap_open - p->gap_ext;
+        int gap_extend_score = score - p->gap_ext;
+        int mismatch_score = score - p->mismatch;
+        const wf_rec *go = (gap_open_score < 0 || !hist[gap_open_score].present) ? NULL : &hist[gap_open_score];
+        const wf_rec *ge = (gap_extend_score < 0 || !hist[gap_extend_score].present) ? NULL : &hist[gap_extend_score];
+        const wf_rec *mm = (mismatch_score < 0 || !hist[mismatch_score].present) ? NULL : &hist[mismatch_score];
+
+        int16_t del_ext = OFFSET_NULL, del_open = OFFSET_NULL, ins_ext = OFFSET_NULL, ins_open = OFFSET_NULL, misms = OFFSET_NULL;
+        if (type != T_I) {
+            if (ge && !ge->d_null && ge->klo <= k + 1 && k + 1 <= ge->khi) del_ext = WD(ge, k + 1);
+            if (gap_open_score >= 0 && go && go->klo <= k + 1 && k + 1 <= go->khi) del_open = WM(go, k + 1);
+        }
+        if (type != T_D) {
+            if (gap_extend_score >= 0 && ge && ge->i != NULL && !ge->i_null && ge->klo <= k - 1 && k - 1 <= ge->khi)
+                ins_ext = (int16_t)(WI(ge, k - 1) + 1);
+            if (gap_open_score >= 0 && go && go->klo <= k - 1 && k - 1 <= go->khi) ins_open = (int16_t)(WM(go, k - 1) + 1);
+        }
+        if (type == T_M) {
+            if (mismatch_score >= 0 && mm && mm->klo <= k && k <= mm->khi) misms = (int16_t)(WM(mm, k) + 1);
+        }
+        int16_t max_del = MAXI(del_ext, del_open);
+        int16_t max_ins = MAXI(ins_ext, ins_open);
+        int16_t max_all = MAXI(misms, MAXI(max_ins, max_del));
+
+        if (type == T_M) {
+            int num_matches = offset - max_all;
+            for (int i = 0; i < num_matches; ++i) PUT('M');
+            offset = max_all;
+            v = offset - k; h = offset;
+            if (v <= 0 || h <= 0) break;
+        }
+        if (max_all == del_ext) { if (valid_location) PUT('D'); score = gap_extend_score; ++k; type = T_D; }
+        else if (max_all == del_open) { if (valid_location) PUT('D'); score = gap_open_score; ++k; type = T_M; }
+        else if (max_all == ins_ext) { if (valid_location) PUT('I'); score = gap_extend_score; --k; --offset; type = T_I; }
+        else if (max_all == ins_open) { if (valid_location) PUT('I'); score = gap_open_score; --k; --offset; type = T_M; }
+        else if (max_all == misms) { if (valid_location) PUT('X'); score = mismatch_score; --offset; }
+        else return ORC_ERR_BACKTRACE;
+        v = offset - k; h = offset;
+    }
+    if (score == 0) {
+        for (int i = 0; i < offset; ++i) PUT('M');
+    } else {
+        while (v > 0) { PUT('D'); --v; }
+        while (h > 0) { PUT('I'); --h; }
+    }
+#undef PUT
+    *begin_offset_io = begin_offset + 1;
+    return ORC_OK;
+}
+
+/* Note on i_null in the ins_ext getter: load_idwavefront_cmpnt_from_mram (dpu_allocator_mram.c:268-346)
+ * leaves iwavefront NULL exactly when the stored i_null flag is set, so "iwavefront != NULL"
+ * (wfa_backtracing.c:124) == !i_null. */
+
+/* WFA/DPU-MRAM/dpu/wfa.c:356-407 affine_wfa_compute + :499-501 ops init + :58-68 cigar init */
+static void wfa_align(const orc_params *p, const char *pattern, const char *text, int plen, int tlen,
+                      orc_result *res, char *ops)
+{
+    res->max_operations = plen + tlen;
+    res->begin_offset = res->max_operations - 1;
+    res->end_offset = res->max_operations;
+    res->score = INT32_MIN;
+    res->status = ORC_OK;
+    if (p->backtrace && ops) memset(ops, 'M', 2 * (size_t)p->read_size);
+
+    wf_rec *hist = (wf_rec *)calloc((size_t)p->max_score + 2, sizeof(wf_rec));
+    wf_alloc(&hist[0], 0, 0, 0);
+    hist[0].m[0] = 0;
+    int score = 0;
+    for (;;) {
+        wf_rec *w = &hist[score];
+        wfa_extend(w, pattern, text, plen, tlen);
+        if (p->reduce) wfa_reduce(w, plen, tlen);
+        if (wfa_end_reached(w, plen, tlen)) {
+            if (p->backtrace && ops)
+                res->status = wfa_backtrace(hist, score, plen, tlen, p, ops, 2 * p->read_size, &res->begin_offset);
+            res->score = score;
+            break;
+        }
+        ++score;
+        if (score > p->max_score) { res->score = score; break; }
+        wfa_compute_next(hist, score, p);
+    }
+    for (int s = 0; s <= p->max_score + 1; ++s) wf_free(&hist[s]);
+    free(hist);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * NW, linear gap (GAP_I = GAP_D = gap_open).  NW/DPU-WRAM/dpu/nw.c:109-153 nw_compute and
+ * :67-107 nw_traceback on the flat int16 table; the NW/DPU-MRAM variant (nw.c:151-236, 91-149)
+ * computes the same values through one-cell MRAM caches.
+ * ------------------------------------------------------------------------------------------ */
+static void nw_align(const orc_params *p, const char *pattern, const char *text, int plen, int tlen,
+                     orc_result *res, char *ops, int16_t *tab)
+{
+    const int GAP_I = p->gap_open, GAP_D = p->gap_open, MISMATCH = p->mismatch;
+    res->max_operations = plen + tlen;
+    res->begin_offset = res->max_operations - 1;
+    res->end_offset = res->max_operations;
+    res->score = 0;
+    res->status = ORC_OK;
+    int num_cols = tlen + 1;
+    int cell = 0;
+    tab[0] = (int16_t)cell;
+    for (int v = 1; v <= plen; ++v) { cell += GAP_D; tab[v] = (int16_t)cell; }
+    cell = 0;
+    for (int h = 1; h <= tlen; ++h) { cell += GAP_I; tab[num_cols * h] = (int16_t)cell; }
+    int16_t score = 0;
+    for (int h = 1; h <= tlen; ++h) {
+        for (int v = 1; v <= plen; ++v) {
+            int16_t del = (int16_t)(tab[num_cols * h + v - 1] + GAP_D);
+            int16_t ins = (int16_t)(tab[num_cols * (h - 1) + v] + GAP_I);
+            int16_t m_match = (int16_t)(tab[num_cols * (h - 1) + v - 1] + ((pattern[v - 1] == text[h - 1]) ? 0 : MISMATCH));
+            score = tab[num_cols * h + v] = (int16_t)MINI(m_match, MINI(ins, del));
+        }
+    }
+    res->score = (int)score;
+    if (!(p->backtrace && ops)) return;
+    memset(ops, 'M', 2 * (size_t)p->read_size);
+    int op_sentinel = res->end_offset - 1;
+    int h = num_cols - 1, v = plen;
+    while (h > 0 && v > 0) {
+        if (tab[num_cols * h + v] == tab[num_cols * h + v - 1] + GAP_D) { ops[op_sentinel--] = 'D'; --v; }
+        else if (tab[num_cols * h + v] == tab[num_cols * (h - 1) + v] + GAP_I) { ops[op_sentinel--] = 'I'; --h; }
+        else {
+            ops[op_sentinel--] = (tab[num_cols * h + v] == tab[num_cols * (h - 1) + v - 1] + MISMATCH) ? 'X' : 'M';
+            --h; --v;
+        }
+    }
+    while (h > 0) { ops[op_sentinel--] = 'I'; --h; }
+    while (v > 0) { ops[op_sentinel--] = 'D'; --v; }
+    res->begin_offset = op_sentinel + 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SWG, gap-affine, int16 cells, MAX_SCORE borders.  SWG/DPU-MRAM/dpu/swg.c:151-217 swg_compute
+ * and :66-148 swg_traceback (the MRAM variant is canonical: SWG/DPU-WRAM switches to int8 cells
+ * when MAX_SCORE < 127, SWG/DPU-WRAM/common/common.h:71-79).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { int16_t M, I, D, pad; } swg_cell;
+
+static void swg_align(const orc_params *p, const char *pattern, const char *text, int plen, int tlen,
+                      orc_result *res, char *ops, swg_cell *tab)
+{
+    const int GAP_O = p->gap_open, GAP_E = p->gap_ext, MATCH = p->match, MISMATCH = p->mismatch, MAX_SCORE = p->max_score;
+    res->max_operations = plen + tlen;
+    res->begin_offset = res->max_operations - 1;
+    res->end_offset = res->max_operations;
+    res->score = INT32_MIN;
+    res->status = ORC_OK;
+    if (p->backtrace && ops) memset(ops, 'M', 2 * (size_t)p->read_size);
+    int num_cols = tlen + 1;
+    tab[0].D = (int16_t)MAX_SCORE; tab[0].I = (int16_t)MAX_SCORE; tab[0].M = 0;
+    for (int v = 1; v <= plen; ++v) {
+        tab[v].D = (int16_t)(GAP_O + v * GAP_E);
+        tab[v].I = (int16_t)MAX_SCORE;
+        tab[v].M = tab[v].D;
+    }
+    for (int h = 1; h <= tlen; ++h) {
+        swg_cell *c = &tab[num_cols * h];
+        c->D = (int16_t)MAX_SCORE;
+        c->I = (int16_t)(GAP_O + h * GAP_E);
+        c->M = c->I;
+    }
+    int score = 0;
+    for (int h = 1; h <= tlen; ++h) {
+        for (int v = 1; v <= plen; ++v) {
+            swg_cell upper = tab[num_cols * h + v - 1];
+            swg_cell diag = tab[num_cols * (h - 1) + v - 1];
+            swg_cell left = tab[num_cols * (h - 1) + v];
+            swg_cell cur;
+            int16_t del_new = (int16_t)(upper.M + GAP_O + GAP_E);
+            int16_t del_ext = (int16_t)(upper.D + GAP_E);
+            int16_t del = MINI(del_new, del_ext);
+            cur.D = del;
+            int16_t ins_new = (int16_t)(left.M + GAP_O + GAP_E);
+            int16_t ins_ext = (int16_t)(left.I + GAP_E);
+            int16_t ins = MINI(ins_new, ins_ext);
+            cur.I = ins;
+            int16_t m_match = (int16_t)(diag.M + ((pattern[v - 1] == text[h - 1]) ? MATCH : MISMATCH));
+            cur.M = MINI(m_match, MINI(ins, del));
+            cur.pad = 0;
+            score = cur.M;
+            tab[num_cols * h + v] = cur;
+        }
+    }
+    res->score = score;
+    if (!(p->backtrace && ops)) return;
+    int op_sentinel = res->end_offset - 1;
+    int h = num_cols - 1, v = plen;
+    enum { L_M, L_I, L_D } layer = L_M;
+    while (h > 0 && v > 0) {
+        swg_cell cell = tab[num_cols * h + v];
+        swg_cell upper = tab[num_cols * h + v - 1];
+        swg_cell diag = tab[num_cols * (h - 1) + v - 1];
+        swg_cell left = tab[num_cols * (h - 1) + v];
+        if (op_sentinel < 0) { res->status = ORC_ERR_BACKTRACE; return; }
+        switch (layer) {
+        case L_D:
+            ops[op_sentinel--] = 'D';
+            if (cell.D == upper.M + GAP_O + GAP_E) layer = L_M;
+            --v;
+            break;
+        case L_I:
+            ops[op_sentinel--] = 'I';
+            if (cell.I == left.M + GAP_O + GAP_E) layer = L_M;
+            --h;
+            break;
+        case L_M:
+            if (cell.M == cell.D) layer = L_D;
+            else if (cell.M == cell.I) layer = L_I;
+            else if (cell.M == diag.M + MATCH) { ops[op_sentinel--] = 'M'; --h; --v; }
+            else if (cell.M == diag.M + MISMATCH) { ops[op_sentinel--] = 'X'; --h; --v; }
+            else { res->status = ORC_ERR_BACKTRACE; return; }
+            break;
+        }
+    }
+    while (h > 0) { ops[op_sentinel--] = 'I'; --h; }
+    while (v > 0) { ops[op_sentinel--] = 'D'; --v; }
+    res->begin_offset = op_sentinel + 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Batch driver: contiguous partition of pairs over host threads, like the host's per-DPU split
+ * (WFA/DPU-MRAM/host/host.c:191-209).  Buffers are laid out as host.c:126-127 lays them out:
+ * pair i's pattern at patterns + i*read_size, ops at ops + i*2*read_size.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const orc_params *p;
+    uint32_t first, last;
+    const int32_t *plen, *tlen;
+    const char *patterns, *texts;
+    orc_result *results;
+    char *ops;
+} orc_job;
+
+static void *orc_worker(void *arg)
+{
+    orc_job *j = (orc_job *)arg;
+    const orc_params *p = j->p;
+    size_t rs = (size_t)p->read_size;
+    void *tab = NULL;
+    if (p->algo == ORC_ALGO_NW) tab = malloc(sizeof(int16_t) * (rs + 2) * (rs + 2));
+    else if (p->algo == ORC_ALGO_SWG) tab = malloc(sizeof(swg_cell) * (rs + 2) * (rs + 2));
+    for (uint32_t i = j->first; i < j->last; ++i) {
+        const char *pat = j->patterns + (size_t)i * rs, *txt = j->texts + (size_t)i * rs;
+        char *ops = j->ops ? j->ops + (size_t)i * 2 * rs : NULL;
+        if (p->algo == ORC_ALGO_WFA) wfa_align(p, pat, txt, j->plen[i], j->tlen[i], &j->results[i], ops);
+        else if (p->algo == ORC_ALGO_NW) nw_align(p, pat, txt, j->plen[i], j->tlen[i], &j->results[i], ops, (int16_t *)tab);
+        else swg_align(p, pat, txt, j->plen[i], j->tlen[i], &j->results[i], ops, (swg_cell *)tab);
+    }
+    free(tab);
+    return NULL;
+}
+
+int orc_align_batch(const orc_params *p, uint32_t n, const int32_t *plen, const int32_t *tlen,
+                    const char *patterns, const char *texts, orc_result *results, char *ops, int nthreads)
+{
+    if (!p || p->algo < 0 || p->algo > 2 || p->read_size <= 0) return -1;
+    for (uint32_t i = 0; i < n; ++i)
+        if (plen[i] < 0 || tlen[i] < 0 || plen[i] > p->read_size || tlen[i] > p->read_size) return -2;
+    if (nthreads < 1) nthreads = 1;
+    if ((uint32_t)nthreads > n) nthreads = n ? (int)n : 1;
+    orc_job *jobs = (orc_job *)calloc((size_t)nthreads, sizeof(orc_job));
+    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+    uint32_t per = (n + (uint32_t)nthreads - 1) / (uint32_t)nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        uint32_t a = (uint32_t)t * per, b = a + per;
+        if (a > n) a = n;
+        if (b > n) b = n;
+        orc_job j = { p, a, b, plen, tlen, patterns, texts, results, p->backtrace ? ops : NULL };
+        jobs[t] = j;
+        if (nthreads == 1) orc_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, orc_worker, &jobs[t]);
+    }
+    if (nthreads > 1) for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    free(jobs); free(th);
+    return 0;
+}
