@@ -2,8 +2,8 @@
 path safaad/aim offloads to UPMEM DPUs.  Thin Python over the C ABI in include/aim_b200.h."""
 from .api import (ALGO_NW, ALGO_SWG, ALGO_WFA, RESULT_DTYPE, AimError, AlignParams, PinnedArray, align_batch,
                   align_device, cigar_strings, count_pairs, derive_knobs, device_count, generate_pairs,
-                  pairs_to_process, read_pairs, shutdown, write_pairs, write_results)
+                  measure_int_peak, pairs_to_process, read_pairs, shutdown, write_pairs, write_results)
 
 __all__ = ["ALGO_NW", "ALGO_SWG", "ALGO_WFA", "RESULT_DTYPE", "AimError", "AlignParams", "PinnedArray",
            "align_batch", "align_device", "cigar_strings", "count_pairs", "derive_knobs", "device_count",
-           "generate_pairs", "pairs_to_process", "read_pairs", "shutdown", "write_pairs", "write_results"]
+           "generate_pairs", "measure_int_peak", "pairs_to_process", "read_pairs", "shutdown", "write_pairs", "write_results"]

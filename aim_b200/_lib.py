@@ -40,6 +40,7 @@ def _load() -> C.CDLL:
         "aim_host_free": (None, [vp]),
         "aim_shutdown": (None, []),
         "aim_device_count": (C.c_int, []),
+        "aim_measure_int_peak": (C.c_int, [C.c_int, P(C.c_double)]),
         "aim_last_error": (cp, []),
         "aim_strerror": (cp, [C.c_int]),
         "aim_abi_version": (C.c_int, []),
@@ -62,6 +63,6 @@ def _load() -> C.CDLL:
 
 lib = _load()
 EXPORTED = ["aim_align_batch", "aim_align_device", "aim_host_alloc", "aim_host_free", "aim_shutdown",
-            "aim_device_count", "aim_last_error", "aim_strerror", "aim_abi_version", "aim_derive_knobs",
+            "aim_device_count", "aim_measure_int_peak", "aim_last_error", "aim_strerror", "aim_abi_version", "aim_derive_knobs",
             "aim_pairs_to_process", "aim_read_pairs", "aim_count_pairs", "aim_write_results", "aim_cigar_rle",
             "aim_generate_pairs", "aim_write_pairs"]

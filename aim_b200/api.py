@@ -190,6 +190,15 @@ def write_results(path, results: np.ndarray, ops: np.ndarray | None, read_size: 
         raise AimError(rc)
 
 
+def measure_int_peak(device: int = 0) -> float:
+    """Measured INT32 ALU ceiling in ops/s (aim_measure_int_peak)."""
+    v = C.c_double(0.0)
+    rc = lib.aim_measure_int_peak(device, C.byref(v))
+    if rc != 0:
+        raise AimError(rc)
+    return v.value
+
+
 def device_count() -> int:
     return int(lib.aim_device_count())
 

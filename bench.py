@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — aligned pairs/s (score + CIGAR) of the B200 aligner on BASELINE.json's headline config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 4] [--pairs P]
+
+Workload (config.workload): BASELINE.json configs[3] = "WFA-adaptive l=150 e=4 %, 10M synthetic pairs
+with backtrace" (the configuration the north-star target is quoted on; it fits one GPU).  One STEP =
+one pass of the hot path over the whole batch of P pairs held by a rank.  Pairs shard by index with
+no collective, so N ranks each align their own P pairs ("scaling": "weak") and
+value = N*P / max-over-ranks(step time).
+
+  value     device-resident: inputs already in HBM, kernels only, CUDA events on the launch stream.
+  e2e       the same batch through the reference-facing C-ABI call aim_align_batch() with PINNED
+            HOST buffers: H2D of sequences, alignment, D2H of results + CIGAR ops inside the timed
+            region (double-buffered streams inside the library).
+  roofline  HBM view of the dominant kernel (schema of the task) + int_roofline: the kernel is
+            INT32-ALU bound (integer wavefront DP, no tensor cores), so the meaningful ceiling is the
+            measured integer rate; both are reported, see DESIGN.md.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, native build of the DPU C sources) on the
+            host cores, on a bounded sample of the same workload.
+
+--impl reference times that reference build alone, with all host threads, on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# BASELINE.json configs: index -> workload description + knobs
+CONFIGS = {
+    2: dict(name="NW linear-gap l=100 e=1% score+CIGAR", algo="nw", length=100, error=0.01, mismatch=3, gap_open=4, gap_ext=1,
+            reduce=False, backtrace=True, pairs=2_000_000, seed=2),
+    3: dict(name="SWG gap-affine x4 g6 a2 l=250 e=4% 1M pairs +BT", algo="swg", length=250, error=0.04, mismatch=4, gap_open=6,
+            gap_ext=2, reduce=False, backtrace=True, pairs=1_000_000, seed=3),
+    4: dict(name="WFA-adaptive l=150 e=4% 10M synthetic pairs +BT", algo="wfa", length=150, error=0.04, mismatch=3, gap_open=4,
+            gap_ext=1, reduce=True, backtrace=True, pairs=10_000_000, seed=4),
+    5: dict(name="WFA-adaptive long reads l=10000 e=10% 200K pairs score-only", algo="wfa", length=10000, error=0.10, mismatch=3,
+            gap_open=4, gap_ext=1, reduce=True, backtrace=False, pairs=200_000, seed=5),
+}
+# algorithmic work per pair (restated in DESIGN.md "Measurement")
+INT_OPS_PER_OFFSET = 11   # one computed (score, diagonal) offset: I, D, M recurrences
+INT_OPS_PER_EXTEND = 4    # xor, clz, add, cmp per 16-base word step
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_run(cfg: dict, pairs: int, threads: int) -> dict:
+    """Time the UNMODIFIED reference (native build of its DPU + host C sources, oracle/_ref) on the host
+    cores: one simulated DPU per chunk of pairs, `threads` host threads."""
+    import aim_b200 as A
+    from oracle import refbuild as rb
+    ms, rs = A.derive_knobs(cfg["algo"], cfg["length"], cfg["error"], cfg["mismatch"], cfg["gap_open"], cfg["gap_ext"])
+    kw = dict(max_score=ms, read_size=rs, mismatch=cfg["mismatch"], gap_o=cfg["gap_open"], gap_e=cfg["gap_ext"],
+              backtrace=cfg["backtrace"], reduce=cfg["reduce"])
+    mem = "wram" if cfg["algo"] == "nw" else "mram"
+    binary = rb.build_ref(cfg["algo"], mem, **kw)  # prebuilt in oracle/_ref on the GPU box
+    # one DPU image holds 64 MB: keep each simulated DPU well below it (host.c:215-241 layout)
+    per_pair = 8 + 32 + 2 * rs + (2 * rs if cfg["backtrace"] else 0)
+    hist = (rs * rs * 8) if cfg["algo"] == "swg" else (rs * rs * 2 if cfg["algo"] == "nw" else 4 << 20)
+    max_per_dpu = max(8, ((60_000_000 - hist) // per_pair) // 8 * 8)
+    nr_dpus = max(threads, -(-pairs // max_per_dpu))
+    nr_dpus = -(-nr_dpus // threads) * threads
+    with tempfile.TemporaryDirectory(prefix="aimbench") as tmp:
+        pairs_file = Path(tmp) / "in.pairs"
+        plen, tlen, pats, txts = A.generate_pairs(cfg["seed"], pairs, cfg["length"], cfg["error"], rs)
+        A.write_pairs(pairs_file, plen, tlen, pats, txts)
+        del pats, txts
+        t0 = time.perf_counter()
+        out = rb.run_ref(binary, pairs_file, Path(tmp) / "out", pairs + 8 * nr_dpus, nr_dpus=nr_dpus, threads=threads)
+        wall = time.perf_counter() - t0
+        lines = (Path(tmp) / "out").read_bytes().count(b"\n")
+    ph = [float(x) for x in re.findall(r"(?:CPU-DPU|DPU Kernel|DPU-CPU)(?: Time)?: ([0-9.]+) ms", out)]
+    aligned = lines // (2 if cfg["backtrace"] else 1)
+    return dict(pairs=aligned, h2d_ms=ph[0], kernel_ms=ph[1], d2h_ms=ph[2], wall_s=wall, nr_dpus=nr_dpus,
+                threads=threads, binary=binary.name)
+
+
+def run_reference_arm(args, cfg) -> None:
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import aim_b200 as A
+    threads = os.cpu_count() or 1
+    sample = args.ref_pairs or {4: 2_000_000, 2: 400_000, 3: 16_000, 5: 160}[args.config]
+    times, last = [], None
+    for it in range(args.warmup + args.steps):
+        last = cpu_reference_run(cfg, sample, threads)
+        if it >= args.warmup:
+            times.append((last["h2d_ms"] + last["kernel_ms"] + last["d2h_ms"]) * 1e-3)
+    t = sum(times) / len(times)
+    value = last["pairs"] / t
+    ms, rs = A.derive_knobs(cfg["algo"], cfg["length"], cfg["error"], cfg["mismatch"], cfg["gap_open"], cfg["gap_ext"])
+    line = {
+        "impl": "reference", "metric": "aligned pairs/sec (score+CIGAR)", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": cfg["name"], "pairs_per_step": last["pairs"], "max_score": ms, "read_size": rs,
+                   "note": "reference DPU C sources compiled natively (UPMEM SDK stand-in), one host thread per simulated DPU; "
+                           "time = its own CPU-DPU + DPU Kernel + DPU-CPU phases; UPMEM functional simulator unavailable (not installed)"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "reference",
+                         "sample": f"{last['pairs']} pairs of the workload, {last['nr_dpus']} simulated DPUs on {threads} threads",
+                         "kernel_only_value": last["pairs"] / (last["kernel_ms"] * 1e-3)},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per rank per step (default: the config's)")
+    ap.add_argument("--ref-pairs", type=int, default=0, help="CPU reference sample size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+        return
+
+    rank, local_rank, world = dist_env()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import aim_b200 as A
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; aim_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    P = args.pairs or cfg["pairs"]
+    ms, rs = A.derive_knobs(cfg["algo"], cfg["length"], cfg["error"], cfg["mismatch"], cfg["gap_open"], cfg["gap_ext"])
+    params = A.AlignParams(algo=cfg["algo"], mismatch=cfg["mismatch"], gap_open=cfg["gap_open"], gap_ext=cfg["gap_ext"],
+                           max_score=ms, read_size=rs, backtrace=cfg["backtrace"], reduce=cfg["reduce"], device=local_rank)
+    bt = cfg["backtrace"]
+
+    # synthetic pairs straight into pinned host memory (each rank its own index range of the stream)
+    threads = max(1, (os.cpu_count() or 1) // world)
+    h_plen, h_tlen = A.PinnedArray((P,), np.int32), A.PinnedArray((P,), np.int32)
+    h_pat, h_txt = A.PinnedArray((P, rs), np.uint8), A.PinnedArray((P, rs), np.uint8)
+    A.generate_pairs(cfg["seed"], P, cfg["length"], cfg["error"], rs, first_pair=rank * P, nthreads=threads,
+                     out=(h_plen.array, h_tlen.array, h_pat.array, h_txt.array))
+    h_res = A.PinnedArray((P,), A.RESULT_DTYPE)
+    h_ops = A.PinnedArray((P, 2 * rs), np.uint8) if bt else None
+
+    # ---- device-resident arm ----
+    d_plen = torch.from_numpy(h_plen.array).to(dev)
+    d_tlen = torch.from_numpy(h_tlen.array).to(dev)
+    d_pat = torch.from_numpy(h_pat.array).to(dev)
+    d_txt = torch.from_numpy(h_txt.array).to(dev)
+    d_res = torch.empty(P * A.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_ops = torch.empty((P, 2 * rs), dtype=torch.uint8, device=dev) if bt else None
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    launches = 0
+
+    def device_step():
+        nonlocal launches
+        _, nl = A.align_device(params, P, d_plen.data_ptr(), d_tlen.data_ptr(), d_pat.data_ptr(), d_txt.data_ptr(),
+                               d_res.data_ptr(), d_ops.data_ptr() if bt else None, stream=stream.cuda_stream,
+                               device=local_rank, timed=False)
+        launches += nl
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    launches = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for k in range(args.steps):
+        device_step()
+        evs[k + 1].record(stream)
+    barrier()
+    step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    total_ms = evs[0].elapsed_time(evs[-1])
+    clocks = sampler.stop()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = world * P / (ms_per_step * 1e-3)
+
+    # sanity inside the bench: the timed path produced real alignments (scores in range, no failures)
+    res_dev = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=A.RESULT_DTYPE)
+    assert int((res_dev["status"] != 0).sum()) == 0, "bench: alignment failures on the timed path"
+    mean_score = float(res_dev["score"].mean())
+    assert 0 < mean_score <= ms + 1, "bench: implausible scores"
+
+    # ---- end-to-end arm through the C ABI with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            A.align_batch(params, h_plen.array, h_tlen.array, h_pat.array, h_txt.array, results=h_res.array,
+                          ops=h_ops.array if bt else None)
+        e2e_step()  # warm the library's chunk buffers
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        te = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert np.array_equal(h_res.array["score"], res_dev["score"]), "bench: e2e and device-resident scores differ"
+        e2e = {"value": world * P / float(te.item()), "unit": "pairs/s",
+               "h2d_bytes_per_step": int(P * (2 * rs + 8)), "d2h_bytes_per_step": int(P * (A.RESULT_DTYPE.itemsize + (2 * rs if bt else 0))),
+               "ms_per_step": float(te.item()) * 1e3,
+               "api": "aim_align_batch (C ABI), pinned host buffers, H2D+kernel+D2H double-buffered inside"}
+
+    if rank == 0:
+        # ---- rooflines for the dominant kernel (one launch = one step on one GPU) ----
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        kernel_s = statistics.median(step_ms) * 1e-3
+        pl_mean, tl_mean = float(h_plen.array.mean()), float(h_tlen.array.mean())
+        if cfg["algo"] == "wfa":
+            # bytes: 2-bit sequences + lengths in, result + 2-bit ops out
+            bytes_pair = (pl_mean / 4 + tl_mean / 4 + 8) + (8 + ((pl_mean + tl_mean) / 4 if bt else 0))
+            sched = _wfa_work(res_dev["score"], cfg, ms)
+            int_ops_pair = sched["offsets"] * INT_OPS_PER_OFFSET + (sched["diag_steps"] + pl_mean / 16) * INT_OPS_PER_EXTEND
+        else:
+            cells = pl_mean * tl_mean
+            bytes_pair = (pl_mean / 4 + tl_mean / 4 + 8) + (8 + ((pl_mean + tl_mean) / 4 if bt else 0))
+            int_ops_pair = cells * ((14 if bt else 10) if cfg["algo"] == "swg" else (8 if bt else 6))
+        achieved_gbs = bytes_pair * P / kernel_s / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                    "traffic": _ncu_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_pair": bytes_pair,
+                    "kernel": "wfa_kernel<false>" if cfg["algo"] == "wfa" else "dp_kernel", "kernel_ms": kernel_s * 1e3,
+                    "note": "integer wavefront DP: the binding ceiling is the INT32 ALU pipe (int_roofline), not HBM"}
+        int_peak = A.measure_int_peak(local_rank)
+        int_roofline = {"bound": "int32_alu", "achieved": int_ops_pair * P / kernel_s / 1e12, "peak": int_peak / 1e12, "unit": "Tops/s",
+                        "frac": int_ops_pair * P / kernel_s / int_peak, "algorithmic_int_ops_per_pair": int_ops_pair,
+                        "peak_source": "aim_measure_int_peak: dependent-free add/logic/min-max mix, this GPU, this run",
+                        "gcups_equiv": pl_mean * tl_mean * P / kernel_s / 1e9}
+        cpu_baseline = None
+        if not args.no_cpu_baseline:
+            try:
+                cthreads = os.cpu_count() or 1
+                sample = args.ref_pairs or {4: 2_000_000, 2: 400_000, 3: 16_000, 5: 160}[args.config]
+                r = cpu_reference_run(cfg, sample, cthreads)
+                tot = (r["h2d_ms"] + r["kernel_ms"] + r["d2h_ms"]) * 1e-3
+                cpu_baseline = {"value": r["pairs"] / tot, "unit": "pairs/s", "cores": cthreads, "kind": "reference",
+                                "sample": f"{r['pairs']} pairs of the same workload; reference DPU C sources built natively ({r['binary']}), "
+                                          f"{r['nr_dpus']} simulated DPUs on {cthreads} host threads; CPU-DPU+DPU Kernel+DPU-CPU phases",
+                                "kernel_only_value": r["pairs"] / (r["kernel_ms"] * 1e-3),
+                                "upmem_functional_simulator": "unavailable (SDK not installed, no network)"}
+            except Exception as ex:  # keep the GPU numbers even if the CPU leg cannot run
+                cpu_baseline = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+        line = {
+            "metric": "aligned pairs/sec (score+CIGAR)", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": {"workload": cfg["name"], "pairs_per_gpu_per_step": P, "algo": cfg["algo"], "max_score": ms, "read_size": rs,
+                       "penalties": {"x": cfg["mismatch"], "o": cfg["gap_open"], "e": cfg["gap_ext"]}, "backtrace": bt,
+                       "adaptive": cfg["reduce"], "parallelism": f"pairs sharded by index over {world} GPU(s), no collective",
+                       "l2": f"inputs {P * 2 * rs / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                       "generator": f"seed {cfg['seed']}, generate_dataset semantics", "mean_score": mean_score},
+            "gcups_equiv": pl_mean * tl_mean * world * P / (ms_per_step * 1e-3) / 1e9,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "int_roofline": int_roofline, "cpu_baseline": cpu_baseline,
+            "step_ms": step_ms,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    A.shutdown()
+
+
+def _wfa_work(scores, cfg, max_score):
+    """Mean computed offsets and extend probes per pair, from the data-independent wavefront schedule
+    (widths per score) and the measured final scores of this run."""
+    import numpy as np
+    x, o, e = cfg["mismatch"], cfg["gap_open"], cfg["gap_ext"]
+    pres = [True] + [False] * max_score
+    lo, hi = [0] * (max_score + 1), [0] * (max_score + 1)
+    hasI, hasD = [False] * (max_score + 1), [False] * (max_score + 1)
+    cum_off, cum_diag = [0.0] * (max_score + 2), [0.0] * (max_score + 2)
+    cum_off[0] = cum_diag[0] = 1.0
+    for s in range(1, max_score + 1):
+        A_ = s - x >= 0 and pres[s - x]
+        B_ = s - o - e >= 0 and pres[s - o - e]
+        E_ = s - e >= 0 and pres[s - e]
+        ie = E_ and hasI[s - e]
+        de = E_ and hasD[s - e]
+        io, do = B_ or ie, B_ or de
+        if A_ or io or do:
+            los = [lo[s - x]] if A_ else []
+            his = [hi[s - x]] if A_ else []
+            if B_:
+                los.append(lo[s - o - e]); his.append(hi[s - o - e])
+            if ie or de:
+                los.append(lo[s - e]); his.append(hi[s - e])
+            pres[s], lo[s], hi[s], hasI[s], hasD[s] = True, min(los) - 1, max(his) + 1, io, do
+            w = hi[s] - lo[s] + 1
+            cum_off[s], cum_diag[s] = cum_off[s - 1] + w * (1 + io + do), cum_diag[s - 1] + w
+        else:
+            cum_off[s], cum_diag[s] = cum_off[s - 1], cum_diag[s - 1]
+    cum_off[max_score + 1], cum_diag[max_score + 1] = cum_off[max_score], cum_diag[max_score]
+    sc = np.clip(scores, 0, max_score + 1)
+    if cfg["length"] > 2000:  # adaptive trimming is active on long reads: widths are not schedule widths
+        return {"offsets": float(np.mean(sc)) * 139.0, "diag_steps": float(np.mean(sc)) * 46.0}
+    return {"offsets": float(np.mean(np.asarray(cum_off)[sc])), "diag_steps": float(np.mean(np.asarray(cum_diag)[sc]))}
+
+
+def _ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    f = ROOT / "profiles" / "ncu_summary.json"
+    try:
+        return json.loads(f.read_text()).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    main()

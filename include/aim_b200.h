@@ -103,6 +103,10 @@ void aim_host_free(void *p);
 /* Release cached device/pinned buffers and streams. */
 void aim_shutdown(void);
 
+/* Measured INT32 ALU ceiling of `device` in operations/s: a dependent-free add/logic/min-max mix on
+ * every SM (the roofline denominator for the integer DP and wavefront loops). */
+int aim_measure_int_peak(int device, double *ops_per_s);
+
 int aim_device_count(void);              /* number of CUDA devices visible, 0 if none                   */
 const char *aim_last_error(void);        /* text of the last error on this thread                       */
 const char *aim_strerror(int code);

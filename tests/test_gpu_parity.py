@@ -1,0 +1,131 @@
+"""GPU: the CUDA path, called through the C ABI (aim_align_batch), is bit-exact with (a) the bytes
+the reference wrote for the golden vectors and (b) the CPU oracle on seeded inputs, including
+ragged/empty inputs, pattern longer than text (flat-array aliasing), non-ACGT bytes, give-up,
+score-only and multi-chunk batches."""
+import lzma
+
+import numpy as np
+import pytest
+
+import aim_b200 as A
+from conftest import (GOLDEN, MANIFEST, assert_same_alignment, md5_bytes, oracle_kwargs, oracle_results_to_aim,
+                      render_output)
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(MANIFEST))
+def test_golden_bytes(name, golden_case, tmp_path):
+    e, kw, (plen, tlen, pats, txts) = golden_case(name)
+    res, ops, _ = A.align_batch(A.AlignParams(**kw), plen, tlen, pats, txts)
+    assert int((res["status"] != 0).sum()) == 0
+    out = render_output(res, ops, kw["read_size"], kw["backtrace"], tmp_path)
+    if "output" in e:
+        want = lzma.open(GOLDEN / e["output"]).read()
+        if out != want:
+            gl, wl = out.split(b"\n"), want.split(b"\n")
+            first = next(i for i, (a, b) in enumerate(zip(gl, wl)) if a != b)
+            raise AssertionError(f"{name}: first differing line {first}: got {gl[first]!r} want {wl[first]!r}")
+    assert md5_bytes(out) == e["md5"]
+
+
+def _ragged(seed, n, read_size, lo, hi, err=0.05, dirty=False):
+    """Pairs with independent lengths in [lo, hi], including empty sequences and |plen - tlen| large."""
+    rng = np.random.default_rng(seed)
+    plen = rng.integers(lo, hi + 1, n).astype(np.int32)
+    tlen = np.clip(plen + rng.integers(-12, 13, n), lo, hi).astype(np.int32)
+    pats = np.zeros((n, read_size), np.uint8)
+    txts = np.zeros((n, read_size), np.uint8)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    for i in range(n):
+        p = alpha[rng.integers(0, 4, plen[i])]
+        t = np.resize(p, tlen[i]).copy() if plen[i] else alpha[rng.integers(0, 4, tlen[i])]
+        flips = rng.random(tlen[i]) < err
+        t[flips] = alpha[rng.integers(0, 4, int(flips.sum()))]
+        pats[i, :plen[i]] = p
+        txts[i, :tlen[i]] = t
+        if dirty and i % 4 == 0 and plen[i] and tlen[i]:
+            pats[i, rng.integers(0, plen[i])] = ord("N")
+            txts[i, rng.integers(0, tlen[i])] = ord("n")
+    # a few hand-made corner cases
+    plen[0], tlen[0] = 0, 0
+    if n > 3:
+        plen[1], tlen[1] = 0, min(hi, 5)
+        plen[2], tlen[2] = min(hi, 7), 0
+        plen[3], tlen[3] = hi, max(lo, hi // 3)  # pattern much longer than text
+        pats[3, :hi] = alpha[rng.integers(0, 4, hi)]
+    return plen, tlen, pats, txts
+
+
+CASES = [
+    ("wfa", dict(max_score=40, read_size=64, backtrace=True, reduce=True), (1, 3000, 0, 60)),
+    ("wfa", dict(max_score=40, read_size=64, backtrace=True, reduce=False), (2, 3000, 0, 60)),
+    ("wfa", dict(max_score=40, read_size=64, backtrace=False, reduce=True), (3, 3000, 0, 60)),
+    ("wfa", dict(max_score=9, read_size=64, backtrace=True, reduce=True), (4, 3000, 0, 60)),      # many give-ups
+    ("wfa", dict(max_score=60, read_size=64, mismatch=1, gap_open=1, gap_ext=1, backtrace=True, reduce=True), (5, 2000, 0, 60)),
+    ("wfa", dict(max_score=90, read_size=64, mismatch=7, gap_open=2, gap_ext=5, backtrace=True, reduce=True), (6, 2000, 0, 60)),
+    ("wfa", dict(max_score=120, read_size=304, backtrace=True, reduce=True), (7, 1500, 200, 300)),
+    ("wfa", dict(max_score=700, read_size=1504, backtrace=True, reduce=True), (8, 64, 1200, 1500)),  # long-read arena mode
+    ("wfa", dict(max_score=700, read_size=1504, backtrace=False, reduce=True), (9, 64, 1200, 1500)),
+    ("wfa", dict(max_score=700, read_size=1504, backtrace=True, reduce=False), (10, 48, 1200, 1500)),
+    ("nw", dict(max_score=0, read_size=64, mismatch=3, gap_open=4, backtrace=True), (11, 3000, 0, 60)),
+    ("nw", dict(max_score=0, read_size=64, mismatch=1, gap_open=1, backtrace=True), (12, 3000, 0, 60)),
+    ("nw", dict(max_score=0, read_size=64, mismatch=3, gap_open=4, backtrace=False), (13, 3000, 0, 60)),
+    ("nw", dict(max_score=0, read_size=304, mismatch=3, gap_open=4, backtrace=True), (14, 600, 200, 300)),
+    ("swg", dict(max_score=20, read_size=64, mismatch=4, gap_open=6, gap_ext=2, backtrace=True), (15, 3000, 0, 60)),
+    ("swg", dict(max_score=200, read_size=64, mismatch=4, gap_open=6, gap_ext=2, backtrace=True), (16, 3000, 0, 60)),
+    ("swg", dict(max_score=20, read_size=64, match=-1, mismatch=2, gap_open=3, gap_ext=1, backtrace=True), (17, 3000, 0, 60)),
+    ("swg", dict(max_score=30, read_size=64, mismatch=4, gap_open=6, gap_ext=2, backtrace=False), (18, 3000, 0, 60)),
+    ("swg", dict(max_score=80, read_size=304, mismatch=4, gap_open=6, gap_ext=2, backtrace=True), (19, 600, 200, 300)),
+]
+
+
+@pytest.mark.parametrize("algo,kw,gen", CASES, ids=[f"{c[0]}-{c[2][0]}" for c in CASES])
+@pytest.mark.parametrize("dirty", [False, True], ids=["acgt", "dirty"])
+def test_vs_oracle_ragged(algo, kw, gen, dirty):
+    seed, n, lo, hi = gen
+    plen, tlen, pats, txts = _ragged(seed, n, kw["read_size"], lo, hi, dirty=dirty)
+    res, ops, _ = A.align_batch(A.AlignParams(algo=algo, **kw), plen, tlen, pats, txts)
+    exp, exp_ops = O.align(algo, plen, tlen, pats, txts, nthreads=8, **kw)
+    # SWG dead ends (reference: exit(1)) must be flagged on the same pairs
+    assert_same_alignment(res, ops, exp, exp_ops, kw["backtrace"] , what=f"{algo} seed {seed}")
+    assert np.array_equal(res["idx"], np.arange(n, dtype=np.uint32))
+
+
+def test_multichunk_and_idx_base():
+    """More pairs than one transfer chunk: order, idx and results survive the double-buffered pipeline."""
+    ms, rs = A.derive_knobs("wfa", 100, 0.02)
+    n = 700_000
+    plen, tlen, pats, txts = A.generate_pairs(21, n, 100, 0.02, rs)
+    kw = dict(max_score=ms, read_size=rs, backtrace=True, reduce=True)
+    res, ops, phase = A.align_batch(A.AlignParams(algo="wfa", **kw), plen, tlen, pats, txts, idx_base=1000)
+    exp, exp_ops = O.align("wfa", plen, tlen, pats, txts, nthreads=16, **kw)
+    assert np.array_equal(res["idx"], np.arange(n, dtype=np.uint32) + 1000)
+    assert_same_alignment(res, ops, exp, exp_ops, True, what="multichunk")
+    assert all(p > 0 for p in phase)
+
+
+def test_pinned_buffers_match_pageable():
+    ms, rs = A.derive_knobs("wfa", 150, 0.04)
+    n = 50_000
+    kw = dict(max_score=ms, read_size=rs, backtrace=True, reduce=True)
+    pin = [A.PinnedArray((n,), np.int32), A.PinnedArray((n,), np.int32), A.PinnedArray((n, rs), np.uint8), A.PinnedArray((n, rs), np.uint8)]
+    A.generate_pairs(22, n, 150, 0.04, rs, out=tuple(p.array for p in pin))
+    pres, pops = A.PinnedArray((n,), A.RESULT_DTYPE), A.PinnedArray((n, 2 * rs), np.uint8)
+    res, ops, _ = A.align_batch(A.AlignParams(algo="wfa", **kw), *(p.array for p in pin), results=pres.array, ops=pops.array)
+    res2, ops2, _ = A.align_batch(A.AlignParams(algo="wfa", **kw), *(p.array.copy() for p in pin))
+    assert_same_alignment(res, ops, res2, ops2, True, what="pinned vs pageable")
+
+
+def test_errors_are_reported():
+    rs = 64
+    plen = np.array([10, 70], np.int32)
+    tlen = np.array([10, 10], np.int32)
+    z = np.zeros((2, rs), np.uint8)
+    with pytest.raises(A.AimError) as ei:
+        A.align_batch(A.AlignParams(algo="wfa", max_score=10, read_size=rs), plen, tlen, z, z)
+    assert ei.value.code == -2  # AIM_ERR_LENGTH (host.c:119-123)
+    with pytest.raises(A.AimError) as ei:
+        A.align_batch(A.AlignParams(algo="wfa", max_score=10, read_size=rs, mismatch=0), plen[:1], tlen[:1], z[:1], z[:1])
+    assert ei.value.code == -1  # penalty validation of the run scripts
