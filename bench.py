@@ -89,9 +89,10 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_run(cfg: dict, pairs: int, threads: int) -> dict:
+def cpu_reference_run(cfg: dict, pairs: int, threads: int, repeats: int = 1, warmup: int = 0) -> dict:
     """Time the UNMODIFIED reference (native build of its DPU + host C sources, oracle/_ref) on the host
-    cores: one simulated DPU per chunk of pairs, `threads` host threads."""
+    cores: one simulated DPU per chunk of pairs, `threads` host threads.  The pair file is written once;
+    the reference host is run warmup + repeats times and the phase timers it prints are averaged."""
     import aim_b200 as A
     from oracle import refbuild as rb
     ms, rs = A.derive_knobs(cfg["algo"], cfg["length"], cfg["error"], cfg["mismatch"], cfg["gap_open"], cfg["gap_ext"])
@@ -105,19 +106,25 @@ def cpu_reference_run(cfg: dict, pairs: int, threads: int) -> dict:
     max_per_dpu = max(8, ((60_000_000 - hist) // per_pair) // 8 * 8)
     nr_dpus = max(threads, -(-pairs // max_per_dpu))
     nr_dpus = -(-nr_dpus // threads) * threads
+    ph_sum, runs, lines, wall = [0.0, 0.0, 0.0], 0, 0, 0.0
     with tempfile.TemporaryDirectory(prefix="aimbench") as tmp:
         pairs_file = Path(tmp) / "in.pairs"
         plen, tlen, pats, txts = A.generate_pairs(cfg["seed"], pairs, cfg["length"], cfg["error"], rs)
         A.write_pairs(pairs_file, plen, tlen, pats, txts)
         del pats, txts
-        t0 = time.perf_counter()
-        out = rb.run_ref(binary, pairs_file, Path(tmp) / "out", pairs + 8 * nr_dpus, nr_dpus=nr_dpus, threads=threads)
-        wall = time.perf_counter() - t0
+        for it in range(warmup + repeats):
+            t0 = time.perf_counter()
+            out = rb.run_ref(binary, pairs_file, Path(tmp) / "out", pairs + 8 * nr_dpus, nr_dpus=nr_dpus, threads=threads)
+            if it < warmup:
+                continue
+            wall += time.perf_counter() - t0
+            ph = [float(x) for x in re.findall(r"(?:CPU-DPU|DPU Kernel|DPU-CPU)(?: Time)?: ([0-9.]+) ms", out)]
+            ph_sum = [a + b for a, b in zip(ph_sum, ph)]
+            runs += 1
         lines = (Path(tmp) / "out").read_bytes().count(b"\n")
-    ph = [float(x) for x in re.findall(r"(?:CPU-DPU|DPU Kernel|DPU-CPU)(?: Time)?: ([0-9.]+) ms", out)]
     aligned = lines // (2 if cfg["backtrace"] else 1)
-    return dict(pairs=aligned, h2d_ms=ph[0], kernel_ms=ph[1], d2h_ms=ph[2], wall_s=wall, nr_dpus=nr_dpus,
-                threads=threads, binary=binary.name)
+    return dict(pairs=aligned, h2d_ms=ph_sum[0] / runs, kernel_ms=ph_sum[1] / runs, d2h_ms=ph_sum[2] / runs, wall_s=wall / runs,
+                nr_dpus=nr_dpus, threads=threads, binary=binary.name)
 
 
 def run_reference_arm(args, cfg) -> None:
@@ -127,12 +134,8 @@ def run_reference_arm(args, cfg) -> None:
     import aim_b200 as A
     threads = os.cpu_count() or 1
     sample = args.ref_pairs or {4: 2_000_000, 2: 400_000, 3: 16_000, 5: 160}[args.config]
-    times, last = [], None
-    for it in range(args.warmup + args.steps):
-        last = cpu_reference_run(cfg, sample, threads)
-        if it >= args.warmup:
-            times.append((last["h2d_ms"] + last["kernel_ms"] + last["d2h_ms"]) * 1e-3)
-    t = sum(times) / len(times)
+    last = cpu_reference_run(cfg, sample, threads, repeats=args.steps, warmup=args.warmup)
+    t = (last["h2d_ms"] + last["kernel_ms"] + last["d2h_ms"]) * 1e-3
     value = last["pairs"] / t
     ms, rs = A.derive_knobs(cfg["algo"], cfg["length"], cfg["error"], cfg["mismatch"], cfg["gap_open"], cfg["gap_ext"])
     line = {
@@ -174,6 +177,7 @@ def main() -> None:
     import torch.distributed as dist
 
     import aim_b200 as A
+    from aim_b200 import shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; aim_b200 has no CPU fallback")
@@ -192,7 +196,7 @@ def main() -> None:
     threads = max(1, (os.cpu_count() or 1) // world)
     h_plen, h_tlen = A.PinnedArray((P,), np.int32), A.PinnedArray((P,), np.int32)
     h_pat, h_txt = A.PinnedArray((P, rs), np.uint8), A.PinnedArray((P, rs), np.uint8)
-    A.generate_pairs(cfg["seed"], P, cfg["length"], cfg["error"], rs, first_pair=rank * P, nthreads=threads,
+    A.generate_pairs(cfg["seed"], P, cfg["length"], cfg["error"], rs, first_pair=shard.weak_first_pair(rank, P), nthreads=threads,
                      out=(h_plen.array, h_tlen.array, h_pat.array, h_txt.array))
     h_res = A.PinnedArray((P,), A.RESULT_DTYPE)
     h_ops = A.PinnedArray((P, 2 * rs), np.uint8) if bt else None
@@ -235,10 +239,7 @@ def main() -> None:
     step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     total_ms = evs[0].elapsed_time(evs[-1])
     clocks = sampler.stop()
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = shard.max_over_ranks(total_ms, dev)
     ms_per_step = total_ms_max / args.steps
     value = world * P / (ms_per_step * 1e-3)
 
@@ -260,13 +261,11 @@ def main() -> None:
         for _ in range(args.steps):
             e2e_step()
         torch.cuda.synchronize(dev)
-        te = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        te_s = shard.max_over_ranks((time.perf_counter() - t0) / args.steps, dev)
         assert np.array_equal(h_res.array["score"], res_dev["score"]), "bench: e2e and device-resident scores differ"
-        e2e = {"value": world * P / float(te.item()), "unit": "pairs/s",
+        e2e = {"value": world * P / te_s, "unit": "pairs/s",
                "h2d_bytes_per_step": int(P * (2 * rs + 8)), "d2h_bytes_per_step": int(P * (A.RESULT_DTYPE.itemsize + (2 * rs if bt else 0))),
-               "ms_per_step": float(te.item()) * 1e3,
+               "ms_per_step": te_s * 1e3,
                "api": "aim_align_batch (C ABI), pinned host buffers, H2D+kernel+D2H double-buffered inside"}
 
     if rank == 0:

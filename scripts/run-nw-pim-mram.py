@@ -1,0 +1,10 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's NW/DPU-MRAM/run-nw-pim-mram.py (same options), backed by the B200 host."""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from aim_b200.run_pim import main  # noqa: E402
+
+if __name__ == "__main__":
+    sys.exit(main("nw", "mram"))
