@@ -298,6 +298,7 @@ extern "C" void aim_shutdown(void)
         free_chunk(c->chunk[0]);
         free_chunk(c->chunk[1]);
         cudaFree(c->scratch.buf);
+        cudaFree(c->scratch.sched_buf);
         delete c;
     }
     g_ctx.clear();

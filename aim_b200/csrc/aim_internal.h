@@ -39,7 +39,8 @@ struct KernelArgs {
 struct Scratch {
     void *buf = nullptr;        // general scratch (WFA global arena / DP rows+flags)
     size_t bytes = 0;
-    uint32_t *counter = nullptr;  // work-queue counters (device), 4 words
+    void *sched_buf = nullptr;  // device copy of the static WFA schedule table
+    size_t sched_bytes = 0;
     int sm_count = 0;
     int device = 0;
 };
@@ -50,6 +51,8 @@ int scratch_reserve(Scratch *s, size_t bytes);
 // Launchers (aim_wfa.cu / aim_dp.cu).  Enqueue on `stream`; return AIM_OK or AIM_ERR_*;
 // *launches is incremented by the number of kernels enqueued.
 int launch_wfa(const KernelArgs &a, Scratch *s, void *stream, int *launches);
+// lockstep short-read kernel; returns 1 when the configuration must go to launch_wfa's warp-per-pair kernel
+int launch_wfa_sub(const KernelArgs &a, Scratch *s, void *stream, int *launches);
 int launch_dp(const KernelArgs &a, Scratch *s, void *stream, int *launches);
 
 }  // namespace aim
