@@ -30,6 +30,8 @@ namespace {
         }                                                                                      \
     } while (0)
 
+constexpr int kNumBuf = 4;  // chunk buffers in flight: upload / align / download of different chunks overlap
+
 struct ChunkBuf {
     // device
     int32_t *d_plen = nullptr, *d_tlen = nullptr;
@@ -39,8 +41,8 @@ struct ChunkBuf {
     int32_t *h_plen = nullptr, *h_tlen = nullptr;
     char *h_pat = nullptr, *h_txt = nullptr, *h_ops = nullptr;
     aim_result *h_res = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, h2d done, kernel done, d2h done
+    // stage boundaries: [0] h2d start, [1] h2d done, [2] kernel start, [3] kernel done, [4] d2h start, [5] d2h done
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t pairs_cap = 0;
     int32_t read_size = 0;
     bool has_ops = false, has_staging = false;
@@ -50,7 +52,8 @@ struct DeviceCtx {
     int device = -1;
     bool ready = false;
     Scratch scratch;
-    ChunkBuf chunk[2];
+    ChunkBuf chunk[kNumBuf];
+    cudaStream_t s_h2d = nullptr, s_kernel = nullptr, s_d2h = nullptr;  // one stream per pipeline stage
     std::mutex mu;
 };
 
@@ -93,7 +96,6 @@ void free_chunk(ChunkBuf &b)
     cudaFree(b.d_plen); cudaFree(b.d_tlen); cudaFree(b.d_pat); cudaFree(b.d_txt); cudaFree(b.d_ops); cudaFree(b.d_res);
     cudaFreeHost(b.h_plen); cudaFreeHost(b.h_tlen); cudaFreeHost(b.h_pat); cudaFreeHost(b.h_txt);
     cudaFreeHost(b.h_ops); cudaFreeHost(b.h_res);
-    if (b.stream) cudaStreamDestroy(b.stream);
     for (auto &e : b.ev) if (e) cudaEventDestroy(e);
     b = ChunkBuf();
 }
@@ -103,7 +105,6 @@ int ensure_chunk(ChunkBuf &b, uint32_t pairs, int32_t read_size, bool ops, bool 
     if (b.pairs_cap >= pairs && b.read_size == read_size && (b.has_ops || !ops) && (b.has_staging || !staging)) return AIM_OK;
     free_chunk(b);
     const size_t rs = (size_t)read_size;
-    AIM_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
     for (auto &e : b.ev) AIM_CUDA(cudaEventCreate(&e));
     AIM_CUDA(cudaMalloc(&b.d_plen, pairs * sizeof(int32_t)));
     AIM_CUDA(cudaMalloc(&b.d_tlen, pairs * sizeof(int32_t)));
@@ -180,10 +181,17 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
     const bool staging = !(pin_in && pin_out);
 
     const size_t per_pair = 2 * rs + (bt ? 2 * rs : 0) + sizeof(aim_result) + 8;
-    uint32_t chunk_pairs = (uint32_t)std::max<size_t>(4096, std::min<size_t>((128u << 20) / per_pair, 1u << 20));
+    // chunk: big enough to fill the GPU many times over, small enough that pipeline fill/drain is short
+    uint32_t chunk_pairs = (uint32_t)std::max<size_t>(16384, std::min<size_t>((96u << 20) / per_pair, 1u << 20));
     chunk_pairs = std::min(chunk_pairs, n);
     const uint32_t nchunks = (n + chunk_pairs - 1) / chunk_pairs;
-    for (int b = 0; b < (nchunks > 1 ? 2 : 1); ++b) {
+    const int nbuf = (int)std::min<uint32_t>(kNumBuf, nchunks);
+    if (!ctx->s_h2d) {
+        AIM_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        AIM_CUDA(cudaStreamCreateWithFlags(&ctx->s_kernel, cudaStreamNonBlocking));
+        AIM_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    }
+    for (int b = 0; b < nbuf; ++b) {
         rc = ensure_chunk(ctx->chunk[b], chunk_pairs, p.read_size, bt, staging);
         if (rc != AIM_OK) return fail(rc);
     }
@@ -191,22 +199,24 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
     std::vector<uint32_t> cn(nchunks);
 
     auto finish = [&](uint32_t c) -> int {
-        ChunkBuf &B = ctx->chunk[c & 1];
+        ChunkBuf &B = ctx->chunk[c % (uint32_t)nbuf];
         const uint32_t off = c * chunk_pairs, m = cn[c];
-        cudaError_t e = cudaEventSynchronize(B.ev[3]);
+        cudaError_t e = cudaEventSynchronize(B.ev[5]);
         if (e != cudaSuccess) { set_error(std::string("chunk sync: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
         if (!pin_out) {
             memcpy(results + off, B.h_res, (size_t)m * sizeof(aim_result));
             if (bt) memcpy(ops + (size_t)off * 2 * rs, B.h_ops, (size_t)m * 2 * rs);
         }
         float t;
-        for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&t, B.ev[k], B.ev[k + 1]); ph[k] += t; }
+        for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&t, B.ev[2 * k], B.ev[2 * k + 1]); ph[k] += t; }
         return AIM_OK;
     };
 
+    // three-stage pipeline on three streams: all uploads in order on s_h2d, all kernels in order on s_kernel
+    // (they share the per-device scratch), all downloads in order on s_d2h; events carry the dependencies.
     for (uint32_t c = 0; c < nchunks; ++c) {
-        ChunkBuf &B = ctx->chunk[c & 1];
-        if (c >= 2) { rc = finish(c - 2); if (rc != AIM_OK) return fail(rc); }
+        ChunkBuf &B = ctx->chunk[c % (uint32_t)nbuf];
+        if (c >= (uint32_t)nbuf) { rc = finish(c - (uint32_t)nbuf); if (rc != AIM_OK) return fail(rc); }
         const uint32_t off = c * chunk_pairs, m = std::min(chunk_pairs, n - off);
         cn[c] = m;
         const int32_t *s_plen = plen + off, *s_tlen = tlen + off;
@@ -216,28 +226,31 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
             memcpy(B.h_pat, s_pat, (size_t)m * rs); memcpy(B.h_txt, s_txt, (size_t)m * rs);
             s_plen = B.h_plen; s_tlen = B.h_tlen; s_pat = B.h_pat; s_txt = B.h_txt;
         }
-        cudaStream_t st = B.stream;
-        AIM_CUDA(cudaEventRecord(B.ev[0], st));
-        AIM_CUDA(cudaMemcpyAsync(B.d_plen, s_plen, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-        AIM_CUDA(cudaMemcpyAsync(B.d_tlen, s_tlen, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-        AIM_CUDA(cudaMemcpyAsync(B.d_pat, s_pat, (size_t)m * rs, cudaMemcpyHostToDevice, st));
-        AIM_CUDA(cudaMemcpyAsync(B.d_txt, s_txt, (size_t)m * rs, cudaMemcpyHostToDevice, st));
-        AIM_CUDA(cudaEventRecord(B.ev[1], st));
-        // kernels of consecutive chunks share the per-device scratch: keep them in order
-        if (c >= 1) AIM_CUDA(cudaStreamWaitEvent(st, ctx->chunk[(c - 1) & 1].ev[2], 0));
+        AIM_CUDA(cudaEventRecord(B.ev[0], ctx->s_h2d));
+        AIM_CUDA(cudaMemcpyAsync(B.d_plen, s_plen, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+        AIM_CUDA(cudaMemcpyAsync(B.d_tlen, s_tlen, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+        AIM_CUDA(cudaMemcpyAsync(B.d_pat, s_pat, (size_t)m * rs, cudaMemcpyHostToDevice, ctx->s_h2d));
+        AIM_CUDA(cudaMemcpyAsync(B.d_txt, s_txt, (size_t)m * rs, cudaMemcpyHostToDevice, ctx->s_h2d));
+        AIM_CUDA(cudaEventRecord(B.ev[1], ctx->s_h2d));
+
+        AIM_CUDA(cudaStreamWaitEvent(ctx->s_kernel, B.ev[1], 0));
+        AIM_CUDA(cudaEventRecord(B.ev[2], ctx->s_kernel));
         KernelArgs a{p, m, idx_base + first + off, B.d_plen, B.d_tlen, B.d_pat, B.d_txt, B.d_res, bt ? B.d_ops : nullptr};
-        rc = launch(a, &ctx->scratch, st, nullptr);
+        rc = launch(a, &ctx->scratch, ctx->s_kernel, nullptr);
         if (rc != AIM_OK) return fail(rc);
-        AIM_CUDA(cudaEventRecord(B.ev[2], st));
+        AIM_CUDA(cudaEventRecord(B.ev[3], ctx->s_kernel));
+
+        AIM_CUDA(cudaStreamWaitEvent(ctx->s_d2h, B.ev[3], 0));
+        AIM_CUDA(cudaEventRecord(B.ev[4], ctx->s_d2h));
         aim_result *o_res = pin_out ? results + off : B.h_res;
-        AIM_CUDA(cudaMemcpyAsync(o_res, B.d_res, (size_t)m * sizeof(aim_result), cudaMemcpyDeviceToHost, st));
+        AIM_CUDA(cudaMemcpyAsync(o_res, B.d_res, (size_t)m * sizeof(aim_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
         if (bt) {
             char *o_ops = pin_out ? ops + (size_t)off * 2 * rs : B.h_ops;
-            AIM_CUDA(cudaMemcpyAsync(o_ops, B.d_ops, (size_t)m * 2 * rs, cudaMemcpyDeviceToHost, st));
+            AIM_CUDA(cudaMemcpyAsync(o_ops, B.d_ops, (size_t)m * 2 * rs, cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
-        AIM_CUDA(cudaEventRecord(B.ev[3], st));
+        AIM_CUDA(cudaEventRecord(B.ev[5], ctx->s_d2h));
     }
-    for (uint32_t c = (nchunks >= 2 ? nchunks - 2 : 0); c < nchunks; ++c) {
+    for (uint32_t c = (nchunks >= (uint32_t)nbuf ? nchunks - (uint32_t)nbuf : 0); c < nchunks; ++c) {
         rc = finish(c);
         if (rc != AIM_OK) return fail(rc);
     }
@@ -295,8 +308,8 @@ extern "C" void aim_shutdown(void)
         if (!c) continue;
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
-        free_chunk(c->chunk[0]);
-        free_chunk(c->chunk[1]);
+        for (auto &b : c->chunk) free_chunk(b);
+        if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_kernel); cudaStreamDestroy(c->s_d2h); }
         cudaFree(c->scratch.buf);
         cudaFree(c->scratch.sched_buf);
         delete c;
