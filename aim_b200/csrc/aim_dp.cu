@@ -190,6 +190,10 @@ int launch_dp(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
     cudaStream_t stream = (cudaStream_t)stream_v;
     const aim_params &p = a.p;
     if (a.n == 0) return AIM_OK;
+    {
+        const int rc = launch_dp_fast(a, sc, stream_v, launches);
+        if (rc != 1) return rc;
+    }
     DpK K{};
     K.plen = a.plen; K.tlen = a.tlen; K.patterns = a.patterns; K.texts = a.texts;
     K.results = a.results; K.ops = a.ops; K.n = a.n; K.idx_base = a.idx_base;

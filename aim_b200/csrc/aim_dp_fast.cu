@@ -1,0 +1,552 @@
+// Fast NW (linear gap) / SWG (gap-affine) full-table DP for sm_100a.
+//
+// Same flat-array semantics as aim_dp.cu (reference: NW/DPU-WRAM/dpu/nw.c:67-153,
+// SWG/DPU-MRAM/dpu/swg.c:66-217), restructured around two observations:
+//
+//   (1) a pair with pattern_len <= text_len never aliases rows of the flat table
+//       (num_cols = text_len+1 > pattern_len), so its fill is the ordinary full DP and may be
+//       evaluated in ANY dependency-respecting order.  dp_strip_kernel walks it in column strips of
+//       16 cells held in registers (previous row's M and I per column), one pair per thread; only
+//       the strip's right boundary column (M, D per row) goes through memory, once per 16 cells.
+//   (2) a pair with pattern_len > text_len aliases: cell (h,0) IS cell (h-1,num_cols) and the tail
+//       cells (h, v >= num_cols) read the current row's head as their "previous row".  The fill is
+//       then one serial chain in the reference's write order; dp_row_kernel keeps that order with
+//       the row in shared memory (conflict-free [column][thread] layout), one pair per thread.
+//
+// A classification pass splits the batch into the two index lists.  Both kernels evaluate the
+// reference's traceback predicates at fill time (DESIGN.md "flat-array semantics": the last writer
+// of a flat word sees the same neighbours the reference's traceback reads from the final table) and
+// keep 4 bits (SWG) / 2 bits (NW) per cell in HBM:
+//     p    = (del <= ins)            q   = (min(del,ins) <= diag + sub)
+//     opD  = D opened at this cell   opI = I opened at this cell          (SWG only)
+// from which the reference's test order (D, I, then diag+MATCH / diag+MISMATCH: swg.c:106-133,
+// nw.c:78-94) is reproduced exactly: q&&p -> D, q&&!p -> I, !q -> 'M' if the writer's two bases are
+// equal else 'X' (when neither gap wins the cell value IS diag+sub, so the reference's value tests
+// reduce to the base comparison).
+//
+// Both kernels compute in 32-bit registers.  They are used only when no int16 truncation can occur
+// ((plen+tlen+2) * max penalty + MAX_SCORE < 32767, checked by the launcher); otherwise, and for
+// rows that do not fit shared memory, aim_dp.cu's literal kernel serves the batch.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
+#include "aim_internal.h"
+
+namespace aim {
+
+namespace {
+
+constexpr int KS = 16;  // columns per register strip
+
+struct FastK {
+    const int32_t *plen;
+    const int32_t *tlen;
+    const char *patterns;
+    const char *texts;
+    aim_result *results;
+    char *ops;
+    uint32_t n, idx_base;
+    int match, x, o, e, max_score, read_size, backtrace;
+    const uint32_t *list;   // pair indices served by this kernel
+    const uint32_t *count;  // how many (device counter written by classify_kernel)
+    int list_step;          // +1: list grows upwards from list[0]; -1: downwards from list[0]
+    uint32_t *bound;        // strip kernel: boundary column, [row][thread]
+    uint32_t *flags;        // predicate bits
+    uint32_t wpr;           // row kernel: flag words per row
+};
+
+// ---- classification: non-aliased pairs to the front of the list, aliased ones to the back ----
+__global__ void classify_kernel(const int32_t *plen, const int32_t *tlen, uint32_t n, int RS, uint32_t *list, uint32_t *counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool valid = i < n, alias = false;
+    if (valid) {
+        const int pl = min(max(plen[i], 0), RS), tl = min(max(tlen[i], 0), RS);
+        alias = pl > tl;
+    }
+    const uint32_t m0 = __ballot_sync(0xffffffffu, valid && !alias), m1 = __ballot_sync(0xffffffffu, valid && alias);
+    uint32_t b0 = 0, b1 = 0;
+    if (lane == 0) {
+        if (m0) b0 = atomicAdd(&counters[0], (uint32_t)__popc(m0));
+        if (m1) b1 = atomicAdd(&counters[1], (uint32_t)__popc(m1));
+    }
+    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    b1 = __shfl_sync(0xffffffffu, b1, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    if (valid && !alias) list[b0 + (uint32_t)__popc(m0 & below)] = i;
+    if (valid && alias) list[n - 1 - (b1 + (uint32_t)__popc(m1 & below))] = i;
+}
+
+// ---- one DP cell in registers ----
+// Returns the new M; updates upI (-> ins) and leftD (-> del); the four differences carry the
+// traceback predicates in their SIGN bits (set = predicate false):
+//   dI = (upI+E) - (upM+O+E)     sign set  <=>  I was NOT opened here   (swg.c:97)
+//   dD = (leftD+E) - (leftM+O+E) sign set  <=>  D was NOT opened here   (swg.c:88)
+//   dP = ins - del               sign set  <=>  !(del <= ins)
+//   dQ = mm - min(del,ins)       sign set  <=>  !(min(del,ins) <= mm)
+template <int ALGO>
+__device__ __forceinline__ int dp_cell(int upM, int &upI, int leftM, int &leftD, int mm, int OE, int E, int &dI, int &dD, int &dP, int &dQ)
+{
+    int ins, del;
+    if (ALGO == AIM_ALGO_NW) {
+        ins = upM + OE;    // GAP_I
+        del = leftM + OE;  // GAP_D
+        dI = dD = 0;
+    } else {
+        const int i1 = upM + OE, i2 = upI + E;
+        ins = min(i1, i2);
+        dI = i2 - i1;
+        const int d1 = leftM + OE, d2 = leftD + E;
+        del = min(d1, d2);
+        dD = d2 - d1;
+        upI = ins;
+        leftD = del;
+    }
+    const int m1 = min(del, ins);
+    dP = ins - del;
+    dQ = mm - m1;
+    return min(m1, mm);
+}
+
+// append the sign bit of d to the accumulator (one SHF.L.W)
+__device__ __forceinline__ uint32_t push_sign(uint32_t acc, int d) { return __funnelshift_l((uint32_t)d, acc, 1); }
+
+// Flag record of 16 consecutive cells: word0 = notP | notQ << 16, word1 (SWG) = notOpD | notOpI << 16,
+// cell j of the record at bit 15-j of each half.
+__device__ __forceinline__ void decode_flags(const uint32_t *rec, int j, bool swg, bool &p, bool &q, bool &opD, bool &opI)
+{
+    const uint32_t w0 = rec[0];
+    p = !((w0 >> (15 - j)) & 1u);
+    q = !((w0 >> (31 - j)) & 1u);
+    opD = opI = false;
+    if (swg) {
+        const uint32_t w1 = rec[1];
+        opD = !((w1 >> (15 - j)) & 1u);
+        opI = !((w1 >> (31 - j)) & 1u);
+    }
+}
+
+// ================= non-aliased pairs: register strips =================
+template <int ALGO, bool MT0>
+__global__ void __launch_bounds__(128) dp_strip_kernel(const FastK K)
+{
+    constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
+    constexpr int FW = SWG ? 2 : 1;  // flag words per 16-cell record
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nth = gridDim.x * blockDim.x;
+    const uint32_t count = *K.count;
+    const int RS = K.read_size;
+    const int X = K.x, E = K.e, MT = MT0 ? 0 : K.match, MS = K.max_score;
+    const int OE = SWG ? K.o + K.e : K.o;  // NW: the single linear gap
+    const int O = K.o;
+    uint32_t sel[4];  // IDP.4A selectors: (X - MT) in byte k
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sel[k] = (uint32_t)(X - MT) << (8 * k);
+    uint32_t *bnd = K.bound + tid;
+    uint32_t *flg = K.flags + (size_t)tid * FW;
+    const size_t fstep = (size_t)nth * FW;  // words between consecutive (strip,row) records
+
+    for (uint32_t li = tid; li < count; li += nth) {
+        const uint32_t i = K.list[li];
+        const int pl = min(max(K.plen[i], 0), RS), tl = min(max(K.tlen[i], 0), RS);
+        const char *gp = K.patterns + (size_t)i * RS;
+        const char *gt = K.texts + (size_t)i * RS;
+        const int nstrips = (pl + KS - 1) / KS;
+        int score = 0;
+
+        for (int s = 0; s < nstrips; ++s) {
+            const int v0 = s * KS;
+            uint32_t pc[KS / 4];
+#pragma unroll
+            for (int w = 0; w < KS / 4; ++w) pc[w] = (v0 + 4 * w < RS) ? __ldg(reinterpret_cast<const uint32_t *>(gp + v0) + w) : 0u;
+            int upM[KS], upI[KS];
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {  // row 0 (nw.c:119-124 / swg.c:167-175)
+                upM[j] = SWG ? O + (v0 + 1 + j) * E : (v0 + 1 + j) * OE;
+                upI[j] = MS;
+            }
+            // M(h-1, v0): the diagonal neighbour of the strip's first cell
+            int dg0 = SWG ? (v0 == 0 ? 0 : O + v0 * E) : v0 * OE;
+            const bool first = (s == 0), last = (s == nstrips - 1);
+            uint32_t tw = 0;
+            uint32_t *frec = flg + (size_t)s * RS * fstep;
+            for (int h = 1; h <= tl; ++h) {
+                if (((h - 1) & 3) == 0) tw = __ldg(reinterpret_cast<const uint32_t *>(gt) + ((h - 1) >> 2));
+                const uint32_t tc4 = (tw & 0xffu) * 0x01010101u;
+                tw >>= 8;
+                uint32_t ne[KS / 4];  // 1 in every byte whose pattern base differs from this row's text base
+#pragma unroll
+                for (int w = 0; w < KS / 4; ++w) ne[w] = __vsetne4(pc[w] ^ tc4, 0u);
+                int leftM, leftD;
+                if (first) {  // column 0 (nw.c:114-118 / swg.c:158-166)
+                    leftM = SWG ? O + h * E : h * OE;
+                    leftD = MS;
+                } else {
+                    const uint32_t b = bnd[(size_t)(h - 1) * nth];
+                    leftM = (int)(short)(b & 0xffffu);
+                    leftD = (int)b >> 16;
+                }
+                int dg = dg0;
+                dg0 = leftM;
+                uint32_t aP = 0, aQ = 0, aD = 0, aI = 0;
+#pragma unroll
+                for (int j = 0; j < KS; ++j) {
+                    const int um = upM[j];
+                    const int mm = (int)__dp4a(ne[j >> 2], sel[j & 3], (uint32_t)(MT0 ? dg : dg + MT));
+                    int dI, dD, dP, dQ;
+                    const int m = dp_cell<ALGO>(um, upI[j], leftM, leftD, mm, OE, E, dI, dD, dP, dQ);
+                    aP = push_sign(aP, dP);
+                    aQ = push_sign(aQ, dQ);
+                    if (SWG) { aD = push_sign(aD, dD); aI = push_sign(aI, dI); }
+                    dg = um;
+                    upM[j] = m;
+                    leftM = m;
+                }
+                if (!last) bnd[(size_t)(h - 1) * nth] = ((uint32_t)leftM & 0xffffu) | ((uint32_t)leftD << 16);
+                if (K.backtrace) {
+                    uint32_t *d = frec + (size_t)(h - 1) * fstep;
+                    if (SWG) *reinterpret_cast<uint2 *>(d) = make_uint2(aP | (aQ << 16), aD | (aI << 16));
+                    else d[0] = aP | (aQ << 16);
+                }
+            }
+            if (last) {
+                const int js = pl - 1 - v0;
+#pragma unroll
+                for (int j = 0; j < KS; ++j) if (j == js) score = upM[j];
+            }
+        }
+        if (pl == 0 || tl == 0) score = 0;
+
+        int begin_offset = pl + tl - 1;
+        int status = AIM_STATUS_OK;
+        if (K.backtrace) {
+            char *ops = K.ops + (size_t)i * 2 * RS;  // pre-filled with 'M' by the launcher
+            int b = pl + tl - 1;
+            int h = tl, v = pl;
+            int layer = 0;  // SWG: 0 M, 1 I, 2 D
+            while (h > 0 && v > 0) {
+                const int s = (v - 1) / KS, j = (v - 1) % KS;
+                bool p, q, opD, opI;
+                decode_flags(flg + ((size_t)s * RS + (h - 1)) * fstep, j, SWG, p, q, opD, opI);
+                if (!SWG) {
+                    if (q) {
+                        if (p) { ops[b--] = 'D'; --v; }
+                        else { ops[b--] = 'I'; --h; }
+                    } else {
+                        if (gp[v - 1] != gt[h - 1]) ops[b] = 'X';
+                        --b; --h; --v;
+                    }
+                } else {
+                    if (b < 0) { status = AIM_STATUS_BACKTRACE; break; }
+                    if (layer == 2) { ops[b--] = 'D'; if (opD) layer = 0; --v; }
+                    else if (layer == 1) { ops[b--] = 'I'; if (opI) layer = 0; --h; }
+                    else if (q) layer = p ? 2 : 1;
+                    else {
+                        if (gp[v - 1] != gt[h - 1]) ops[b] = 'X';
+                        --b; --h; --v;
+                    }
+                }
+            }
+            if (status == AIM_STATUS_OK) {
+                while (h > 0) { ops[b--] = 'I'; --h; }
+                while (v > 0) { ops[b--] = 'D'; --v; }
+                begin_offset = b + 1;
+            }
+        }
+        aim_result res;
+        res.max_operations = pl + tl;
+        res.begin_offset = begin_offset;
+        res.end_offset = pl + tl;
+        res.score = score;
+        res.status = status;
+        res.idx = K.idx_base + i;
+        K.results[i] = res;
+    }
+}
+
+// ================= aliased pairs: serial row-major fill, row in shared memory =================
+// Shared memory per thread: (RS+1) row words [column][thread] (NW: M; SWG: M | I << 16) followed
+// by RS/4 pattern words [word][thread].  Flags: one 16-cell record per 16 columns of a row.
+template <int ALGO>
+__global__ void __launch_bounds__(256) dp_row_kernel(const FastK K)
+{
+    constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
+    constexpr int FW = SWG ? 2 : 1;
+    extern __shared__ uint32_t smem[];
+    const uint32_t T = blockDim.x;
+    const uint32_t tid = blockIdx.x * T + threadIdx.x;
+    const uint32_t nth = gridDim.x * T;
+    const uint32_t count = *K.count;
+    const int RS = K.read_size;
+    const int X = K.x, E = K.e, MT = SWG ? K.match : 0, MS = K.max_score;
+    const int OE = SWG ? K.o + K.e : K.o;
+    const int O = K.o;
+    uint32_t sel[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sel[k] = (uint32_t)(X - MT) << (8 * k);
+    uint32_t *row = smem + threadIdx.x;                         // row[v * T]
+    uint32_t *pat = smem + (size_t)(RS + 1) * T + threadIdx.x;  // pat[w * T]
+    uint32_t *flg = K.flags + (size_t)tid * FW;
+    const size_t fstep = (size_t)nth * FW;
+    const uint32_t rpr = K.wpr;  // records per row
+
+    auto unpackM = [](uint32_t w) -> int { return SWG ? (int)(short)(w & 0xffffu) : (int)w; };
+    auto unpackI = [](uint32_t w) -> int { return (int)w >> 16; };
+    auto pack = [](int m, int i) -> uint32_t { return SWG ? (((uint32_t)m & 0xffffu) | ((uint32_t)i << 16)) : (uint32_t)m; };
+
+    for (uint32_t li = tid; li < count; li += nth) {
+        const uint32_t i = K.list[(int64_t)K.list_step * (int64_t)li];
+        const int pl = min(max(K.plen[i], 0), RS), tl = min(max(K.tlen[i], 0), RS);
+        const char *gp = K.patterns + (size_t)i * RS;
+        const char *gt = K.texts + (size_t)i * RS;
+        const int nc = tl + 1;
+        const bool alias = pl >= nc;
+        int score = 0;
+
+        for (int w = 0; w * 4 < pl; ++w) pat[(size_t)w * T] = __ldg(reinterpret_cast<const uint32_t *>(gp) + w);
+        // row 0 (nw.c:119-124 / swg.c:167-175)
+        row[0] = pack(0, MS);
+        for (int v = 1; v <= pl; ++v) row[(size_t)v * T] = pack(SWG ? O + v * E : v * OE, MS);
+        int tailM = 0, tailI = 0, tailD = 0;  // cell (h-1, nc): column 0 of row h when aliased
+        const int headend = min(pl, nc - 1);  // columns 1..headend read the true previous row
+
+        uint32_t tw = 0;
+        for (int h = 1; h <= tl; ++h) {
+            if (((h - 1) & 3) == 0) tw = __ldg(reinterpret_cast<const uint32_t *>(gt) + ((h - 1) >> 2));
+            const uint32_t tc4 = (tw & 0xffu) * 0x01010101u;
+            tw >>= 8;
+            int leftM, leftD, c0I;
+            if (alias && h >= 2) { leftM = tailM; c0I = tailI; leftD = tailD; }
+            else if (!SWG) { leftM = h * OE; c0I = 0; leftD = 0; }
+            else { leftD = MS; c0I = O + h * E; leftM = c0I; }
+            int dg = unpackM(row[0]);
+            row[0] = pack(leftM, c0I);
+            uint32_t *frow = flg + (size_t)(h - 1) * rpr * fstep;
+
+            // ---- head, full 16-cell records ----
+            int v = 1;
+            for (; v + 15 <= headend; v += 16) {
+                uint32_t aP = 0, aQ = 0, aD = 0, aI = 0;
+                uint32_t ne = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int vv = v + j;
+                    if ((j & 3) == 0) ne = __vsetne4(pat[(size_t)((vv - 1) >> 2) * T] ^ tc4, 0u);
+                    const uint32_t old = row[(size_t)vv * T];
+                    const int upM = unpackM(old);
+                    int upI = SWG ? unpackI(old) : 0;
+                    const int mm = (int)__dp4a(ne, sel[j & 3], (uint32_t)(dg + MT));
+                    int dI, dD, dP, dQ;
+                    const int m = dp_cell<ALGO>(upM, upI, leftM, leftD, mm, OE, E, dI, dD, dP, dQ);
+                    row[(size_t)vv * T] = pack(m, upI);
+                    aP = push_sign(aP, dP);
+                    aQ = push_sign(aQ, dQ);
+                    if (SWG) { aD = push_sign(aD, dD); aI = push_sign(aI, dI); }
+                    dg = upM;
+                    leftM = m;
+                }
+                if (K.backtrace) {
+                    uint32_t *d = frow + (size_t)((v - 1) >> 4) * fstep;
+                    d[0] = aP | (aQ << 16);
+                    if (SWG) d[1] = aD | (aI << 16);
+                }
+            }
+            // ---- remaining head cells, then the aliased tail: columns nc..pl read the CURRENT row's
+            // head as their "previous row" (flat word nc*(h-1)+v is cell (h, v-nc)) ----
+            uint32_t w0 = 0, w1 = 0;  // record under construction
+            for (; v <= pl; ++v) {
+                const bool tail = v >= nc;
+                if (!tail && v > headend) break;
+                uint32_t upw;
+                if (!tail) upw = row[(size_t)v * T];
+                else {
+                    upw = row[(size_t)(v - nc) * T];
+                    if (v - 1 >= nc) dg = unpackM(row[(size_t)(v - 1 - nc) * T]);
+                }
+                const int upM = unpackM(upw);
+                int upI = SWG ? unpackI(upw) : 0;
+                const uint32_t pw = pat[(size_t)((v - 1) >> 2) * T] ^ tc4;
+                const bool nev = (pw >> (8 * ((v - 1) & 3))) & 0xffu;
+                const int mm = dg + (nev ? X : MT);
+                int dI, dD, dP, dQ;
+                const int m = dp_cell<ALGO>(upM, upI, leftM, leftD, mm, OE, E, dI, dD, dP, dQ);
+                const uint32_t old = row[(size_t)v * T];
+                row[(size_t)v * T] = pack(m, upI);
+                if (v == nc) { tailM = m; tailI = upI; tailD = leftD; }
+                const int j = (v - 1) & 15;
+                w0 |= (((uint32_t)dP >> 31) << (15 - j)) | (((uint32_t)dQ >> 31) << (31 - j));
+                if (SWG) w1 |= (((uint32_t)dD >> 31) << (15 - j)) | (((uint32_t)dI >> 31) << (31 - j));
+                if (K.backtrace && (j == 15 || v == pl)) {
+                    uint32_t *d = frow + (size_t)((v - 1) >> 4) * fstep;
+                    d[0] = w0;
+                    if (SWG) d[1] = w1;
+                    w0 = w1 = 0;
+                }
+                dg = unpackM(old);
+                leftM = m;
+            }
+            score = leftM;
+        }
+        if (pl == 0 || tl == 0) score = 0;
+
+        int begin_offset = pl + tl - 1;
+        int status = AIM_STATUS_OK;
+        if (K.backtrace) {
+            char *ops = K.ops + (size_t)i * 2 * RS;
+            int b = pl + tl - 1;
+            int h = tl, v = pl;
+            int layer = 0;
+            while (h > 0 && v > 0) {
+                const int fi = nc * h + v;             // flat word the reference's traceback reads
+                const int r = min(tl, (fi - 1) / nc);  // its last writer (row r, column c)
+                const int c = fi - nc * r;
+                bool p, q, opD, opI;
+                decode_flags(flg + ((size_t)(r - 1) * rpr + (size_t)((c - 1) >> 4)) * fstep, (c - 1) & 15, SWG, p, q, opD, opI);
+                if (!SWG) {
+                    if (q) {
+                        if (p) { ops[b--] = 'D'; --v; }
+                        else { ops[b--] = 'I'; --h; }
+                    } else {
+                        if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                        --b; --h; --v;
+                    }
+                } else {
+                    if (b < 0) { status = AIM_STATUS_BACKTRACE; break; }
+                    if (layer == 2) { ops[b--] = 'D'; if (opD) layer = 0; --v; }
+                    else if (layer == 1) { ops[b--] = 'I'; if (opI) layer = 0; --h; }
+                    else if (q) layer = p ? 2 : 1;
+                    else {
+                        if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                        --b; --h; --v;
+                    }
+                }
+            }
+            if (status == AIM_STATUS_OK) {
+                while (h > 0) { ops[b--] = 'I'; --h; }
+                while (v > 0) { ops[b--] = 'D'; --v; }
+                begin_offset = b + 1;
+            }
+        }
+        aim_result res;
+        res.max_operations = pl + tl;
+        res.begin_offset = begin_offset;
+        res.end_offset = pl + tl;
+        res.score = score;
+        res.status = status;
+        res.idx = K.idx_base + i;
+        K.results[i] = res;
+    }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// Returns AIM_OK after enqueueing, 1 when this parameter set must be served by aim_dp.cu's literal
+// kernel (possible int16 truncation, or a row that does not fit shared memory), or an AIM_ERR_*.
+int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
+{
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const aim_params &p = a.p;
+    if (const char *m = getenv("AIM_DP_MODE")) { if (std::string(m) == "literal") return 1; }
+    const int RS = p.read_size;
+    const bool nw = p.algo == AIM_ALGO_NW;
+    {   // every intermediate stays inside int16: the reference's truncations are identities
+        const int64_t pen = nw ? std::max(p.mismatch, p.gap_open)
+                               : std::max(std::max(p.mismatch, p.gap_open + p.gap_ext), -p.match);
+        const int64_t bound = (2 * (int64_t)RS + 2) * pen + (nw ? 0 : (int64_t)p.max_score + p.gap_open + p.gap_ext);
+        if (bound >= 32767 || p.max_score < 0) return 1;
+    }
+    // aliased pairs: threads per block from the shared-memory row + pattern stage
+    const size_t per_thread_smem = ((size_t)RS + 1 + (size_t)RS / 4) * 4;
+    const size_t kSmemBudget = 227u * 1024u;
+    int row_threads = 0, row_blocks_per_sm = 0;
+    for (int t = 256; t >= 32; t -= 32) {  // block size that keeps the most threads resident per SM
+        const size_t blk = per_thread_smem * (size_t)t;
+        if (blk > kSmemBudget) continue;
+        const int bps = (int)std::min<size_t>(16, (228u * 1024u) / (blk + 1024));
+        if (t * bps > row_threads * row_blocks_per_sm) { row_threads = t; row_blocks_per_sm = bps; }
+    }
+    if (row_threads < 32) return 1;
+
+    const int FW = nw ? 1 : 2;                         // flag words per 16-cell record
+    const uint32_t wpr = ((uint32_t)RS + 15) / 16;     // records per row (row kernel)
+    const int nstrips_max = (RS + KS - 1) / KS;
+
+    // grids: persistent threads striding over the lists, sized by what is actually resident
+    const int strip_block = 128;
+    int strip_bps = 0;
+    {
+        cudaError_t oe;
+        if (nw) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&strip_bps, dp_strip_kernel<AIM_ALGO_NW, true>, strip_block, 0);
+        else if (p.match == 0) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&strip_bps, dp_strip_kernel<AIM_ALGO_SWG, true>, strip_block, 0);
+        else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&strip_bps, dp_strip_kernel<AIM_ALGO_SWG, false>, strip_block, 0);
+        if (oe != cudaSuccess || strip_bps < 1) { cudaGetLastError(); strip_bps = 4; }
+    }
+    int strip_grid = sc->sm_count * strip_bps;
+    strip_grid = (int)std::min<uint64_t>((uint64_t)strip_grid, ((uint64_t)a.n + strip_block - 1) / strip_block);
+    const size_t strip_threads = (size_t)strip_grid * strip_block;
+    int row_grid = sc->sm_count * row_blocks_per_sm;  // shared memory filled on every SM
+    row_grid = (int)std::min<uint64_t>((uint64_t)row_grid, ((uint64_t)a.n + row_threads - 1) / row_threads);
+    const size_t rowk_threads = (size_t)row_grid * row_threads;
+
+    // scratch: counters | list | strip boundary | strip flags | row flags
+    const size_t off_list = 256;
+    const size_t off_bound = align_up(off_list + (size_t)a.n * 4, 256);
+    const size_t off_sflags = align_up(off_bound + strip_threads * (size_t)RS * 4, 256);
+    const size_t sflag_bytes = p.backtrace ? strip_threads * (size_t)nstrips_max * RS * FW * 4 : 0;
+    const size_t off_rflags = align_up(off_sflags + sflag_bytes, 256);
+    const size_t rflag_bytes = p.backtrace ? rowk_threads * (size_t)RS * wpr * FW * 4 : 0;
+    int rc = scratch_reserve(sc, off_rflags + rflag_bytes);
+    if (rc != AIM_OK) return rc;
+    unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
+    uint32_t *counters = reinterpret_cast<uint32_t *>(base);
+    uint32_t *list = reinterpret_cast<uint32_t *>(base + off_list);
+
+    FastK K{};
+    K.plen = a.plen; K.tlen = a.tlen; K.patterns = a.patterns; K.texts = a.texts;
+    K.results = a.results; K.ops = a.ops; K.n = a.n; K.idx_base = a.idx_base;
+    K.match = p.match; K.x = p.mismatch; K.o = p.gap_open; K.e = p.gap_ext;
+    K.max_score = p.max_score; K.read_size = RS; K.backtrace = p.backtrace;
+    K.wpr = wpr;
+
+    cudaError_t err = cudaMemsetAsync(counters, 0, 8, stream);
+    if (err == cudaSuccess && p.backtrace) err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * RS, stream);
+    if (err == cudaSuccess) {
+        classify_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(a.plen, a.tlen, a.n, RS, list, counters);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) {
+        FastK S = K;
+        S.list = list; S.count = counters; S.list_step = 1;
+        S.bound = reinterpret_cast<uint32_t *>(base + off_bound);
+        S.flags = reinterpret_cast<uint32_t *>(base + off_sflags);
+        if (nw) dp_strip_kernel<AIM_ALGO_NW, true><<<strip_grid, strip_block, 0, stream>>>(S);
+        else if (p.match == 0) dp_strip_kernel<AIM_ALGO_SWG, true><<<strip_grid, strip_block, 0, stream>>>(S);
+        else dp_strip_kernel<AIM_ALGO_SWG, false><<<strip_grid, strip_block, 0, stream>>>(S);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) {
+        FastK R = K;
+        R.list = list + (a.n - 1); R.count = counters + 1; R.list_step = -1;
+        R.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
+        const size_t smem = per_thread_smem * (size_t)row_threads;
+        if (nw) {
+            err = cudaFuncSetAttribute(dp_row_kernel<AIM_ALGO_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err == cudaSuccess) dp_row_kernel<AIM_ALGO_NW><<<row_grid, row_threads, smem, stream>>>(R);
+        } else {
+            err = cudaFuncSetAttribute(dp_row_kernel<AIM_ALGO_SWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err == cudaSuccess) dp_row_kernel<AIM_ALGO_SWG><<<row_grid, row_threads, smem, stream>>>(R);
+        }
+        if (err == cudaSuccess) err = cudaGetLastError();
+    }
+    if (err != cudaSuccess) { set_error(std::string("dp_fast launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
+    if (launches) *launches += 3;
+    return AIM_OK;
+}
+
+}  // namespace aim

@@ -84,6 +84,30 @@ CASES = [
 @pytest.mark.parametrize("algo,kw,gen", CASES, ids=[f"{c[0]}-{c[2][0]}" for c in CASES])
 @pytest.mark.parametrize("dirty", [False, True], ids=["acgt", "dirty"])
 def test_vs_oracle_ragged(algo, kw, gen, dirty):
+    _vs_oracle_ragged(algo, kw, gen, dirty)
+
+
+DP_CASES = [c for c in CASES if c[0] in ("nw", "swg")]
+
+
+@pytest.mark.parametrize("algo,kw,gen", DP_CASES, ids=[f"{c[0]}-{c[2][0]}" for c in DP_CASES])
+def test_vs_oracle_ragged_literal_dp_kernel(algo, kw, gen, monkeypatch):
+    """NW/SWG are normally served by the register-strip / shared-memory-row kernels (aim_dp_fast.cu); the
+    literal int16 kernel (aim_dp.cu) that backs them up for over-long reads must stay bit-exact too."""
+    monkeypatch.setenv("AIM_DP_MODE", "literal")
+    _vs_oracle_ragged(algo, kw, gen, True)
+
+
+def test_dp_long_rows_fall_back_to_literal_kernel():
+    """(2*READ_SIZE+2)*max penalty >= 32767: int16 truncation is possible, the literal kernel must serve."""
+    kw = dict(max_score=50, read_size=2304, mismatch=6, gap_open=7, backtrace=True)
+    plen, tlen, pats, txts = _ragged(31, 24, kw["read_size"], 1800, 2300, dirty=True)
+    res, ops, _ = A.align_batch(A.AlignParams(algo="nw", **kw), plen, tlen, pats, txts)
+    exp, exp_ops = O.align("nw", plen, tlen, pats, txts, nthreads=8, **kw)
+    assert_same_alignment(res, ops, exp, exp_ops, True, what="nw long rows")
+
+
+def _vs_oracle_ragged(algo, kw, gen, dirty):
     seed, n, lo, hi = gen
     plen, tlen, pats, txts = _ragged(seed, n, kw["read_size"], lo, hi, dirty=dirty)
     res, ops, _ = A.align_batch(A.AlignParams(algo=algo, **kw), plen, tlen, pats, txts)
