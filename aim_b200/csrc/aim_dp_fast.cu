@@ -55,7 +55,8 @@ struct FastK {
     int list_step;          // +1: list grows upwards from list[0]; -1: downwards from list[0]
     uint32_t *bound;        // strip kernel: boundary column, [row][thread]
     uint32_t *flags;        // predicate bits
-    uint32_t wpr;           // row kernel: flag words per row
+    uint32_t wpr;           // row kernel: flag records per row
+    int neg1;               // -1, kept opaque to the compiler (see dp_cell)
 };
 
 // ---- classification: non-aliased pairs to the front of the list, aliased ones to the back ----
@@ -88,8 +89,13 @@ __global__ void classify_kernel(const int32_t *plen, const int32_t *tlen, uint32
 //   dD = (leftD+E) - (leftM+O+E) sign set  <=>  D was NOT opened here   (swg.c:88)
 //   dP = ins - del               sign set  <=>  !(del <= ins)
 //   dQ = mm - min(del,ins)       sign set  <=>  !(min(del,ins) <= mm)
+//
+// Adds/subs are left to ptxas, which splits them between the alu pipe (VIADD) and the fma pipe
+// (IMAD.IADD): min / funnel-shift / logic only run on the alu pipe, and forcing more adds onto IMAD
+// was measured slower (integer IMAD only issues on the heavy half of the fma pipe).
 template <int ALGO>
-__device__ __forceinline__ int dp_cell(int upM, int &upI, int leftM, int &leftD, int mm, int OE, int E, int &dI, int &dD, int &dP, int &dQ)
+__device__ __forceinline__ int dp_cell(int upM, int &upI, int leftM, int &leftD, int mm, int OE, int E, int neg1, int &dI, int &dD, int &dP,
+                                       int &dQ)
 {
     int ins, del;
     if (ALGO == AIM_ALGO_NW) {
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(128) dp_strip_kernel(const FastK K)
     const int RS = K.read_size;
     const int X = K.x, E = K.e, MT = MT0 ? 0 : K.match, MS = K.max_score;
     const int OE = SWG ? K.o + K.e : K.o;  // NW: the single linear gap
-    const int O = K.o;
+    const int O = K.o, neg1 = K.neg1;
     uint32_t sel[4];  // IDP.4A selectors: (X - MT) in byte k
 #pragma unroll
     for (int k = 0; k < 4; ++k) sel[k] = (uint32_t)(X - MT) << (8 * k);
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(128) dp_strip_kernel(const FastK K)
                     const int um = upM[j];
                     const int mm = (int)__dp4a(ne[j >> 2], sel[j & 3], (uint32_t)(MT0 ? dg : dg + MT));
                     int dI, dD, dP, dQ;
-                    const int m = dp_cell<ALGO>(um, upI[j], leftM, leftD, mm, OE, E, dI, dD, dP, dQ);
+                    const int m = dp_cell<ALGO>(um, upI[j], leftM, leftD, mm, OE, E, neg1, dI, dD, dP, dQ);
                     aP = push_sign(aP, dP);
                     aQ = push_sign(aQ, dQ);
                     if (SWG) { aD = push_sign(aD, dD); aI = push_sign(aI, dI); }
@@ -269,27 +275,35 @@ __global__ void __launch_bounds__(128) dp_strip_kernel(const FastK K)
 }
 
 // ================= aliased pairs: serial row-major fill, row in shared memory =================
-// Shared memory per thread: (RS+1) row words [column][thread] (NW: M; SWG: M | I << 16) followed
-// by RS/4 pattern words [word][thread].  Flags: one 16-cell record per 16 columns of a row.
-template <int ALGO>
-__global__ void __launch_bounds__(256) dp_row_kernel(const FastK K)
+// Shared memory per thread: (RS+1) row words [column][lane] (NW: M; SWG: M | I << 16).  Pattern bases
+// come through L1 (16 bytes per record, fetched one record ahead).  Flags: one record per 16 columns.
+// One warp per block: the [column][lane] stride is a compile-time 128 bytes, so every access inside a
+// 16-cell record is base + immediate, and the next record's 16 "previous row" words are fetched into
+// registers before the current record's dependent chain runs (each pair is one serial chain; with a
+// handful of warps per SM the shared-memory latency must be hidden inside the thread).
+// PSMEM: the pattern bases are staged in shared memory after the row (RS/4 words per lane).  Worth it
+// when many warps still fit (short reads: L1 is too small for their patterns); for long rows the
+// launcher prefers one more resident warp and reads the pattern through L1 one record ahead.
+constexpr uint32_t RT = 32;
+template <int ALGO, bool PSMEM>
+__global__ void __launch_bounds__(RT) dp_row_kernel(const FastK K)
 {
     constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
     constexpr int FW = SWG ? 2 : 1;
     extern __shared__ uint32_t smem[];
-    const uint32_t T = blockDim.x;
+    constexpr uint32_t T = RT;
     const uint32_t tid = blockIdx.x * T + threadIdx.x;
     const uint32_t nth = gridDim.x * T;
     const uint32_t count = *K.count;
     const int RS = K.read_size;
     const int X = K.x, E = K.e, MT = SWG ? K.match : 0, MS = K.max_score;
     const int OE = SWG ? K.o + K.e : K.o;
-    const int O = K.o;
+    const int O = K.o, neg1 = K.neg1;
     uint32_t sel[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) sel[k] = (uint32_t)(X - MT) << (8 * k);
     uint32_t *row = smem + threadIdx.x;                         // row[v * T]
-    uint32_t *pat = smem + (size_t)(RS + 1) * T + threadIdx.x;  // pat[w * T]
+    uint32_t *pat = smem + (size_t)(RS + 1) * T + threadIdx.x;  // pat[w * T] (PSMEM only)
     uint32_t *flg = K.flags + (size_t)tid * FW;
     const size_t fstep = (size_t)nth * FW;
     const uint32_t rpr = K.wpr;  // records per row
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(256) dp_row_kernel(const FastK K)
         const bool alias = pl >= nc;
         int score = 0;
 
-        for (int w = 0; w * 4 < pl; ++w) pat[(size_t)w * T] = __ldg(reinterpret_cast<const uint32_t *>(gp) + w);
+        if (PSMEM) for (int w = 0; w * 4 < pl; ++w) pat[(size_t)w * T] = __ldg(reinterpret_cast<const uint32_t *>(gp) + w);
         // row 0 (nw.c:119-124 / swg.c:167-175)
         row[0] = pack(0, MS);
         for (int v = 1; v <= pl; ++v) row[(size_t)v * T] = pack(SWG ? O + v * E : v * OE, MS);
@@ -329,30 +343,64 @@ __global__ void __launch_bounds__(256) dp_row_kernel(const FastK K)
 
             // ---- head, full 16-cell records ----
             int v = 1;
+            uint32_t cur[16], nxt[16];
+            uint2 pcur[2], pnxt[2];  // the record's 16 pattern bases
+            if (headend >= 16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cur[j] = row[(size_t)(1 + j) * T];
+                if (!PSMEM) {
+                    pcur[0] = __ldg(reinterpret_cast<const uint2 *>(gp));
+                    pcur[1] = __ldg(reinterpret_cast<const uint2 *>(gp) + 1);
+                }
+            }
             for (; v + 15 <= headend; v += 16) {
+                uint32_t *rv = row + (size_t)v * T;
+                const bool more = v + 31 <= headend;
+                if (more) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) nxt[j] = rv[(size_t)(16 + j) * T];
+                    if (!PSMEM) {
+                        pnxt[0] = __ldg(reinterpret_cast<const uint2 *>(gp + v + 15));
+                        pnxt[1] = __ldg(reinterpret_cast<const uint2 *>(gp + v + 15) + 1);
+                    }
+                }
+                if (PSMEM) {
+                    const uint32_t *pv = pat + (size_t)((v - 1) >> 2) * T;
+                    pcur[0] = make_uint2(pv[0], pv[T]);
+                    pcur[1] = make_uint2(pv[2 * T], pv[3 * T]);
+                }
+                uint32_t ne[4];
+                ne[0] = __vsetne4(pcur[0].x ^ tc4, 0u);
+                ne[1] = __vsetne4(pcur[0].y ^ tc4, 0u);
+                ne[2] = __vsetne4(pcur[1].x ^ tc4, 0u);
+                ne[3] = __vsetne4(pcur[1].y ^ tc4, 0u);
                 uint32_t aP = 0, aQ = 0, aD = 0, aI = 0;
-                uint32_t ne = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int vv = v + j;
-                    if ((j & 3) == 0) ne = __vsetne4(pat[(size_t)((vv - 1) >> 2) * T] ^ tc4, 0u);
-                    const uint32_t old = row[(size_t)vv * T];
+                    const uint32_t old = cur[j];
                     const int upM = unpackM(old);
                     int upI = SWG ? unpackI(old) : 0;
-                    const int mm = (int)__dp4a(ne, sel[j & 3], (uint32_t)(dg + MT));
+                    const int mm = (int)__dp4a(ne[j >> 2], sel[j & 3], (uint32_t)(dg + MT));
                     int dI, dD, dP, dQ;
-                    const int m = dp_cell<ALGO>(upM, upI, leftM, leftD, mm, OE, E, dI, dD, dP, dQ);
-                    row[(size_t)vv * T] = pack(m, upI);
+                    const int m = dp_cell<ALGO>(upM, upI, leftM, leftD, mm, OE, E, neg1, dI, dD, dP, dQ);
+                    cur[j] = pack(m, upI);
                     aP = push_sign(aP, dP);
                     aQ = push_sign(aQ, dQ);
                     if (SWG) { aD = push_sign(aD, dD); aI = push_sign(aI, dI); }
                     dg = upM;
                     leftM = m;
                 }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) rv[(size_t)j * T] = cur[j];
                 if (K.backtrace) {
                     uint32_t *d = frow + (size_t)((v - 1) >> 4) * fstep;
-                    d[0] = aP | (aQ << 16);
-                    if (SWG) d[1] = aD | (aI << 16);
+                    if (SWG) *reinterpret_cast<uint2 *>(d) = make_uint2(aP | (aQ << 16), aD | (aI << 16));
+                    else d[0] = aP | (aQ << 16);
+                }
+                if (more) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+                    if (!PSMEM) { pcur[0] = pnxt[0]; pcur[1] = pnxt[1]; }
                 }
             }
             // ---- remaining head cells, then the aliased tail: columns nc..pl read the CURRENT row's
@@ -369,11 +417,10 @@ __global__ void __launch_bounds__(256) dp_row_kernel(const FastK K)
                 }
                 const int upM = unpackM(upw);
                 int upI = SWG ? unpackI(upw) : 0;
-                const uint32_t pw = pat[(size_t)((v - 1) >> 2) * T] ^ tc4;
-                const bool nev = (pw >> (8 * ((v - 1) & 3))) & 0xffu;
+                const bool nev = (uint32_t)(unsigned char)__ldg(gp + v - 1) != (tc4 & 0xffu);  // (L1; few cells per row)
                 const int mm = dg + (nev ? X : MT);
                 int dI, dD, dP, dQ;
-                const int m = dp_cell<ALGO>(upM, upI, leftM, leftD, mm, OE, E, dI, dD, dP, dQ);
+                const int m = dp_cell<ALGO>(upM, upI, leftM, leftD, mm, OE, E, neg1, dI, dD, dP, dQ);
                 const uint32_t old = row[(size_t)v * T];
                 row[(size_t)v * T] = pack(m, upI);
                 if (v == nc) { tailM = m; tailI = upI; tailD = leftD; }
@@ -462,16 +509,14 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         if (bound >= 32767 || p.max_score < 0) return 1;
     }
     // aliased pairs: threads per block from the shared-memory row + pattern stage
-    const size_t per_thread_smem = ((size_t)RS + 1 + (size_t)RS / 4) * 4;
+    // stage the pattern in shared memory only if that still leaves >= 8 warps per SM resident
+    size_t per_thread_smem = ((size_t)RS + 1 + (size_t)RS / 4) * 4;
+    const bool psmem = (228u * 1024u) / (per_thread_smem * 32 + 1024) >= 8;
+    if (!psmem) per_thread_smem = ((size_t)RS + 1) * 4;
     const size_t kSmemBudget = 227u * 1024u;
-    int row_threads = 0, row_blocks_per_sm = 0;
-    for (int t = 256; t >= 32; t -= 32) {  // block size that keeps the most threads resident per SM
-        const size_t blk = per_thread_smem * (size_t)t;
-        if (blk > kSmemBudget) continue;
-        const int bps = (int)std::min<size_t>(16, (228u * 1024u) / (blk + 1024));
-        if (t * bps > row_threads * row_blocks_per_sm) { row_threads = t; row_blocks_per_sm = bps; }
-    }
-    if (row_threads < 32) return 1;
+    const int row_threads = (int)RT;  // one warp per block (compile-time strides), as many blocks as shared memory holds
+    const int row_blocks_per_sm = (int)std::min<size_t>(32, (228u * 1024u) / (per_thread_smem * RT + 1024));
+    if (per_thread_smem * RT > kSmemBudget || row_blocks_per_sm < 1) return 1;
 
     const int FW = nw ? 1 : 2;                         // flag words per 16-cell record
     const uint32_t wpr = ((uint32_t)RS + 15) / 16;     // records per row (row kernel)
@@ -513,6 +558,7 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     K.match = p.match; K.x = p.mismatch; K.o = p.gap_open; K.e = p.gap_ext;
     K.max_score = p.max_score; K.read_size = RS; K.backtrace = p.backtrace;
     K.wpr = wpr;
+    K.neg1 = -1;
 
     cudaError_t err = cudaMemsetAsync(counters, 0, 8, stream);
     if (err == cudaSuccess && p.backtrace) err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * RS, stream);
@@ -535,13 +581,16 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         R.list = list + (a.n - 1); R.count = counters + 1; R.list_step = -1;
         R.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
         const size_t smem = per_thread_smem * (size_t)row_threads;
-        if (nw) {
-            err = cudaFuncSetAttribute(dp_row_kernel<AIM_ALGO_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (err == cudaSuccess) dp_row_kernel<AIM_ALGO_NW><<<row_grid, row_threads, smem, stream>>>(R);
-        } else {
-            err = cudaFuncSetAttribute(dp_row_kernel<AIM_ALGO_SWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (err == cudaSuccess) dp_row_kernel<AIM_ALGO_SWG><<<row_grid, row_threads, smem, stream>>>(R);
-        }
+#define AIM_ROW_LAUNCH(A, PS)                                                                                          \
+    do {                                                                                                              \
+        err = cudaFuncSetAttribute(dp_row_kernel<A, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        if (err == cudaSuccess) dp_row_kernel<A, PS><<<row_grid, row_threads, smem, stream>>>(R);                      \
+    } while (0)
+        if (nw && psmem) AIM_ROW_LAUNCH(AIM_ALGO_NW, true);
+        else if (nw) AIM_ROW_LAUNCH(AIM_ALGO_NW, false);
+        else if (psmem) AIM_ROW_LAUNCH(AIM_ALGO_SWG, true);
+        else AIM_ROW_LAUNCH(AIM_ALGO_SWG, false);
+#undef AIM_ROW_LAUNCH
         if (err == cudaSuccess) err = cudaGetLastError();
     }
     if (err != cudaSuccess) { set_error(std::string("dp_fast launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
