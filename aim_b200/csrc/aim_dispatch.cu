@@ -184,7 +184,8 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
     // chunk: big enough to fill the GPU many times over, small enough that pipeline fill/drain is short
     // (the full-table DP kernels hold one pair per thread for milliseconds: give them several times the
     // resident thread count per chunk so the last, partially filled pass stays short)
-    const size_t chunk_bytes = (p.algo == AIM_ALGO_WFA) ? (96u << 20) : (384u << 20);
+    // (long reads: a chunk must hold several pairs per resident pair slot, ~6.5 K slots on a B200)
+    const size_t chunk_bytes = (p.algo != AIM_ALGO_WFA) ? (384u << 20) : (p.read_size >= 2048 ? (768u << 20) : (96u << 20));
     uint32_t chunk_pairs = (uint32_t)std::max<size_t>(16384, std::min<size_t>(chunk_bytes / per_pair, 1u << 20));
     chunk_pairs = std::min(chunk_pairs, n);
     const uint32_t nchunks = (n + chunk_pairs - 1) / chunk_pairs;

@@ -48,6 +48,20 @@ struct Scratch {
 // Ensure scratch->buf holds at least `bytes` (grows, never shrinks).  Returns AIM_OK/AIM_ERR_*.
 int scratch_reserve(Scratch *s, size_t bytes);
 
+// Launch configuration of the warp-per-pair WFA kernel (aim_wfa.cu), split from the launch so that the
+// long-read kernel can size one scratch for itself plus this kernel serving its leftovers.
+struct WarpPlan {
+    int rc;
+    int grid, block;
+    bool hg;
+    size_t smem_block, meta_bytes, scratch_bytes;
+    alignas(8) unsigned char kernel_args[192];
+};
+WarpPlan wfa_warp_plan(const KernelArgs &a, int sm_count, uint32_t max_pairs);
+int wfa_warp_launch(const WarpPlan &W, void *scratch, const uint32_t *list, const uint32_t *list_count, void *stream, int *launches);
+// long-read score-only kernel (aim_wfa_long.cu); returns 1 when not applicable
+int launch_wfa_long(const KernelArgs &a, Scratch *s, void *stream, int *launches);
+
 // Launchers (aim_wfa.cu / aim_dp.cu).  Enqueue on `stream`; return AIM_OK or AIM_ERR_*;
 // *launches is incremented by the number of kernels enqueued.
 int launch_wfa(const KernelArgs &a, Scratch *s, void *stream, int *launches);

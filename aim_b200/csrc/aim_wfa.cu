@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,8 @@ struct WfaK {
     int16_t *g_hist;           // long-read mode: per-warp history arenas
     size_t g_meta_stride;      // words
     size_t g_hist_stride;      // slots
+    const uint32_t *list;      // optional: pair indices to serve (the long-read kernel's leftovers) ...
+    const uint32_t *list_count;  // ... and how many (device counter)
 };
 
 struct Rec {
@@ -392,6 +395,11 @@ __global__ void __launch_bounds__(256) wfa_kernel(const WfaK K)
         hist = reinterpret_cast<int16_t *>(meta + K.meta_words);
         sOps = reinterpret_cast<char *>(hist + K.hist_cap);
     }
+    if (K.list) {
+        const uint32_t cnt = *K.list_count;
+        for (uint32_t j = gw; j < cnt; j += nw) wfa_pair<HG>(K, lane, K.list[j], sP, sT, meta, hist, sOps);
+        return;
+    }
     for (uint32_t i = gw; i < K.n; i += nw) wfa_pair<HG>(K, lane, i, sP, sT, meta, hist, sOps);
 }
 
@@ -425,16 +433,11 @@ WfaSchedule wfa_schedule(int max_score, int x, int o, int e)
     return out;
 }
 
-int launch_wfa(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
+// Launch configuration of the warp-per-pair kernel for one batch (sizes only, nothing enqueued).
+WarpPlan wfa_warp_plan(const KernelArgs &a, int sm_count, uint32_t max_pairs)
 {
-    cudaStream_t stream = (cudaStream_t)stream_v;
     const aim_params &p = a.p;
-    if (p.max_score < 0 || p.max_score > 32000) { set_error("MAX_SCORE out of range for int16 offsets"); return AIM_ERR_ARG; }
-    if (a.n == 0) return AIM_OK;
-    {   // short reads: several pairs per warp in lockstep (aim_wfa_sub.cu); falls through when not applicable
-        const int rc = launch_wfa_sub(a, sc, stream_v, launches);
-        if (rc != 1) return rc;
-    }
+    WarpPlan W{};
     WfaK K{};
     K.plen = a.plen; K.tlen = a.tlen; K.patterns = a.patterns; K.texts = a.texts;
     K.results = a.results; K.ops = a.ops; K.n = a.n; K.idx_base = a.idx_base;
@@ -459,7 +462,6 @@ int launch_wfa(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
     const bool hg = short_bytes > kSmemBudget / 8;  // fewer than 8 warps/SM would fit: long-read mode
 
     int warps_per_block, blocks_per_sm;
-    size_t smem_block;
     const uint32_t kSmemPerSm = 228u * 1024u, kBlockReserve = 1024u;
     if (!hg) {
         K.warp_smem_bytes = round_up((uint32_t)short_bytes, 16);
@@ -477,39 +479,79 @@ int launch_wfa(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
         }
         warps_per_block = 1;
     }
-    smem_block = (size_t)warps_per_block * K.warp_smem_bytes;
-    if (smem_block > kSmemBudget) { set_error("READ_SIZE too large for the shared-memory sequence stage"); return AIM_ERR_ARG; }
-    blocks_per_sm = (int)std::min<uint32_t>(kSmemPerSm / ((uint32_t)smem_block + kBlockReserve), 32u);
+    W.smem_block = (size_t)warps_per_block * K.warp_smem_bytes;
+    if (W.smem_block > kSmemBudget) { W.rc = AIM_ERR_ARG; return W; }
+    blocks_per_sm = (int)std::min<uint32_t>(kSmemPerSm / ((uint32_t)W.smem_block + kBlockReserve), 32u);
     blocks_per_sm = std::max(1, std::min(blocks_per_sm, (hg ? 32 : 64) / warps_per_block));
-    int grid = sc->sm_count * blocks_per_sm;
+    int grid = sm_count * blocks_per_sm;
     uint32_t total_warps = (uint32_t)grid * (uint32_t)warps_per_block;
-    if (total_warps > a.n) {
-        grid = (int)((a.n + warps_per_block - 1) / warps_per_block);
+    if (total_warps > max_pairs) {
+        grid = (int)((max_pairs + warps_per_block - 1) / warps_per_block);
         total_warps = (uint32_t)grid * (uint32_t)warps_per_block;
     }
+    W.grid = grid;
+    W.block = warps_per_block * 32;
+    W.hg = hg;
     if (hg) {
         K.g_meta_stride = K.meta_words;
         K.g_hist_stride = round_up(K.hist_cap, 8);
-        size_t meta_bytes = (size_t)total_warps * K.g_meta_stride * 4;
-        meta_bytes = (meta_bytes + 255) / 256 * 256;
-        size_t hist_bytes = (size_t)total_warps * K.g_hist_stride * 2;
-        int rc = scratch_reserve(sc, meta_bytes + hist_bytes);
-        if (rc != AIM_OK) return rc;
-        K.g_meta = reinterpret_cast<uint32_t *>(sc->buf);
-        K.g_hist = reinterpret_cast<int16_t *>(reinterpret_cast<unsigned char *>(sc->buf) + meta_bytes);
+        W.meta_bytes = ((size_t)total_warps * K.g_meta_stride * 4 + 255) / 256 * 256;
+        W.scratch_bytes = W.meta_bytes + (size_t)total_warps * K.g_hist_stride * 2;
     }
+    static_assert(sizeof(WfaK) <= sizeof(W.kernel_args), "WarpPlan::kernel_args too small");
+    memcpy(W.kernel_args, &K, sizeof(K));
+    W.rc = AIM_OK;
+    return W;
+}
+
+// Enqueue the warp-per-pair kernel; `scratch` holds W.scratch_bytes.  With list != nullptr only the
+// pairs list[0 .. *list_count) are served.
+int wfa_warp_launch(const WarpPlan &W, void *scratch, const uint32_t *list, const uint32_t *list_count, void *stream_v, int *launches)
+{
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    WfaK K;
+    memcpy(&K, W.kernel_args, sizeof(K));
+    if (W.hg) {
+        K.g_meta = reinterpret_cast<uint32_t *>(scratch);
+        K.g_hist = reinterpret_cast<int16_t *>(reinterpret_cast<unsigned char *>(scratch) + W.meta_bytes);
+    }
+    K.list = list;
+    K.list_count = list_count;
     cudaError_t err;
-    if (hg) {
-        err = cudaFuncSetAttribute(wfa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
-        if (err == cudaSuccess) wfa_kernel<true><<<grid, warps_per_block * 32, smem_block, stream>>>(K);
+    if (W.hg) {
+        err = cudaFuncSetAttribute(wfa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W.smem_block);
+        if (err == cudaSuccess) wfa_kernel<true><<<W.grid, W.block, W.smem_block, stream>>>(K);
     } else {
-        err = cudaFuncSetAttribute(wfa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
-        if (err == cudaSuccess) wfa_kernel<false><<<grid, warps_per_block * 32, smem_block, stream>>>(K);
+        err = cudaFuncSetAttribute(wfa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W.smem_block);
+        if (err == cudaSuccess) wfa_kernel<false><<<W.grid, W.block, W.smem_block, stream>>>(K);
     }
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { set_error(std::string("wfa launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
     if (launches) ++*launches;
     return AIM_OK;
+}
+
+int launch_wfa(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
+{
+    const aim_params &p = a.p;
+    if (p.max_score < 0 || p.max_score > 32000) { set_error("MAX_SCORE out of range for int16 offsets"); return AIM_ERR_ARG; }
+    if (a.n == 0) return AIM_OK;
+    {   // short reads: several pairs per warp in lockstep (aim_wfa_sub.cu); falls through when not applicable
+        const int rc = launch_wfa_sub(a, sc, stream_v, launches);
+        if (rc != 1) return rc;
+    }
+    {   // long reads, score only: windowed rings in shared memory (aim_wfa_long.cu); its leftovers come back
+        // through wfa_warp_launch with a list
+        const int rc = launch_wfa_long(a, sc, stream_v, launches);
+        if (rc != 1) return rc;
+    }
+    const WarpPlan W = wfa_warp_plan(a, sc->sm_count, a.n);
+    if (W.rc != AIM_OK) { set_error("READ_SIZE too large for the shared-memory sequence stage"); return W.rc; }
+    if (W.scratch_bytes) {
+        const int rc = scratch_reserve(sc, W.scratch_bytes);
+        if (rc != AIM_OK) return rc;
+    }
+    return wfa_warp_launch(W, sc->buf, nullptr, nullptr, stream_v, launches);
 }
 
 }  // namespace aim

@@ -1,0 +1,418 @@
+// Long-read WFA / WFA-adaptive, score only, for sm_100a: G lanes per pair, 32/G pairs per warp in
+// LOCKSTEP over the scores, wavefronts in WINDOWED shared-memory rings.
+//
+// Same algorithm and literal semantics as aim_wfa.cu / aim_wfa_sub.cu (reference:
+// WFA/DPU-MRAM/dpu/wfa.c:70-407).  What changes for reads of thousands of bases:
+//   * MAX_SCORE is in the thousands, so the static wavefront range (2s+1 diagonals) is useless; with
+//     adaptive trimming (wfa.c:70-141) the live range stays around 50-130 diagonals.  Every ring slot
+//     is therefore a 256-diagonal window addressed modulo 256 (diagonal k lives in cell k & 255): no
+//     per-slot origin to track while the window drifts with the alignment's diagonal.  A pair whose
+//     wavefront outgrows the window (254 diagonals) is handed to the warp-per-pair kernel of
+//     aim_wfa.cu (global-memory wavefronts) through a device-side list; so is a pair holding a byte
+//     outside {A,C,G,T} (the reference compares raw bytes, wfa.c:209).
+//   * compute_offsets only reads M of scores s-x, s-o-e and I/D of score s-e: the rings hold
+//     max(x,o+e)+1 M wavefronts and e+1 I/D wavefronts plus one (lo|hi) word per live score - about
+//     5 KB per pair at x3 o4 e1, i.e. ~44 pairs resident per SM.
+//   * the sequences are packed 2 bits/base by a pre-pass into HBM in a DUPLICATED layout (entry i =
+//     {word i, word i+1}) so that the 16-base window at any offset is one 8-byte load + one funnel
+//     shift; the extend loop reads them through L1 (only the ~100 bases around the current offsets
+//     are hot at any time).
+//   * the per-score schedule (which scores exist, which components they carry, ring slot offsets)
+//     depends only on the penalties: a 16-byte record per score, read warp-uniformly from global.
+//   * pairs are handed out by an atomic counter (cost per pair varies with its score).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "aim_internal.h"
+#include "aim_wfa_common.cuh"
+
+namespace aim {
+
+namespace {
+
+constexpr uint32_t L_PRESENT = 1, L_SUB_NULL = 2, L_O_NULL = 4, L_IE_NULL = 8, L_DE_NULL = 16, L_HAS_I = 32, L_HAS_D = 64;
+constexpr int WC = 256;                        // cells (diagonals) per ring slot, power of two
+constexpr int W_CAP = WC - 2;                  // widest wavefront served here
+constexpr uint32_t M_SLOT_BYTES = WC * 2;      // one int16 array
+constexpr uint32_t ID_SLOT_BYTES = 2 * WC * 2; // I array then D array
+// per-score plan (4 words): w0 flags
+//                           w1 M slot offset of s   | M slot offset of s-x << 16      (bytes)
+//                           w2 M slot offset of s-o-e | I/D slot offset of s-e << 16
+//                           w3 I/D slot offset of s | range-ring index of s-e << 16
+
+struct LongK {
+    const int32_t *plen;
+    const int32_t *tlen;
+    const uint2 *packed;        // [pair][2][pk_words] duplicated 2-bit words
+    const unsigned char *dirty; // pair holds a non-ACGT byte
+    aim_result *results;
+    const uint4 *plan;
+    uint32_t *work_ctr;
+    uint32_t *fail_list;
+    uint32_t *fail_count;
+    uint32_t n, idx_base;
+    int x, o, e;
+    int max_score, read_size;
+    uint32_t pk_words;    // entries per packed sequence
+    uint32_t dyn_words;   // range ring words per pair (multiple of 4, >= ring_m)
+    uint32_t mring_bytes; // ring_m * M_SLOT_BYTES
+    uint32_t pair_words;  // shared-memory words per pair slot
+};
+
+// ---- pre-pass: ASCII rows -> duplicated 2-bit words; one warp per sequence ----
+__global__ void __launch_bounds__(256) pack_kernel(const int32_t *plen, const int32_t *tlen, const char *patterns, const char *texts, uint32_t n,
+                                                   int RS, uint32_t pk_words, uint2 *packed, unsigned char *dirty)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint64_t u = gw; u < 2ull * n; u += nw) {
+        const uint32_t i = (uint32_t)(u >> 1);
+        const bool is_text = u & 1;
+        const int len = min(max(is_text ? tlen[i] : plen[i], 0), RS);
+        const char *g = (is_text ? texts : patterns) + (size_t)i * RS;
+        uint2 *out = packed + (size_t)u * pk_words;
+        bool ok = true;
+        for (uint32_t e = lane; e < pk_words; e += 32) {
+            uint32_t w[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int b0 = 16 * (int)(e + q);  // first base of word e+q
+                uint32_t v = 0;
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int off = b0 + 8 * hlf;
+                    uint2 raw = make_uint2(0u, 0u);
+                    if (off < len) raw = __ldg(reinterpret_cast<const uint2 *>(g + off));
+                    v = (v << 16) | pack8(raw, len - off, &ok);
+                }
+                w[q] = v;
+            }
+            out[e] = make_uint2(w[0], w[1]);
+        }
+        if (!__all_sync(kFull, ok) && lane == 0) dirty[i] = 1;
+    }
+}
+
+__device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// byte offset of diagonal k inside a ring array
+__device__ __forceinline__ uint32_t cell(int k) { return ((uint32_t)k & (uint32_t)(WC - 1)) << 1; }
+
+// equal bases from pattern[v], text[h], at most lim (> 0); duplicated packed words through L1
+__device__ __forceinline__ int match_packed_g(const uint2 *P2, const uint2 *T2, int v, int h, int lim)
+{
+    int cnt = 0;
+    for (;;) {
+        const int pv = v + cnt, ph = h + cnt;
+        const uint2 a2 = __ldg(P2 + (pv >> 4)), b2 = __ldg(T2 + (ph >> 4));
+        const uint32_t a = __funnelshift_l(a2.y, a2.x, (pv & 15) * 2);
+        const uint32_t b = __funnelshift_l(b2.y, b2.x, (ph & 15) * 2);
+        const uint32_t d = a ^ b;
+        if (d) { cnt += __clz(d) >> 1; break; }
+        cnt += 16;
+        if (cnt >= lim) break;
+    }
+    return min(cnt, lim);
+}
+
+template <int G>
+__device__ __forceinline__ int group_min(int v)
+{
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(kFull, v, d));
+    return v;
+}
+
+__device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
+__device__ __forceinline__ int hi16s(uint32_t w) { return (int)(short)(w >> 16); }
+__device__ __forceinline__ bool in_range(int k, int lo, int hi) { return (unsigned)(k - lo) <= (unsigned)(hi - lo) && lo <= hi; }
+
+template <int G, bool REDUCE>
+__global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
+{
+    constexpr int PPW = 32 / G;
+    constexpr uint32_t GM = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+    extern __shared__ __align__(16) uint32_t smem_w[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int sub = lane / G, sl = lane % G, subshift = sub * G;
+    const int RS = K.read_size, MS = K.max_score;
+
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_w);
+    const uint32_t aDyn = sbase + (uint32_t)(wib * PPW + sub) * K.pair_words * 4u;  // (lo | hi << 16) per live score
+    const uint32_t aMR = aDyn + K.dyn_words * 4u;                                  // M ring
+    const uint32_t aIDR = aMR + K.mring_bytes;                                     // I/D ring
+
+    for (;;) {
+        uint32_t base_i = 0;
+        if (lane == 0) base_i = atomicAdd(K.work_ctr, (uint32_t)PPW);
+        base_i = __shfl_sync(kFull, base_i, 0);
+        if (base_i >= K.n) break;  // warp-uniform
+        const uint32_t i = base_i + (uint32_t)sub;
+        bool active = i < K.n;
+        bool failed = false;
+        if (active && K.dirty[i]) { failed = true; active = false; }
+        const int pl = active ? min(max(K.plen[i], 0), RS) : 0;
+        const int tl = active ? min(max(K.tlen[i], 0), RS) : 0;
+        const uint2 *P2 = K.packed + (size_t)(active ? i : 0) * 2 * K.pk_words;
+        const uint2 *T2 = P2 + K.pk_words;
+        const int ak = tl - pl;
+
+        bool done = !active;
+        int fscore = MS + 1;  // give-up value (wfa.c:399-404)
+
+        for (int s = 0; s <= MS; ++s) {
+            const uint4 pw = __ldg(K.plan + s);  // warp-uniform
+            const uint32_t fl = pw.x;
+            if (!(fl & L_PRESENT)) continue;
+            const bool sub_null = fl & L_SUB_NULL, o_null = fl & L_O_NULL, ie_null = fl & L_IE_NULL, de_null = fl & L_DE_NULL;
+            const bool has_i = fl & L_HAS_I, has_d = fl & L_HAS_D;
+            const uint32_t offN = pw.y & 0xffffu, offA = pw.y >> 16, offB = pw.z & 0xffffu;
+
+            // this pair's range (wfa.c:318-343) from the (trimmed) ranges of the three source wavefronts
+            int lo = 0, hi = 0;
+            int a_lo = 1, a_hi = -1, b_lo = 1, b_hi = -1, e_lo = 1, e_hi = -1;
+            if (s > 0) {
+                if (!sub_null) { const uint32_t w = lds_u32(aDyn + (offA / M_SLOT_BYTES) * 4u); a_lo = lo16(w); a_hi = hi16s(w); }
+                if (!o_null) { const uint32_t w = lds_u32(aDyn + (offB / M_SLOT_BYTES) * 4u); b_lo = lo16(w); b_hi = hi16s(w); }
+                if (!(ie_null && de_null)) { const uint32_t w = lds_u32(aDyn + (pw.w >> 16) * 4u); e_lo = lo16(w); e_hi = hi16s(w); }
+                lo = min(min(a_lo, b_lo), e_lo) - 1;
+                hi = max(max(a_hi, b_hi), e_hi) + 1;
+            }
+            if (!done && hi - lo + 1 > W_CAP) { done = true; failed = true; }  // window outgrown: leave it to the warp-per-pair kernel
+            const uint32_t aNM = aMR + offN, aAM = aMR + offA, aBM = aMR + offB;
+            const uint32_t aEI = aIDR + (pw.z >> 16), aED = aEI + M_SLOT_BYTES;
+            const uint32_t aNI = aIDR + (pw.w & 0xffffu), aND = aNI + M_SLOT_BYTES;
+
+            // ---- compute_offsets (wfa.c:238-273) fused with extend (wfa.c:193-215) ----
+            int md = max(pl, tl);
+            bool hit_end = false;
+            if (!done) {
+                for (int k = lo + sl; k <= hi; k += G) {
+                    const uint32_t ck = cell(k), ckm = cell(k - 1), ckp = cell(k + 1);
+                    int m = 0;
+                    if (s > 0) {
+                        int ins = -10, del = -10, sb = -10;
+                        if (has_i) {
+                            const int g = in_range(k - 1, b_lo, b_hi) ? lds_s16(aBM + ckm) : kNull;
+                            const int ii = (!ie_null && in_range(k - 1, e_lo, e_hi)) ? lds_s16(aEI + ckm) : kNull;
+                            ins = (g == kNull && ii == kNull) ? kNull : (int)(short)(max(g, ii) + 1);
+                            sts_u16(aNI + ck, ins);
+                        }
+                        if (has_d) {
+                            const int g = in_range(k + 1, b_lo, b_hi) ? lds_s16(aBM + ckp) : kNull;
+                            const int dd = (!de_null && in_range(k + 1, e_lo, e_hi)) ? lds_s16(aED + ckp) : kNull;
+                            del = max(g, dd);
+                            sts_u16(aND + ck, del);
+                        }
+                        if (!sub_null) sb = in_range(k, a_lo, a_hi) ? (int)(short)(lds_s16(aAM + ck) + 1) : kNull;
+                        m = max(del, max(sb, ins));
+                    }
+                    const int v = m - k;
+                    if ((m | v) >= 0) {
+                        const int lim = min(pl - v, tl - m);
+                        if (lim > 0) m += match_packed_g(P2, T2, v, m, lim);
+                    }
+                    sts_u16(aNM + ck, m);
+                    if (REDUCE) md = min(md, max(pl - (m - k), tl - m));
+                    if (k == ak && m >= tl) hit_end = true;
+                }
+            }
+            // ---- end reached (wfa.c:217-237); trimming never removes diagonal ak, so testing before the
+            // reduction is equivalent and the finishing wavefront's trimmed range is never read again ----
+            const uint32_t eb = __ballot_sync(kFull, hit_end);
+            if (!done && ((eb >> subshift) & GM)) { done = true; fscore = s; }
+            if (__all_sync(kFull, done)) break;
+
+            // ---- adaptive reduction (wfa.c:70-141) on the pairs still running ----
+            int newlo = lo, newhi = hi;
+            if (REDUCE) {
+                __syncwarp();
+                const bool wide = !done && (hi - lo + 1) >= 10;
+                if (__any_sync(kFull, wide)) {
+                    md = group_min<G>(md);
+                    const int top_limit = min(ak - 1, hi);
+                    bool pend = wide && lo < top_limit;
+                    if (pend) newlo = top_limit;
+                    for (int c = 0; __any_sync(kFull, pend && (lo + c < top_limit)); c += G) {
+                        const int k = lo + c + sl;
+                        bool hit = false;
+                        if (pend && k < top_limit) {
+                            const int off = lds_s16(aNM + cell(k));
+                            hit = (max(pl - (off - k), tl - off) - md) <= 50;
+                        }
+                        const uint32_t mine = (__ballot_sync(kFull, hit) >> subshift) & GM;
+                        if (pend && mine) { newlo = lo + c + __ffs(mine) - 1; pend = false; }
+                        if (lo + c + G >= top_limit) pend = false;
+                    }
+                    const int bottom_limit = max(ak + 1, newlo);
+                    pend = wide && hi > bottom_limit;
+                    if (pend) newhi = bottom_limit;
+                    for (int c = 0; __any_sync(kFull, pend && (hi - c > bottom_limit)); c += G) {
+                        const int k = hi - c - sl;
+                        bool hit = false;
+                        if (pend && k > bottom_limit) {
+                            const int off = lds_s16(aNM + cell(k));
+                            hit = (max(pl - (off - k), tl - off) - md) <= 50;
+                        }
+                        const uint32_t mine = (__ballot_sync(kFull, hit) >> subshift) & GM;
+                        if (pend && mine) { newhi = hi - c - (__ffs(mine) - 1); pend = false; }
+                        if (hi - c - G <= bottom_limit) pend = false;
+                    }
+                }
+            }
+            if (sl == 0 && !done) sts_u32(aDyn + (offN / M_SLOT_BYTES) * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)newhi << 16));
+            __syncwarp();
+        }
+        __syncwarp();
+
+        if (sl == 0) {
+            if (failed) {
+                K.fail_list[atomicAdd(K.fail_count, 1u)] = i;
+            } else if (active) {
+                aim_result r;
+                r.max_operations = pl + tl;
+                r.begin_offset = pl + tl - 1;
+                r.end_offset = pl + tl;
+                r.score = fscore;
+                r.status = AIM_STATUS_OK;
+                r.idx = K.idx_base + i;
+                K.results[i] = r;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+template <int G>
+cudaError_t launch_g(const LongK &K, bool reduce, int sm_count, size_t pair_bytes, cudaStream_t st, int *grid_out)
+{
+    const int block = 128;
+    const size_t smem = (size_t)(block / 32) * (32 / G) * pair_bytes;
+    cudaError_t e;
+    int bps = 0;
+#define AIM_LAUNCH(R)                                                                                               \
+    do {                                                                                                            \
+        e = cudaFuncSetAttribute(wfa_long_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, wfa_long_kernel<G, R>, block, smem); \
+        if (e == cudaSuccess) {                                                                                     \
+            const int grid = sm_count * std::max(1, bps);                                                           \
+            *grid_out = grid;                                                                                       \
+            wfa_long_kernel<G, R><<<grid, block, smem, st>>>(K);                                                    \
+        }                                                                                                           \
+    } while (0)
+    if (reduce) AIM_LAUNCH(true);
+    else AIM_LAUNCH(false);
+#undef AIM_LAUNCH
+    return e;
+}
+
+}  // namespace
+
+// Returns AIM_OK after enqueueing, 1 if this configuration is not served here, or an AIM_ERR_*.
+int launch_wfa_long(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
+{
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const aim_params &p = a.p;
+    if (p.backtrace) return 1;  // history arena: warp-per-pair kernel
+    if (const char *mode = getenv("AIM_WFA_MODE")) { if (std::string(mode) == "warp") return 1; }
+    const int MS = p.max_score, x = p.mismatch, o = p.gap_open, e = p.gap_ext;
+    const uint32_t ring_m = (uint32_t)std::max(x, o + e) + 1, ring_e = (uint32_t)e + 1;
+    if (ring_m * M_SLOT_BYTES > 0xffffu || ring_e * ID_SLOT_BYTES > 0xffffu) return 1;
+
+    // ---- static schedule (presence and components only; ranges are dynamic here) ----
+    struct S { bool present, has_i, has_d; };
+    std::vector<S> w((size_t)MS + 1);
+    std::vector<uint4> plan((size_t)MS + 1, make_uint4(0, 0, 0, 0));
+    w[0] = {true, false, false};
+    auto m_off = [&](int s) -> uint32_t { return s < 0 ? 0u : ((uint32_t)s % ring_m) * M_SLOT_BYTES; };
+    auto id_off = [&](int s) -> uint32_t { return s < 0 ? 0u : ((uint32_t)s % ring_e) * ID_SLOT_BYTES; };
+    for (int s = 0; s <= MS; ++s) {
+        const bool A = s - x >= 0 && w[s - x].present, B = s - o - e >= 0 && w[s - o - e].present, E = s - e >= 0 && w[s - e].present;
+        const bool ie_null = !(E && w[s - e].has_i), de_null = !(E && w[s - e].has_d);
+        if (s > 0) {
+            const bool i_out_null = !B && ie_null, d_out_null = !B && de_null;
+            if (!A && i_out_null && d_out_null) { w[s] = {false, false, false}; continue; }
+            w[s] = {true, !i_out_null, !d_out_null};
+        }
+        uint4 q;
+        q.x = L_PRESENT | (A ? 0u : L_SUB_NULL) | (B ? 0u : L_O_NULL) | (ie_null ? L_IE_NULL : 0u) | (de_null ? L_DE_NULL : 0u) |
+              (w[s].has_i ? L_HAS_I : 0u) | (w[s].has_d ? L_HAS_D : 0u);
+        q.y = m_off(s) | (m_off(s - x) << 16);
+        q.z = m_off(s - o - e) | (id_off(s - e) << 16);
+        q.w = id_off(s) | ((s - e < 0 ? 0u : (uint32_t)(s - e) % ring_m) << 16);
+        plan[(size_t)s] = q;
+    }
+
+    LongK K{};
+    K.plen = a.plen; K.tlen = a.tlen; K.results = a.results; K.n = a.n; K.idx_base = a.idx_base;
+    K.x = x; K.o = o; K.e = e; K.max_score = MS; K.read_size = p.read_size;
+    K.pk_words = (uint32_t)p.read_size / 16 + 1;
+    K.dyn_words = round_up(ring_m, 4);
+    K.mring_bytes = ring_m * M_SLOT_BYTES;
+    int G = 16;
+    if (const char *gs = getenv("AIM_WFA_LONG_G")) { int g = atoi(gs); if (g == 8 || g == 16 || g == 32) G = g; }
+    const uint32_t PPW = 32u / (uint32_t)G;
+    {   // stagger the pair slots of one warp over the banks
+        const uint32_t raw = K.dyn_words + (K.mring_bytes + ring_e * ID_SLOT_BYTES) / 4;
+        const uint32_t want = PPW > 1 ? std::max(4u, 32u / PPW) : 0u;
+        K.pair_words = raw + ((want + 32u - raw % 32u) % 32u);
+    }
+    const size_t pair_bytes = (size_t)K.pair_words * 4;
+    if (pair_bytes * 4 * PPW > 227u * 1024u / 2) return 1;  // fewer than two blocks per SM: not worth it
+
+    // the warp-per-pair kernel serves what this one hands back
+    const WarpPlan W = wfa_warp_plan(a, sc->sm_count, a.n);
+    if (W.rc != AIM_OK) { set_error("READ_SIZE too large for the shared-memory sequence stage"); return W.rc; }
+
+    // scratch: counters | plan | dirty | fail list | packed sequences | warp-per-pair scratch
+    const size_t plan_bytes = plan.size() * sizeof(uint4);
+    const size_t off_plan = 256;
+    const size_t off_dirty = align256(off_plan + plan_bytes);
+    const size_t off_fail = align256(off_dirty + a.n);
+    const size_t off_packed = align256(off_fail + (size_t)a.n * 4);
+    const size_t packed_bytes = (size_t)a.n * 2 * K.pk_words * sizeof(uint2);
+    const size_t off_warp = align256(off_packed + packed_bytes);
+    int rc = scratch_reserve(sc, off_warp + W.scratch_bytes);
+    if (rc != AIM_OK) return rc;
+    unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
+    K.work_ctr = reinterpret_cast<uint32_t *>(base);
+    K.fail_count = K.work_ctr + 1;
+    K.plan = reinterpret_cast<const uint4 *>(base + off_plan);
+    K.dirty = base + off_dirty;
+    K.fail_list = reinterpret_cast<uint32_t *>(base + off_fail);
+    K.packed = reinterpret_cast<const uint2 *>(base + off_packed);
+
+    cudaError_t err = cudaMemsetAsync(base, 0, 256, stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(base + off_dirty, 0, a.n, stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(base + off_plan, plan.data(), plan_bytes, cudaMemcpyHostToDevice, stream);
+    if (err == cudaSuccess) {
+        const uint64_t warps = std::min<uint64_t>(2ull * a.n, (uint64_t)sc->sm_count * 64);
+        const int grid = (int)((warps * 32 + 255) / 256);
+        pack_kernel<<<grid, 256, 0, stream>>>(a.plen, a.tlen, a.patterns, a.texts, a.n, p.read_size, K.pk_words,
+                                              reinterpret_cast<uint2 *>(base + off_packed), base + off_dirty);
+        err = cudaGetLastError();
+    }
+    int grid = 0;
+    if (err == cudaSuccess) {
+        if (G == 8) err = launch_g<8>(K, p.reduce != 0, sc->sm_count, pair_bytes, stream, &grid);
+        else if (G == 16) err = launch_g<16>(K, p.reduce != 0, sc->sm_count, pair_bytes, stream, &grid);
+        else err = launch_g<32>(K, p.reduce != 0, sc->sm_count, pair_bytes, stream, &grid);
+        if (err == cudaSuccess) err = cudaGetLastError();
+    }
+    if (err != cudaSuccess) { set_error(std::string("wfa_long launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
+    if (launches) *launches += 2;
+    // leftovers (window outgrown, non-ACGT bytes)
+    return wfa_warp_launch(W, base + off_warp, K.fail_list, K.fail_count, stream_v, launches);
+}
+
+}  // namespace aim

@@ -69,6 +69,10 @@ CASES = [
     ("wfa", dict(max_score=700, read_size=1504, backtrace=True, reduce=True), (8, 64, 1200, 1500)),  # long-read arena mode
     ("wfa", dict(max_score=700, read_size=1504, backtrace=False, reduce=True), (9, 64, 1200, 1500)),
     ("wfa", dict(max_score=700, read_size=1504, backtrace=True, reduce=False), (10, 48, 1200, 1500)),
+    # score-only long reads: windowed-ring kernel; without trimming the window is outgrown -> hand-over list
+    ("wfa", dict(max_score=700, read_size=1504, backtrace=False, reduce=False), (20, 48, 1200, 1500)),
+    ("wfa", dict(max_score=2500, read_size=3008, backtrace=False, reduce=True), (21, 300, 2000, 3000)),
+    ("wfa", dict(max_score=2500, read_size=3008, mismatch=2, gap_open=3, gap_ext=2, backtrace=False, reduce=True), (22, 200, 2000, 3000)),
     ("nw", dict(max_score=0, read_size=64, mismatch=3, gap_open=4, backtrace=True), (11, 3000, 0, 60)),
     ("nw", dict(max_score=0, read_size=64, mismatch=1, gap_open=1, backtrace=True), (12, 3000, 0, 60)),
     ("nw", dict(max_score=0, read_size=64, mismatch=3, gap_open=4, backtrace=False), (13, 3000, 0, 60)),
@@ -96,6 +100,13 @@ def test_vs_oracle_ragged_literal_dp_kernel(algo, kw, gen, monkeypatch):
     literal int16 kernel (aim_dp.cu) that backs them up for over-long reads must stay bit-exact too."""
     monkeypatch.setenv("AIM_DP_MODE", "literal")
     _vs_oracle_ragged(algo, kw, gen, True)
+
+
+@pytest.mark.parametrize("g", ["8", "32"])
+def test_long_read_kernel_lane_groups(g, monkeypatch):
+    """The windowed-ring long-read kernel with 8 and 32 lanes per pair (default 16)."""
+    monkeypatch.setenv("AIM_WFA_LONG_G", g)
+    _vs_oracle_ragged("wfa", dict(max_score=2500, read_size=3008, backtrace=False, reduce=True), (23, 200, 2000, 3000), True)
 
 
 def test_dp_long_rows_fall_back_to_literal_kernel():
