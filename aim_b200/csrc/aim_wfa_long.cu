@@ -7,9 +7,15 @@
 //     adaptive trimming (wfa.c:70-141) the live range stays around 50-130 diagonals.  Every ring slot
 //     is therefore a 256-diagonal window addressed modulo 256 (diagonal k lives in cell k & 255): no
 //     per-slot origin to track while the window drifts with the alignment's diagonal.  A pair whose
-//     wavefront outgrows the window (254 diagonals) is handed to the warp-per-pair kernel of
+//     wavefront outgrows the window (224 diagonals) is handed to the warp-per-pair kernel of
 //     aim_wfa.cu (global-memory wavefronts) through a device-side list; so is a pair holding a byte
 //     outside {A,C,G,T} (the reference compares raw bytes, wfa.c:209).
+//   * every stored wavefront is framed by PAD cells of NULL on both sides.  From score ~o+e+x on every
+//     score carries all three components; when in addition the three source ranges start and end within
+//     PAD-2 diagonals of each other (the normal case: trimming moves the ends by a diagonal or two),
+//     out-of-range reads land on the frame and return exactly the NULL the reference substitutes
+//     (wfa.c:243-266), so the inner loop needs no range tests - only the "M[k]+1 on an out-of-range
+//     diagonal stays NULL" rule of the substitution term keeps one.  Otherwise the literal loop runs.
 //   * compute_offsets only reads M of scores s-x, s-o-e and I/D of score s-e: the rings hold
 //     max(x,o+e)+1 M wavefronts and e+1 I/D wavefronts plus one (lo|hi) word per live score - about
 //     5 KB per pair at x3 o4 e1, i.e. ~44 pairs resident per SM.
@@ -36,7 +42,8 @@ namespace {
 
 constexpr uint32_t L_PRESENT = 1, L_SUB_NULL = 2, L_O_NULL = 4, L_IE_NULL = 8, L_DE_NULL = 16, L_HAS_I = 32, L_HAS_D = 64;
 constexpr int WC = 256;                        // cells (diagonals) per ring slot, power of two
-constexpr int W_CAP = WC - 2;                  // widest wavefront served here
+constexpr int PAD = 16;                        // NULL cells kept on both sides of every stored wavefront
+constexpr int W_CAP = WC - 2 * PAD;            // widest wavefront served here
 constexpr uint32_t M_SLOT_BYTES = WC * 2;      // one int16 array
 constexpr uint32_t ID_SLOT_BYTES = 2 * WC * 2; // I array then D array
 // per-score plan (4 words): w0 flags
@@ -111,7 +118,7 @@ __device__ __forceinline__ int match_packed_g(const uint2 *P2, const uint2 *T2, 
     int cnt = 0;
     for (;;) {
         const int pv = v + cnt, ph = h + cnt;
-        const uint2 a2 = __ldg(P2 + (pv >> 4)), b2 = __ldg(T2 + (ph >> 4));
+        const uint2 a2 = __ldg(P2 + ((uint32_t)pv >> 4)), b2 = __ldg(T2 + ((uint32_t)ph >> 4));
         const uint32_t a = __funnelshift_l(a2.y, a2.x, (pv & 15) * 2);
         const uint32_t b = __funnelshift_l(b2.y, b2.x, (ph & 15) * 2);
         const uint32_t d = a ^ b;
@@ -193,7 +200,36 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
             // ---- compute_offsets (wfa.c:238-273) fused with extend (wfa.c:193-215) ----
             int md = max(pl, tl);
             bool hit_end = false;
-            if (!done) {
+            // frame-based loop: all components present and the source ranges nearly aligned, for every running pair of the warp
+            bool framed = (fl & (L_SUB_NULL | L_O_NULL | L_IE_NULL | L_DE_NULL | L_HAS_I | L_HAS_D)) == (L_HAS_I | L_HAS_D);
+            if (framed) {
+                const int lo_max = max(max(a_lo, b_lo), e_lo), hi_min = min(min(a_hi, b_hi), e_hi);
+                const bool ok = done || ((lo_max - (lo + 1) + 2 <= PAD) && ((hi - 1) - hi_min + 2 <= PAD));
+                framed = __all_sync(kFull, ok);
+            }
+            if (!done && framed) {
+                const uint32_t a_w = (uint32_t)(a_hi - a_lo);
+                for (int k = lo + sl; k <= hi; k += G) {
+                    const uint32_t k2 = (uint32_t)k << 1;
+                    const uint32_t ck = k2 & (2 * WC - 2), ckm = (k2 - 2u) & (2 * WC - 2), ckp = (k2 + 2u) & (2 * WC - 2);
+                    const int mx = max(lds_s16(aBM + ckm), lds_s16(aEI + ckm));
+                    const int ins = (mx == kNull) ? kNull : mx + 1;
+                    const int del = max(lds_s16(aBM + ckp), lds_s16(aED + ckp));
+                    const int sa = lds_s16(aAM + ck) + 1;
+                    const int sb = ((uint32_t)(k - a_lo) <= a_w) ? sa : kNull;
+                    sts_u16(aNI + ck, ins);
+                    sts_u16(aND + ck, del);
+                    int m = max(del, max(sb, ins));
+                    const int v = m - k;
+                    if ((m | v) >= 0) {
+                        const int lim = min(pl - v, tl - m);
+                        if (lim > 0) m += match_packed_g(P2, T2, v, m, lim);
+                    }
+                    sts_u16(aNM + ck, m);
+                    if (REDUCE) md = min(md, max(pl - (m - k), tl - m));
+                    if (k == ak && m >= tl) hit_end = true;
+                }
+            } else if (!done) {
                 for (int k = lo + sl; k <= hi; k += G) {
                     const uint32_t ck = cell(k), ckm = cell(k - 1), ckp = cell(k + 1);
                     int m = 0;
@@ -267,7 +303,16 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
                     }
                 }
             }
-            if (sl == 0 && !done) sts_u32(aDyn + (offN / M_SLOT_BYTES) * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)newhi << 16));
+            if (!done) {
+                if (sl == 0) sts_u32(aDyn + (offN / M_SLOT_BYTES) * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)newhi << 16));
+                // NULL frame around the (trimmed) wavefront: PAD cells below newlo and above newhi, every component
+                for (int j = sl; j < 2 * PAD; j += G) {
+                    const uint32_t cf = cell(j < PAD ? newlo - 1 - j : newhi + 1 + (j - PAD));
+                    sts_u16(aNM + cf, kNull);
+                    if (has_i) sts_u16(aNI + cf, kNull);
+                    if (has_d) sts_u16(aND + cf, kNull);
+                }
+            }
             __syncwarp();
         }
         __syncwarp();

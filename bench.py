@@ -49,6 +49,9 @@ CONFIGS = {
     5: dict(name="WFA-adaptive long reads l=10000 e=10% 200K pairs score-only", algo="wfa", length=10000, error=0.10, mismatch=3,
             gap_open=4, gap_ext=1, reduce=True, backtrace=False, pairs=200_000, seed=5),
 }
+# dominant kernel of each config (the one `roofline` describes; one step = all kernels of the launch)
+KERNELS = {2: "dp_strip_kernel<NW> + dp_row_kernel<NW> (aim_dp_fast.cu)", 3: "dp_strip_kernel<SWG> + dp_row_kernel<SWG> (aim_dp_fast.cu)",
+           4: "wfa_sub_kernel<8, reduce, backtrace> (aim_wfa_sub.cu)", 5: "wfa_long_kernel<16, reduce> (aim_wfa_long.cu)"}
 # algorithmic work per pair (restated in DESIGN.md "Measurement")
 INT_OPS_PER_OFFSET = 11   # one computed (score, diagonal) offset: I, D, M recurrences
 INT_OPS_PER_EXTEND = 4    # xor, clz, add, cmp per 16-base word step
@@ -290,8 +293,9 @@ def main() -> None:
             int_ops_pair = cells * ((14 if bt else 10) if cfg["algo"] == "swg" else (8 if bt else 6))
         achieved_gbs = bytes_pair * P / kernel_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                    "traffic": _ncu_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_pair": bytes_pair,
-                    "kernel": "wfa_kernel<false>" if cfg["algo"] == "wfa" else "dp_kernel", "kernel_ms": kernel_s * 1e3,
+                    "traffic": _ncu_traffic(args.config, P), "traffic_source": _ncu_entry(args.config).get("source"),
+                    "peak_source": peak_src, "algorithmic_bytes_per_pair": bytes_pair,
+                    "kernel": KERNELS[args.config], "kernel_ms": kernel_s * 1e3,
                     "note": "integer wavefront DP: the binding ceiling is the INT32 ALU pipe (int_roofline), not HBM"}
         int_peak = A.measure_int_peak(local_rank)
         int_roofline = {"bound": "int32_alu", "achieved": int_ops_pair * P / kernel_s / 1e12, "peak": int_peak / 1e12, "unit": "Tops/s",
@@ -369,13 +373,20 @@ def _wfa_work(scores, cfg, max_score):
     return {"offsets": float(np.mean(np.asarray(cum_off)[sc])), "diag_steps": float(np.mean(np.asarray(cum_diag)[sc]))}
 
 
-def _ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def _ncu_entry(config: int) -> dict:
+    """The committed `ncu --set full` summary of this config's dominant kernel (profiles/ncu_summary.json)."""
     f = ROOT / "profiles" / "ncu_summary.json"
     try:
-        return json.loads(f.read_text()).get("dram_bytes_per_launch")
+        return json.loads(f.read_text()).get(str(config), {})
     except Exception:
-        return None
+        return {}
+
+
+def _ncu_traffic(config: int, pairs: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for one launch over `pairs`
+    pairs: measured per pair in the committed capture, scaled to this launch (None without a capture)."""
+    per_pair = _ncu_entry(config).get("dram_bytes_per_pair")
+    return None if per_pair is None else per_pair * pairs
 
 
 if __name__ == "__main__":
