@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -185,7 +186,8 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
     // (the full-table DP kernels hold one pair per thread for milliseconds: give them several times the
     // resident thread count per chunk so the last, partially filled pass stays short)
     // (long reads: a chunk must hold several pairs per resident pair slot, ~6.5 K slots on a B200)
-    const size_t chunk_bytes = (p.algo != AIM_ALGO_WFA) ? (384u << 20) : (p.read_size >= 2048 ? (768u << 20) : (96u << 20));
+    size_t chunk_bytes = (p.algo != AIM_ALGO_WFA) ? (384u << 20) : (p.read_size >= 2048 ? (768u << 20) : (96u << 20));
+    if (const char *cm = getenv("AIM_CHUNK_MB")) { const long v = atol(cm); if (v >= 1 && v <= 4096) chunk_bytes = (size_t)v << 20; }
     uint32_t chunk_pairs = (uint32_t)std::max<size_t>(16384, std::min<size_t>(chunk_bytes / per_pair, 1u << 20));
     chunk_pairs = std::min(chunk_pairs, n);
     const uint32_t nchunks = (n + chunk_pairs - 1) / chunk_pairs;
@@ -224,6 +226,19 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
         const uint32_t off = c * chunk_pairs, m = std::min(chunk_pairs, n - off);
         cn[c] = m;
         const int32_t *s_plen = plen + off, *s_tlen = tlen + off;
+        {   // host.c:119-123 rejects reads longer than READ_SIZE (there: message + exit)
+            int32_t lo = 0, hi = 0;
+            for (uint32_t i = 0; i < m; ++i) {
+                lo = std::min(lo, std::min(s_plen[i], s_tlen[i]));
+                hi = std::max(hi, std::max(s_plen[i], s_tlen[i]));
+            }
+            if (lo < 0 || hi > p.read_size) {
+                cudaDeviceSynchronize();  // drain the chunks in flight before the caller reclaims its buffers
+                if (lo < 0) { set_error("negative sequence length"); return fail(AIM_ERR_ARG); }
+                set_error("READ LENGTH less than length of the input reads");
+                return fail(AIM_ERR_LENGTH);
+            }
+        }
         const char *s_pat = patterns + (size_t)off * rs, *s_txt = texts + (size_t)off * rs;
         if (!pin_in) {
             memcpy(B.h_plen, s_plen, (size_t)m * 4); memcpy(B.h_tlen, s_tlen, (size_t)m * 4);
@@ -364,13 +379,7 @@ extern "C" int aim_align_batch(const aim_params *params, uint32_t n, uint32_t id
     int rc = validate(params, true, ops);
     if (rc != AIM_OK) return rc;
     if (n > 0 && (!plen || !tlen || !patterns || !texts || !results)) { set_error("NULL host buffer"); return AIM_ERR_ARG; }
-    for (uint32_t i = 0; i < n; ++i) {
-        if (plen[i] < 0 || tlen[i] < 0) { set_error("negative sequence length"); return AIM_ERR_ARG; }
-        if (plen[i] > params->read_size || tlen[i] > params->read_size) {
-            set_error("READ LENGTH less than length of the input reads");
-            return AIM_ERR_LENGTH;
-        }
-    }
+    // (sequence lengths are validated chunk by chunk inside run_shard, overlapped with the GPU's work)
     if (phase_ms) phase_ms[0] = phase_ms[1] = phase_ms[2] = 0.0;
     int ndev = aim_device_count();
     if (ndev == 0) { set_error("no CUDA device (aim_b200 has no CPU fallback)"); return AIM_ERR_NO_DEVICE; }

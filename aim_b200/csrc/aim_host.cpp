@@ -4,6 +4,12 @@
 #include "aim_b200.h"
 #include "aim_internal.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -58,107 +64,251 @@ extern "C" uint32_t aim_pairs_to_process(uint32_t pairs_in_file, uint32_t n_arg,
 }
 
 namespace {
-struct LineReader {
-    FILE *f;
-    char *buf = nullptr;
-    size_t cap = 0;
-    explicit LineReader(FILE *fp) : f(fp) {}
-    ~LineReader() { free(buf); }
-    // getline(3) semantics: length including the newline, -1 at EOF.
-    long next() { return (long)getline(&buf, &cap, f); }
+
+// Read-only mapping of a whole file (empty files map to nothing).
+struct Mapped {
+    const char *p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    bool ok = false;
+    explicit Mapped(const char *path)
+    {
+        fd = open(path, O_RDONLY);
+        if (fd < 0) return;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return;
+        n = (size_t)st.st_size;
+        if (n) {
+            void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) return;
+            madvise(m, n, MADV_SEQUENTIAL);
+            p = (const char *)m;
+        }
+        ok = true;
+    }
+    ~Mapped()
+    {
+        if (p) munmap((void *)p, n);
+        if (fd >= 0) close(fd);
+    }
 };
+
+int io_threads(size_t work_bytes)
+{
+    int t = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("AIM_IO_THREADS")) { int v = atoi(e); if (v >= 1) return std::min(v, 64); }  // exact, for tests
+    t = std::max(1, std::min(t, 64));
+    const size_t by_size = work_bytes / (4u << 20) + 1;  // at least ~4 MB per thread
+    return (int)std::min<size_t>((size_t)t, by_size);
+}
+
+size_t count_nl(const char *p, size_t n)
+{
+    size_t c = 0;
+    const char *e = p + n;
+    while (p < e) {
+        const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+        if (!q) break;
+        ++c;
+        p = q + 1;
+    }
+    return c;
+}
+
+template <typename F>
+void parallel_for(int nthreads, F &&fn)
+{
+    if (nthreads <= 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    th.reserve((size_t)nthreads);
+    for (int t = 0; t < nthreads; ++t) th.emplace_back([&fn, t]() { fn(t); });
+    for (auto &x : th) x.join();
+}
+
+// Lines of a mapped file as getline(3) sees them: every '\n' ends a line, a final unterminated run is a line too.
+struct LineIndex {
+    int nthreads = 1;
+    std::vector<size_t> begin;  // byte range of every slice: [begin[t], begin[t+1])
+    std::vector<size_t> nl_before;  // newlines in [0, begin[t])
+    size_t lines = 0;
+};
+
+LineIndex index_lines(const Mapped &m)
+{
+    LineIndex ix;
+    ix.nthreads = io_threads(m.n);
+    const int T = ix.nthreads;
+    ix.begin.resize((size_t)T + 1);
+    for (int t = 0; t <= T; ++t) ix.begin[(size_t)t] = m.n / (size_t)T * (size_t)t;
+    ix.begin[(size_t)T] = m.n;
+    std::vector<size_t> nl((size_t)T, 0);
+    parallel_for(T, [&](int t) { nl[(size_t)t] = count_nl(m.p + ix.begin[(size_t)t], ix.begin[(size_t)t + 1] - ix.begin[(size_t)t]); });
+    ix.nl_before.assign((size_t)T + 1, 0);
+    for (int t = 0; t < T; ++t) ix.nl_before[(size_t)t + 1] = ix.nl_before[(size_t)t] + nl[(size_t)t];
+    ix.lines = ix.nl_before[(size_t)T] + ((m.n && m.p[m.n - 1] != '\n') ? 1 : 0);
+    return ix;
+}
+
 }  // namespace
 
 extern "C" int64_t aim_count_pairs(const char *path)
 {
-    FILE *f = fopen(path, "r");
-    if (!f) { aim::set_error(std::string("Input file '") + path + "' couldn't be opened"); return AIM_ERR_IO; }
-    int64_t lines = 0;
-    std::vector<char> chunk(1 << 20);
-    size_t got;
-    char last = '\n';
-    while ((got = fread(chunk.data(), 1, chunk.size(), f)) > 0) {
-        for (size_t i = 0; i < got; ++i) lines += chunk[i] == '\n';
-        last = chunk[got - 1];
-    }
-    if (last != '\n') ++lines;  // getline also returns a final unterminated line
-    fclose(f);
-    return lines / 2;
+    Mapped m(path);
+    if (!m.ok) { aim::set_error(std::string("Input file '") + path + "' couldn't be opened"); return AIM_ERR_IO; }
+    const LineIndex ix = index_lines(m);
+    return (int64_t)(ix.lines / 2);
 }
 
 // host.c:91-134 get_reads.  pattern = line+1, length = line_length-2 (the first character and the
-// last one, assumed '\n', are dropped without being looked at).
+// last one, assumed '\n', are dropped without being looked at).  The file is mapped and cut into
+// one slice per host thread; a newline count per slice gives every slice the number of its first
+// line, so all slices are copied into the n x read_size rows concurrently.
 extern "C" int64_t aim_read_pairs(const char *path, uint32_t max_pairs, int32_t read_size,
                                   int32_t *plen, int32_t *tlen, char *patterns, char *texts)
 {
-    FILE *f = fopen(path, "r");
-    if (!f) { aim::set_error(std::string("Input file '") + path + "' couldn't be opened"); return AIM_ERR_IO; }
-    LineReader l1(f), l2(f);
-    int64_t n = 0;
-    for (; n < (int64_t)max_pairs; ++n) {
-        long len1 = l1.next();
-        if (len1 == -1) break;
-        long len2 = l2.next();
-        if (len2 == -1) break;
-        long pl = len1 - 2, tl = len2 - 2;
-        if (tl > read_size || pl > read_size) {
-            fclose(f);
+    Mapped m(path);
+    if (!m.ok) { aim::set_error(std::string("Input file '") + path + "' couldn't be opened"); return AIM_ERR_IO; }
+    const LineIndex ix = index_lines(m);
+    const size_t want = std::min<size_t>(ix.lines / 2, max_pairs);
+    std::vector<int64_t> bad((size_t)ix.nthreads, -1);  // first pair with a read longer than read_size, per slice
+    parallel_for(ix.nthreads, [&](int t) {
+        size_t pos = ix.begin[(size_t)t];
+        const size_t end = ix.begin[(size_t)t + 1];
+        size_t line = ix.nl_before[(size_t)t];  // number of the line starting at pos, if one starts there
+        if (pos > 0 && m.p[pos - 1] != '\n') {  // skip the tail of a line that started in an earlier slice
+            const char *q = (const char *)memchr(m.p + pos, '\n', m.n - pos);
+            if (!q) return;
+            pos = (size_t)(q - m.p) + 1;
+            ++line;
+        }
+        for (; pos < end && line < 2 * want; ++line) {  // lines that START in this slice
+            const char *q = (const char *)memchr(m.p + pos, '\n', m.n - pos);
+            const size_t len_with_nl = q ? (size_t)(q - (m.p + pos)) + 1 : m.n - pos;  // what getline returns
+            long sl = (long)len_with_nl - 2;
+            const size_t pair = line >> 1;
+            if (sl > read_size) {
+                if (bad[(size_t)t] < 0) bad[(size_t)t] = (int64_t)pair;
+            } else {
+                if (sl < 0) sl = 0;  // a 1-character line: the reference would index pattern[-1]; we clamp
+                char *dst = ((line & 1) ? texts : patterns) + pair * (size_t)read_size;
+                memcpy(dst, m.p + pos + 1, (size_t)sl);
+                if (sl < read_size) memset(dst + sl, 0, (size_t)(read_size - sl));
+                ((line & 1) ? tlen : plen)[pair] = (int32_t)sl;
+            }
+            pos += len_with_nl;
+        }
+    });
+    for (int t = 0; t < ix.nthreads; ++t) {
+        if (bad[(size_t)t] >= 0) {
             aim::set_error("READ LENGTH less than length of the input reads");
             return AIM_ERR_LENGTH;
         }
-        if (pl < 0) pl = 0;  // a 1-character line: the reference would index pattern[-1]; we clamp
-        if (tl < 0) tl = 0;
-        char *pd = patterns + (size_t)n * read_size, *td = texts + (size_t)n * read_size;
-        memcpy(pd, l1.buf + 1, (size_t)pl);
-        memcpy(td, l2.buf + 1, (size_t)tl);
-        if (pl < read_size) memset(pd + pl, 0, (size_t)(read_size - pl));
-        if (tl < read_size) memset(td + tl, 0, (size_t)(read_size - tl));
-        plen[n] = (int32_t)pl;
-        tlen[n] = (int32_t)tl;
     }
-    fclose(f);
-    return n;
+    return (int64_t)want;
 }
+
+namespace {
+// decimal digits of v at out (no NUL); returns the number written
+inline size_t put_uint(char *out, uint32_t v)
+{
+    char tmp[10];
+    size_t k = 0;
+    do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    for (size_t i = 0; i < k; ++i) out[i] = tmp[k - 1 - i];
+    return k;
+}
+inline size_t put_int(char *out, int32_t v)
+{
+    if (v < 0) { *out = '-'; return 1 + put_uint(out + 1, (uint32_t)(-(int64_t)v)); }
+    return put_uint(out, (uint32_t)v);
+}
+// length of the run of bytes equal to ops[0], at most n (> 0)
+inline size_t run_length(const char *ops, size_t n)
+{
+    const unsigned char c = (unsigned char)ops[0];
+    const uint64_t pat = 0x0101010101010101ull * c;
+    size_t i = 1;
+    while (i + 8 <= n) {
+        uint64_t w;
+        memcpy(&w, ops + i, 8);
+        const uint64_t d = w ^ pat;
+        if (d) return i + (size_t)(__builtin_ctzll(d) >> 3);
+        i += 8;
+    }
+    while (i < n && (unsigned char)ops[i] == c) ++i;
+    return i;
+}
+// RLE of ops[b..e) (b < e) at out; the caller guarantees room for 11 bytes per op
+inline size_t put_cigar(char *out, const char *ops, int32_t b, int32_t e)
+{
+    size_t pos = 0;
+    ptrdiff_t i = b;  // (an empty alignment has b = -1: the reference prints the byte before its span, host.c:73)
+    const ptrdiff_t end = e;
+    while (i < end) {
+        const size_t r = run_length(ops + i, (size_t)(end - i));
+        pos += put_uint(out + pos, (uint32_t)r);
+        out[pos++] = ops[i];
+        i += (ptrdiff_t)r;
+    }
+    return pos;
+}
+}  // namespace
 
 // host.c:69-89 edit_cigar_print.
 extern "C" int aim_cigar_rle(const char *ops, int32_t begin_offset, int32_t end_offset, char *out, size_t cap)
 {
-    size_t pos = 0;
-    char last_op = ops[begin_offset];
-    int last_len = 1;
-    for (int i = begin_offset + 1; i < end_offset; ++i) {
-        if (ops[i] == last_op) { ++last_len; continue; }
-        int w = snprintf(out + pos, cap - pos, "%d%c", last_len, last_op);
-        if (w < 0 || (size_t)w >= cap - pos) return -1;
-        pos += (size_t)w;
-        last_op = ops[i];
-        last_len = 1;
-    }
-    int w = snprintf(out + pos, cap - pos, "%d%c", last_len, last_op);
-    if (w < 0 || (size_t)w >= cap - pos) return -1;
-    return (int)(pos + (size_t)w);
+    // edit_cigar_print always emits the op at begin_offset, even for an empty span
+    const int32_t e = end_offset > begin_offset ? end_offset : begin_offset + 1;
+    if ((size_t)(e - begin_offset) * 11 <= cap) return (int)put_cigar(out, ops, begin_offset, e);
+    std::vector<char> tmp((size_t)(e - begin_offset) * 11);
+    const size_t len = put_cigar(tmp.data(), ops, begin_offset, e);
+    if (len > cap) return -1;
+    memcpy(out, tmp.data(), len);
+    return (int)len;
 }
 
-// host.c:332-353: "%d, %d, \n" then (BACKTRACE only) the RLE CIGAR on its own line.
+// host.c:332-353: "%d, %d, \n" then (BACKTRACE only) the RLE CIGAR on its own line.  Blocks of pairs
+// are formatted by all host threads into private buffers and written in pair order.
 extern "C" int aim_write_results(const char *path, uint32_t n, int32_t read_size, int32_t backtrace,
                                  const aim_result *results, const char *ops)
 {
     FILE *f = fopen(path, "w");
     if (!f) { aim::set_error(std::string("Output file '") + path + "' couldn't be opened"); return AIM_ERR_IO; }
-    std::vector<char> obuf(1 << 22);
-    setvbuf(f, obuf.data(), _IOFBF, obuf.size());
-    std::vector<char> line((size_t)read_size * 2 * 12 + 64);
-    for (uint32_t i = 0; i < n; ++i) {
-        fprintf(f, "%d, %d, \n", (int)results[i].idx, results[i].score);
-        if (backtrace) {
-            int len = aim_cigar_rle(ops + (size_t)i * 2 * read_size, results[i].begin_offset,
-                                    results[i].end_offset, line.data(), line.size() - 1);
-            if (len < 0) { fclose(f); return AIM_ERR_IO; }
-            line[(size_t)len] = '\n';
-            fwrite(line.data(), 1, (size_t)len + 1, f);
+    const size_t rs2 = (size_t)read_size * 2;
+    const uint32_t block = 16384;  // pairs per formatting block
+    const int T = io_threads((size_t)n * (backtrace ? rs2 : 64));
+    const size_t per_pair_cap = 40 + (backtrace ? rs2 * 11 + 1 : 0);
+    std::vector<std::vector<char>> buf((size_t)T);
+    std::vector<size_t> len((size_t)T, 0);
+    int rc = AIM_OK;
+    for (uint64_t base = 0; base < n && rc == AIM_OK; base += (uint64_t)block * (uint64_t)T) {
+        parallel_for(T, [&](int t) {
+            const uint64_t lo = base + (uint64_t)t * block, hi = std::min<uint64_t>(n, lo + block);
+            len[(size_t)t] = 0;
+            if (lo >= hi) return;
+            std::vector<char> &b = buf[(size_t)t];
+            size_t pos = 0;
+            for (uint64_t i = lo; i < hi; ++i) {
+                if (b.size() < pos + per_pair_cap) b.resize(std::max(b.size() * 2, pos + per_pair_cap));
+                char *o = b.data();
+                pos += put_int(o + pos, (int32_t)results[i].idx);
+                o[pos++] = ','; o[pos++] = ' ';
+                pos += put_int(o + pos, results[i].score);
+                o[pos++] = ','; o[pos++] = ' '; o[pos++] = '\n';
+                if (backtrace) {
+                    const int32_t bo = results[i].begin_offset;
+                    const int32_t eo = results[i].end_offset > bo ? results[i].end_offset : bo + 1;
+                    pos += put_cigar(o + pos, ops + i * rs2, bo, eo);
+                    o[pos++] = '\n';
+                }
+            }
+            len[(size_t)t] = pos;
+        });
+        for (int t = 0; t < T; ++t) {
+            if (len[(size_t)t] && fwrite(buf[(size_t)t].data(), 1, len[(size_t)t], f) != len[(size_t)t]) { rc = AIM_ERR_IO; break; }
         }
     }
-    int rc = ferror(f) ? AIM_ERR_IO : AIM_OK;
+    if (ferror(f)) rc = AIM_ERR_IO;
     fclose(f);
     return rc;
 }

@@ -169,3 +169,56 @@ def test_wfa_schedule_sizes_history():
     plen, tlen, pats, txts = A.generate_pairs(5, 200, 150, 0.04, 168)
     res, _ = O.align("wfa", plen, tlen, pats, txts, max_score=30, read_size=168, backtrace=False, reduce=False)
     assert res["score"].max() <= 30
+
+
+@pytest.mark.parametrize("threads", ["1", "2", "3", "7", "16"])
+def test_parallel_reader_and_writer_match_a_plain_python_restatement(tmp_path, monkeypatch, threads):
+    """The mmap/multi-thread reader (host.c:91-134 semantics) and writer (host.c:332-353, 69-89) against a
+    line-by-line Python restatement, with slice boundaries falling anywhere (tiny file, many threads)."""
+    monkeypatch.setenv("AIM_IO_THREADS", threads)
+    rng = np.random.default_rng(int(threads))
+    lines = []
+    for i in range(101):  # odd number of lines: the last pattern has no text and is dropped
+        ln = int(rng.integers(0, 24))
+        lines.append((">" if i % 2 == 0 else "<") + "".join(rng.choice(list("ACGT"), ln)))
+    body = "\n".join(lines)  # no trailing newline: the final line loses its last base (T11)
+    f = tmp_path / "ragged.pairs"
+    f.write_text(body)
+    rs = 24
+    assert A.count_pairs(f) == 50
+    plen, tlen, pats, txts = A.read_pairs(f, rs)
+    assert len(plen) == 50
+    for i in range(50):
+        for arr, ln_arr, line in ((pats, plen, lines[2 * i] + "\n"), (txts, tlen, lines[2 * i + 1] + "\n")):
+            want = line[1:-1]
+            assert ln_arr[i] == len(want)
+            assert bytes(arr[i, :len(want)]).decode() == want
+            assert not arr[i, len(want):].any()
+    f2 = tmp_path / "nl.pairs"
+    f2.write_text(body + "\n")
+    assert A.count_pairs(f2) == 50  # 101 lines -> 50 pairs
+    p2 = A.read_pairs(f2, rs, 7)
+    assert len(p2[0]) == 7
+
+    n = 300
+    res = np.zeros(n, A.RESULT_DTYPE)
+    res["idx"] = np.arange(n) + 5
+    res["score"] = rng.integers(-3, 4000, n)
+    ops = rng.choice(np.frombuffer(b"MMMMMMXID", np.uint8), (n, 2 * rs))
+    res["begin_offset"] = rng.integers(0, 2 * rs - 1, n)
+    res["end_offset"] = [int(rng.integers(b + 1, 2 * rs + 1)) for b in res["begin_offset"]]
+    out = tmp_path / "w.out"
+    A.write_results(out, res, ops, rs, True)
+    want = []
+    for i in range(n):
+        want.append(f"{int(res['idx'][i])}, {int(res['score'][i])}, ")
+        span = bytes(ops[i, res["begin_offset"][i]:res["end_offset"][i]]).decode()
+        cig, j = "", 0
+        while j < len(span):
+            k = j
+            while k < len(span) and span[k] == span[j]:
+                k += 1
+            cig += f"{k - j}{span[j]}"
+            j = k
+        want.append(cig)
+    assert out.read_text() == "\n".join(want) + "\n"
