@@ -175,6 +175,9 @@ def main() -> None:
         return
 
     rank, local_rank, world = dist_env()
+    # stdout carries exactly ONE JSON line: library chatter (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -330,7 +333,7 @@ def main() -> None:
             "roofline": roofline, "int_roofline": int_roofline, "cpu_baseline": cpu_baseline,
             "step_ms": step_ms,
         }
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
