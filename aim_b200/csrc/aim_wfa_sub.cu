@@ -253,6 +253,20 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
                 if (__any_sync(kFull, wide)) {
                     md = group_min<G>(md);
                     const int top_limit = min(ak - 1, hi);
+                    // Quick exit: the two scans below stop at their first cell when both END diagonals are already
+                    // within the distance threshold - the normal case for short reads, where nothing is ever trimmed.
+                    bool quick = true;
+                    if (wide) {
+                        if (lo < top_limit) {
+                            const int off = lds_s16(aNM + (uint32_t)(lo * 2));
+                            quick = (max(pl - (off - lo), tl - off) - md) <= 50;
+                        }
+                        if (quick && hi > max(ak + 1, lo)) {
+                            const int off = lds_s16(aNM + (uint32_t)(hi * 2));
+                            quick = (max(pl - (off - hi), tl - off) - md) <= 50;
+                        }
+                    }
+                    if (!__all_sync(kFull, quick)) {
                     bool pend = wide && lo < top_limit;
                     if (pend) newlo = top_limit;
                     for (int c = 0; __any_sync(kFull, pend && (lo + c < top_limit)); c += G) {
@@ -279,6 +293,7 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
                         const uint32_t mine = (__ballot_sync(kFull, hit) >> subshift) & GM;
                         if (pend && mine) { newhi = hi - c - (__ffs(mine) - 1); pend = false; }
                         if (hi - c - G <= bottom_limit) pend = false;
+                    }
                     }
                 }
                 if (sl == 0 && !done) sts_u32(aDyn + (uint32_t)s * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)newhi << 16));
@@ -490,7 +505,10 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     const uint32_t pair_words_raw = 2 * K.seq_words + K.dyn_words + round_up(K.mring_bytes + idring_bytes, 16) / 4;
 
     // lanes per pair; env override for tuning
-    int G = 8;
+    // lanes per pair: wavefronts are about MAX_SCORE diagonals wide on average; a few iterations per score keeps the
+    // lanes busy while the per-score bookkeeping is shared by 32/G pairs (measured at config 4: G=4 193 M, G=8 178 M,
+    // G=16 143 M pairs/s)
+    int G = MS <= 40 ? 4 : MS <= 100 ? 8 : MS <= 300 ? 16 : 32;
     if (const char *gs = getenv("AIM_WFA_G")) { int g = atoi(gs); if (g == 4 || g == 8 || g == 16 || g == 32) G = g; }
     const int PPW = 32 / G;
     {   // stagger the pair slots of one warp over the banks: slot stride == 32/PPW words (mod 32)
@@ -500,7 +518,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     const uint32_t kSmemBudget = 227u * 1024u, kSmemPerSm = 228u * 1024u, kBlockReserve = 1024u;
     const size_t pair_bytes = (size_t)K.pair_words * 4;
     const size_t plan_bytes = (size_t)K.plan_words * 4;
-    int warps_per_block = 4;
+    int warps_per_block = G == 4 ? 2 : 4;
     if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v == 1 || v == 2 || v == 4) warps_per_block = v; }
     size_t smem_block = plan_bytes + (size_t)warps_per_block * PPW * pair_bytes;
     if (smem_block > kSmemBudget / 3) return 1;  // too few warps/SM would fit: leave it to the long-read kernel

@@ -51,7 +51,7 @@ CONFIGS = {
 }
 # dominant kernel of each config (the one `roofline` describes; one step = all kernels of the launch)
 KERNELS = {2: "dp_strip_kernel<NW> + dp_row_kernel<NW> (aim_dp_fast.cu)", 3: "dp_strip_kernel<SWG> + dp_row_kernel<SWG> (aim_dp_fast.cu)",
-           4: "wfa_sub_kernel<8, reduce, backtrace> (aim_wfa_sub.cu)", 5: "wfa_long_kernel<16, reduce> (aim_wfa_long.cu)"}
+           4: "wfa_sub_kernel<4, reduce, backtrace> (aim_wfa_sub.cu)", 5: "wfa_long_kernel<16, reduce> (aim_wfa_long.cu)"}
 # algorithmic work per pair (restated in DESIGN.md "Measurement")
 INT_OPS_PER_OFFSET = 11   # one computed (score, diagonal) offset: I, D, M recurrences
 INT_OPS_PER_EXTEND = 4    # xor, clz, add, cmp per 16-base word step
