@@ -59,27 +59,34 @@ struct FastK {
     int neg1;               // -1, kept opaque to the compiler (see dp_cell)
 };
 
-// ---- classification: non-aliased pairs to the front of the list, aliased ones to the back ----
-__global__ void classify_kernel(const int32_t *plen, const int32_t *tlen, uint32_t n, int RS, uint32_t *list, uint32_t *counters)
+// ---- classification: non-aliased pairs to the front of `list`, aliased ones that fit the register-row
+// kernel (tlen >= reg_cols, plen - tlen <= 16) to its back, the other aliased ones to `list2` ----
+__global__ void classify_kernel(const int32_t *plen, const int32_t *tlen, uint32_t n, int RS, int reg_cols, uint32_t *list, uint32_t *list2,
+                                uint32_t *counters)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool valid = i < n, alias = false;
+    bool valid = i < n, alias = false, regrow = false;
     if (valid) {
         const int pl = min(max(plen[i], 0), RS), tl = min(max(tlen[i], 0), RS);
         alias = pl > tl;
+        regrow = alias && reg_cols > 0 && tl >= reg_cols && pl - tl <= 16;
     }
-    const uint32_t m0 = __ballot_sync(0xffffffffu, valid && !alias), m1 = __ballot_sync(0xffffffffu, valid && alias);
-    uint32_t b0 = 0, b1 = 0;
+    const uint32_t m0 = __ballot_sync(0xffffffffu, valid && !alias), m1 = __ballot_sync(0xffffffffu, regrow),
+                   m2 = __ballot_sync(0xffffffffu, valid && alias && !regrow);
+    uint32_t b0 = 0, b1 = 0, b2 = 0;
     if (lane == 0) {
         if (m0) b0 = atomicAdd(&counters[0], (uint32_t)__popc(m0));
         if (m1) b1 = atomicAdd(&counters[1], (uint32_t)__popc(m1));
+        if (m2) b2 = atomicAdd(&counters[2], (uint32_t)__popc(m2));
     }
     b0 = __shfl_sync(0xffffffffu, b0, 0);
     b1 = __shfl_sync(0xffffffffu, b1, 0);
+    b2 = __shfl_sync(0xffffffffu, b2, 0);
     const uint32_t below = (1u << lane) - 1u;
     if (valid && !alias) list[b0 + (uint32_t)__popc(m0 & below)] = i;
-    if (valid && alias) list[n - 1 - (b1 + (uint32_t)__popc(m1 & below))] = i;
+    if (regrow) list[n - 1 - (b1 + (uint32_t)__popc(m1 & below))] = i;
+    if (valid && alias && !regrow) list2[b2 + (uint32_t)__popc(m2 & below)] = i;
 }
 
 // ---- one DP cell in registers ----
@@ -284,9 +291,13 @@ __global__ void __launch_bounds__(128) dp_strip_kernel(const FastK K)
 // PSMEM: the pattern bases are staged in shared memory after the row (RS/4 words per lane).  Worth it
 // when many warps still fit (short reads: L1 is too small for their patterns); for long rows the
 // launcher prefers one more resident warp and reads the pattern through L1 one record ahead.
+// R > 0: columns 1..R of the row live in REGISTERS (R/16 fully unrolled records); shared memory keeps column 0, a
+// write-through copy of columns 1..15 (what the aliased tail reads back: plen - tlen <= 16 is a precondition of this
+// variant, as is tlen >= R) and columns R+1..: the register file is idle in this kernel while shared memory bounds the
+// resident warps, so moving part of the row there raises the occupancy by half.
 constexpr uint32_t RT = 32;
-template <int ALGO, bool PSMEM>
-__global__ void __launch_bounds__(RT) dp_row_kernel(const FastK K)
+template <int ALGO, bool PSMEM, int R>
+__global__ void __launch_bounds__(RT) __maxnreg__(R > 0 ? 224 : 128) dp_row_kernel(const FastK K)
 {
     constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
     constexpr int FW = SWG ? 2 : 1;
@@ -302,8 +313,11 @@ __global__ void __launch_bounds__(RT) dp_row_kernel(const FastK K)
     uint32_t sel[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) sel[k] = (uint32_t)(X - MT) << (8 * k);
-    uint32_t *row = smem + threadIdx.x;                         // row[v * T]
-    uint32_t *pat = smem + (size_t)(RS + 1) * T + threadIdx.x;  // pat[w * T] (PSMEM only)
+    // shared-memory word of column v: v for v <= 15 (R > 0) or any v (R == 0); v - R + 15 for v > R (R > 0)
+    uint32_t *row0 = smem + threadIdx.x;                         // row0[v * T], v <= 15 when R > 0
+    uint32_t *row = R > 0 ? row0 + (15 - R) * (int)T : row0;     // row[v * T],  v > R  when R > 0
+    const int smem_cols = R > 0 ? RS + 16 - R : RS + 1;
+    uint32_t *pat = smem + (size_t)smem_cols * T + threadIdx.x;  // pat[w * T] (PSMEM only)
     uint32_t *flg = K.flags + (size_t)tid * FW;
     const size_t fstep = (size_t)nth * FW;
     const uint32_t rpr = K.wpr;  // records per row
@@ -323,8 +337,14 @@ __global__ void __launch_bounds__(RT) dp_row_kernel(const FastK K)
 
         if (PSMEM) for (int w = 0; w * 4 < pl; ++w) pat[(size_t)w * T] = __ldg(reinterpret_cast<const uint32_t *>(gp) + w);
         // row 0 (nw.c:119-124 / swg.c:167-175)
-        row[0] = pack(0, MS);
-        for (int v = 1; v <= pl; ++v) row[(size_t)v * T] = pack(SWG ? O + v * E : v * OE, MS);
+        row0[0] = pack(0, MS);
+        uint32_t reg[R > 0 ? R : 1];
+        if (R > 0) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) reg[j] = pack(SWG ? O + (j + 1) * E : (j + 1) * OE, MS);
+            for (int v = 1; v <= 15; ++v) row0[(size_t)v * T] = pack(SWG ? O + v * E : v * OE, MS);
+        }
+        for (int v = R + 1; v <= pl; ++v) row[(size_t)v * T] = pack(SWG ? O + v * E : v * OE, MS);
         int tailM = 0, tailI = 0, tailD = 0;  // cell (h-1, nc): column 0 of row h when aliased
         const int headend = min(pl, nc - 1);  // columns 1..headend read the true previous row
 
@@ -337,20 +357,56 @@ __global__ void __launch_bounds__(RT) dp_row_kernel(const FastK K)
             if (alias && h >= 2) { leftM = tailM; c0I = tailI; leftD = tailD; }
             else if (!SWG) { leftM = h * OE; c0I = 0; leftD = 0; }
             else { leftD = MS; c0I = O + h * E; leftM = c0I; }
-            int dg = unpackM(row[0]);
-            row[0] = pack(leftM, c0I);
+            int dg = unpackM(row0[0]);
+            row0[0] = pack(leftM, c0I);
             uint32_t *frow = flg + (size_t)(h - 1) * rpr * fstep;
 
             // ---- head, full 16-cell records ----
-            int v = 1;
+            int v = R + 1;
             uint32_t cur[16], nxt[16];
             uint2 pcur[2], pnxt[2];  // the record's 16 pattern bases
-            if (headend >= 16) {
+            if (headend >= R + 16) {  // first shared-memory record: fetch early
 #pragma unroll
-                for (int j = 0; j < 16; ++j) cur[j] = row[(size_t)(1 + j) * T];
+                for (int j = 0; j < 16; ++j) cur[j] = row[(size_t)(R + 1 + j) * T];
                 if (!PSMEM) {
-                    pcur[0] = __ldg(reinterpret_cast<const uint2 *>(gp));
-                    pcur[1] = __ldg(reinterpret_cast<const uint2 *>(gp) + 1);
+                    pcur[0] = __ldg(reinterpret_cast<const uint2 *>(gp + R));
+                    pcur[1] = __ldg(reinterpret_cast<const uint2 *>(gp + R) + 1);
+                }
+            }
+            if (R > 0) {  // columns 1..R from registers
+#pragma unroll
+                for (int rec = 0; rec < R / 16; ++rec) {
+                    uint32_t ne[4];
+                    if (PSMEM) {
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) ne[w] = __vsetne4(pat[(size_t)(rec * 4 + w) * T] ^ tc4, 0u);
+                    } else {
+                        const uint2 pa = __ldg(reinterpret_cast<const uint2 *>(gp + rec * 16)), pb = __ldg(reinterpret_cast<const uint2 *>(gp + rec * 16) + 1);
+                        ne[0] = __vsetne4(pa.x ^ tc4, 0u); ne[1] = __vsetne4(pa.y ^ tc4, 0u);
+                        ne[2] = __vsetne4(pb.x ^ tc4, 0u); ne[3] = __vsetne4(pb.y ^ tc4, 0u);
+                    }
+                    uint32_t aP = 0, aQ = 0, aD = 0, aI = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t old = reg[rec * 16 + j];
+                        const int upM = unpackM(old);
+                        int upI = SWG ? unpackI(old) : 0;
+                        const int mm = (int)__dp4a(ne[j >> 2], sel[j & 3], (uint32_t)(dg + MT));
+                        int dI, dD, dP, dQ;
+                        const int m = dp_cell<ALGO>(upM, upI, leftM, leftD, mm, OE, E, neg1, dI, dD, dP, dQ);
+                        reg[rec * 16 + j] = pack(m, upI);
+                        if (rec == 0 && j < 15) row0[(size_t)(1 + j) * T] = reg[j];  // what the aliased tail reads back
+                        aP = push_sign(aP, dP);
+                        aQ = push_sign(aQ, dQ);
+                        if (SWG) { aD = push_sign(aD, dD); aI = push_sign(aI, dI); }
+                        dg = upM;
+                        leftM = m;
+                    }
+                    if (K.backtrace) {
+                        uint32_t *d = frow + (size_t)rec * fstep;
+                        if (SWG) *reinterpret_cast<uint2 *>(d) = make_uint2(aP | (aQ << 16), aD | (aI << 16));
+                        else d[0] = aP | (aQ << 16);
+                    }
                 }
             }
             for (; v + 15 <= headend; v += 16) {
@@ -412,8 +468,8 @@ __global__ void __launch_bounds__(RT) dp_row_kernel(const FastK K)
                 uint32_t upw;
                 if (!tail) upw = row[(size_t)v * T];
                 else {
-                    upw = row[(size_t)(v - nc) * T];
-                    if (v - 1 >= nc) dg = unpackM(row[(size_t)(v - 1 - nc) * T]);
+                    upw = row0[(size_t)(v - nc) * T];
+                    if (v - 1 >= nc) dg = unpackM(row0[(size_t)(v - 1 - nc) * T]);
                 }
                 const int upM = unpackM(upw);
                 int upI = SWG ? unpackI(upw) : 0;
@@ -509,17 +565,29 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         if (bound >= 32767 || p.max_score < 0) return 1;
     }
     // aliased pairs: threads per block from the shared-memory row + pattern stage
-    // stage the pattern in shared memory only if that still leaves >= 8 warps per SM resident
-    size_t per_thread_smem = ((size_t)RS + 1 + (size_t)RS / 4) * 4;
-    const bool psmem = (228u * 1024u) / (per_thread_smem * 32 + 1024) >= 8;
-    if (!psmem) per_thread_smem = ((size_t)RS + 1) * 4;
+    // aliased pairs: one-warp blocks; stage the pattern in shared memory only if that still leaves >= 8 warps per SM
     const size_t kSmemBudget = 227u * 1024u;
-    const int row_threads = (int)RT;  // one warp per block (compile-time strides), as many blocks as shared memory holds
-    const int row_blocks_per_sm = (int)std::min<size_t>(32, (228u * 1024u) / (per_thread_smem * RT + 1024));
-    if (per_thread_smem * RT > kSmemBudget || row_blocks_per_sm < 1) return 1;
+    auto row_cfg = [&](int reg_cols, size_t *per_thread, bool *psm, int *bps) -> bool {
+        const size_t cols = reg_cols > 0 ? (size_t)RS + 16 - (size_t)reg_cols : (size_t)RS + 1;
+        size_t pt = (cols + (size_t)RS / 4) * 4;
+        *psm = (228u * 1024u) / (pt * RT + 1024) >= 8;
+        if (!*psm) pt = cols * 4;
+        *per_thread = pt;
+        *bps = (int)std::min<size_t>(32, (228u * 1024u) / (pt * RT + 1024));
+        return pt * RT <= kSmemBudget && *bps >= 1;
+    };
+    size_t pt0 = 0, pt1 = 0;
+    bool psm0 = false, psm1 = false;
+    int bps0 = 0, bps1 = 0;
+    if (!row_cfg(0, &pt0, &psm0, &bps0)) return 1;
+    // register-row variant when shared memory would hold fewer than 8 warps per SM (long rows)
+    int reg_cols = (bps0 < 8 && RS >= 160) ? 96 : 0;  // (112 spills: measured slower)
+    if (const char *rc_s = getenv("AIM_DP_REGCOLS")) { const int v = atoi(rc_s); if (v == 0 || v == 96 || v == 112) reg_cols = v; }
+    if (reg_cols > 0 && !row_cfg(reg_cols, &pt1, &psm1, &bps1)) reg_cols = 0;
+    const int row_threads = (int)RT;
 
     const int FW = nw ? 1 : 2;                         // flag words per 16-cell record
-    const uint32_t wpr = ((uint32_t)RS + 15) / 16;     // records per row (row kernel)
+    const uint32_t wpr = ((uint32_t)RS + 15) / 16;     // records per row (row kernels)
     const int nstrips_max = (RS + KS - 1) / KS;
 
     // grids: persistent threads striding over the lists, sized by what is actually resident
@@ -535,13 +603,38 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     int strip_grid = sc->sm_count * strip_bps;
     strip_grid = (int)std::min<uint64_t>((uint64_t)strip_grid, ((uint64_t)a.n + strip_block - 1) / strip_block);
     const size_t strip_threads = (size_t)strip_grid * strip_block;
-    int row_grid = sc->sm_count * row_blocks_per_sm;  // shared memory filled on every SM
-    row_grid = (int)std::min<uint64_t>((uint64_t)row_grid, ((uint64_t)a.n + row_threads - 1) / row_threads);
-    const size_t rowk_threads = (size_t)row_grid * row_threads;
 
-    // scratch: counters | list | strip boundary | strip flags | row flags
+    // row kernels: launch helper (sets the shared-memory attribute, asks the occupancy, returns the grid)
+    struct RowLaunch { void (*fn)(const FastK); size_t smem; int grid; };
+    auto pick_row = [&](int rcols, bool psm) -> void (*)(const FastK) {
+#define AIM_ROW_PICK(A)                                                                                    \
+    (rcols == 112 ? (psm ? dp_row_kernel<A, true, 112> : dp_row_kernel<A, false, 112>)                     \
+     : rcols == 96 ? (psm ? dp_row_kernel<A, true, 96> : dp_row_kernel<A, false, 96>)                      \
+                   : (psm ? dp_row_kernel<A, true, 0> : dp_row_kernel<A, false, 0>))
+        return nw ? AIM_ROW_PICK(AIM_ALGO_NW) : AIM_ROW_PICK(AIM_ALGO_SWG);
+#undef AIM_ROW_PICK
+    };
+    auto prep_row = [&](int rcols, bool psm, size_t pt, int bps_smem, RowLaunch *out) -> cudaError_t {
+        out->fn = pick_row(rcols, psm);
+        out->smem = pt * RT;
+        cudaError_t e = cudaFuncSetAttribute(out->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->smem);
+        int bps = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, out->fn, (int)RT, out->smem);
+        if (e != cudaSuccess) return e;
+        bps = std::max(1, std::min(bps, bps_smem));
+        out->grid = (int)std::min<uint64_t>((uint64_t)sc->sm_count * (uint64_t)bps, ((uint64_t)a.n + RT - 1) / RT);
+        return cudaSuccess;
+    };
+    RowLaunch L0{}, L1{};
+    cudaError_t err = prep_row(0, psm0, pt0, bps0, &L0);
+    if (err == cudaSuccess && reg_cols > 0) err = prep_row(reg_cols, psm1, pt1, bps1, &L1);
+    if (err != cudaSuccess) { set_error(std::string("dp_fast setup: ") + cudaGetErrorString(err)); cudaGetLastError(); return AIM_ERR_CUDA; }
+    const size_t rowk_threads = (size_t)std::max(L0.grid, L1.grid) * row_threads;
+
+    // scratch: counters | list | list2 | strip boundary | strip flags | row flags
     const size_t off_list = 256;
-    const size_t off_bound = align_up(off_list + (size_t)a.n * 4, 256);
+    const size_t off_list2 = align_up(off_list + (size_t)a.n * 4, 256);
+    const size_t off_bound = align_up(off_list2 + (size_t)a.n * 4, 256);
     const size_t off_sflags = align_up(off_bound + strip_threads * (size_t)RS * 4, 256);
     const size_t sflag_bytes = p.backtrace ? strip_threads * (size_t)nstrips_max * RS * FW * 4 : 0;
     const size_t off_rflags = align_up(off_sflags + sflag_bytes, 256);
@@ -551,6 +644,7 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
     uint32_t *counters = reinterpret_cast<uint32_t *>(base);
     uint32_t *list = reinterpret_cast<uint32_t *>(base + off_list);
+    uint32_t *list2 = reinterpret_cast<uint32_t *>(base + off_list2);
 
     FastK K{};
     K.plen = a.plen; K.tlen = a.tlen; K.patterns = a.patterns; K.texts = a.texts;
@@ -560,10 +654,10 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     K.wpr = wpr;
     K.neg1 = -1;
 
-    cudaError_t err = cudaMemsetAsync(counters, 0, 8, stream);
+    err = cudaMemsetAsync(counters, 0, 16, stream);
     if (err == cudaSuccess && p.backtrace) err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * RS, stream);
     if (err == cudaSuccess) {
-        classify_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(a.plen, a.tlen, a.n, RS, list, counters);
+        classify_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(a.plen, a.tlen, a.n, RS, reg_cols, list, list2, counters);
         err = cudaGetLastError();
     }
     if (err == cudaSuccess) {
@@ -576,25 +670,25 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         else dp_strip_kernel<AIM_ALGO_SWG, false><<<strip_grid, strip_block, 0, stream>>>(S);
         err = cudaGetLastError();
     }
-    if (err == cudaSuccess) {
-        FastK R = K;
-        R.list = list + (a.n - 1); R.count = counters + 1; R.list_step = -1;
-        R.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
-        const size_t smem = per_thread_smem * (size_t)row_threads;
-#define AIM_ROW_LAUNCH(A, PS)                                                                                          \
-    do {                                                                                                              \
-        err = cudaFuncSetAttribute(dp_row_kernel<A, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-        if (err == cudaSuccess) dp_row_kernel<A, PS><<<row_grid, row_threads, smem, stream>>>(R);                      \
-    } while (0)
-        if (nw && psmem) AIM_ROW_LAUNCH(AIM_ALGO_NW, true);
-        else if (nw) AIM_ROW_LAUNCH(AIM_ALGO_NW, false);
-        else if (psmem) AIM_ROW_LAUNCH(AIM_ALGO_SWG, true);
-        else AIM_ROW_LAUNCH(AIM_ALGO_SWG, false);
-#undef AIM_ROW_LAUNCH
-        if (err == cudaSuccess) err = cudaGetLastError();
+    int nlaunch = 2;
+    if (err == cudaSuccess && reg_cols > 0) {  // aliased pairs that fit the register-row variant
+        FastK Rr = K;
+        Rr.list = list + (a.n - 1); Rr.count = counters + 1; Rr.list_step = -1;
+        Rr.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
+        L1.fn<<<L1.grid, row_threads, L1.smem, stream>>>(Rr);
+        err = cudaGetLastError();
+        ++nlaunch;
+    }
+    if (err == cudaSuccess) {  // the other aliased pairs (all of them when reg_cols == 0)
+        FastK Rs = K;
+        Rs.list = list2; Rs.count = counters + 2; Rs.list_step = 1;
+        Rs.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
+        L0.fn<<<L0.grid, row_threads, L0.smem, stream>>>(Rs);
+        err = cudaGetLastError();
+        ++nlaunch;
     }
     if (err != cudaSuccess) { set_error(std::string("dp_fast launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
-    if (launches) *launches += 3;
+    if (launches) *launches += nlaunch;
     return AIM_OK;
 }
 
