@@ -1,4 +1,4 @@
-// Long-read WFA / WFA-adaptive, score only, for sm_100a: G lanes per pair, 32/G pairs per warp in
+// Long-read WFA / WFA-adaptive (score, optionally + CIGAR) for sm_100a: G lanes per pair, 32/G pairs per warp in
 // LOCKSTEP over the scores, wavefronts in WINDOWED shared-memory rings.
 //
 // Same algorithm and literal semantics as aim_wfa.cu / aim_wfa_sub.cu (reference:
@@ -26,6 +26,11 @@
 //   * the per-score schedule (which scores exist, which components they carry, ring slot offsets)
 //     depends only on the penalties: a 16-byte record per score, read warp-uniformly from global.
 //   * pairs are handed out by an atomic counter (cost per pair varies with its score).
+//   * with BACKTRACE every computed (score, diagonal) cell is also streamed as one 8-byte {M | I << 16, D} record
+//     to a per-pair-slot HBM arena, plus one 16-byte record per score (trimmed range, array origin, arena base):
+//     the reference's wfa_component store (common.h:126-138, dpu_allocator_mram.c).  The backtrace
+//     (wfa_backtracing.c:219-375) is walked by the first lane of every sub-warp with the reference's candidate
+//     order; a pair whose history outgrows the slot is handed to the warp-per-pair kernel as well.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -68,6 +73,11 @@ struct LongK {
     uint32_t dyn_words;   // range ring words per pair (multiple of 4, >= ring_m)
     uint32_t mring_bytes; // ring_m * M_SLOT_BYTES
     uint32_t pair_words;  // shared-memory words per pair slot
+    // backtrace only
+    char *ops;
+    uint2 *arena;         // history cells, arena_cells per pair slot
+    uint4 *meta;          // per pair slot and score: {lo | hi << 16 (trimmed), array origin lo, arena base, -}
+    uint32_t arena_cells;
 };
 
 // ---- pre-pass: ASCII rows -> duplicated 2-bit words; one warp per sequence ----
@@ -141,7 +151,7 @@ __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffff
 __device__ __forceinline__ int hi16s(uint32_t w) { return (int)(short)(w >> 16); }
 __device__ __forceinline__ bool in_range(int k, int lo, int hi) { return (unsigned)(k - lo) <= (unsigned)(hi - lo) && lo <= hi; }
 
-template <int G, bool REDUCE>
+template <int G, bool REDUCE, bool BT>
 __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
 {
     constexpr int PPW = 32 / G;
@@ -155,6 +165,10 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
     const uint32_t aDyn = sbase + (uint32_t)(wib * PPW + sub) * K.pair_words * 4u;  // (lo | hi << 16) per live score
     const uint32_t aMR = aDyn + K.dyn_words * 4u;                                  // M ring
     const uint32_t aIDR = aMR + K.mring_bytes;                                     // I/D ring
+    const uint32_t slot_global = (blockIdx.x * (blockDim.x >> 5) + (uint32_t)wib) * PPW + (uint32_t)sub;
+    uint2 *arena = BT ? K.arena + (size_t)slot_global * K.arena_cells : nullptr;
+    uint4 *meta = BT ? K.meta + (size_t)slot_global * (size_t)(MS + 1) : nullptr;
+    const int X = K.x, OE = K.o + K.e, E = K.e;
 
     for (;;) {
         uint32_t base_i = 0;
@@ -173,6 +187,13 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
 
         bool done = !active;
         int fscore = MS + 1;  // give-up value (wfa.c:399-404)
+        bool reached = false;
+        uint32_t abase = 0;   // arena cells used so far
+        char *gops = BT ? K.ops + (size_t)(active ? i : 0) * 2 * RS : nullptr;
+        if (BT && active) {   // op row: 'M' everywhere (wfa.c:499-501); the backtrace overwrites the edits
+            uint4 *dst = reinterpret_cast<uint4 *>(gops);
+            for (int c = sl; c < (2 * RS) / 16; c += G) dst[c] = make_uint4(0x4d4d4d4du, 0x4d4d4d4du, 0x4d4d4d4du, 0x4d4d4d4du);
+        }
 
         for (int s = 0; s <= MS; ++s) {
             const uint4 pw = __ldg(K.plan + s);  // warp-uniform
@@ -193,6 +214,9 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
                 hi = max(max(a_hi, b_hi), e_hi) + 1;
             }
             if (!done && hi - lo + 1 > W_CAP) { done = true; failed = true; }  // window outgrown: leave it to the warp-per-pair kernel
+            if (BT && !done && abase + (uint32_t)(hi - lo + 1) > K.arena_cells) { done = true; failed = true; }  // history outgrown
+            const bool ran = !done;
+            uint2 *hC = BT ? arena + abase - lo : nullptr;  // this score's history cells, indexed by k
             const uint32_t aNM = aMR + offN, aAM = aMR + offA, aBM = aMR + offB;
             const uint32_t aEI = aIDR + (pw.z >> 16), aED = aEI + M_SLOT_BYTES;
             const uint32_t aNI = aIDR + (pw.w & 0xffffu), aND = aNI + M_SLOT_BYTES;
@@ -226,15 +250,16 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
                         if (lim > 0) m += match_packed_g(P2, T2, v, m, lim);
                     }
                     sts_u16(aNM + ck, m);
+                    if (BT) hC[k] = make_uint2(((uint32_t)m & 0xffffu) | ((uint32_t)ins << 16), (uint32_t)del & 0xffffu);
                     if (REDUCE) md = min(md, max(pl - (m - k), tl - m));
                     if (k == ak && m >= tl) hit_end = true;
                 }
             } else if (!done) {
                 for (int k = lo + sl; k <= hi; k += G) {
                     const uint32_t ck = cell(k), ckm = cell(k - 1), ckp = cell(k + 1);
-                    int m = 0;
+                    int m = 0, ins = -10, del = -10;
                     if (s > 0) {
-                        int ins = -10, del = -10, sb = -10;
+                        int sb = -10;
                         if (has_i) {
                             const int g = in_range(k - 1, b_lo, b_hi) ? lds_s16(aBM + ckm) : kNull;
                             const int ii = (!ie_null && in_range(k - 1, e_lo, e_hi)) ? lds_s16(aEI + ckm) : kNull;
@@ -256,6 +281,7 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
                         if (lim > 0) m += match_packed_g(P2, T2, v, m, lim);
                     }
                     sts_u16(aNM + ck, m);
+                    if (BT) hC[k] = make_uint2(((uint32_t)m & 0xffffu) | ((uint32_t)ins << 16), (uint32_t)del & 0xffffu);
                     if (REDUCE) md = min(md, max(pl - (m - k), tl - m));
                     if (k == ak && m >= tl) hit_end = true;
                 }
@@ -263,7 +289,8 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
             // ---- end reached (wfa.c:217-237); trimming never removes diagonal ak, so testing before the
             // reduction is equivalent and the finishing wavefront's trimmed range is never read again ----
             const uint32_t eb = __ballot_sync(kFull, hit_end);
-            if (!done && ((eb >> subshift) & GM)) { done = true; fscore = s; }
+            if (!done && ((eb >> subshift) & GM)) { done = true; reached = true; fscore = s; }
+            if (BT && ran && sl == 0 && done) meta[s] = make_uint4(((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16), (uint32_t)lo, abase, 0u);
             if (__all_sync(kFull, done)) break;
 
             // ---- adaptive reduction (wfa.c:70-141) on the pairs still running ----
@@ -305,6 +332,10 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
             }
             if (!done) {
                 if (sl == 0) sts_u32(aDyn + (offN / M_SLOT_BYTES) * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)newhi << 16));
+                if (BT) {
+                    if (sl == 0) meta[s] = make_uint4(((uint32_t)newlo & 0xffffu) | ((uint32_t)newhi << 16), (uint32_t)lo, abase, 0u);
+                    abase += (uint32_t)(hi - lo + 1);
+                }
                 // NULL frame around the (trimmed) wavefront: PAD cells below newlo and above newhi, every component
                 for (int j = sl; j < 2 * PAD; j += G) {
                     const uint32_t cf = cell(j < PAD ? newlo - 1 - j : newhi + 1 + (j - PAD));
@@ -317,16 +348,107 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
         }
         __syncwarp();
 
+        // ---- backtrace (wfa_backtracing.c:219-375): first lane of every sub-warp, concurrently ----
+        const int max_ops = pl + tl;
+        int begin_offset = max_ops - 1;
+        int status = AIM_STATUS_OK;
+        if (BT && reached && !failed && sl == 0) {
+            __threadfence_block();
+            const int ops_cap = 2 * RS;
+            int b = begin_offset;
+            int score = fscore, k = ak;
+            int offset;
+            {
+                const uint4 mf = meta[fscore];
+                offset = lo16(arena[mf.z + (uint32_t)(k - (int)mf.y)].x);
+            }
+            int v = offset - k, h = offset;
+            bool valid = (v > 0 && v <= pl && h > 0 && h <= tl);
+            int type = 0;  // 0 M, 1 I, 2 D
+            bool bad = false;
+#define AIM_PUT(ch) do { if (b < 0 || b >= ops_cap) { bad = true; } else { gops[b] = (ch); } --b; } while (0)
+            while (v > 0 && h > 0 && score > 0 && !bad) {
+                if (!valid) {
+                    valid = (v > 0 && v <= pl && h > 0 && h <= tl);
+                    if (valid) {  // add_trailing_gap (wfa_backtracing.c:48-69)
+                        if (k < ak) { for (int j = k; j < ak; ++j) AIM_PUT('I'); }
+                        else if (k > ak) { for (int j = ak; j < k; ++j) AIM_PUT('D'); }
+                    }
+                }
+                const int s_open = score - OE, s_ext = score - E, s_mis = score - X;
+                // records: flags from the plan, trimmed range / origin / arena base from the per-score meta
+                uint32_t go_f = 0, ge_f = 0, mm_f = 0, go_base = 0, ge_base = 0, mm_base = 0;
+                int go_lo = 1, go_hi = -1, ge_lo = 1, ge_hi = -1, mm_lo = 1, mm_hi = -1, go_l0 = 0, ge_l0 = 0, mm_l0 = 0;
+                if (s_open >= 0) {
+                    go_f = __ldg(&K.plan[s_open].x);
+                    if (go_f & L_PRESENT) { const uint4 q = meta[s_open]; go_lo = lo16(q.x); go_hi = hi16s(q.x); go_l0 = (int)q.y; go_base = q.z; }
+                }
+                if (s_ext >= 0) {
+                    ge_f = __ldg(&K.plan[s_ext].x);
+                    if (ge_f & L_PRESENT) { const uint4 q = meta[s_ext]; ge_lo = lo16(q.x); ge_hi = hi16s(q.x); ge_l0 = (int)q.y; ge_base = q.z; }
+                }
+                if (s_mis >= 0) {
+                    mm_f = __ldg(&K.plan[s_mis].x);
+                    if (mm_f & L_PRESENT) { const uint4 q = meta[s_mis]; mm_lo = lo16(q.x); mm_hi = hi16s(q.x); mm_l0 = (int)q.y; mm_base = q.z; }
+                }
+                int del_ext = kNull, del_open = kNull, ins_ext = kNull, ins_open = kNull, misms = kNull;
+                if (type != 1) {
+                    if ((ge_f & L_PRESENT) && (ge_f & L_HAS_D) && ge_lo <= k + 1 && k + 1 <= ge_hi)
+                        del_ext = lo16(arena[ge_base + (uint32_t)(k + 1 - ge_l0)].y);
+                    if ((go_f & L_PRESENT) && go_lo <= k + 1 && k + 1 <= go_hi) del_open = lo16(arena[go_base + (uint32_t)(k + 1 - go_l0)].x);
+                }
+                if (type != 2) {
+                    if ((ge_f & L_PRESENT) && (ge_f & L_HAS_I) && ge_lo <= k - 1 && k - 1 <= ge_hi)
+                        ins_ext = (int16_t)(hi16s(arena[ge_base + (uint32_t)(k - 1 - ge_l0)].x) + 1);
+                    if ((go_f & L_PRESENT) && go_lo <= k - 1 && k - 1 <= go_hi)
+                        ins_open = (int16_t)(lo16(arena[go_base + (uint32_t)(k - 1 - go_l0)].x) + 1);
+                }
+                if (type == 0) {
+                    if ((mm_f & L_PRESENT) && mm_lo <= k && k <= mm_hi) misms = (int16_t)(lo16(arena[mm_base + (uint32_t)(k - mm_l0)].x) + 1);
+                }
+                const int max_all = max(misms, max(max(ins_ext, ins_open), max(del_ext, del_open)));
+                if (type == 0) {
+                    const int num_matches = offset - max_all;  // ops are 'M' already
+                    if (num_matches > 0) {
+                        if (num_matches > b + 1) { bad = true; break; }
+                        b -= num_matches;
+                    }
+                    offset = max_all;
+                    v = offset - k;
+                    h = offset;
+                    if (v <= 0 || h <= 0) break;
+                }
+                if (max_all == del_ext) { if (valid) AIM_PUT('D'); score = s_ext; ++k; type = 2; }
+                else if (max_all == del_open) { if (valid) AIM_PUT('D'); score = s_open; ++k; type = 0; }
+                else if (max_all == ins_ext) { if (valid) AIM_PUT('I'); score = s_ext; --k; --offset; type = 1; }
+                else if (max_all == ins_open) { if (valid) AIM_PUT('I'); score = s_open; --k; --offset; type = 0; }
+                else if (max_all == misms) { if (valid) AIM_PUT('X'); score = s_mis; --offset; }
+                else { bad = true; break; }
+                v = offset - k;
+                h = offset;
+            }
+            if (!bad) {
+                if (score == 0) {
+                    if (offset > 0) { if (offset > b + 1) bad = true; else b -= offset; }
+                } else {
+                    while (v > 0 && !bad) { AIM_PUT('D'); --v; }
+                    while (h > 0 && !bad) { AIM_PUT('I'); --h; }
+                }
+            }
+#undef AIM_PUT
+            if (bad) status = AIM_STATUS_BACKTRACE;
+            begin_offset = b + 1;
+        }
         if (sl == 0) {
             if (failed) {
                 K.fail_list[atomicAdd(K.fail_count, 1u)] = i;
             } else if (active) {
                 aim_result r;
-                r.max_operations = pl + tl;
-                r.begin_offset = pl + tl - 1;
-                r.end_offset = pl + tl;
+                r.max_operations = max_ops;
+                r.begin_offset = begin_offset;
+                r.end_offset = max_ops;
                 r.score = fscore;
-                r.status = AIM_STATUS_OK;
+                r.status = status;
                 r.idx = K.idx_base + i;
                 K.results[i] = r;
             }
@@ -338,27 +460,13 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
+// Picks the instantiation, sets its shared-memory attribute and returns its resident grid.
+typedef void (*LongKernel)(const LongK);
 template <int G>
-cudaError_t launch_g(const LongK &K, bool reduce, int sm_count, size_t pair_bytes, cudaStream_t st, int *grid_out)
+LongKernel pick_g(bool reduce, bool bt)
 {
-    const int block = 128;
-    const size_t smem = (size_t)(block / 32) * (32 / G) * pair_bytes;
-    cudaError_t e;
-    int bps = 0;
-#define AIM_LAUNCH(R)                                                                                               \
-    do {                                                                                                            \
-        e = cudaFuncSetAttribute(wfa_long_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, wfa_long_kernel<G, R>, block, smem); \
-        if (e == cudaSuccess) {                                                                                     \
-            const int grid = sm_count * std::max(1, bps);                                                           \
-            *grid_out = grid;                                                                                       \
-            wfa_long_kernel<G, R><<<grid, block, smem, st>>>(K);                                                    \
-        }                                                                                                           \
-    } while (0)
-    if (reduce) AIM_LAUNCH(true);
-    else AIM_LAUNCH(false);
-#undef AIM_LAUNCH
-    return e;
+    if (reduce) return bt ? wfa_long_kernel<G, true, true> : wfa_long_kernel<G, true, false>;
+    return bt ? wfa_long_kernel<G, false, true> : wfa_long_kernel<G, false, false>;
 }
 
 }  // namespace
@@ -368,9 +476,9 @@ int launch_wfa_long(const KernelArgs &a, Scratch *sc, void *stream_v, int *launc
 {
     cudaStream_t stream = (cudaStream_t)stream_v;
     const aim_params &p = a.p;
-    if (p.backtrace) return 1;  // history arena: warp-per-pair kernel
     if (const char *mode = getenv("AIM_WFA_MODE")) { if (std::string(mode) == "warp") return 1; }
     const int MS = p.max_score, x = p.mismatch, o = p.gap_open, e = p.gap_ext;
+    if (!p.reduce && MS > 2 * W_CAP) return 1;  // untrimmed wavefronts (2s+1 wide) would mostly outgrow the window
     const uint32_t ring_m = (uint32_t)std::max(x, o + e) + 1, ring_e = (uint32_t)e + 1;
     if (ring_m * M_SLOT_BYTES > 0xffffu || ring_e * ID_SLOT_BYTES > 0xffffu) return 1;
 
@@ -415,18 +523,42 @@ int launch_wfa_long(const KernelArgs &a, Scratch *sc, void *stream_v, int *launc
     const size_t pair_bytes = (size_t)K.pair_words * 4;
     if (pair_bytes * 4 * PPW > 227u * 1024u / 2) return 1;  // fewer than two blocks per SM: not worth it
 
-    // the warp-per-pair kernel serves what this one hands back
-    const WarpPlan W = wfa_warp_plan(a, sc->sm_count, a.n);
+    // the warp-per-pair kernel serves what this one hands back (rare: a few resident warps are enough)
+    // (without trimming the window is outgrown at score ~W_CAP/2: hand-overs are then common, keep the full grid)
+    const WarpPlan W = wfa_warp_plan(a, sc->sm_count, p.reduce ? std::min<uint32_t>(a.n, (uint32_t)sc->sm_count * 4u) : a.n);
     if (W.rc != AIM_OK) { set_error("READ_SIZE too large for the shared-memory sequence stage"); return W.rc; }
 
-    // scratch: counters | plan | dirty | fail list | packed sequences | warp-per-pair scratch
+    // kernel instantiation and its resident grid
+    const bool bt = p.backtrace != 0;
+    LongKernel fn = G == 8 ? pick_g<8>(p.reduce != 0, bt) : G == 16 ? pick_g<16>(p.reduce != 0, bt) : pick_g<32>(p.reduce != 0, bt);
+    const int block = 128;
+    const size_t smem = (size_t)(block / 32) * PPW * pair_bytes;
+    int bps = 0;
+    cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, block, smem);
+    if (err != cudaSuccess) { set_error(std::string("wfa_long setup: ") + cudaGetErrorString(err)); cudaGetLastError(); return AIM_ERR_CUDA; }
+    int grid = sc->sm_count * std::max(1, bps);
+    {
+        const uint64_t per_block = (uint64_t)(block / 32) * PPW;
+        grid = (int)std::min<uint64_t>((uint64_t)grid, (a.n + per_block - 1) / per_block);
+    }
+    const size_t slots = (size_t)grid * (block / 32) * PPW;
+    // history arena per resident pair slot (backtrace): 4 MiB by default = 512 K cells, ~3x what a 10 Kbp / 10 % pair
+    // writes; a pair that needs more is handed to the warp-per-pair kernel with its own (arena_mb) arena
+    K.arena_cells = bt ? (uint32_t)(((size_t)(p.arena_mb > 0 ? p.arena_mb : 4) << 20) / sizeof(uint2)) : 0;
+
+    // scratch: counters | plan | dirty | fail list | packed sequences | meta | arena | warp-per-pair scratch
     const size_t plan_bytes = plan.size() * sizeof(uint4);
     const size_t off_plan = 256;
     const size_t off_dirty = align256(off_plan + plan_bytes);
     const size_t off_fail = align256(off_dirty + a.n);
     const size_t off_packed = align256(off_fail + (size_t)a.n * 4);
     const size_t packed_bytes = (size_t)a.n * 2 * K.pk_words * sizeof(uint2);
-    const size_t off_warp = align256(off_packed + packed_bytes);
+    const size_t off_meta = align256(off_packed + packed_bytes);
+    const size_t meta_bytes = bt ? slots * ((size_t)MS + 1) * sizeof(uint4) : 0;
+    const size_t off_arena = align256(off_meta + meta_bytes);
+    const size_t arena_bytes = bt ? slots * (size_t)K.arena_cells * sizeof(uint2) : 0;
+    const size_t off_warp = align256(off_arena + arena_bytes);
     int rc = scratch_reserve(sc, off_warp + W.scratch_bytes);
     if (rc != AIM_OK) return rc;
     unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
@@ -436,27 +568,27 @@ int launch_wfa_long(const KernelArgs &a, Scratch *sc, void *stream_v, int *launc
     K.dirty = base + off_dirty;
     K.fail_list = reinterpret_cast<uint32_t *>(base + off_fail);
     K.packed = reinterpret_cast<const uint2 *>(base + off_packed);
+    K.ops = a.ops;
+    K.meta = reinterpret_cast<uint4 *>(base + off_meta);
+    K.arena = reinterpret_cast<uint2 *>(base + off_arena);
 
-    cudaError_t err = cudaMemsetAsync(base, 0, 256, stream);
+    err = cudaMemsetAsync(base, 0, 256, stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(base + off_dirty, 0, a.n, stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(base + off_plan, plan.data(), plan_bytes, cudaMemcpyHostToDevice, stream);
     if (err == cudaSuccess) {
         const uint64_t warps = std::min<uint64_t>(2ull * a.n, (uint64_t)sc->sm_count * 64);
-        const int grid = (int)((warps * 32 + 255) / 256);
-        pack_kernel<<<grid, 256, 0, stream>>>(a.plen, a.tlen, a.patterns, a.texts, a.n, p.read_size, K.pk_words,
-                                              reinterpret_cast<uint2 *>(base + off_packed), base + off_dirty);
+        const int pgrid = (int)((warps * 32 + 255) / 256);
+        pack_kernel<<<pgrid, 256, 0, stream>>>(a.plen, a.tlen, a.patterns, a.texts, a.n, p.read_size, K.pk_words,
+                                               reinterpret_cast<uint2 *>(base + off_packed), base + off_dirty);
         err = cudaGetLastError();
     }
-    int grid = 0;
     if (err == cudaSuccess) {
-        if (G == 8) err = launch_g<8>(K, p.reduce != 0, sc->sm_count, pair_bytes, stream, &grid);
-        else if (G == 16) err = launch_g<16>(K, p.reduce != 0, sc->sm_count, pair_bytes, stream, &grid);
-        else err = launch_g<32>(K, p.reduce != 0, sc->sm_count, pair_bytes, stream, &grid);
-        if (err == cudaSuccess) err = cudaGetLastError();
+        fn<<<grid, block, smem, stream>>>(K);
+        err = cudaGetLastError();
     }
     if (err != cudaSuccess) { set_error(std::string("wfa_long launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
     if (launches) *launches += 2;
-    // leftovers (window outgrown, non-ACGT bytes)
+    // leftovers (window or history outgrown, non-ACGT bytes)
     return wfa_warp_launch(W, base + off_warp, K.fail_list, K.fail_count, stream_v, launches);
 }
 

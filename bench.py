@@ -48,10 +48,14 @@ CONFIGS = {
             gap_ext=1, reduce=True, backtrace=True, pairs=10_000_000, seed=4),
     5: dict(name="WFA-adaptive long reads l=10000 e=10% 200K pairs score-only", algo="wfa", length=10000, error=0.10, mismatch=3,
             gap_open=4, gap_ext=1, reduce=True, backtrace=False, pairs=200_000, seed=5),
+    # config 5 WITH backtrace: beyond what the reference can run, informational
+    6: dict(name="WFA-adaptive long reads l=10000 e=10% +BT (beyond the reference's limits)", algo="wfa", length=10000, error=0.10,
+            mismatch=3, gap_open=4, gap_ext=1, reduce=True, backtrace=True, pairs=50_000, seed=5),
 }
 # dominant kernel of each config (the one `roofline` describes; one step = all kernels of the launch)
 KERNELS = {2: "dp_strip_kernel<NW> + dp_row_kernel<NW> (aim_dp_fast.cu)", 3: "dp_strip_kernel<SWG> + dp_row_kernel<SWG> (aim_dp_fast.cu)",
-           4: "wfa_sub_kernel<4, reduce, backtrace> (aim_wfa_sub.cu)", 5: "wfa_long_kernel<16, reduce> (aim_wfa_long.cu)"}
+           4: "wfa_sub_kernel<4, reduce, backtrace> (aim_wfa_sub.cu)", 5: "wfa_long_kernel<16, reduce> (aim_wfa_long.cu)",
+           6: "wfa_kernel<true> (aim_wfa.cu)"}
 # algorithmic work per pair (restated in DESIGN.md "Measurement")
 INT_OPS_PER_OFFSET = 11   # one computed (score, diagonal) offset: I, D, M recurrences
 INT_OPS_PER_EXTEND = 4    # xor, clz, add, cmp per 16-base word step
@@ -136,7 +140,7 @@ def run_reference_arm(args, cfg) -> None:
         return
     import aim_b200 as A
     threads = os.cpu_count() or 1
-    sample = args.ref_pairs or {4: 2_000_000, 2: 400_000, 3: 16_000, 5: 160}[args.config]
+    sample = args.ref_pairs or {4: 2_000_000, 2: 400_000, 3: 16_000, 5: 160, 6: 160}[args.config]
     last = cpu_reference_run(cfg, sample, threads, repeats=args.steps, warmup=args.warmup)
     t = (last["h2d_ms"] + last["kernel_ms"] + last["d2h_ms"]) * 1e-3
     value = last["pairs"] / t
@@ -309,7 +313,7 @@ def main() -> None:
         if not args.no_cpu_baseline:
             try:
                 cthreads = os.cpu_count() or 1
-                sample = args.ref_pairs or {4: 2_000_000, 2: 400_000, 3: 16_000, 5: 160}[args.config]
+                sample = args.ref_pairs or {4: 2_000_000, 2: 400_000, 3: 16_000, 5: 160, 6: 160}[args.config]
                 r = cpu_reference_run(cfg, sample, cthreads)
                 tot = (r["h2d_ms"] + r["kernel_ms"] + r["d2h_ms"]) * 1e-3
                 cpu_baseline = {"value": r["pairs"] / tot, "unit": "pairs/s", "cores": cthreads, "kind": "reference",
