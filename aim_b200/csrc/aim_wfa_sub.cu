@@ -17,6 +17,16 @@
 //     store, and read back only along the backtrace path; the arena is reused pair after pair and
 //     stays L2-resident;
 //   * compute_offsets and extend are fused per diagonal (extending diagonal k touches only M[k]);
+//   * every ring row is NULL-FRAMED: cells outside the occupant wavefront's (trimmed) range hold exactly the NULL
+//     the reference substitutes for an out-of-range read (wfa.c:243-266), and missing components point at a
+//     block-wide all-NULL row, so the inner loop has no range or existence tests.  The frame is kept by three small
+//     clean-ups: rows are NULL-filled when a pair starts, cells an adaptive trim cuts off are NULLed at once, and
+//     cells a slot's previous occupant left outside the new wavefront's range are NULLed before the slot is reused.
+//     The reference's -10 "component missing" sentinel is one max() with a per-score floor (-10 when any of I / D /
+//     sub is missing, 0 for score 0);
+//   * the ASCII -> 2-bit packing (and the non-ACGT check) is a separate HBM-bound kernel, wfa_prep_kernel, that
+//     writes every 16-base window as one aligned 8-byte entry {word j, word j+1}; extend is one 8-byte shared load
+//     + one funnel shift per sequence; the 'M' pre-fill of the op rows (wfa.c:499-501) is a cudaMemsetAsync;
 //   * backtraces of the 32/G pairs run concurrently on the sub-warps' first lanes and write the few
 //     non-'M' ops straight into the 'M'-filled global op rows.
 #include <cuda_runtime.h>
@@ -36,15 +46,16 @@ namespace {
 // plan flags
 constexpr uint32_t P_PRESENT = 1, P_SUB_NULL = 2, P_O_NULL = 4, P_IE_NULL = 8, P_DE_NULL = 16, P_HAS_I = 32, P_HAS_D = 64;
 constexpr int PLAN_WORDS = 8;
-// per-score plan: w0 flags
+constexpr uint32_t OFF_NULL = 0xffffu;  // row offset meaning "the block-wide all-NULL row"; also "no score"
+// per-score plan: w0 flags | floor (int16) << 16
 //                 w1 lo_s (int16) | width_s << 16        static range of the wavefront
-//                 w2 byte offset of this score's M ring slot | of score s-x's slot << 16
-//                 w3 byte offset of score s-o-e's M slot     | of score s-e's I/D slot << 16
-//                 w4 byte offset of this score's I/D slot
+//                 w2 row offset of this score's M row   | of score s-x's M row << 16
+//                 w3 row offset of score s-o-e's M row  | of score s-e's I row << 16
+//                 w4 row offset of score s-e's D row    | of this score's I row << 16
 //                 w5 arena cell index of diagonal lo_s
-//                 w6 static a_lo (int16) | a_hi << 16      range of score s-x   (non-adaptive runs)
-//                 w7 unused
-// ring slots: M slot = cw halfwords; I/D slot = I array (cw halfwords) followed by D array (cw).
+//                 w6 row offset of this score's D row   | previous occupant (score) of this M row << 16
+//                 w7 previous occupant (score) of this I/D row pair
+// rows: cw halfwords each (cw % 8 == 0), byte offsets from the pair's first row; M ring, then I ring, then D ring.
 
 struct SubK {
     const int32_t *plen;
@@ -53,6 +64,8 @@ struct SubK {
     const char *texts;
     aim_result *results;
     char *ops;
+    const uint4 *packed;    // wfa_prep_kernel's output: per pair seq_entries 8-byte entries of the pattern, then of the text
+    const uint8_t *flags;   // per pair: 1 = a byte outside {A,C,G,T} inside the sequences (compare raw bytes)
     const uint32_t *plan;   // device copy of the plan
     uint2 *arena;           // history arena (BT only): {M | I << 16, D} per (score, diagonal)
     size_t arena_stride;    // cells per pair slot
@@ -61,16 +74,22 @@ struct SubK {
     int max_score, read_size;
     int koff;               // ring cell of diagonal k is k + koff
     uint32_t plan_words;    // PLAN_WORDS * (max_score + 1)
-    uint32_t seq_words;     // words per packed sequence (multiple of 4)
+    uint32_t seq_entries;   // 8-byte window entries per packed sequence (even)
     uint32_t dyn_words;     // trimmed-range words per pair (multiple of 4; 0 when !reduce)
-    uint32_t cw;            // ring array width in halfwords (even)
-    uint32_t mring_bytes;   // M ring bytes
+    uint32_t cw;            // row width in halfwords (multiple of 8)
+    uint32_t rows_v4;       // 16-byte units of all rows of a pair
     uint32_t pair_words;    // shared-memory words per pair slot
 };
 
 // ---- shared-memory accessors on 32-bit shared-window addresses ----
 __device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t a)
 {
     uint4 v;
@@ -79,20 +98,61 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a)
 }
 __device__ __forceinline__ void sts_u16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
-// equal bases from pattern[v], text[h], at most lim (> 0); sequences 2-bit packed at shared addresses aP/aT
-__device__ __forceinline__ int match_packed_s(uint32_t aP, uint32_t aT, int v, int h, int lim)
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v)
 {
-    int cnt = 0;
-    for (;;) {
-        const int pv = v + cnt, ph = h + cnt;
-        const uint32_t pa = aP + ((pv >> 4) << 2), ta = aT + ((ph >> 4) << 2);
-        const uint32_t a = __funnelshift_l(lds_u32(pa + 4), lds_u32(pa), (pv & 15) * 2);
-        const uint32_t b = __funnelshift_l(lds_u32(ta + 4), lds_u32(ta), (ph & 15) * 2);
-        const uint32_t d = a ^ b;
-        if (d) { cnt += __clz(d) >> 1; break; }
-        cnt += 16;
-        if (cnt >= lim) break;
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 16 bases starting at base b of an ASCII row -> one 32-bit word, first base in the two most significant bits;
+// bases at or beyond len (or the row) read as 'A'.  *ok is cleared by a byte outside {A,C,G,T} below len.
+__device__ __forceinline__ uint32_t pack16(const char *row, int b, int len, int RS, bool *ok)
+{
+    uint32_t w = 0;
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        const int bb = b + 8 * hlf;
+        uint32_t h16 = 0;
+        if (bb < len && bb < RS) h16 = pack8(__ldg(reinterpret_cast<const uint2 *>(row + bb)), len - bb, ok);
+        w = (w << 16) | h16;
+    }
+    return w;
+}
+
+// One thread per (pair, sequence, window entry): entry j = {bases 16j..16j+15, bases 16j+16..16j+31}.  HBM-bound.
+__global__ void __launch_bounds__(256) wfa_prep_kernel(const char *patterns, const char *texts, const int32_t *plen, const int32_t *tlen,
+                                                       uint32_t n, int RS, uint32_t SE, uint2 *packed, uint8_t *flags)
+{
+    const uint64_t total = (uint64_t)n * 2u * SE;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(t % SE);
+        const uint64_t r = t / SE;
+        const uint32_t q = (uint32_t)(r & 1u), i = (uint32_t)(r >> 1);
+        const int len = min(max(q ? tlen[i] : plen[i], 0), RS);
+        const char *row = (q ? texts : patterns) + (size_t)i * RS;
+        bool ok = true;
+        uint2 e;
+        e.x = pack16(row, (int)j * 16, len, RS, &ok);
+        e.y = pack16(row, (int)j * 16 + 16, len, RS, &ok);
+        packed[t] = e;
+        if (!ok) flags[i] = 1;
+    }
+}
+
+// equal bases from pattern[v], text[h], at most lim (> 0); aP/aT = shared addresses of the 8-byte window entries
+__device__ __forceinline__ int extend_dup(uint32_t aP, uint32_t aT, int v, int h, int lim)
+{
+    const uint2 x = lds_v2(aP + ((uint32_t)(v >> 4) << 3)), y = lds_v2(aT + ((uint32_t)(h >> 4) << 3));
+    const uint32_t d = __funnelshift_l(x.y, x.x, 2 * v) ^ __funnelshift_l(y.y, y.x, 2 * h);
+    int cnt = __clz(d) >> 1;  // 16 when the whole window matches
+    if (d == 0 && lim > 16) {
+        for (;;) {
+            const int pv = v + cnt, ph = h + cnt;
+            const uint2 x2 = lds_v2(aP + ((uint32_t)(pv >> 4) << 3)), y2 = lds_v2(aT + ((uint32_t)(ph >> 4) << 3));
+            const uint32_t d2 = __funnelshift_l(x2.y, x2.x, 2 * pv) ^ __funnelshift_l(y2.y, y2.x, 2 * ph);
+            if (d2) { cnt += __clz(d2) >> 1; break; }
+            cnt += 16;
+            if (cnt >= lim) break;
+        }
     }
     return min(cnt, lim);
 }
@@ -114,27 +174,30 @@ template <int G, bool REDUCE, bool BT>
 __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
 {
     constexpr int PPW = 32 / G;
-    constexpr uint32_t GM = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
     extern __shared__ __align__(16) uint32_t smem_w[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int sub = lane / G, sl = lane % G, subshift = sub * G;
+    const int sub = lane / G, sl = lane % G;
     const uint32_t wpb = blockDim.x >> 5;
     const int RS = K.read_size, MS = K.max_score;
     const int X = K.x, OE = K.o + K.e, E = K.e;
+    const uint4 null4 = make_uint4(0xc000c000u, 0xc000c000u, 0xc000c000u, 0xc000c000u);  // kNull in every halfword
 
-    // block-wide: the plan
+    // block-wide: the plan and the all-NULL row
     for (uint32_t j = threadIdx.x; j < K.plan_words; j += blockDim.x) smem_w[j] = K.plan[j];
+    for (uint32_t j = threadIdx.x; j < K.cw / 2; j += blockDim.x) smem_w[K.plan_words + j] = 0xc000c000u;
     __syncthreads();
 
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_w);
     const uint32_t aPlan = sbase;
-    const uint32_t aSlot = sbase + (K.plan_words + (uint32_t)(wib * PPW + sub) * K.pair_words) * 4u;
+    const uint32_t aSlot = sbase + (K.plan_words + K.cw / 2 + (uint32_t)(wib * PPW + sub) * K.pair_words) * 4u;
     const uint32_t aP = aSlot;
-    const uint32_t aT = aP + K.seq_words * 4u;
-    const uint32_t aDyn = aT + K.seq_words * 4u;
-    const uint32_t aMR = aDyn + K.dyn_words * 4u + (uint32_t)(K.koff * 2);  // M ring, diagonal 0 of slot 0
-    const uint32_t aIDR = aMR + K.mring_bytes;                               // I/D ring
-    const uint32_t CW2 = K.cw * 2u;
+    const uint32_t aT = aP + K.seq_entries * 8u;
+    const uint32_t aDyn = aT + K.seq_entries * 8u;
+    const uint32_t aRows = aDyn + K.dyn_words * 4u;
+    const uint32_t aK0 = aRows + (uint32_t)(K.koff * 2);                        // diagonal 0 of the pair's first row
+    const uint32_t nullrel = (sbase + K.plan_words * 4u + (uint32_t)(K.koff * 2)) - aK0;  // the NULL row, relative to aK0
+    // address of diagonal 0 of the row at plan offset `off`
+#define AIM_ROW(off) (aK0 + ((off) == OFF_NULL ? nullrel : (off)))
 
     const uint32_t slot_global = (blockIdx.x * wpb + wib) * PPW + sub;
     const uint32_t nslots = gridDim.x * wpb * PPW;
@@ -150,21 +213,13 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
         char *gops = BT ? K.ops + (size_t)(active ? i : 0) * 2 * RS : nullptr;
         const int ak = tl - pl;
 
-        // ---- stage + 2-bit pack (8-byte loads, contiguous inside a sub-warp) ----
-        bool ok = true;
-        for (int c = sl; c * 8 < pl; c += G) {
-            const uint2 w = __ldg(reinterpret_cast<const uint2 *>(gp) + c);
-            sts_u16(aP + (uint32_t)(c ^ 1) * 2u, (int)pack8(w, pl - c * 8, &ok));
+        // ---- stage the packed windows (16-byte copies), NULL-fill the rows ----
+        if (active) {
+            const uint4 *src = K.packed + (size_t)i * K.seq_entries;
+            for (uint32_t c = sl; c < K.seq_entries; c += G) sts_v4(aP + c * 16u, __ldg(src + c));
         }
-        for (int c = sl; c * 8 < tl; c += G) {
-            const uint2 w = __ldg(reinterpret_cast<const uint2 *>(gt) + c);
-            sts_u16(aT + (uint32_t)(c ^ 1) * 2u, (int)pack8(w, tl - c * 8, &ok));
-        }
-        const bool packed = ((__ballot_sync(kFull, ok) >> subshift) & GM) == GM;
-        if (BT && active) {  // op row: 'M' everywhere (wfa.c:499-501); the backtrace overwrites the few edits
-            uint4 *dst = reinterpret_cast<uint4 *>(gops);
-            for (int c = sl; c < (2 * RS) / 16; c += G) dst[c] = make_uint4(0x4d4d4d4du, 0x4d4d4d4du, 0x4d4d4d4du, 0x4d4d4d4du);
-        }
+        const bool packed = active ? (K.flags[i] == 0) : true;
+        for (uint32_t c = sl; c < K.rows_v4; c += G) sts_v4(aRows + c * 16u, null4);
         __syncwarp();
 
         bool done = !active;
@@ -176,85 +231,99 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
             const uint32_t fl = p0.x;
             if (!(fl & P_PRESENT)) continue;
             const uint4 p1 = lds_v4(aPlan + (uint32_t)s * (PLAN_WORDS * 4) + 16);
-            const bool sub_null = fl & P_SUB_NULL, o_null = fl & P_O_NULL, ie_null = fl & P_IE_NULL, de_null = fl & P_DE_NULL;
-            const bool has_i = fl & P_HAS_I, has_d = fl & P_HAS_D;
+            const int floor_m = hi16s(fl);
             const int lo_s = lo16(p0.y);
 
-            // this pair's range (wfa.c:318-343) and the ranges of the three source wavefronts
+            // this pair's range (wfa.c:318-343): from the (trimmed) ranges of the source wavefronts
             int lo = lo_s, hi = lo_s + (int)(p0.y >> 16) - 1;
-            int a_lo = lo16(p1.z), a_hi = hi16s(p1.z), b_lo = 1, b_hi = -1, e_lo = 1, e_hi = -1;
-            if (s > 0) {
-                if (REDUCE) {
-                    a_lo = 1; a_hi = -1;
-                    if (!sub_null) { const uint32_t w = lds_u32(aDyn + (uint32_t)(s - X) * 4u); a_lo = lo16(w); a_hi = hi16s(w); }
-                    if (!o_null) { const uint32_t w = lds_u32(aDyn + (uint32_t)(s - OE) * 4u); b_lo = lo16(w); b_hi = hi16s(w); }
-                    if (!(ie_null && de_null)) { const uint32_t w = lds_u32(aDyn + (uint32_t)(s - E) * 4u); e_lo = lo16(w); e_hi = hi16s(w); }
-                    lo = min(min(a_lo, b_lo), e_lo) - 1;
-                    hi = max(max(a_hi, b_hi), e_hi) + 1;
-                } else {
-                    if (!o_null) { const uint32_t w = lds_u32(aPlan + (uint32_t)(s - OE) * (PLAN_WORDS * 4) + 4); b_lo = lo16(w); b_hi = b_lo + (int)(w >> 16) - 1; }
-                    if (!(ie_null && de_null)) { const uint32_t w = lds_u32(aPlan + (uint32_t)(s - E) * (PLAN_WORDS * 4) + 4); e_lo = lo16(w); e_hi = e_lo + (int)(w >> 16) - 1; }
-                }
+            if (REDUCE && s > 0) {
+                int a_lo = 1, a_hi = -1, b_lo = 1, b_hi = -1, e_lo = 1, e_hi = -1;
+                if (!(fl & P_SUB_NULL)) { const uint32_t w = lds_u32(aDyn + (uint32_t)(s - X) * 4u); a_lo = lo16(w); a_hi = hi16s(w); }
+                if (!(fl & P_O_NULL)) { const uint32_t w = lds_u32(aDyn + (uint32_t)(s - OE) * 4u); b_lo = lo16(w); b_hi = hi16s(w); }
+                if ((fl & (P_IE_NULL | P_DE_NULL)) != (P_IE_NULL | P_DE_NULL)) { const uint32_t w = lds_u32(aDyn + (uint32_t)(s - E) * 4u); e_lo = lo16(w); e_hi = hi16s(w); }
+                lo = min(min(a_lo, b_lo), e_lo) - 1;
+                hi = max(max(a_hi, b_hi), e_hi) + 1;
             }
-            // ring addresses of cell k = base + 2*k
-            const uint32_t aNM = aMR + (p0.z & 0xffffu);
-            const uint32_t aAM = aMR + (p0.z >> 16);
-            const uint32_t aBM = aMR + (p0.w & 0xffffu);
-            const uint32_t aEI = aIDR + (p0.w >> 16);
-            const uint32_t aNI = aIDR + p1.x;
+            // row addresses of diagonal 0
+            const uint32_t aNM = aK0 + (p0.z & 0xffffu);
+            const uint32_t aAM = AIM_ROW(p0.z >> 16);
+            const uint32_t aBM = AIM_ROW(p0.w & 0xffffu);
+            const uint32_t aEI = AIM_ROW(p0.w >> 16);
+            const uint32_t aED = AIM_ROW(p1.x & 0xffffu);
+            const uint32_t aNI = aK0 + (p1.x >> 16);
+            const uint32_t aND = aK0 + (p1.z & 0xffffu);
             uint2 *hC = BT ? arena + p1.y - lo_s : nullptr;  // arena cells of this score, indexed by k
 
-            // ---- compute_offsets (wfa.c:238-273) fused with extend (wfa.c:193-215) ----
-            int md = max(pl, tl);
-            bool hit_end = false;
-            if (!done) {
-                for (int k = lo + sl; k <= hi; k += G) {
-                    const uint32_t k2 = (uint32_t)(k * 2);
-                    int m = 0, ins = -10, del = -10;
-                    if (s > 0) {
-                        int sb = -10;
-                        if (has_i) {
-                            const int g = in_range(k - 1, b_lo, b_hi) ? lds_s16(aBM + k2 - 2) : kNull;
-                            const int ii = (!ie_null && in_range(k - 1, e_lo, e_hi)) ? lds_s16(aEI + k2 - 2) : kNull;
-                            ins = (g == kNull && ii == kNull) ? kNull : (int)(short)(max(g, ii) + 1);
-                            sts_u16(aNI + k2, ins);
-                        }
-                        if (has_d) {
-                            const int g = in_range(k + 1, b_lo, b_hi) ? lds_s16(aBM + k2 + 2) : kNull;
-                            const int dd = (!de_null && in_range(k + 1, e_lo, e_hi)) ? lds_s16(aEI + CW2 + k2 + 2) : kNull;
-                            del = max(g, dd);
-                            sts_u16(aNI + CW2 + k2, del);
-                        }
-                        if (!sub_null) sb = in_range(k, a_lo, a_hi) ? (int)(short)(lds_s16(aAM + k2) + 1) : kNull;
-                        m = max(del, max(sb, ins));
+            // ---- keep the frame: NULL what the rows' previous occupants left outside [lo,hi] ----
+            {
+                const uint32_t prevM = p1.z >> 16, prevID = p1.w & 0xffffu;
+                int plo = 1, phi = -1, qlo = 1, qhi = -1;
+                if (prevM != OFF_NULL) {
+                    if (REDUCE) { const uint32_t w = lds_u32(aDyn + prevM * 4u); plo = lo16(w); phi = hi16s(w); }
+                    else { const uint32_t w = lds_u32(aPlan + prevM * (PLAN_WORDS * 4) + 4); plo = lo16(w); phi = plo + (int)(w >> 16) - 1; }
+                }
+                if (prevID != OFF_NULL) {
+                    if (REDUCE) { const uint32_t w = lds_u32(aDyn + prevID * 4u); qlo = lo16(w); qhi = hi16s(w); }
+                    else { const uint32_t w = lds_u32(aPlan + prevID * (PLAN_WORDS * 4) + 4); qlo = lo16(w); qhi = qlo + (int)(w >> 16) - 1; }
+                }
+                const bool left = !done && ((plo <= phi && (plo < lo || phi > hi)) || (qlo <= qhi && (qlo < lo || qhi > hi)));
+                if (__any_sync(kFull, left)) {
+                    if (left) {
+                        for (int k = plo + sl; k <= phi; k += G)
+                            if (k < lo || k > hi) sts_u16(aNM + (uint32_t)(k * 2), kNull);
+                        for (int k = qlo + sl; k <= qhi; k += G)
+                            if (k < lo || k > hi) { sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull); }
                     }
+                }
+            }
+
+            // ---- compute_offsets (wfa.c:238-273) fused with extend (wfa.c:193-215); no range tests: see the header ----
+            int md = max(pl, tl);
+            if (!done) {
+                // one cell: diagonal k, row byte offset k2 = 2k, arena cell pointer hp
+                auto cell = [&](const int k, const uint32_t k2, uint2 *hp) {
+                    const int g1 = lds_s16(aBM + k2 - 2), ii = lds_s16(aEI + k2 - 2);
+                    const int g2 = lds_s16(aBM + k2 + 2), dd = lds_s16(aED + k2 + 2);
+                    const int sb = lds_s16(aAM + k2) + 1;
+                    const int t = max(g1, ii) + 1;
+                    const int ins = t == kNull + 1 ? kNull : t;  // both NULL -> NULL (wfa.c:249-252)
+                    const int del = max(g2, dd);
+                    int m = max(max(del, sb), max(ins, floor_m));
+                    sts_u16(aNI + k2, ins);
+                    sts_u16(aND + k2, del);
                     const int v = m - k;
                     if ((m | v) >= 0) {
                         const int lim = min(pl - v, tl - m);
-                        if (lim > 0) m += packed ? match_packed_s(aP, aT, v, m, lim) : match_bytes(gp, gt, v, m, lim);
+                        if (lim > 0) m += packed ? extend_dup(aP, aT, v, m, lim) : match_bytes(gp, gt, v, m, lim);
                     }
                     sts_u16(aNM + k2, m);
-                    if (BT) hC[k] = make_uint2(((uint32_t)m & 0xffffu) | ((uint32_t)ins << 16), (uint32_t)del & 0xffffu);
-                    if (REDUCE) md = min(md, max(pl - (m - k), tl - m));
-                    if (k == ak && m >= tl) hit_end = true;
+                    if (BT) *hp = make_uint2(((uint32_t)m & 0xffffu) | ((uint32_t)ins << 16), (uint32_t)del & 0xffffu);
+                    if (REDUCE) md = min(md, max(pl + k, tl) - m);
+                };
+                uint2 *hp = BT ? hC + (lo + sl) : nullptr;
+                int k = lo + sl;
+                for (; k + G <= hi; k += 2 * G, hp += 2 * G) {  // two cells per trip: independent chains, shared address math
+                    const uint32_t k2 = (uint32_t)(k * 2);
+                    cell(k, k2, hp);
+                    cell(k + G, k2 + 2 * G, hp + G);
                 }
+                if (k <= hi) cell(k, (uint32_t)(k * 2), hp);
             }
+            __syncwarp();
             // ---- end reached (wfa.c:217-237).  Trimming never removes diagonal ak, so testing before the
             // reduction is equivalent, and the finishing wavefront's trimmed range is never read again. ----
-            const uint32_t eb = __ballot_sync(kFull, hit_end);
-            if (!done && ((eb >> subshift) & GM)) { done = true; reached = true; fscore = s; }
+            if (!done && in_range(ak, lo, hi) && lds_s16(aNM + (uint32_t)(ak * 2)) >= tl) { done = true; reached = true; fscore = s; }
             if (__all_sync(kFull, done)) break;
 
             // ---- adaptive reduction (wfa.c:70-141) on the pairs still running ----
             if (REDUCE) {
-                __syncwarp();
                 const bool wide = !done && (hi - lo + 1) >= 10;
                 int newlo = lo, newhi = hi;
                 if (__any_sync(kFull, wide)) {
                     md = group_min<G>(md);
                     const int top_limit = min(ak - 1, hi);
                     // Quick exit: the two scans below stop at their first cell when both END diagonals are already
-                    // within the distance threshold - the normal case for short reads, where nothing is ever trimmed.
+                    // within the distance threshold.
                     bool quick = true;
                     if (wide) {
                         if (lo < top_limit) {
@@ -267,33 +336,44 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
                         }
                     }
                     if (!__all_sync(kFull, quick)) {
-                    bool pend = wide && lo < top_limit;
-                    if (pend) newlo = top_limit;
-                    for (int c = 0; __any_sync(kFull, pend && (lo + c < top_limit)); c += G) {
-                        const int k = lo + c + sl;
-                        bool hit = false;
-                        if (pend && k < top_limit) {
-                            const int off = lds_s16(aNM + (uint32_t)(k * 2));
-                            hit = (max(pl - (off - k), tl - off) - md) <= 50;
+                        constexpr uint32_t GM = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+                        const int subshift = sub * G;
+                        bool pend = wide && lo < top_limit;
+                        if (pend) newlo = top_limit;
+                        for (int c = 0; __any_sync(kFull, pend && (lo + c < top_limit)); c += G) {
+                            const int k = lo + c + sl;
+                            bool hit = false;
+                            if (pend && k < top_limit) {
+                                const int off = lds_s16(aNM + (uint32_t)(k * 2));
+                                hit = (max(pl - (off - k), tl - off) - md) <= 50;
+                            }
+                            const uint32_t mine = (__ballot_sync(kFull, hit) >> subshift) & GM;
+                            if (pend && mine) { newlo = lo + c + __ffs(mine) - 1; pend = false; }
+                            if (lo + c + G >= top_limit) pend = false;
                         }
-                        const uint32_t mine = (__ballot_sync(kFull, hit) >> subshift) & GM;
-                        if (pend && mine) { newlo = lo + c + __ffs(mine) - 1; pend = false; }
-                        if (lo + c + G >= top_limit) pend = false;
-                    }
-                    const int bottom_limit = max(ak + 1, newlo);
-                    pend = wide && hi > bottom_limit;
-                    if (pend) newhi = bottom_limit;
-                    for (int c = 0; __any_sync(kFull, pend && (hi - c > bottom_limit)); c += G) {
-                        const int k = hi - c - sl;
-                        bool hit = false;
-                        if (pend && k > bottom_limit) {
-                            const int off = lds_s16(aNM + (uint32_t)(k * 2));
-                            hit = (max(pl - (off - k), tl - off) - md) <= 50;
+                        const int bottom_limit = max(ak + 1, newlo);
+                        pend = wide && hi > bottom_limit;
+                        if (pend) newhi = bottom_limit;
+                        for (int c = 0; __any_sync(kFull, pend && (hi - c > bottom_limit)); c += G) {
+                            const int k = hi - c - sl;
+                            bool hit = false;
+                            if (pend && k > bottom_limit) {
+                                const int off = lds_s16(aNM + (uint32_t)(k * 2));
+                                hit = (max(pl - (off - k), tl - off) - md) <= 50;
+                            }
+                            const uint32_t mine = (__ballot_sync(kFull, hit) >> subshift) & GM;
+                            if (pend && mine) { newhi = hi - c - (__ffs(mine) - 1); pend = false; }
+                            if (hi - c - G <= bottom_limit) pend = false;
                         }
-                        const uint32_t mine = (__ballot_sync(kFull, hit) >> subshift) & GM;
-                        if (pend && mine) { newhi = hi - c - (__ffs(mine) - 1); pend = false; }
-                        if (hi - c - G <= bottom_limit) pend = false;
-                    }
+                        // keep the frame: the cells the trim cut off read as NULL from now on
+                        if (wide) {
+                            for (int k = lo + sl; k < newlo; k += G) {
+                                sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull);
+                            }
+                            for (int k = newhi + 1 + sl; k <= hi; k += G) {
+                                sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull);
+                            }
+                        }
                     }
                 }
                 if (sl == 0 && !done) sts_u32(aDyn + (uint32_t)s * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)newhi << 16));
@@ -414,6 +494,7 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
         }
         __syncwarp();
     }
+#undef AIM_ROW
 }
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
@@ -469,30 +550,39 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     const uint32_t ring_m = (uint32_t)std::max(x, o + e) + 1, ring_e = (uint32_t)e + 1;
     SubK K{};
-    K.cw = round_up((uint32_t)(kmax - kmin + 3), 2);
+    K.cw = round_up((uint32_t)(kmax - kmin + 3), 8);  // one frame cell on both sides; rows are 16-byte multiples
     K.koff = 1 - kmin;
-    K.mring_bytes = ring_m * K.cw * 2;
-    const uint32_t idring_bytes = ring_e * 2 * K.cw * 2;
-    if (K.mring_bytes > 0xfff0u || idring_bytes > 0xfff0u) return 1;
+    const uint32_t row_bytes = K.cw * 2;
+    const uint32_t rows_bytes = (ring_m + 2 * ring_e) * row_bytes;
+    if (rows_bytes > 0xfff0u) return 1;
+    K.rows_v4 = rows_bytes / 16;
     K.plan_words = (uint32_t)PLAN_WORDS * ((uint32_t)MS + 1);
     std::vector<uint32_t> plan(K.plan_words, 0u);
     uint64_t arena_cells = 0;
-    auto m_off = [&](int s) -> uint32_t { return s < 0 ? 0u : ((uint32_t)s % ring_m) * K.cw * 2u; };
-    auto id_off = [&](int s) -> uint32_t { return s < 0 ? 0u : ((uint32_t)s % ring_e) * 2u * K.cw * 2u; };
+    // rows: M ring, then I ring, then D ring
+    auto m_off = [&](int s) -> uint32_t { return ((uint32_t)s % ring_m) * row_bytes; };
+    auto i_off = [&](int s) -> uint32_t { return (ring_m + (uint32_t)s % ring_e) * row_bytes; };
+    auto d_off = [&](int s) -> uint32_t { return (ring_m + ring_e + (uint32_t)s % ring_e) * row_bytes; };
+    std::vector<uint32_t> last_m(ring_m, OFF_NULL), last_id(ring_e, OFF_NULL);  // score whose cells sit in each row
     for (int s = 0; s <= MS; ++s) {
         if (!w[s].present) continue;
         uint32_t *q = &plan[(size_t)s * PLAN_WORDS];
         const bool A = s - x >= 0 && w[s - x].present, B = s - o - e >= 0 && w[s - o - e].present, E = s - e >= 0 && w[s - e].present;
         const bool ie_null = !(E && w[s - e].has_i), de_null = !(E && w[s - e].has_d);
         const uint32_t width = (uint32_t)(w[s].hi - w[s].lo + 1);
+        // the reference's -10 for a missing I / D / sub candidate (wfa.c:243,255,266) is a floor under the max; score 0 starts at offset 0
+        const int floor_m = s == 0 ? 0 : ((!A || !w[s].has_i || !w[s].has_d) ? -10 : -32768);
         q[0] = P_PRESENT | (A ? 0u : P_SUB_NULL) | (B ? 0u : P_O_NULL) | (ie_null ? P_IE_NULL : 0u) | (de_null ? P_DE_NULL : 0u) |
-               (w[s].has_i ? P_HAS_I : 0u) | (w[s].has_d ? P_HAS_D : 0u);
+               (w[s].has_i ? P_HAS_I : 0u) | (w[s].has_d ? P_HAS_D : 0u) | (((uint32_t)floor_m & 0xffffu) << 16);
         q[1] = ((uint32_t)w[s].lo & 0xffffu) | (width << 16);
-        q[2] = m_off(s) | (m_off(s - x) << 16);
-        q[3] = m_off(s - o - e) | (id_off(s - e) << 16);
-        q[4] = id_off(s);
+        q[2] = m_off(s) | ((A ? m_off(s - x) : OFF_NULL) << 16);
+        q[3] = (B ? m_off(s - o - e) : OFF_NULL) | ((ie_null ? OFF_NULL : i_off(s - e)) << 16);
+        q[4] = (de_null ? OFF_NULL : d_off(s - e)) | (i_off(s) << 16);
         q[5] = (uint32_t)arena_cells;
-        q[6] = A ? (((uint32_t)w[s - x].lo & 0xffffu) | ((uint32_t)w[s - x].hi << 16)) : (1u | (0xffffu << 16));
+        q[6] = d_off(s) | (last_m[(uint32_t)s % ring_m] << 16);
+        q[7] = last_id[(uint32_t)s % ring_e];
+        last_m[(uint32_t)s % ring_m] = (uint32_t)s;
+        last_id[(uint32_t)s % ring_e] = (uint32_t)s;
         arena_cells += width;
     }
     if (arena_cells > 0x0fffffffu) return 1;
@@ -500,27 +590,25 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     K.plen = a.plen; K.tlen = a.tlen; K.patterns = a.patterns; K.texts = a.texts;
     K.results = a.results; K.ops = a.ops; K.n = a.n; K.idx_base = a.idx_base;
     K.x = x; K.o = o; K.e = e; K.max_score = MS; K.read_size = p.read_size;
-    K.seq_words = round_up((uint32_t)p.read_size / 16 + 2, 4);
+    K.seq_entries = round_up((uint32_t)p.read_size / 16 + 2, 2);
     K.dyn_words = p.reduce ? round_up((uint32_t)MS + 1, 4) : 0;
-    const uint32_t pair_words_raw = 2 * K.seq_words + K.dyn_words + round_up(K.mring_bytes + idring_bytes, 16) / 4;
+    const uint32_t pair_words_raw = 4 * K.seq_entries + K.dyn_words + rows_bytes / 4;
 
-    // lanes per pair; env override for tuning
     // lanes per pair: wavefronts are about MAX_SCORE diagonals wide on average; a few iterations per score keeps the
-    // lanes busy while the per-score bookkeeping is shared by 32/G pairs (measured at config 4: G=4 193 M, G=8 178 M,
-    // G=16 143 M pairs/s)
+    // lanes busy while the per-score bookkeeping is shared by 32/G pairs; env override for tuning
     int G = MS <= 40 ? 4 : MS <= 100 ? 8 : MS <= 300 ? 16 : 32;
     if (const char *gs = getenv("AIM_WFA_G")) { int g = atoi(gs); if (g == 4 || g == 8 || g == 16 || g == 32) G = g; }
     const int PPW = 32 / G;
-    {   // stagger the pair slots of one warp over the banks: slot stride == 32/PPW words (mod 32)
+    {   // stagger the pair slots of one warp over the banks: slot stride == 32/PPW words (mod 32); slots stay 16-byte aligned
         const uint32_t want = PPW > 1 ? std::max(4u, 32u / (uint32_t)PPW) : 0u;
         K.pair_words = pair_words_raw + ((want + 32u - pair_words_raw % 32u) % 32u);
     }
     const uint32_t kSmemBudget = 227u * 1024u, kSmemPerSm = 228u * 1024u, kBlockReserve = 1024u;
     const size_t pair_bytes = (size_t)K.pair_words * 4;
-    const size_t plan_bytes = (size_t)K.plan_words * 4;
+    const size_t fixed_bytes = (size_t)K.plan_words * 4 + row_bytes;  // plan + the all-NULL row
     int warps_per_block = G == 4 ? 2 : 4;
     if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v == 1 || v == 2 || v == 4) warps_per_block = v; }
-    size_t smem_block = plan_bytes + (size_t)warps_per_block * PPW * pair_bytes;
+    size_t smem_block = fixed_bytes + (size_t)warps_per_block * PPW * pair_bytes;
     if (smem_block > kSmemBudget / 3) return 1;  // too few warps/SM would fit: leave it to the long-read kernel
     int blocks_per_sm = (int)std::min<uint32_t>(kSmemPerSm / ((uint32_t)smem_block + kBlockReserve), 32u);
     int max_warps = 48;
@@ -533,15 +621,33 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     const uint64_t total_slots = (uint64_t)grid * warps_per_block * PPW;
 
-    // device copies: plan + (BT) history arena
+    // device scratch: plan | non-ACGT flags | packed windows | (BT) history arena
+    const size_t plan_bytes = (size_t)K.plan_words * 4;
     const size_t plan_dev = (plan_bytes + 255) / 256 * 256;
+    const size_t flags_dev = ((size_t)a.n + 255) / 256 * 256;
+    const size_t packed_dev = ((size_t)a.n * 2 * K.seq_entries * 8 + 255) / 256 * 256;
     K.arena_stride = p.backtrace ? (size_t)round_up((uint32_t)arena_cells, 16) : 0;
     const size_t arena_bytes = (size_t)total_slots * K.arena_stride * 8;
-    int rc = scratch_reserve(sc, plan_dev + arena_bytes);
+    int rc = scratch_reserve(sc, plan_dev + flags_dev + packed_dev + arena_bytes);
     if (rc != AIM_OK) return rc;
-    cudaError_t err = cudaMemcpyAsync(sc->buf, plan.data(), plan_bytes, cudaMemcpyHostToDevice, stream);
-    K.plan = reinterpret_cast<const uint32_t *>(sc->buf);
-    K.arena = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(sc->buf) + plan_dev);
+    unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
+    uint8_t *flags = base + plan_dev;
+    uint2 *packed = reinterpret_cast<uint2 *>(base + plan_dev + flags_dev);
+    K.plan = reinterpret_cast<const uint32_t *>(base);
+    K.flags = flags;
+    K.packed = reinterpret_cast<const uint4 *>(packed);
+    K.arena = reinterpret_cast<uint2 *>(base + plan_dev + flags_dev + packed_dev);
+    cudaError_t err = cudaMemcpyAsync(base, plan.data(), plan_bytes, cudaMemcpyHostToDevice, stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(flags, 0, flags_dev, stream);
+    if (err == cudaSuccess && p.backtrace)  // op rows: 'M' everywhere (wfa.c:499-501); the backtrace overwrites the few edits
+        err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * (size_t)p.read_size, stream);
+    if (err == cudaSuccess) {
+        const uint64_t total = (uint64_t)a.n * 2 * K.seq_entries;
+        const int pgrid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sc->sm_count * 64);
+        wfa_prep_kernel<<<pgrid, 256, 0, stream>>>(a.patterns, a.texts, a.plen, a.tlen, a.n, p.read_size, K.seq_entries, packed, flags);
+        err = cudaGetLastError();
+        if (launches) ++*launches;
+    }
     if (err == cudaSuccess) {
         const int block = warps_per_block * 32;
         if (G == 4) err = launch_g<4>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
