@@ -32,6 +32,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -44,11 +45,13 @@ namespace aim {
 namespace {
 
 // plan flags
-constexpr uint32_t P_PRESENT = 1, P_SUB_NULL = 2, P_O_NULL = 4, P_IE_NULL = 8, P_DE_NULL = 16, P_HAS_I = 32, P_HAS_D = 64;
+constexpr uint32_t P_PRESENT = 1, P_SUB_NULL = 2, P_O_NULL = 4, P_IE_NULL = 8, P_DE_NULL = 16, P_HAS_I = 32, P_HAS_D = 64, P_NULL_ROW = 128;
 constexpr int PLAN_WORDS = 8;
+constexpr uint32_t kNoRange = 0x7fff7fffu;  // {lo, -hi} of an empty range: neutral for the packed min
 constexpr uint32_t OFF_NULL = 0xffffu;  // row offset meaning "the block-wide all-NULL row"; also "no score"
 // per-score plan: w0 flags | floor (int16) << 16
-//                 w1 lo_s (int16) | width_s << 16        static range of the wavefront
+//                 w1 lo_s (int16) | (-hi_s) << 16        static range of the wavefront (ranges are kept as {lo, -hi}
+//                                                        so that one packed min() merges them)
 //                 w2 row offset of this score's M row   | of score s-x's M row << 16
 //                 w3 row offset of score s-o-e's M row  | of score s-e's I row << 16
 //                 w4 row offset of score s-e's D row    | of this score's I row << 16
@@ -65,7 +68,7 @@ struct SubK {
     aim_result *results;
     char *ops;
     const uint4 *packed;    // wfa_prep_kernel's output: per pair seq_entries 8-byte entries of the pattern, then of the text
-    const uint8_t *flags;   // per pair: 1 = a byte outside {A,C,G,T} inside the sequences (compare raw bytes)
+    const uint32_t *flags;  // one bit per pair: a byte outside {A,C,G,T} inside the sequences -> the pair is on the hand-over list
     const uint32_t *plan;   // device copy of the plan
     uint2 *arena;           // history arena (BT only): {M | I << 16, D} per (score, diagonal)
     size_t arena_stride;    // cells per pair slot
@@ -119,8 +122,11 @@ __device__ __forceinline__ uint32_t pack16(const char *row, int b, int len, int 
 }
 
 // One thread per (pair, sequence, window entry): entry j = {bases 16j..16j+15, bases 16j+16..16j+31}.  HBM-bound.
+// A pair holding a byte outside {A,C,G,T} (the reference compares raw bytes, wfa.c:209) cannot be 2-bit packed: it is
+// flagged and listed once for the warp-per-pair kernel of aim_wfa.cu, which compares bytes.
 __global__ void __launch_bounds__(256) wfa_prep_kernel(const char *patterns, const char *texts, const int32_t *plen, const int32_t *tlen,
-                                                       uint32_t n, int RS, uint32_t SE, uint2 *packed, uint8_t *flags)
+                                                       uint32_t n, int RS, uint32_t SE, uint2 *packed, uint32_t *flags,
+                                                       uint32_t *list, uint32_t *list_count)
 {
     const uint64_t total = (uint64_t)n * 2u * SE;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
@@ -134,19 +140,25 @@ __global__ void __launch_bounds__(256) wfa_prep_kernel(const char *patterns, con
         e.x = pack16(row, (int)j * 16, len, RS, &ok);
         e.y = pack16(row, (int)j * 16 + 16, len, RS, &ok);
         packed[t] = e;
-        if (!ok) flags[i] = 1;
+        if (!ok && !(atomicOr(&flags[i >> 5], 1u << (i & 31)) & (1u << (i & 31)))) list[atomicAdd(list_count, 1u)] = i;  // first to flag it
     }
 }
 
-// equal bases from pattern[v], text[h], at most lim (> 0); aP/aT = shared addresses of the 8-byte window entries
-__device__ __forceinline__ int extend_dup(uint32_t aP, uint32_t aT, int v, int h, int lim)
+// Extend offset m on diagonal k (wfa.c:193-215): the number of equal bases from pattern[v = m - k], text[m] while both
+// stay inside the sequences; 0 for a negative offset or v.  aP/aT = shared addresses of the 8-byte window entries.
+// Branch-free for the first 16-base window (nearly every call ends inside it); longer runs take the loop.
+__device__ __forceinline__ int extend_dup(uint32_t aP, uint32_t aT, int k, int m, int pl, int tl)
 {
-    const uint2 x = lds_v2(aP + ((uint32_t)(v >> 4) << 3)), y = lds_v2(aT + ((uint32_t)(h >> 4) << 3));
-    const uint32_t d = __funnelshift_l(x.y, x.x, 2 * v) ^ __funnelshift_l(y.y, y.x, 2 * h);
+    const int v = m - k;
+    const bool ok = (m | v) >= 0;
+    const int lim = ok ? min(pl - v, tl - m) : 0;
+    const int vc = max(v, 0), hc = max(m, 0);  // any in-buffer window will do when !ok
+    const uint2 x = lds_v2(aP + ((uint32_t)(vc >> 4) << 3)), y = lds_v2(aT + ((uint32_t)(hc >> 4) << 3));
+    const uint32_t d = __funnelshift_l(x.y, x.x, 2 * vc) ^ __funnelshift_l(y.y, y.x, 2 * hc);
     int cnt = __clz(d) >> 1;  // 16 when the whole window matches
     if (d == 0 && lim > 16) {
         for (;;) {
-            const int pv = v + cnt, ph = h + cnt;
+            const int pv = v + cnt, ph = m + cnt;
             const uint2 x2 = lds_v2(aP + ((uint32_t)(pv >> 4) << 3)), y2 = lds_v2(aT + ((uint32_t)(ph >> 4) << 3));
             const uint32_t d2 = __funnelshift_l(x2.y, x2.x, 2 * pv) ^ __funnelshift_l(y2.y, y2.x, 2 * ph);
             if (d2) { cnt += __clz(d2) >> 1; break; }
@@ -154,9 +166,16 @@ __device__ __forceinline__ int extend_dup(uint32_t aP, uint32_t aT, int v, int h
             if (cnt >= lim) break;
         }
     }
-    return min(cnt, lim);
+    return max(min(cnt, lim), 0);
 }
 
+template <int G>
+__device__ __forceinline__ int group_max(int v)
+{
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(kFull, v, d));
+    return v;
+}
 template <int G>
 __device__ __forceinline__ int group_min(int v)
 {
@@ -205,11 +224,9 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
 
     for (uint32_t base_i = 0; base_i < K.n; base_i += nslots) {  // warp-uniform trip count
         const uint32_t i = base_i + slot_global;
-        const bool active = i < K.n;
+        const bool active = i < K.n && !((K.flags[i >> 5] >> (i & 31)) & 1u);  // flagged pairs go to the warp-per-pair kernel
         const int pl = active ? min(max(K.plen[i], 0), RS) : 0;
         const int tl = active ? min(max(K.tlen[i], 0), RS) : 0;
-        const char *gp = K.patterns + (size_t)(active ? i : 0) * RS;
-        const char *gt = K.texts + (size_t)(active ? i : 0) * RS;
         char *gops = BT ? K.ops + (size_t)(active ? i : 0) * 2 * RS : nullptr;
         const int ak = tl - pl;
 
@@ -218,7 +235,6 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
             const uint4 *src = K.packed + (size_t)i * K.seq_entries;
             for (uint32_t c = sl; c < K.seq_entries; c += G) sts_v4(aP + c * 16u, __ldg(src + c));
         }
-        const bool packed = active ? (K.flags[i] == 0) : true;
         for (uint32_t c = sl; c < K.rows_v4; c += G) sts_v4(aRows + c * 16u, null4);
         __syncwarp();
 
@@ -234,41 +250,36 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
             const int floor_m = hi16s(fl);
             const int lo_s = lo16(p0.y);
 
-            // this pair's range (wfa.c:318-343): from the (trimmed) ranges of the source wavefronts
-            int lo = lo_s, hi = lo_s + (int)(p0.y >> 16) - 1;
+            // this pair's range (wfa.c:318-343): from the (trimmed) ranges of the source wavefronts; ranges are {lo, -hi}
+            uint32_t rng = p0.y;
             if (REDUCE && s > 0) {
-                int a_lo = 1, a_hi = -1, b_lo = 1, b_hi = -1, e_lo = 1, e_hi = -1;
-                if (!(fl & P_SUB_NULL)) { const uint32_t w = lds_u32(aDyn + (uint32_t)(s - X) * 4u); a_lo = lo16(w); a_hi = hi16s(w); }
-                if (!(fl & P_O_NULL)) { const uint32_t w = lds_u32(aDyn + (uint32_t)(s - OE) * 4u); b_lo = lo16(w); b_hi = hi16s(w); }
-                if ((fl & (P_IE_NULL | P_DE_NULL)) != (P_IE_NULL | P_DE_NULL)) { const uint32_t w = lds_u32(aDyn + (uint32_t)(s - E) * 4u); e_lo = lo16(w); e_hi = hi16s(w); }
-                lo = min(min(a_lo, b_lo), e_lo) - 1;
-                hi = max(max(a_hi, b_hi), e_hi) + 1;
+                uint32_t ra = kNoRange, rb = kNoRange, re = kNoRange;
+                if (!(fl & P_SUB_NULL)) ra = lds_u32(aDyn + (uint32_t)(s - X) * 4u);
+                if (!(fl & P_O_NULL)) rb = lds_u32(aDyn + (uint32_t)(s - OE) * 4u);
+                if ((fl & (P_IE_NULL | P_DE_NULL)) != (P_IE_NULL | P_DE_NULL)) re = lds_u32(aDyn + (uint32_t)(s - E) * 4u);
+                rng = __vadd2(__vimin3_s16x2(ra, rb, re), 0xffffffffu);  // {min lo - 1, -(max hi + 1)}
             }
+            const int lo = lo16(rng), hi = -hi16s(rng);
             // row addresses of diagonal 0
             const uint32_t aNM = aK0 + (p0.z & 0xffffu);
-            const uint32_t aAM = AIM_ROW(p0.z >> 16);
-            const uint32_t aBM = AIM_ROW(p0.w & 0xffffu);
-            const uint32_t aEI = AIM_ROW(p0.w >> 16);
-            const uint32_t aED = AIM_ROW(p1.x & 0xffffu);
+            uint32_t aAM = aK0 + (p0.z >> 16), aBM = aK0 + (p0.w & 0xffffu), aEI = aK0 + (p0.w >> 16), aED = aK0 + (p1.x & 0xffffu);
+            if (fl & P_NULL_ROW) {  // early scores only: a missing source reads the all-NULL row
+                aAM = AIM_ROW(p0.z >> 16); aBM = AIM_ROW(p0.w & 0xffffu); aEI = AIM_ROW(p0.w >> 16); aED = AIM_ROW(p1.x & 0xffffu);
+            }
             const uint32_t aNI = aK0 + (p1.x >> 16);
             const uint32_t aND = aK0 + (p1.z & 0xffffu);
-            uint2 *hC = BT ? arena + p1.y - lo_s : nullptr;  // arena cells of this score, indexed by k
 
             // ---- keep the frame: NULL what the rows' previous occupants left outside [lo,hi] ----
             {
                 const uint32_t prevM = p1.z >> 16, prevID = p1.w & 0xffffu;
-                int plo = 1, phi = -1, qlo = 1, qhi = -1;
-                if (prevM != OFF_NULL) {
-                    if (REDUCE) { const uint32_t w = lds_u32(aDyn + prevM * 4u); plo = lo16(w); phi = hi16s(w); }
-                    else { const uint32_t w = lds_u32(aPlan + prevM * (PLAN_WORDS * 4) + 4); plo = lo16(w); phi = plo + (int)(w >> 16) - 1; }
-                }
-                if (prevID != OFF_NULL) {
-                    if (REDUCE) { const uint32_t w = lds_u32(aDyn + prevID * 4u); qlo = lo16(w); qhi = hi16s(w); }
-                    else { const uint32_t w = lds_u32(aPlan + prevID * (PLAN_WORDS * 4) + 4); qlo = lo16(w); qhi = qlo + (int)(w >> 16) - 1; }
-                }
-                const bool left = !done && ((plo <= phi && (plo < lo || phi > hi)) || (qlo <= qhi && (qlo < lo || qhi > hi)));
+                uint32_t pr = kNoRange, qr = kNoRange;
+                if (prevM != OFF_NULL) pr = REDUCE ? lds_u32(aDyn + prevM * 4u) : lds_u32(aPlan + prevM * (PLAN_WORDS * 4) + 4);
+                if (prevID != OFF_NULL) qr = REDUCE ? lds_u32(aDyn + prevID * 4u) : lds_u32(aPlan + prevID * (PLAN_WORDS * 4) + 4);
+                // {lo,-hi} inside this range <=> elementwise >= ; an empty previous range is kNoRange
+                const bool left = !done && (__vmins2(pr, rng) != rng || __vmins2(qr, rng) != rng);
                 if (__any_sync(kFull, left)) {
                     if (left) {
+                        const int plo = lo16(pr), phi = -hi16s(pr), qlo = lo16(qr), qhi = -hi16s(qr);
                         for (int k = plo + sl; k <= phi; k += G)
                             if (k < lo || k > hi) sts_u16(aNM + (uint32_t)(k * 2), kNull);
                         for (int k = qlo + sl; k <= qhi; k += G)
@@ -291,16 +302,12 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
                     int m = max(max(del, sb), max(ins, floor_m));
                     sts_u16(aNI + k2, ins);
                     sts_u16(aND + k2, del);
-                    const int v = m - k;
-                    if ((m | v) >= 0) {
-                        const int lim = min(pl - v, tl - m);
-                        if (lim > 0) m += packed ? extend_dup(aP, aT, v, m, lim) : match_bytes(gp, gt, v, m, lim);
-                    }
+                    m += extend_dup(aP, aT, k, m, pl, tl);
                     sts_u16(aNM + k2, m);
                     if (BT) *hp = make_uint2(((uint32_t)m & 0xffffu) | ((uint32_t)ins << 16), (uint32_t)del & 0xffffu);
                     if (REDUCE) md = min(md, max(pl + k, tl) - m);
                 };
-                uint2 *hp = BT ? hC + (lo + sl) : nullptr;
+                uint2 *hp = BT ? arena + (p1.y + (uint32_t)(lo + sl - lo_s)) : nullptr;  // arena cell of (s, k)
                 int k = lo + sl;
                 for (; k + G <= hi; k += 2 * G, hp += 2 * G) {  // two cells per trip: independent chains, shared address math
                     const uint32_t k2 = (uint32_t)(k * 2);
@@ -316,67 +323,40 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
             if (__all_sync(kFull, done)) break;
 
             // ---- adaptive reduction (wfa.c:70-141) on the pairs still running ----
+            // The reference scans up from lo and down from hi and stops at the first diagonal within 50 of the minimum
+            // distance (or at its limit).  Here every lane scans its OWN cells (stride G) from both ends; the first
+            // stopping diagonal overall is the min (max) of the lanes' first stopping cells.
             if (REDUCE) {
                 const bool wide = !done && (hi - lo + 1) >= 10;
                 int newlo = lo, newhi = hi;
                 if (__any_sync(kFull, wide)) {
-                    md = group_min<G>(md);
+                    md = group_min<G>(md) + 50;  // keep while distance <= md
                     const int top_limit = min(ak - 1, hi);
-                    // Quick exit: the two scans below stop at their first cell when both END diagonals are already
-                    // within the distance threshold.
-                    bool quick = true;
+                    const int kf = lo + sl;
+                    const int kl = hi - ((hi - kf) & (G - 1));  // this lane's last cell (when kf <= hi)
+                    int kb = kf;
+                    if (wide)
+                        while (kb < top_limit && (max(pl + kb, tl) - lds_s16(aNM + (uint32_t)(kb * 2))) > md) kb += G;
+                    kb = group_min<G>(kb);
+                    if (wide) newlo = max(lo, min(kb, top_limit));
+                    const int bottom_limit = max(ak + 1, newlo);
+                    int kt = kf <= hi ? kl : INT_MIN;
+                    if (wide)
+                        while (kt > bottom_limit && (max(pl + kt, tl) - lds_s16(aNM + (uint32_t)(kt * 2))) > md) kt -= G;
+                    kt = group_max<G>(kt);
                     if (wide) {
-                        if (lo < top_limit) {
-                            const int off = lds_s16(aNM + (uint32_t)(lo * 2));
-                            quick = (max(pl - (off - lo), tl - off) - md) <= 50;
-                        }
-                        if (quick && hi > max(ak + 1, lo)) {
-                            const int off = lds_s16(aNM + (uint32_t)(hi * 2));
-                            quick = (max(pl - (off - hi), tl - off) - md) <= 50;
-                        }
-                    }
-                    if (!__all_sync(kFull, quick)) {
-                        constexpr uint32_t GM = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
-                        const int subshift = sub * G;
-                        bool pend = wide && lo < top_limit;
-                        if (pend) newlo = top_limit;
-                        for (int c = 0; __any_sync(kFull, pend && (lo + c < top_limit)); c += G) {
-                            const int k = lo + c + sl;
-                            bool hit = false;
-                            if (pend && k < top_limit) {
-                                const int off = lds_s16(aNM + (uint32_t)(k * 2));
-                                hit = (max(pl - (off - k), tl - off) - md) <= 50;
-                            }
-                            const uint32_t mine = (__ballot_sync(kFull, hit) >> subshift) & GM;
-                            if (pend && mine) { newlo = lo + c + __ffs(mine) - 1; pend = false; }
-                            if (lo + c + G >= top_limit) pend = false;
-                        }
-                        const int bottom_limit = max(ak + 1, newlo);
-                        pend = wide && hi > bottom_limit;
-                        if (pend) newhi = bottom_limit;
-                        for (int c = 0; __any_sync(kFull, pend && (hi - c > bottom_limit)); c += G) {
-                            const int k = hi - c - sl;
-                            bool hit = false;
-                            if (pend && k > bottom_limit) {
-                                const int off = lds_s16(aNM + (uint32_t)(k * 2));
-                                hit = (max(pl - (off - k), tl - off) - md) <= 50;
-                            }
-                            const uint32_t mine = (__ballot_sync(kFull, hit) >> subshift) & GM;
-                            if (pend && mine) { newhi = hi - c - (__ffs(mine) - 1); pend = false; }
-                            if (hi - c - G <= bottom_limit) pend = false;
-                        }
+                        newhi = min(hi, max(kt, bottom_limit));
                         // keep the frame: the cells the trim cut off read as NULL from now on
-                        if (wide) {
-                            for (int k = lo + sl; k < newlo; k += G) {
-                                sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull);
-                            }
-                            for (int k = newhi + 1 + sl; k <= hi; k += G) {
-                                sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull);
-                            }
+                        for (int k = kf; k < newlo; k += G) {
+                            sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull);
                         }
+                        if (kf <= hi)
+                            for (int k = kl; k > newhi; k -= G) {
+                                sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull);
+                            }
                     }
                 }
-                if (sl == 0 && !done) sts_u32(aDyn + (uint32_t)s * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)newhi << 16));
+                if (sl == 0 && !done) sts_u32(aDyn + (uint32_t)s * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)(-newhi) << 16));
             }
             __syncwarp();
         }
@@ -417,22 +397,22 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
                     const uint32_t a = aPlan + (uint32_t)s_open * (PLAN_WORDS * 4);
                     go_f = lds_u32(a);
                     const uint32_t r = lds_u32(a + 4);
-                    go_base = lds_u32(a + 20); go_l0 = lo16(r); go_lo = go_l0; go_hi = go_l0 + (int)(r >> 16) - 1;
-                    if (REDUCE && (go_f & P_PRESENT)) { const uint32_t w = lds_u32(aDyn + (uint32_t)s_open * 4u); go_lo = lo16(w); go_hi = hi16s(w); }
+                    go_base = lds_u32(a + 20); go_l0 = lo16(r); go_lo = go_l0; go_hi = -hi16s(r);
+                    if (REDUCE && (go_f & P_PRESENT)) { const uint32_t w = lds_u32(aDyn + (uint32_t)s_open * 4u); go_lo = lo16(w); go_hi = -hi16s(w); }
                 }
                 if (s_ext >= 0) {
                     const uint32_t a = aPlan + (uint32_t)s_ext * (PLAN_WORDS * 4);
                     ge_f = lds_u32(a);
                     const uint32_t r = lds_u32(a + 4);
-                    ge_base = lds_u32(a + 20); ge_l0 = lo16(r); ge_lo = ge_l0; ge_hi = ge_l0 + (int)(r >> 16) - 1;
-                    if (REDUCE && (ge_f & P_PRESENT)) { const uint32_t w = lds_u32(aDyn + (uint32_t)s_ext * 4u); ge_lo = lo16(w); ge_hi = hi16s(w); }
+                    ge_base = lds_u32(a + 20); ge_l0 = lo16(r); ge_lo = ge_l0; ge_hi = -hi16s(r);
+                    if (REDUCE && (ge_f & P_PRESENT)) { const uint32_t w = lds_u32(aDyn + (uint32_t)s_ext * 4u); ge_lo = lo16(w); ge_hi = -hi16s(w); }
                 }
                 if (s_mis >= 0) {
                     const uint32_t a = aPlan + (uint32_t)s_mis * (PLAN_WORDS * 4);
                     mm_f = lds_u32(a);
                     const uint32_t r = lds_u32(a + 4);
-                    mm_base = lds_u32(a + 20); mm_l0 = lo16(r); mm_lo = mm_l0; mm_hi = mm_l0 + (int)(r >> 16) - 1;
-                    if (REDUCE && (mm_f & P_PRESENT)) { const uint32_t w = lds_u32(aDyn + (uint32_t)s_mis * 4u); mm_lo = lo16(w); mm_hi = hi16s(w); }
+                    mm_base = lds_u32(a + 20); mm_l0 = lo16(r); mm_lo = mm_l0; mm_hi = -hi16s(r);
+                    if (REDUCE && (mm_f & P_PRESENT)) { const uint32_t w = lds_u32(aDyn + (uint32_t)s_mis * 4u); mm_lo = lo16(w); mm_hi = -hi16s(w); }
                 }
                 int del_ext = kNull, del_open = kNull, ins_ext = kNull, ins_open = kNull, misms = kNull;
                 if (type != 1) {
@@ -573,8 +553,9 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         // the reference's -10 for a missing I / D / sub candidate (wfa.c:243,255,266) is a floor under the max; score 0 starts at offset 0
         const int floor_m = s == 0 ? 0 : ((!A || !w[s].has_i || !w[s].has_d) ? -10 : -32768);
         q[0] = P_PRESENT | (A ? 0u : P_SUB_NULL) | (B ? 0u : P_O_NULL) | (ie_null ? P_IE_NULL : 0u) | (de_null ? P_DE_NULL : 0u) |
-               (w[s].has_i ? P_HAS_I : 0u) | (w[s].has_d ? P_HAS_D : 0u) | (((uint32_t)floor_m & 0xffffu) << 16);
-        q[1] = ((uint32_t)w[s].lo & 0xffffu) | (width << 16);
+               (w[s].has_i ? P_HAS_I : 0u) | (w[s].has_d ? P_HAS_D : 0u) | ((!A || !B || ie_null || de_null) ? P_NULL_ROW : 0u) |
+               (((uint32_t)floor_m & 0xffffu) << 16);
+        q[1] = ((uint32_t)w[s].lo & 0xffffu) | ((uint32_t)(-w[s].hi) << 16);
         q[2] = m_off(s) | ((A ? m_off(s - x) : OFF_NULL) << 16);
         q[3] = (B ? m_off(s - o - e) : OFF_NULL) | ((ie_null ? OFF_NULL : i_off(s - e)) << 16);
         q[4] = (de_null ? OFF_NULL : d_off(s - e)) | (i_off(s) << 16);
@@ -621,30 +602,39 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     const uint64_t total_slots = (uint64_t)grid * warps_per_block * PPW;
 
-    // device scratch: plan | non-ACGT flags | packed windows | (BT) history arena
+    // pairs the prep kernel flags (non-ACGT bytes) are served by the warp-per-pair kernel from a device-side list
+    const WarpPlan W = wfa_warp_plan(a, sc->sm_count, std::min<uint32_t>(a.n, (uint32_t)sc->sm_count * 8u));
+    if (W.rc != AIM_OK) return 1;
+
+    // device scratch: plan | list count + non-ACGT flag bits | hand-over list | packed windows | (BT) history arena | warp-kernel scratch
+    auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t plan_bytes = (size_t)K.plan_words * 4;
-    const size_t plan_dev = (plan_bytes + 255) / 256 * 256;
-    const size_t flags_dev = ((size_t)a.n + 255) / 256 * 256;
-    const size_t packed_dev = ((size_t)a.n * 2 * K.seq_entries * 8 + 255) / 256 * 256;
+    const size_t plan_dev = up256(plan_bytes);
+    const size_t flags_dev = up256(256 + ((size_t)a.n + 31) / 32 * 4);
+    const size_t list_dev = up256((size_t)a.n * 4);
+    const size_t packed_dev = up256((size_t)a.n * 2 * K.seq_entries * 8);
     K.arena_stride = p.backtrace ? (size_t)round_up((uint32_t)arena_cells, 16) : 0;
-    const size_t arena_bytes = (size_t)total_slots * K.arena_stride * 8;
-    int rc = scratch_reserve(sc, plan_dev + flags_dev + packed_dev + arena_bytes);
+    const size_t arena_bytes = up256((size_t)total_slots * K.arena_stride * 8);
+    int rc = scratch_reserve(sc, plan_dev + flags_dev + list_dev + packed_dev + arena_bytes + W.scratch_bytes);
     if (rc != AIM_OK) return rc;
     unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
-    uint8_t *flags = base + plan_dev;
-    uint2 *packed = reinterpret_cast<uint2 *>(base + plan_dev + flags_dev);
+    uint32_t *list_count = reinterpret_cast<uint32_t *>(base + plan_dev);
+    uint32_t *flags = list_count + 64;
+    uint32_t *list = reinterpret_cast<uint32_t *>(base + plan_dev + flags_dev);
+    uint2 *packed = reinterpret_cast<uint2 *>(base + plan_dev + flags_dev + list_dev);
     K.plan = reinterpret_cast<const uint32_t *>(base);
     K.flags = flags;
     K.packed = reinterpret_cast<const uint4 *>(packed);
-    K.arena = reinterpret_cast<uint2 *>(base + plan_dev + flags_dev + packed_dev);
+    K.arena = reinterpret_cast<uint2 *>(base + plan_dev + flags_dev + list_dev + packed_dev);
+    void *warp_scratch = base + plan_dev + flags_dev + list_dev + packed_dev + arena_bytes;
     cudaError_t err = cudaMemcpyAsync(base, plan.data(), plan_bytes, cudaMemcpyHostToDevice, stream);
-    if (err == cudaSuccess) err = cudaMemsetAsync(flags, 0, flags_dev, stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(list_count, 0, flags_dev, stream);
     if (err == cudaSuccess && p.backtrace)  // op rows: 'M' everywhere (wfa.c:499-501); the backtrace overwrites the few edits
         err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * (size_t)p.read_size, stream);
     if (err == cudaSuccess) {
         const uint64_t total = (uint64_t)a.n * 2 * K.seq_entries;
         const int pgrid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sc->sm_count * 64);
-        wfa_prep_kernel<<<pgrid, 256, 0, stream>>>(a.patterns, a.texts, a.plen, a.tlen, a.n, p.read_size, K.seq_entries, packed, flags);
+        wfa_prep_kernel<<<pgrid, 256, 0, stream>>>(a.patterns, a.texts, a.plen, a.tlen, a.n, p.read_size, K.seq_entries, packed, flags, list, list_count);
         err = cudaGetLastError();
         if (launches) ++*launches;
     }
@@ -658,7 +648,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { set_error(std::string("wfa_sub launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
     if (launches) ++*launches;
-    return AIM_OK;
+    return wfa_warp_launch(W, warp_scratch, list, list_count, stream_v, launches);
 }
 
 }  // namespace aim
