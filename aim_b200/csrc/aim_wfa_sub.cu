@@ -47,18 +47,21 @@ namespace {
 // plan flags
 constexpr uint32_t P_PRESENT = 1, P_SUB_NULL = 2, P_O_NULL = 4, P_IE_NULL = 8, P_DE_NULL = 16, P_HAS_I = 32, P_HAS_D = 64, P_NULL_ROW = 128;
 constexpr int PLAN_WORDS = 8;
+constexpr uint32_t kNull2 = 0xc000c000u;    // kNull in both halfwords
 constexpr uint32_t kNoRange = 0x7fff7fffu;  // {lo, -hi} of an empty range: neutral for the packed min
 constexpr uint32_t OFF_NULL = 0xffffu;  // row offset meaning "the block-wide all-NULL row"; also "no score"
 // per-score plan: w0 flags | floor (int16) << 16
 //                 w1 lo_s (int16) | (-hi_s) << 16        static range of the wavefront (ranges are kept as {lo, -hi}
 //                                                        so that one packed min() merges them)
 //                 w2 row offset of this score's M row   | of score s-x's M row << 16
-//                 w3 row offset of score s-o-e's M row  | of score s-e's I row << 16
-//                 w4 row offset of score s-e's D row    | of this score's I row << 16
+//                 w3 row offset of score s-o-e's M row  | of score s-e's {I,D} row << 16
+//                 w4 row offset of this score's {I,D} row
 //                 w5 arena cell index of diagonal lo_s
-//                 w6 row offset of this score's D row   | previous occupant (score) of this M row << 16
-//                 w7 previous occupant (score) of this I/D row pair
-// rows: cw halfwords each (cw % 8 == 0), byte offsets from the pair's first row; M ring, then I ring, then D ring.
+//                 w6 previous occupant (score) of this M row << 16
+//                 w7 previous occupant (score) of this {I,D} row
+// rows: byte offsets from the pair's first row; M ring (cw int16 each, cw % 8 == 0), then the {I,D} ring (cw 32-bit cells
+// each: I in the low half, D in the high half).  A present score writes all of M, I, D over its range - a component the
+// reference does not have comes out as NULL by itself because its sources are NULL rows.
 
 struct SubK {
     const int32_t *plen;
@@ -144,29 +147,31 @@ __global__ void __launch_bounds__(256) wfa_prep_kernel(const char *patterns, con
     }
 }
 
-// Extend offset m on diagonal k (wfa.c:193-215): the number of equal bases from pattern[v = m - k], text[m] while both
-// stay inside the sequences; 0 for a negative offset or v.  aP/aT = shared addresses of the 8-byte window entries.
-// Branch-free for the first 16-base window (nearly every call ends inside it); longer runs take the loop.
-__device__ __forceinline__ int extend_dup(uint32_t aP, uint32_t aT, int k, int m, int pl, int tl)
+// Extend (wfa.c:193-215) in two steps so that several diagonals' first steps can be scheduled together.
+// extend_first: the number of equal bases in the first 16-base window from pattern[v = m - k], text[m] (16 = all equal) and
+// *lim = how far the run may go (<= 0: nothing to extend, which includes negative m or v).  aP/aT = shared addresses of
+// the 8-byte window entries.  Nearly every run ends inside the first window; extend_more continues the others.
+__device__ __forceinline__ int extend_first(uint32_t aP, uint32_t aT, int k, int m, int pl, int tl, int *lim)
 {
     const int v = m - k;
-    const bool ok = (m | v) >= 0;
-    const int lim = ok ? min(pl - v, tl - m) : 0;
-    const int vc = max(v, 0), hc = max(m, 0);  // any in-buffer window will do when !ok
+    *lim = (m | v) >= 0 ? min(pl - v, tl - m) : 0;
+    const int vc = max(v, 0), hc = max(m, 0);  // any in-buffer window will do when there is nothing to extend
     const uint2 x = lds_v2(aP + ((uint32_t)(vc >> 4) << 3)), y = lds_v2(aT + ((uint32_t)(hc >> 4) << 3));
     const uint32_t d = __funnelshift_l(x.y, x.x, 2 * vc) ^ __funnelshift_l(y.y, y.x, 2 * hc);
-    int cnt = __clz(d) >> 1;  // 16 when the whole window matches
-    if (d == 0 && lim > 16) {
-        for (;;) {
-            const int pv = v + cnt, ph = m + cnt;
-            const uint2 x2 = lds_v2(aP + ((uint32_t)(pv >> 4) << 3)), y2 = lds_v2(aT + ((uint32_t)(ph >> 4) << 3));
-            const uint32_t d2 = __funnelshift_l(x2.y, x2.x, 2 * pv) ^ __funnelshift_l(y2.y, y2.x, 2 * ph);
-            if (d2) { cnt += __clz(d2) >> 1; break; }
-            cnt += 16;
-            if (cnt >= lim) break;
-        }
+    return __clz(d) >> 1;
+}
+__device__ __noinline__ int extend_more(uint32_t aP, uint32_t aT, int v, int h, int lim)
+{
+    int cnt = 16;
+    for (;;) {
+        const int pv = v + cnt, ph = h + cnt;
+        const uint2 x2 = lds_v2(aP + ((uint32_t)(pv >> 4) << 3)), y2 = lds_v2(aT + ((uint32_t)(ph >> 4) << 3));
+        const uint32_t d2 = __funnelshift_l(x2.y, x2.x, 2 * pv) ^ __funnelshift_l(y2.y, y2.x, 2 * ph);
+        if (d2) { cnt += __clz(d2) >> 1; break; }
+        cnt += 16;
+        if (cnt >= lim) break;
     }
-    return max(min(cnt, lim), 0);
+    return cnt;
 }
 
 template <int G>
@@ -203,20 +208,23 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
 
     // block-wide: the plan and the all-NULL row
     for (uint32_t j = threadIdx.x; j < K.plan_words; j += blockDim.x) smem_w[j] = K.plan[j];
-    for (uint32_t j = threadIdx.x; j < K.cw / 2; j += blockDim.x) smem_w[K.plan_words + j] = 0xc000c000u;
+    for (uint32_t j = threadIdx.x; j < K.cw; j += blockDim.x) smem_w[K.plan_words + j] = 0xc000c000u;  // wide enough for an {I,D} row
     __syncthreads();
 
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_w);
     const uint32_t aPlan = sbase;
-    const uint32_t aSlot = sbase + (K.plan_words + K.cw / 2 + (uint32_t)(wib * PPW + sub) * K.pair_words) * 4u;
+    const uint32_t aSlot = sbase + (K.plan_words + K.cw + (uint32_t)(wib * PPW + sub) * K.pair_words) * 4u;
     const uint32_t aP = aSlot;
     const uint32_t aT = aP + K.seq_entries * 8u;
     const uint32_t aDyn = aT + K.seq_entries * 8u;
     const uint32_t aRows = aDyn + K.dyn_words * 4u;
-    const uint32_t aK0 = aRows + (uint32_t)(K.koff * 2);                        // diagonal 0 of the pair's first row
-    const uint32_t nullrel = (sbase + K.plan_words * 4u + (uint32_t)(K.koff * 2)) - aK0;  // the NULL row, relative to aK0
-    // address of diagonal 0 of the row at plan offset `off`
+    // M rows hold one int16 per diagonal, {I,D} rows one 32-bit cell (I low, D high); diagonal 0 of the row at plan
+    // offset `off` is aK0 + off (M rows) / aK0D + off ({I,D} rows); OFF_NULL = the block-wide all-NULL row
+    const uint32_t aK0 = aRows + (uint32_t)(K.koff * 2), aK0D = aRows + (uint32_t)(K.koff * 4);
+    const uint32_t nullrel = (sbase + K.plan_words * 4u + (uint32_t)(K.koff * 2)) - aK0;
+    const uint32_t nullrelD = (sbase + K.plan_words * 4u + (uint32_t)(K.koff * 4)) - aK0D;
 #define AIM_ROW(off) (aK0 + ((off) == OFF_NULL ? nullrel : (off)))
+#define AIM_ROWD(off) (aK0D + ((off) == OFF_NULL ? nullrelD : (off)))
 
     const uint32_t slot_global = (blockIdx.x * wpb + wib) * PPW + sub;
     const uint32_t nslots = gridDim.x * wpb * PPW;
@@ -261,13 +269,11 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
             }
             const int lo = lo16(rng), hi = -hi16s(rng);
             // row addresses of diagonal 0
-            const uint32_t aNM = aK0 + (p0.z & 0xffffu);
-            uint32_t aAM = aK0 + (p0.z >> 16), aBM = aK0 + (p0.w & 0xffffu), aEI = aK0 + (p0.w >> 16), aED = aK0 + (p1.x & 0xffffu);
+            const uint32_t aNM = aK0 + (p0.z & 0xffffu), aN = aK0D + (p1.x & 0xffffu);
+            uint32_t aAM = aK0 + (p0.z >> 16), aBM = aK0 + (p0.w & 0xffffu), aE = aK0D + (p0.w >> 16);
             if (fl & P_NULL_ROW) {  // early scores only: a missing source reads the all-NULL row
-                aAM = AIM_ROW(p0.z >> 16); aBM = AIM_ROW(p0.w & 0xffffu); aEI = AIM_ROW(p0.w >> 16); aED = AIM_ROW(p1.x & 0xffffu);
+                aAM = AIM_ROW(p0.z >> 16); aBM = AIM_ROW(p0.w & 0xffffu); aE = AIM_ROWD(p0.w >> 16);
             }
-            const uint32_t aNI = aK0 + (p1.x >> 16);
-            const uint32_t aND = aK0 + (p1.z & 0xffffu);
 
             // ---- keep the frame: NULL what the rows' previous occupants left outside [lo,hi] ----
             {
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
                         for (int k = plo + sl; k <= phi; k += G)
                             if (k < lo || k > hi) sts_u16(aNM + (uint32_t)(k * 2), kNull);
                         for (int k = qlo + sl; k <= qhi; k += G)
-                            if (k < lo || k > hi) { sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull); }
+                            if (k < lo || k > hi) sts_u32(aN + (uint32_t)(k * 4), kNull2);
                     }
                 }
             }
@@ -291,30 +297,50 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
             // ---- compute_offsets (wfa.c:238-273) fused with extend (wfa.c:193-215); no range tests: see the header ----
             int md = max(pl, tl);
             if (!done) {
-                // one cell: diagonal k, row byte offset k2 = 2k, arena cell pointer hp
-                auto cell = [&](const int k, const uint32_t k2, uint2 *hp) {
-                    const int g1 = lds_s16(aBM + k2 - 2), ii = lds_s16(aEI + k2 - 2);
-                    const int g2 = lds_s16(aBM + k2 + 2), dd = lds_s16(aED + k2 + 2);
-                    const int sb = lds_s16(aAM + k2) + 1;
+                // this lane's cells are k0, k0 + G, ...; row pointers at k0, advanced once per trip
+                const int k0 = lo + sl;
+                uint32_t rB = aBM + (uint32_t)(k0 * 2), rA = aAM + (uint32_t)(k0 * 2), rNM = aNM + (uint32_t)(k0 * 2);
+                uint32_t rE = aE + (uint32_t)(k0 * 4), rN = aN + (uint32_t)(k0 * 4);
+                uint2 *hp = BT ? arena + (p1.y + (uint32_t)(k0 - lo_s)) : nullptr;  // arena cell of (s, k0)
+                // front half of a cell at j*G past the pointers: the recurrences, the {I,D} store, the first extend window
+                auto front = [&](const int k, const int j, int &m, uint32_t &id, int &cnt, int &lim) {
+                    const uint32_t o2 = (uint32_t)(j * 2 * G), o4 = (uint32_t)(j * 4 * G);
+                    const int g1 = lds_s16(rB + o2 - 2), g2 = lds_s16(rB + o2 + 2);
+                    const int ii = lds_s16(rE + o4 - 4), dd = lds_s16(rE + o4 + 6);
+                    const int sb = lds_s16(rA + o2) + 1;
                     const int t = max(g1, ii) + 1;
                     const int ins = t == kNull + 1 ? kNull : t;  // both NULL -> NULL (wfa.c:249-252)
                     const int del = max(g2, dd);
-                    int m = max(max(del, sb), max(ins, floor_m));
-                    sts_u16(aNI + k2, ins);
-                    sts_u16(aND + k2, del);
-                    m += extend_dup(aP, aT, k, m, pl, tl);
-                    sts_u16(aNM + k2, m);
-                    if (BT) *hp = make_uint2(((uint32_t)m & 0xffffu) | ((uint32_t)ins << 16), (uint32_t)del & 0xffffu);
+                    m = max(max(del, sb), max(ins, floor_m));
+                    id = ((uint32_t)ins & 0xffffu) | ((uint32_t)del << 16);
+                    sts_u32(rN + o4, id);
+                    cnt = extend_first(aP, aT, k, m, pl, tl, &lim);
+                };
+                // back half: finish the extend, store M, history cell, distance for the reduction
+                auto back = [&](const int k, const int j, int m, const uint32_t id, int cnt, const int lim) {
+                    if (cnt == 16 && lim > 16) cnt = extend_more(aP, aT, m - k, m, lim);  // rare
+                    m += max(min(cnt, lim), 0);
+                    sts_u16(rNM + (uint32_t)(j * 2 * G), m);
+                    if (BT) hp[j * G] = make_uint2((uint32_t)m & 0xffffu, id);
                     if (REDUCE) md = min(md, max(pl + k, tl) - m);
                 };
-                uint2 *hp = BT ? arena + (p1.y + (uint32_t)(lo + sl - lo_s)) : nullptr;  // arena cell of (s, k)
-                int k = lo + sl;
-                for (; k + G <= hi; k += 2 * G, hp += 2 * G) {  // two cells per trip: independent chains, shared address math
-                    const uint32_t k2 = (uint32_t)(k * 2);
-                    cell(k, k2, hp);
-                    cell(k + G, k2 + 2 * G, hp + G);
+                int k = k0;
+                for (; k + G <= hi; k += 2 * G) {  // two cells per trip: independent chains the scheduler can interleave
+                    int m0, m1, c0, c1, l0, l1;
+                    uint32_t id0, id1;
+                    front(k, 0, m0, id0, c0, l0);
+                    front(k + G, 1, m1, id1, c1, l1);
+                    back(k, 0, m0, id0, c0, l0);
+                    back(k + G, 1, m1, id1, c1, l1);
+                    rB += 4 * G; rA += 4 * G; rNM += 4 * G; rE += 8 * G; rN += 8 * G;
+                    if (BT) hp += 2 * G;
                 }
-                if (k <= hi) cell(k, (uint32_t)(k * 2), hp);
+                if (k <= hi) {
+                    int m0, c0, l0;
+                    uint32_t id0;
+                    front(k, 0, m0, id0, c0, l0);
+                    back(k, 0, m0, id0, c0, l0);
+                }
             }
             __syncwarp();
             // ---- end reached (wfa.c:217-237).  Trimming never removes diagonal ak, so testing before the
@@ -347,13 +373,9 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
                     if (wide) {
                         newhi = min(hi, max(kt, bottom_limit));
                         // keep the frame: the cells the trim cut off read as NULL from now on
-                        for (int k = kf; k < newlo; k += G) {
-                            sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull);
-                        }
+                        for (int k = kf; k < newlo; k += G) { sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u32(aN + (uint32_t)(k * 4), kNull2); }
                         if (kf <= hi)
-                            for (int k = kl; k > newhi; k -= G) {
-                                sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u16(aNI + (uint32_t)(k * 2), kNull); sts_u16(aND + (uint32_t)(k * 2), kNull);
-                            }
+                            for (int k = kl; k > newhi; k -= G) { sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u32(aN + (uint32_t)(k * 4), kNull2); }
                     }
                 }
                 if (sl == 0 && !done) sts_u32(aDyn + (uint32_t)s * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)(-newhi) << 16));
@@ -417,12 +439,12 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
                 int del_ext = kNull, del_open = kNull, ins_ext = kNull, ins_open = kNull, misms = kNull;
                 if (type != 1) {
                     if ((ge_f & P_PRESENT) && (ge_f & P_HAS_D) && ge_lo <= k + 1 && k + 1 <= ge_hi)
-                        del_ext = lo16(arena[ge_base + (uint32_t)(k + 1 - ge_l0)].y);
+                        del_ext = hi16s(arena[ge_base + (uint32_t)(k + 1 - ge_l0)].y);
                     if ((go_f & P_PRESENT) && go_lo <= k + 1 && k + 1 <= go_hi) del_open = lo16(arena[go_base + (uint32_t)(k + 1 - go_l0)].x);
                 }
                 if (type != 2) {
                     if ((ge_f & P_PRESENT) && (ge_f & P_HAS_I) && ge_lo <= k - 1 && k - 1 <= ge_hi)
-                        ins_ext = (int16_t)(hi16s(arena[ge_base + (uint32_t)(k - 1 - ge_l0)].x) + 1);
+                        ins_ext = (int16_t)(lo16(arena[ge_base + (uint32_t)(k - 1 - ge_l0)].y) + 1);
                     if ((go_f & P_PRESENT) && go_lo <= k - 1 && k - 1 <= go_hi)
                         ins_open = (int16_t)(lo16(arena[go_base + (uint32_t)(k - 1 - go_l0)].x) + 1);
                 }
@@ -475,6 +497,7 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
         __syncwarp();
     }
 #undef AIM_ROW
+#undef AIM_ROWD
 }
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
@@ -539,10 +562,9 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     K.plan_words = (uint32_t)PLAN_WORDS * ((uint32_t)MS + 1);
     std::vector<uint32_t> plan(K.plan_words, 0u);
     uint64_t arena_cells = 0;
-    // rows: M ring, then I ring, then D ring
+    // rows: M ring, then the {I,D} ring
     auto m_off = [&](int s) -> uint32_t { return ((uint32_t)s % ring_m) * row_bytes; };
-    auto i_off = [&](int s) -> uint32_t { return (ring_m + (uint32_t)s % ring_e) * row_bytes; };
-    auto d_off = [&](int s) -> uint32_t { return (ring_m + ring_e + (uint32_t)s % ring_e) * row_bytes; };
+    auto id_off = [&](int s) -> uint32_t { return (ring_m + 2 * ((uint32_t)s % ring_e)) * row_bytes; };
     std::vector<uint32_t> last_m(ring_m, OFF_NULL), last_id(ring_e, OFF_NULL);  // score whose cells sit in each row
     for (int s = 0; s <= MS; ++s) {
         if (!w[s].present) continue;
@@ -553,14 +575,14 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         // the reference's -10 for a missing I / D / sub candidate (wfa.c:243,255,266) is a floor under the max; score 0 starts at offset 0
         const int floor_m = s == 0 ? 0 : ((!A || !w[s].has_i || !w[s].has_d) ? -10 : -32768);
         q[0] = P_PRESENT | (A ? 0u : P_SUB_NULL) | (B ? 0u : P_O_NULL) | (ie_null ? P_IE_NULL : 0u) | (de_null ? P_DE_NULL : 0u) |
-               (w[s].has_i ? P_HAS_I : 0u) | (w[s].has_d ? P_HAS_D : 0u) | ((!A || !B || ie_null || de_null) ? P_NULL_ROW : 0u) |
+               (w[s].has_i ? P_HAS_I : 0u) | (w[s].has_d ? P_HAS_D : 0u) | ((!A || !B || !E) ? P_NULL_ROW : 0u) |
                (((uint32_t)floor_m & 0xffffu) << 16);
         q[1] = ((uint32_t)w[s].lo & 0xffffu) | ((uint32_t)(-w[s].hi) << 16);
         q[2] = m_off(s) | ((A ? m_off(s - x) : OFF_NULL) << 16);
-        q[3] = (B ? m_off(s - o - e) : OFF_NULL) | ((ie_null ? OFF_NULL : i_off(s - e)) << 16);
-        q[4] = (de_null ? OFF_NULL : d_off(s - e)) | (i_off(s) << 16);
+        q[3] = (B ? m_off(s - o - e) : OFF_NULL) | ((E ? id_off(s - e) : OFF_NULL) << 16);
+        q[4] = id_off(s);
         q[5] = (uint32_t)arena_cells;
-        q[6] = d_off(s) | (last_m[(uint32_t)s % ring_m] << 16);
+        q[6] = last_m[(uint32_t)s % ring_m] << 16;
         q[7] = last_id[(uint32_t)s % ring_e];
         last_m[(uint32_t)s % ring_m] = (uint32_t)s;
         last_id[(uint32_t)s % ring_e] = (uint32_t)s;
@@ -586,7 +608,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     const uint32_t kSmemBudget = 227u * 1024u, kSmemPerSm = 228u * 1024u, kBlockReserve = 1024u;
     const size_t pair_bytes = (size_t)K.pair_words * 4;
-    const size_t fixed_bytes = (size_t)K.plan_words * 4 + row_bytes;  // plan + the all-NULL row
+    const size_t fixed_bytes = (size_t)K.plan_words * 4 + 2 * row_bytes;  // plan + the all-NULL row ({I,D} width)
     int warps_per_block = G == 4 ? 2 : 4;
     if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v == 1 || v == 2 || v == 4) warps_per_block = v; }
     size_t smem_block = fixed_bytes + (size_t)warps_per_block * PPW * pair_bytes;
