@@ -286,10 +286,11 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
                 if (__any_sync(kFull, left)) {
                     if (left) {
                         const int plo = lo16(pr), phi = -hi16s(pr), qlo = lo16(qr), qhi = -hi16s(qr);
-                        for (int k = plo + sl; k <= phi; k += G)
-                            if (k < lo || k > hi) sts_u16(aNM + (uint32_t)(k * 2), kNull);
-                        for (int k = qlo + sl; k <= qhi; k += G)
-                            if (k < lo || k > hi) sts_u32(aN + (uint32_t)(k * 4), kNull2);
+                        // only the (few) cells of the previous range that stick out below lo or above hi are visited
+                        for (int k = plo + sl; k <= min(phi, lo - 1); k += G) sts_u16(aNM + (uint32_t)(k * 2), kNull);
+                        for (int k = max(plo, hi + 1) + sl; k <= phi; k += G) sts_u16(aNM + (uint32_t)(k * 2), kNull);
+                        for (int k = qlo + sl; k <= min(qhi, lo - 1); k += G) sts_u32(aN + (uint32_t)(k * 4), kNull2);
+                        for (int k = max(qlo, hi + 1) + sl; k <= qhi; k += G) sts_u32(aN + (uint32_t)(k * 4), kNull2);
                     }
                 }
             }

@@ -39,7 +39,8 @@ def main():
         if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
             insts.append((cur, l.split("*/", 1)[1].strip().rstrip(";")))
     if len(insts) != len(rows):
-        print(f"warning: {len(insts)} disassembled vs {len(rows)} profiled instructions", file=sys.stderr)
+        sys.exit(f"error: {len(insts)} disassembled vs {len(rows)} profiled instructions - the kernel substring must select exactly "
+                 "the profiled template instantiation of the same build")
     agg = defaultdict(lambda: [0, 0, 0])
     tot = [0, 0, 0]
     for (loc, _), r in zip(insts, rows):

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Summarise an `ncu --set full` capture into profiles/ (tracked): key counters + per-source-line shares.
 
-    python tools/ncu_summary.py <report.ncu-rep> <kernel-substring> <out-prefix> [pairs-in-launch] [cubin]
+    python tools/ncu_summary.py <report.ncu-rep> <kernel-substring> <out-prefix> [pairs-in-launch] [cubin] [mangled-kernel-substring]
+
+The mangled substring (e.g. wfa_sub_kernelILi4ELb1ELb1) must select ONE template instantiation in the cubin: the join in
+ncu_lines.py is by instruction order.
 """
 import csv
 import io
@@ -39,6 +42,7 @@ def main():
     rep, kern, prefix = sys.argv[1:4]
     pairs = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     cubin = sys.argv[5] if len(sys.argv) > 5 else None
+    mangled = sys.argv[6] if len(sys.argv) > 6 else kern
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -65,7 +69,7 @@ def main():
                 summary["warp_inst_per_pair"] = summary["warp_inst"] / pairs
     if cubin:
         here = Path(__file__).resolve().parent
-        lines = subprocess.run([sys.executable, str(here / "ncu_lines.py"), rep, cubin, kern.replace("<", "IL").replace(">", "")[:14], "40"],
+        lines = subprocess.run([sys.executable, str(here / "ncu_lines.py"), rep, cubin, mangled, "40"],
                                capture_output=True, text=True).stdout
         out.append("\n== instruction share per CUDA source line (top 40) ==\n" + lines)
     Path(prefix + ".txt").write_text("\n".join(out) + "\n")
