@@ -70,7 +70,7 @@ struct SubK {
     const char *texts;
     aim_result *results;
     char *ops;
-    const uint4 *packed;    // wfa_prep_kernel's output: per pair seq_entries 8-byte entries of the pattern, then of the text
+    const uint4 *packed;    // wfa_prep_kernel's output: per pair seq_words 2-bit packed words of the pattern, then of the text
     const uint32_t *flags;  // one bit per pair: a byte outside {A,C,G,T} inside the sequences -> the pair is on the hand-over list
     const uint32_t *plan;   // device copy of the plan
     uint2 *arena;           // history arena (BT only): {M | I << 16, D} per (score, diagonal)
@@ -80,7 +80,7 @@ struct SubK {
     int max_score, read_size;
     int koff;               // ring cell of diagonal k is k + koff
     uint32_t plan_words;    // PLAN_WORDS * (max_score + 1)
-    uint32_t seq_entries;   // 8-byte window entries per packed sequence (even)
+    uint32_t seq_words;     // 32-bit words per packed sequence (multiple of 4, one spare word past the last base)
     uint32_t dyn_words;     // trimmed-range words per pair (multiple of 4; 0 when !reduce)
     uint32_t cw;            // row width in halfwords (multiple of 8)
     uint32_t rows_v4;       // 16-byte units of all rows of a pair
@@ -124,25 +124,22 @@ __device__ __forceinline__ uint32_t pack16(const char *row, int b, int len, int 
     return w;
 }
 
-// One thread per (pair, sequence, window entry): entry j = {bases 16j..16j+15, bases 16j+16..16j+31}.  HBM-bound.
+// One thread per (pair, sequence, 16-base word): word j = bases 16j..16j+15, first base in the top two bits.  HBM-bound.
 // A pair holding a byte outside {A,C,G,T} (the reference compares raw bytes, wfa.c:209) cannot be 2-bit packed: it is
 // flagged and listed once for the warp-per-pair kernel of aim_wfa.cu, which compares bytes.
 __global__ void __launch_bounds__(256) wfa_prep_kernel(const char *patterns, const char *texts, const int32_t *plen, const int32_t *tlen,
-                                                       uint32_t n, int RS, uint32_t SE, uint2 *packed, uint32_t *flags,
+                                                       uint32_t n, int RS, uint32_t SW, uint32_t *packed, uint32_t *flags,
                                                        uint32_t *list, uint32_t *list_count)
 {
-    const uint64_t total = (uint64_t)n * 2u * SE;
+    const uint64_t total = (uint64_t)n * 2u * SW;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t j = (uint32_t)(t % SE);
-        const uint64_t r = t / SE;
+        const uint32_t j = (uint32_t)(t % SW);
+        const uint64_t r = t / SW;
         const uint32_t q = (uint32_t)(r & 1u), i = (uint32_t)(r >> 1);
         const int len = min(max(q ? tlen[i] : plen[i], 0), RS);
         const char *row = (q ? texts : patterns) + (size_t)i * RS;
         bool ok = true;
-        uint2 e;
-        e.x = pack16(row, (int)j * 16, len, RS, &ok);
-        e.y = pack16(row, (int)j * 16 + 16, len, RS, &ok);
-        packed[t] = e;
+        packed[t] = pack16(row, (int)j * 16, len, RS, &ok);
         if (!ok && !(atomicOr(&flags[i >> 5], 1u << (i & 31)) & (1u << (i & 31)))) list[atomicAdd(list_count, 1u)] = i;  // first to flag it
     }
 }
@@ -150,14 +147,15 @@ __global__ void __launch_bounds__(256) wfa_prep_kernel(const char *patterns, con
 // Extend (wfa.c:193-215) in two steps so that several diagonals' first steps can be scheduled together.
 // extend_first: the number of equal bases in the first 16-base window from pattern[v = m - k], text[m] (16 = all equal) and
 // *lim = how far the run may go (<= 0: nothing to extend, which includes negative m or v).  aP/aT = shared addresses of
-// the 8-byte window entries.  Nearly every run ends inside the first window; extend_more continues the others.
+// the packed words (two 4-byte loads + one funnel shift per sequence).  Nearly every run ends inside the first window; extend_more continues the others.
 __device__ __forceinline__ int extend_first(uint32_t aP, uint32_t aT, int k, int m, int pl, int tl, int *lim)
 {
     const int v = m - k;
     *lim = (m | v) >= 0 ? min(pl - v, tl - m) : 0;
     const int vc = max(v, 0), hc = max(m, 0);  // any in-buffer window will do when there is nothing to extend
-    const uint2 x = lds_v2(aP + ((uint32_t)(vc >> 4) << 3)), y = lds_v2(aT + ((uint32_t)(hc >> 4) << 3));
-    const uint32_t d = __funnelshift_l(x.y, x.x, 2 * vc) ^ __funnelshift_l(y.y, y.x, 2 * hc);
+    const uint32_t ax = aP + ((uint32_t)(vc >> 4) << 2), ay = aT + ((uint32_t)(hc >> 4) << 2);
+    const uint32_t x0 = lds_u32(ax), x1 = lds_u32(ax + 4), y0 = lds_u32(ay), y1 = lds_u32(ay + 4);
+    const uint32_t d = __funnelshift_l(x1, x0, 2 * vc) ^ __funnelshift_l(y1, y0, 2 * hc);
     return __clz(d) >> 1;
 }
 __device__ __noinline__ int extend_more(uint32_t aP, uint32_t aT, int v, int h, int lim)
@@ -165,8 +163,8 @@ __device__ __noinline__ int extend_more(uint32_t aP, uint32_t aT, int v, int h, 
     int cnt = 16;
     for (;;) {
         const int pv = v + cnt, ph = h + cnt;
-        const uint2 x2 = lds_v2(aP + ((uint32_t)(pv >> 4) << 3)), y2 = lds_v2(aT + ((uint32_t)(ph >> 4) << 3));
-        const uint32_t d2 = __funnelshift_l(x2.y, x2.x, 2 * pv) ^ __funnelshift_l(y2.y, y2.x, 2 * ph);
+        const uint32_t ax = aP + ((uint32_t)(pv >> 4) << 2), ay = aT + ((uint32_t)(ph >> 4) << 2);
+        const uint32_t d2 = __funnelshift_l(lds_u32(ax + 4), lds_u32(ax), 2 * pv) ^ __funnelshift_l(lds_u32(ay + 4), lds_u32(ay), 2 * ph);
         if (d2) { cnt += __clz(d2) >> 1; break; }
         cnt += 16;
         if (cnt >= lim) break;
@@ -194,8 +192,8 @@ __device__ __forceinline__ int hi16s(uint32_t w) { return (int)(short)(w >> 16);
 // lo <= k <= hi
 __device__ __forceinline__ bool in_range(int k, int lo, int hi) { return (unsigned)(k - lo) <= (unsigned)(hi - lo) && lo <= hi; }
 
-template <int G, bool REDUCE, bool BT>
-__global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
+template <int G, bool REDUCE, bool BT, int MAXT = 128>
+__global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
 {
     constexpr int PPW = 32 / G;
     extern __shared__ __align__(16) uint32_t smem_w[];
@@ -215,8 +213,8 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
     const uint32_t aPlan = sbase;
     const uint32_t aSlot = sbase + (K.plan_words + K.cw + (uint32_t)(wib * PPW + sub) * K.pair_words) * 4u;
     const uint32_t aP = aSlot;
-    const uint32_t aT = aP + K.seq_entries * 8u;
-    const uint32_t aDyn = aT + K.seq_entries * 8u;
+    const uint32_t aT = aP + K.seq_words * 4u;
+    const uint32_t aDyn = aT + K.seq_words * 4u;
     const uint32_t aRows = aDyn + K.dyn_words * 4u;
     // M rows hold one int16 per diagonal, {I,D} rows one 32-bit cell (I low, D high); diagonal 0 of the row at plan
     // offset `off` is aK0 + off (M rows) / aK0D + off ({I,D} rows); OFF_NULL = the block-wide all-NULL row
@@ -240,8 +238,8 @@ __global__ void __launch_bounds__(128) wfa_sub_kernel(const SubK K)
 
         // ---- stage the packed windows (16-byte copies), NULL-fill the rows ----
         if (active) {
-            const uint4 *src = K.packed + (size_t)i * K.seq_entries;
-            for (uint32_t c = sl; c < K.seq_entries; c += G) sts_v4(aP + c * 16u, __ldg(src + c));
+            const uint4 *src = K.packed + (size_t)i * (K.seq_words / 2);
+            for (uint32_t c = sl; c < K.seq_words / 2; c += G) sts_v4(aP + c * 16u, __ldg(src + c));
         }
         for (uint32_t c = sl; c < K.rows_v4; c += G) sts_v4(aRows + c * 16u, null4);
         __syncwarp();
@@ -507,10 +505,19 @@ template <int G>
 cudaError_t launch_g(const SubK &K, bool reduce, bool bt, int grid, int block, size_t smem, cudaStream_t st)
 {
     cudaError_t e;
-#define AIM_LAUNCH(R, B)                                                                                             \
-    do {                                                                                                             \
-        e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        if (e == cudaSuccess) wfa_sub_kernel<G, R, B><<<grid, block, smem, st>>>(K);                                  \
+    // blocks of more than 4 warps (G = 4 only: one big block fills an SM's shared memory with less per-block overhead)
+    // use a second instantiation whose register budget allows them
+#define AIM_LAUNCH(R, B)                                                                                                  \
+    do {                                                                                                                  \
+        if (block <= 128) {                                                                                               \
+            e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            if (e == cudaSuccess) wfa_sub_kernel<G, R, B><<<grid, block, smem, st>>>(K);                                   \
+        } else if constexpr (G == 4) {                                                                                    \
+            e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e == cudaSuccess) wfa_sub_kernel<G, R, B, 768><<<grid, block, smem, st>>>(K);                              \
+        } else {                                                                                                          \
+            e = cudaErrorInvalidConfiguration;                                                                            \
+        }                                                                                                                 \
     } while (0)
     if (reduce && bt) AIM_LAUNCH(true, true);
     else if (reduce) AIM_LAUNCH(true, false);
@@ -594,26 +601,43 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     K.plen = a.plen; K.tlen = a.tlen; K.patterns = a.patterns; K.texts = a.texts;
     K.results = a.results; K.ops = a.ops; K.n = a.n; K.idx_base = a.idx_base;
     K.x = x; K.o = o; K.e = e; K.max_score = MS; K.read_size = p.read_size;
-    K.seq_entries = round_up((uint32_t)p.read_size / 16 + 2, 2);
+    K.seq_words = round_up((uint32_t)p.read_size / 16 + 2, 4);
     K.dyn_words = p.reduce ? round_up((uint32_t)MS + 1, 4) : 0;
-    const uint32_t pair_words_raw = 4 * K.seq_entries + K.dyn_words + rows_bytes / 4;
+    const uint32_t pair_words_raw = 2 * K.seq_words + K.dyn_words + rows_bytes / 4;
 
     // lanes per pair: wavefronts are about MAX_SCORE diagonals wide on average; a few iterations per score keeps the
     // lanes busy while the per-score bookkeeping is shared by 32/G pairs; env override for tuning
     int G = MS <= 40 ? 4 : MS <= 100 ? 8 : MS <= 300 ? 16 : 32;
     if (const char *gs = getenv("AIM_WFA_G")) { int g = atoi(gs); if (g == 4 || g == 8 || g == 16 || g == 32) G = g; }
     const int PPW = 32 / G;
-    {   // stagger the pair slots of one warp over the banks: slot stride == 32/PPW words (mod 32); slots stay 16-byte aligned
-        const uint32_t want = PPW > 1 ? std::max(4u, 32u / (uint32_t)PPW) : 0u;
-        K.pair_words = pair_words_raw + ((want + 32u - pair_words_raw % 32u) % 32u);
+    {   // stagger the pair slots of one warp over the banks with the least padding: a slot stride that is an ODD multiple of
+        // 32/PPW words puts the PPW slots on distinct bank groups; slots stay 16-byte aligned
+        K.pair_words = (pair_words_raw + 3u) & ~3u;
+        if (PPW > 1 && !getenv("AIM_WFA_NOSTAGGER")) {
+            const uint32_t unit = std::max(4u, 32u / (uint32_t)PPW);
+            while (K.pair_words % (2 * unit) != unit) K.pair_words += 4;
+        }
     }
     const uint32_t kSmemBudget = 227u * 1024u, kSmemPerSm = 228u * 1024u, kBlockReserve = 1024u;
     const size_t pair_bytes = (size_t)K.pair_words * 4;
     const size_t fixed_bytes = (size_t)K.plan_words * 4 + 2 * row_bytes;  // plan + the all-NULL row ({I,D} width)
-    int warps_per_block = G == 4 ? 2 : 4;
-    if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v == 1 || v == 2 || v == 4) warps_per_block = v; }
+    // G = 4 and a large per-pair footprint: ONE block per SM with as many warps as its shared memory holds (20 at config 4
+    // against 16 as two-warp blocks) - the per-block plan copy and reserve are paid once, and the kernel, latency-bound at
+    // these occupancies, gains ~10 %.  Small footprints keep the two-warp blocks (registers cap those at 32 warps/SM).
+    const int default_wpb = G == 4 ? 2 : 4;
+    int warps_per_block = default_wpb;
+    if (G == 4) {
+        const size_t small_block = fixed_bytes + (size_t)default_wpb * PPW * pair_bytes;
+        const int small_warps = (int)std::min<size_t>(32, kSmemPerSm / (small_block + kBlockReserve) * default_wpb);
+        int big_warps = (int)std::min<size_t>(24, (kSmemBudget - fixed_bytes) / ((size_t)PPW * pair_bytes));
+        if (big_warps >= 8) big_warps &= ~3;  // the same number of warps on each of the SM's four schedulers (20 beats 21: 300 vs 290 M pairs/s)
+        if (big_warps > small_warps) warps_per_block = big_warps;
+    }
+    if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v >= 1 && v <= (G == 4 ? 24 : 4)) warps_per_block = v; }
+    if (warps_per_block < 1) return 1;
     size_t smem_block = fixed_bytes + (size_t)warps_per_block * PPW * pair_bytes;
-    if (smem_block > kSmemBudget / 3) return 1;  // too few warps/SM would fit: leave it to the long-read kernel
+    if (smem_block > kSmemBudget) return 1;
+    if (fixed_bytes + (size_t)default_wpb * PPW * pair_bytes > kSmemBudget / 3) return 1;  // too few warps/SM would fit: leave it to the long-read kernel
     int blocks_per_sm = (int)std::min<uint32_t>(kSmemPerSm / ((uint32_t)smem_block + kBlockReserve), 32u);
     int max_warps = 48;
     if (const char *ws = getenv("AIM_WFA_MAXWARPS")) { int v = atoi(ws); if (v >= 4 && v <= 64) max_warps = v; }
@@ -635,7 +659,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     const size_t plan_dev = up256(plan_bytes);
     const size_t flags_dev = up256(256 + ((size_t)a.n + 31) / 32 * 4);
     const size_t list_dev = up256((size_t)a.n * 4);
-    const size_t packed_dev = up256((size_t)a.n * 2 * K.seq_entries * 8);
+    const size_t packed_dev = up256((size_t)a.n * 2 * K.seq_words * 4);
     K.arena_stride = p.backtrace ? (size_t)round_up((uint32_t)arena_cells, 16) : 0;
     const size_t arena_bytes = up256((size_t)total_slots * K.arena_stride * 8);
     int rc = scratch_reserve(sc, plan_dev + flags_dev + list_dev + packed_dev + arena_bytes + W.scratch_bytes);
@@ -644,7 +668,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     uint32_t *list_count = reinterpret_cast<uint32_t *>(base + plan_dev);
     uint32_t *flags = list_count + 64;
     uint32_t *list = reinterpret_cast<uint32_t *>(base + plan_dev + flags_dev);
-    uint2 *packed = reinterpret_cast<uint2 *>(base + plan_dev + flags_dev + list_dev);
+    uint32_t *packed = reinterpret_cast<uint32_t *>(base + plan_dev + flags_dev + list_dev);
     K.plan = reinterpret_cast<const uint32_t *>(base);
     K.flags = flags;
     K.packed = reinterpret_cast<const uint4 *>(packed);
@@ -655,9 +679,9 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     if (err == cudaSuccess && p.backtrace)  // op rows: 'M' everywhere (wfa.c:499-501); the backtrace overwrites the few edits
         err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * (size_t)p.read_size, stream);
     if (err == cudaSuccess) {
-        const uint64_t total = (uint64_t)a.n * 2 * K.seq_entries;
+        const uint64_t total = (uint64_t)a.n * 2 * K.seq_words;
         const int pgrid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sc->sm_count * 64);
-        wfa_prep_kernel<<<pgrid, 256, 0, stream>>>(a.patterns, a.texts, a.plen, a.tlen, a.n, p.read_size, K.seq_entries, packed, flags, list, list_count);
+        wfa_prep_kernel<<<pgrid, 256, 0, stream>>>(a.patterns, a.texts, a.plen, a.tlen, a.n, p.read_size, K.seq_words, packed, flags, list, list_count);
         err = cudaGetLastError();
         if (launches) ++*launches;
     }
