@@ -4,7 +4,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Iinclude -Iaim_b200/csrc -Xcompiler -fPIC,-Wall,-Wextra -cudart static
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Iinclude -Iaim_b200/csrc -Xcompiler -fPIC,-Wall,-Wextra -cudart static $(EXTRA_NVFLAGS)
 CSRC      := aim_b200/csrc
 OBJDIR    := build/obj
 CU_SRCS   := $(CSRC)/aim_wfa.cu $(CSRC)/aim_wfa_sub.cu $(CSRC)/aim_wfa_long.cu $(CSRC)/aim_dp.cu $(CSRC)/aim_dp_fast.cu $(CSRC)/aim_dispatch.cu $(CSRC)/aim_peak.cu

@@ -35,6 +35,7 @@
 #include <climits>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "aim_internal.h"
@@ -301,21 +302,7 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
                 uint32_t rB = aBM + (uint32_t)(k0 * 2), rA = aAM + (uint32_t)(k0 * 2), rNM = aNM + (uint32_t)(k0 * 2);
                 uint32_t rE = aE + (uint32_t)(k0 * 4), rN = aN + (uint32_t)(k0 * 4);
                 uint2 *hp = BT ? arena + (p1.y + (uint32_t)(k0 - lo_s)) : nullptr;  // arena cell of (s, k0)
-                // front half of a cell at j*G past the pointers: the recurrences, the {I,D} store, the first extend window
-                auto front = [&](const int k, const int j, int &m, uint32_t &id, int &cnt, int &lim) {
-                    const uint32_t o2 = (uint32_t)(j * 2 * G), o4 = (uint32_t)(j * 4 * G);
-                    const int g1 = lds_s16(rB + o2 - 2), g2 = lds_s16(rB + o2 + 2);
-                    const int ii = lds_s16(rE + o4 - 4), dd = lds_s16(rE + o4 + 6);
-                    const int sb = lds_s16(rA + o2) + 1;
-                    const int t = max(g1, ii) + 1;
-                    const int ins = t == kNull + 1 ? kNull : t;  // both NULL -> NULL (wfa.c:249-252)
-                    const int del = max(g2, dd);
-                    m = max(max(del, sb), max(ins, floor_m));
-                    id = ((uint32_t)ins & 0xffffu) | ((uint32_t)del << 16);
-                    sts_u32(rN + o4, id);
-                    cnt = extend_first(aP, aT, k, m, pl, tl, &lim);
-                };
-                // back half: finish the extend, store M, history cell, distance for the reduction
+                // back half of a cell at j*G past the pointers: finish the extend, store M, history cell, distance for the reduction
                 auto back = [&](const int k, const int j, int m, const uint32_t id, int cnt, const int lim) {
                     if (cnt == 16 && lim > 16) cnt = extend_more(aP, aT, m - k, m, lim);  // rare
                     m += max(min(cnt, lim), 0);
@@ -324,22 +311,44 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
                     if (REDUCE) md = min(md, max(pl + k, tl) - m);
                 };
                 int k = k0;
-                for (; k + G <= hi; k += 2 * G) {  // two cells per trip: independent chains the scheduler can interleave
-                    int m0, m1, c0, c1, l0, l1;
-                    uint32_t id0, id1;
-                    front(k, 0, m0, id0, c0, l0);
-                    front(k + G, 1, m1, id1, c1, l1);
-                    back(k, 0, m0, id0, c0, l0);
-                    back(k + G, 1, m1, id1, c1, l1);
-                    rB += 4 * G; rA += 4 * G; rNM += 4 * G; rE += 8 * G; rN += 8 * G;
-                    if (BT) hp += 2 * G;
-                }
-                if (k <= hi) {
-                    int m0, c0, l0;
-                    uint32_t id0;
-                    front(k, 0, m0, id0, c0, l0);
-                    back(k, 0, m0, id0, c0, l0);
-                }
+                // N cells per trip in PHASES - all source loads, the recurrences, the {I,D} stores, the first extend windows,
+                // the back halves - so that the N cells' shared-memory loads are in flight together (a store between two
+                // cells' loads would order them: the rows may alias as far as the compiler knows)
+                auto trip = [&](auto nc) {
+                    constexpr int N = decltype(nc)::value;
+                    int g1[N], g2[N], ii[N], dd[N], sb[N], mm[N], cc[N], ll[N];
+                    uint32_t idd[N];
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const uint32_t o2 = (uint32_t)(j * 2 * G), o4 = (uint32_t)(j * 4 * G);
+                        g1[j] = lds_s16(rB + o2 - 2); g2[j] = lds_s16(rB + o2 + 2);
+                        ii[j] = lds_s16(rE + o4 - 4); dd[j] = lds_s16(rE + o4 + 6);
+                        sb[j] = lds_s16(rA + o2);
+                    }
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const int t = max(g1[j], ii[j]) + 1;
+                        const int ins = t == kNull + 1 ? kNull : t;  // both NULL -> NULL (wfa.c:249-252)
+                        const int del = max(g2[j], dd[j]);
+                        mm[j] = max(max(del, sb[j] + 1), max(ins, floor_m));
+                        idd[j] = ((uint32_t)ins & 0xffffu) | ((uint32_t)del << 16);
+                    }
+#pragma unroll
+                    for (int j = 0; j < N; ++j) sts_u32(rN + (uint32_t)(j * 4 * G), idd[j]);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) cc[j] = extend_first(aP, aT, k + j * G, mm[j], pl, tl, &ll[j]);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) back(k + j * G, j, mm[j], idd[j], cc[j], ll[j]);
+                    rB += 2 * N * G; rA += 2 * N * G; rNM += 2 * N * G; rE += 4 * N * G; rN += 4 * N * G;
+                    if (BT) hp += N * G;
+                    k += N * G;
+                };
+#ifndef AIM_CPT
+#define AIM_CPT 2
+#endif
+                while (k + (AIM_CPT - 1) * G <= hi) trip(std::integral_constant<int, AIM_CPT>{});
+                if (AIM_CPT > 2 && k + G <= hi) trip(std::integral_constant<int, 2>{});
+                if (k <= hi) trip(std::integral_constant<int, 1>{});
             }
             __syncwarp();
             // ---- end reached (wfa.c:217-237).  Trimming never removes diagonal ak, so testing before the
