@@ -16,7 +16,7 @@ LIB_PATH = Path(os.environ.get("AIM_B200_LIB", _HERE / "libaim_b200.so"))
 class AimParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "algo", "match", "mismatch", "gap_open", "gap_ext", "max_score", "read_size",
-        "backtrace", "reduce", "ngpus", "device", "arena_mb")] + [("reserved", C.c_int32 * 4)]
+        "backtrace", "reduce", "ngpus", "device", "arena_mb", "variant")] + [("reserved", C.c_int32 * 3)]
 
 
 class AimResult(C.Structure):

@@ -14,8 +14,9 @@ import numpy as np
 
 from ._lib import AimParams, AimResult, lib
 
-ALGO_NW, ALGO_SWG, ALGO_WFA = 0, 1, 2
-_ALGO = {"nw": ALGO_NW, "swg": ALGO_SWG, "wfa": ALGO_WFA}
+ALGO_NW, ALGO_SWG, ALGO_WFA, ALGO_GENASM_DC, ALGO_GENASM_FILTER = 0, 1, 2, 3, 4
+_ALGO = {"nw": ALGO_NW, "swg": ALGO_SWG, "wfa": ALGO_WFA, "genasm_dc": ALGO_GENASM_DC, "genasm_filter": ALGO_GENASM_FILTER}
+STATUS_GENASM_UNDEFINED, STATUS_GENASM_NOALIGN = 3, 4
 
 RESULT_DTYPE = np.dtype([("max_operations", "<i4"), ("begin_offset", "<i4"), ("end_offset", "<i4"),
                          ("score", "<i4"), ("status", "<i4"), ("idx", "<u4")])
@@ -43,6 +44,14 @@ class AlignParams:
     ngpus: int = 1
     device: int = 0
     arena_mb: int = 0
+    variant: int = 0       # GenASM-DC: 1 = DPU-MRAM-DC ('S' for substitutions, pattern 'N' is no wildcard)
+
+    def __post_init__(self):
+        # GenASM-DC always returns its CIGAR string in the ops rows; the filter has none (include/aim_b200.h)
+        if self.algo == "genasm_dc":
+            self.backtrace = True
+        elif self.algo == "genasm_filter":
+            self.backtrace = False
 
     def to_c(self) -> AimParams:
         p = AimParams()
@@ -50,7 +59,7 @@ class AlignParams:
         p.match, p.mismatch, p.gap_open, p.gap_ext = self.match, self.mismatch, self.gap_open, self.gap_ext
         p.max_score, p.read_size = self.max_score, self.read_size
         p.backtrace, p.reduce = int(self.backtrace), int(self.reduce)
-        p.ngpus, p.device, p.arena_mb = self.ngpus, self.device, self.arena_mb
+        p.ngpus, p.device, p.arena_mb, p.variant = self.ngpus, self.device, self.arena_mb, self.variant
         return p
 
 

@@ -140,7 +140,7 @@ bool is_pinned(const void *p)
 int validate(const aim_params *p, bool need_ops, const void *ops)
 {
     if (!p) { set_error("params is NULL"); return AIM_ERR_ARG; }
-    if (p->algo < AIM_ALGO_NW || p->algo > AIM_ALGO_WFA) { set_error("unknown algo"); return AIM_ERR_ARG; }
+    if (p->algo < AIM_ALGO_NW || p->algo > AIM_ALGO_GENASM_FILTER) { set_error("unknown algo"); return AIM_ERR_ARG; }
     if (p->read_size <= 0 || (p->read_size % 8) != 0) { set_error("read_size must be a positive multiple of 8"); return AIM_ERR_ARG; }
     // the run scripts' penalty validation (run-wfa-pim-mram.py:44-46; NW has no gap_ext)
     if (p->match > 0 || p->mismatch <= 0 || p->gap_open <= 0 || (p->algo != AIM_ALGO_NW && p->gap_ext <= 0)) {
@@ -152,9 +152,19 @@ int validate(const aim_params *p, bool need_ops, const void *ops)
     return AIM_OK;
 }
 
+// GenASM-DC always returns its CIGAR string in the ops rows, the filter never has ops
+aim_params normalized(const aim_params *p)
+{
+    aim_params q = *p;
+    if (q.algo == AIM_ALGO_GENASM_DC) q.backtrace = 1;
+    if (q.algo == AIM_ALGO_GENASM_FILTER) q.backtrace = 0;
+    return q;
+}
+
 int launch(const KernelArgs &a, Scratch *s, cudaStream_t stream, int *launches)
 {
     if (a.p.algo == AIM_ALGO_WFA) return launch_wfa(a, s, stream, launches);
+    if (a.p.algo == AIM_ALGO_GENASM_DC || a.p.algo == AIM_ALGO_GENASM_FILTER) return launch_genasm(a, s, stream, launches);
     return launch_dp(a, s, stream, launches);
 }
 
@@ -341,6 +351,9 @@ extern "C" int aim_align_device(const aim_params *params, int device, uint32_t n
                                 const char *d_texts, aim_result *d_results, char *d_ops, void *stream,
                                 float *kernel_ms, int32_t *launches)
 {
+    if (!params) { set_error("params is NULL"); return AIM_ERR_ARG; }
+    const aim_params norm = normalized(params);
+    params = &norm;
     int rc = validate(params, true, d_ops);
     if (rc != AIM_OK) return rc;
     if (!d_plen || !d_tlen || !d_patterns || !d_texts || !d_results) { set_error("NULL device buffer"); return AIM_ERR_ARG; }
@@ -376,6 +389,9 @@ extern "C" int aim_align_batch(const aim_params *params, uint32_t n, uint32_t id
                                const int32_t *tlen, const char *patterns, const char *texts,
                                aim_result *results, char *ops, double phase_ms[3])
 {
+    if (!params) { set_error("params is NULL"); return AIM_ERR_ARG; }
+    const aim_params norm = normalized(params);
+    params = &norm;
     int rc = validate(params, true, ops);
     if (rc != AIM_OK) return rc;
     if (n > 0 && (!plen || !tlen || !patterns || !texts || !results)) { set_error("NULL host buffer"); return AIM_ERR_ARG; }

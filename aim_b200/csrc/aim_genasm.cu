@@ -1,0 +1,341 @@
+// GenASM-DC / GenASM-filter for sm_100a (the aim-genasm submodule's DPU kernels).
+//
+// Reference: aim-genasm/GenASM/DPU-WRAM-DC/dpu/genasmDC.c (pattern bitmasks :40-88, genasmDC :338-556,
+// genasmTB :90-336) and aim-genasm/GenASM/DPU-WRAM-filter/dpu/genasm_filter.c:52-239.  Bitap with k = MAX_SCORE
+// error levels over the WHOLE pattern (m-bit vectors of count = (m + 64) / 64 words), text walked from its last
+// character to its first; R[d] = del & sub & ins & match with del = oldR[d-1], sub = oldR[d-1] << 1,
+// ins = R[d-1] << 1 (the NEW R of the level below), match = (oldR[d] << 1) | mask[c].
+//
+// B200 mapping.  `ins` chains the levels inside one text step, so the levels run as a SYSTOLIC array over the
+// lanes of a sub-warp: lane j owns levels j*LPL .. j*LPL+LPL-1 in registers and works one text step behind lane
+// j-1, from which it pulls (two shuffles per word) that lane's top level after steps u and u-1.  G = 4..32 lanes
+// per pair, 32/G pairs per warp, persistent warps striding over the pairs.  The pattern bitmasks and the text's
+// 2-bit codes sit in shared memory.  The reference's traceback matrix (4 vectors per text step and level,
+// genasmDC.c:386,461-470,515-525) is not stored: all four are shifts of R, so only R[level][text step] streams to
+// a per-pair-slot HBM arena (one quarter of the bytes) and the traceback - first lane of every sub-warp, side by
+// side - reads the three or four BITS it tests per step (genasmDC.c:107-322) straight from it; row n (the state
+// before any text) is known in closed form.  The CIGAR leaves in the reference's own format: run lengths with
+// their decimal digits REVERSED (genasmDC.c:128-135), NUL-terminated, max_operations = strlen + 1.
+//
+// Pairs whose reference output depends on memory the reference never wrote for them get a status instead
+// (AIM_STATUS_GENASM_UNDEFINED: a text byte outside ACGTacgt skips the traceback rows of that step; the traceback
+// walks to text row n) - see oracle/aim_oracle.c.  "No alignment found" (genasmDC.c:543-547): score -1,
+// AIM_STATUS_GENASM_NOALIGN.  variant 1 = DPU-MRAM-DC: substitutions print as 'S' and a pattern 'N' is no wildcard.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+
+#include "aim_internal.h"
+
+namespace aim {
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+struct GenK {
+    const int32_t *plen;
+    const int32_t *tlen;
+    const char *patterns;
+    const char *texts;
+    aim_result *results;
+    char *ops;
+    u64 *hist;          // DC only: per pair slot [level][text step][count] words (word 0 = bits 0..63)
+    size_t hist_stride; // words per pair slot
+    uint32_t n, idx_base;
+    int k, read_size, G, variant;
+    int match, mismatch, gap_oe, gap_e;
+    uint32_t slot_bytes; // shared memory per pair slot: 4 * W bitmask words, then read_size text codes
+};
+
+__device__ __forceinline__ int base_code(int c)
+{   // genasmDC.c:57-74: upper or lower case A, C, G, T; anything else is 4
+    c &= ~0x20;
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+}
+
+template <int W>
+__device__ __forceinline__ void shl1(u64 (&dst)[W], const u64 (&src)[W])
+{
+#pragma unroll
+    for (int w = 0; w < W; ++w) dst[w] = (src[w] << 1) | (w ? src[w - 1] >> 63 : 0ull);
+}
+
+template <int W, int LPL, bool DC>
+__global__ void __launch_bounds__(128) genasm_kernel(const GenK K)
+{
+    extern __shared__ __align__(16) unsigned char smem_g[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int G = K.G, PPW = 32 / G;
+    const int sub = lane / G, sl = lane - sub * G;
+    unsigned char *slot = smem_g + (size_t)(wib * PPW + sub) * K.slot_bytes;
+    u64 *pm = reinterpret_cast<u64 *>(slot);
+    unsigned char *codes = slot + 4 * W * 8;
+    const uint32_t wpb = blockDim.x >> 5;
+    const uint32_t slot_global = (blockIdx.x * wpb + wib) * PPW + sub;
+    const uint32_t nslots = gridDim.x * wpb * PPW;
+    u64 *hist = DC ? K.hist + (size_t)slot_global * K.hist_stride : nullptr;
+    const int k = K.k, RS = K.read_size;
+
+    for (uint32_t base_i = 0; base_i < K.n; base_i += nslots) {  // warp-uniform trip count
+        const uint32_t i = base_i + slot_global;
+        const bool active = i < K.n;
+        const int m = active ? min(max(K.plen[i], 0), RS) : 0;
+        const int n = active ? min(max(K.tlen[i], 0), RS) : 0;
+        const int count = (m + 64) / 64;
+        const char *gp = K.patterns + (size_t)(active ? i : 0) * RS, *gt = K.texts + (size_t)(active ? i : 0) * RS;
+
+        // ---- stage: text codes, all-ones bitmasks, then clear the pattern's bits (genasmDC.c:40-88) ----
+        for (int q = sl; q < 4 * W; q += G) pm[q] = ~0ull;
+        bool text_ok = true;
+        for (int j8 = sl; j8 * 8 < n; j8 += G) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(gt + j8 * 8));
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c0 = base_code((int)((v.x >> (8 * b)) & 0xffu)), c1 = base_code((int)((v.y >> (8 * b)) & 0xffu));
+                if (j8 * 8 + b < n && c0 > 3) text_ok = false;
+                if (j8 * 8 + 4 + b < n && c1 > 3) text_ok = false;
+                lo |= (uint32_t)c0 << (8 * b);
+                hi |= (uint32_t)c1 << (8 * b);
+            }
+            *reinterpret_cast<uint2 *>(codes + j8 * 8) = make_uint2(lo, hi);
+        }
+        __syncwarp();
+        for (int j = sl; j < m; j += G) {
+            const int ch = gp[j], c = base_code(ch), b = m - 1 - j;
+            unsigned *w32 = reinterpret_cast<unsigned *>(pm) + (b >> 5);  // 32-bit half of word b / 64 (little-endian words)
+            const unsigned clr = ~(1u << (b & 31));
+            if (c < 4) atomicAnd(w32 + c * W * 2, clr);
+            else if ((ch & ~0x20) == 'N' && K.variant == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) atomicAnd(w32 + q * W * 2, clr);
+            }
+        }
+        // the whole sub-warp must agree on text_ok
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int o = __shfl_xor_sync(kFullMask, (int)text_ok, off);
+            if (off < G) text_ok = text_ok && o;
+        }
+        __syncwarp();
+
+        // ---- initial state (genasmDC.c:401-425): level d = all ones shifted left by d ----
+        u64 cur[LPL][W], prev[W];
+#pragma unroll
+        for (int l = 0; l < LPL; ++l) {
+            const int d = sl * LPL + l;
+#pragma unroll
+            for (int w = 0; w < W; ++w) cur[l][w] = d >= 64 * (w + 1) ? 0ull : (d <= 64 * w ? ~0ull : (~0ull << (d - 64 * w)));
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) prev[w] = cur[LPL - 1][w];
+
+        // ---- the fill: tick t, lane j is on text step u = t - j, i.e. text index n - 1 - u (genasmDC.c:428-527) ----
+        const int tmax = __reduce_max_sync(kFullMask, n) + G - 1;
+        for (int t = 0; t < tmax; ++t) {
+            const int u = t - sl;
+            u64 lo_new[W], lo_old[W];  // the level below this lane's first level: after steps u and u - 1
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                lo_new[w] = __shfl_up_sync(kFullMask, cur[LPL - 1][w], 1, G);
+                lo_old[w] = __shfl_up_sync(kFullMask, prev[w], 1, G);
+            }
+            if (u >= 0 && u < n) {
+                const int ti = n - 1 - u;
+                const int c = codes[ti];
+                if (c < 4) {
+                    u64 pmw[W], save[W];
+#pragma unroll
+                    for (int w = 0; w < W; ++w) { pmw[w] = pm[c * W + w]; save[w] = cur[LPL - 1][w]; }
+#pragma unroll
+                    for (int l = 0; l < LPL; ++l) {
+                        const int d = sl * LPL + l;
+                        u64 old_d[W], mat[W], nw[W];
+#pragma unroll
+                        for (int w = 0; w < W; ++w) old_d[w] = cur[l][w];
+                        shl1<W>(mat, old_d);
+#pragma unroll
+                        for (int w = 0; w < W; ++w) mat[w] |= pmw[w];
+                        if (d == 0) {
+#pragma unroll
+                            for (int w = 0; w < W; ++w) nw[w] = mat[w];
+                        } else {
+                            u64 sb[W], in[W];
+                            shl1<W>(sb, lo_old);
+                            shl1<W>(in, lo_new);
+#pragma unroll
+                            for (int w = 0; w < W; ++w) nw[w] = lo_old[w] & sb[w] & in[w] & mat[w];
+                        }
+#pragma unroll
+                        for (int w = 0; w < W; ++w) { lo_old[w] = old_d[w]; lo_new[w] = nw[w]; cur[l][w] = nw[w]; }
+                        if (DC && d <= k) {
+                            u64 *h = hist + ((size_t)d * RS + ti) * count;
+#pragma unroll
+                            for (int w = 0; w < W; ++w) if (w < count) h[w] = nw[w];
+                        }
+                    }
+#pragma unroll
+                    for (int w = 0; w < W; ++w) prev[w] = save[w];
+                } else {  // the reference skips the step: R is unchanged
+#pragma unroll
+                    for (int w = 0; w < W; ++w) prev[w] = cur[LPL - 1][w];
+                }
+            }
+        }
+
+        // ---- lowest level whose end bit is clear (genasmDC.c:389-399,530-541: word 0 of the reference = word count-1) ----
+        const int end_bit = (count - 1) * 64 + ((m & 63) ? (m & 63) - 1 : 63);
+        int lvl = 1 << 20;
+#pragma unroll
+        for (int l = LPL - 1; l >= 0; --l) {
+            const int d = sl * LPL + l;
+            u64 word = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) if (w == (end_bit >> 6)) word = cur[l][w];
+            if (d <= k && !((word >> (end_bit & 63)) & 1ull)) lvl = d;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int o = __shfl_xor_sync(kFullMask, lvl, off);
+            if (off < G) lvl = min(lvl, o);
+        }
+        const int min_error = lvl > k ? -1 : lvl;
+        __syncwarp();  // the arena stores of every lane are visible to the traceback lane
+
+        if (active && sl == 0) {
+            aim_result r;
+            r.max_operations = DC ? m + n : 0;
+            r.begin_offset = 0;
+            r.end_offset = 0;
+            r.score = DC ? -1 : min_error;
+            r.status = AIM_STATUS_OK;
+            r.idx = K.idx_base + i;
+            if (DC) {
+                char *cig = K.ops + (size_t)i * 2 * RS;
+                const int cap = 2 * RS;
+                if (min_error < 0) { r.status = AIM_STATUS_GENASM_NOALIGN; cig[0] = '\0'; }
+                else if (!text_ok) { r.status = AIM_STATUS_GENASM_UNDEFINED; cig[0] = '\0'; }
+                else {
+                    // genasmTB (genasmDC.c:90-336).  bit b of R[d] after text index ti; ti == n is the initial state
+                    auto hbit = [&](int ti, int d, int b) -> unsigned {
+                        if (b < 0) return 0u;
+                        if (ti >= n) return b >= d ? 1u : 0u;
+                        return (unsigned)((hist[((size_t)d * RS + ti) * count + (b >> 6)] >> (b & 63)) & 1ull);
+                    };
+                    int cp = m - 1, ct = 0, ce = min_error, c = 0;
+                    int nM = 0, nS = 0, nOpen = 0, nExt = 0, run = 0;
+                    char last = '0';
+                    bool first = true, undefined = false;
+                    const char sub_ch = K.variant ? 'S' : 'X';
+                    auto flush = [&]() {
+                        if (first) return;
+                        int num = run;
+                        while (num != 0 && c < cap - 2) { cig[c++] = (char)('0' + num % 10); num /= 10; }
+                        if (c < cap - 1) cig[c++] = last;
+                    };
+                    while (cp >= 0 && ce >= 0) {
+                        if (ct >= n) { undefined = true; break; }
+                        unsigned t0, t1 = 1u, t2 = 1u, t3 = 1u;
+                        if (ce == 0) t0 = hbit(ct, 0, cp);
+                        else {
+                            const unsigned a = hbit(ct + 1, ce, cp - 1), s1 = hbit(ct + 1, ce - 1, cp - 1);
+                            const unsigned i1 = hbit(ct, ce - 1, cp - 1), d1 = hbit(ct + 1, ce - 1, cp);
+                            const int cc = codes[ct];
+                            t0 = a | (unsigned)((pm[cc * W + (cp >> 6)] >> (cp & 63)) & 1ull);
+                            t1 = s1; t2 = i1; t3 = d1;
+                        }
+                        if (last == 'I' && t2 == 0) { --cp; --ce; ++run; ++nExt; }
+                        else if (last == 'D' && t3 == 0) { ++ct; --ce; ++run; ++nExt; }
+                        else if (t0 == 0) {
+                            ++ct; --cp;
+                            if (last == 'M') ++run; else { flush(); run = 1; last = 'M'; }
+                            ++nM;
+                        } else if (t1 == 0) {
+                            ++ct; --cp; --ce;
+                            if (last == sub_ch) ++run; else { flush(); run = 1; last = sub_ch; }
+                            ++nS;
+                        } else if (t3 == 0) { ++ct; --ce; flush(); run = 1; last = 'D'; ++nOpen; }
+                        else if (t2 == 0) { --cp; --ce; flush(); run = 1; last = 'I'; ++nOpen; }
+                        else { undefined = true; break; }  // the reference would spin forever
+                        first = false;
+                    }
+                    if (undefined) { r.status = AIM_STATUS_GENASM_UNDEFINED; cig[0] = '\0'; }
+                    else {
+                        int num = run;
+                        while (num != 0 && c < cap - 2) { cig[c++] = (char)('0' + num % 10); num /= 10; }
+                        if (c < cap - 1) cig[c++] = last;
+                        cig[c] = '\0';
+                        r.max_operations = c + 1;
+                        r.end_offset = c;
+                        r.score = nM * K.match + nS * K.mismatch + nOpen * K.gap_oe + nExt * K.gap_e;
+                    }
+                }
+            }
+            K.results[i] = r;
+        }
+        __syncwarp();
+    }
+}
+
+template <int W, int LPL>
+cudaError_t launch_wl(const GenK &K, bool dc, int grid, size_t smem, cudaStream_t st)
+{
+    if (dc) genasm_kernel<W, LPL, true><<<grid, 128, smem, st>>>(K);
+    else genasm_kernel<W, LPL, false><<<grid, 128, smem, st>>>(K);
+    return cudaGetLastError();
+}
+template <int W>
+cudaError_t launch_w(const GenK &K, int lpl, bool dc, int grid, size_t smem, cudaStream_t st)
+{
+    if (lpl == 1) return launch_wl<W, 1>(K, dc, grid, smem, st);
+    if (lpl == 2) return launch_wl<W, 2>(K, dc, grid, smem, st);
+    return launch_wl<W, 4>(K, dc, grid, smem, st);
+}
+
+}  // namespace
+
+int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
+{
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const aim_params &p = a.p;
+    const bool dc = p.algo == AIM_ALGO_GENASM_DC;
+    const int k = p.max_score;
+    const int count_max = (p.read_size + 64) / 64;
+    if (k + 1 > 128) { set_error("GenASM: MAX_SCORE above 127 is not served by the B200 kernel"); return AIM_ERR_ARG; }
+    if (count_max > 8) { set_error("GenASM: READ_SIZE above 448 is not served by the B200 kernel"); return AIM_ERR_ARG; }
+    const int lpl = k + 1 <= 32 ? 1 : (k + 1 <= 64 ? 2 : 4);
+    int G = 4;
+    while (G * lpl < k + 1) G *= 2;
+    const int W = count_max <= 2 ? 2 : (count_max <= 4 ? 4 : 8);
+
+    GenK K{};
+    K.plen = a.plen; K.tlen = a.tlen; K.patterns = a.patterns; K.texts = a.texts; K.results = a.results; K.ops = a.ops;
+    K.n = a.n; K.idx_base = a.idx_base; K.k = k; K.read_size = p.read_size; K.G = G; K.variant = p.variant;
+    K.match = p.match; K.mismatch = p.mismatch; K.gap_oe = p.gap_open + p.gap_ext; K.gap_e = p.gap_ext;
+    K.slot_bytes = (uint32_t)(4 * W * 8 + p.read_size);
+    const int PPW = 32 / G;
+    const size_t smem = (size_t)4 * PPW * K.slot_bytes;
+    int blocks_per_sm = W == 8 || lpl == 4 ? 4 : (W == 4 || lpl == 2 ? 8 : 16);
+    K.hist_stride = dc ? (size_t)(k + 1) * (size_t)p.read_size * (size_t)count_max : 0;
+    while (blocks_per_sm > 1 && (size_t)sc->sm_count * blocks_per_sm * 4 * PPW * K.hist_stride * 8 > ((size_t)6 << 30)) blocks_per_sm /= 2;
+    int grid = sc->sm_count * blocks_per_sm;
+    {
+        const uint64_t per_block = (uint64_t)4 * PPW;
+        if ((uint64_t)grid * per_block > a.n) grid = (int)std::max<uint64_t>(1, (a.n + per_block - 1) / per_block);
+    }
+    if (a.n == 0) return AIM_OK;
+    const size_t hist_bytes = (size_t)grid * 4 * PPW * K.hist_stride * 8;
+    int rc = scratch_reserve(sc, std::max<size_t>(hist_bytes, 256));
+    if (rc != AIM_OK) return rc;
+    K.hist = reinterpret_cast<u64 *>(sc->buf);
+    cudaError_t err = W == 2 ? launch_w<2>(K, lpl, dc, grid, smem, stream)
+                             : (W == 4 ? launch_w<4>(K, lpl, dc, grid, smem, stream) : launch_w<8>(K, lpl, dc, grid, smem, stream));
+    if (err != cudaSuccess) { set_error(std::string("genasm launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
+    if (launches) ++*launches;
+    return AIM_OK;
+}
+
+}  // namespace aim

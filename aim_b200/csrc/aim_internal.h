@@ -68,6 +68,8 @@ int launch_wfa(const KernelArgs &a, Scratch *s, void *stream, int *launches);
 // lockstep short-read kernel; returns 1 when the configuration must go to launch_wfa's warp-per-pair kernel
 int launch_wfa_sub(const KernelArgs &a, Scratch *s, void *stream, int *launches);
 int launch_dp(const KernelArgs &a, Scratch *s, void *stream, int *launches);
+// GenASM-DC / GenASM-filter (aim_genasm.cu)
+int launch_genasm(const KernelArgs &a, Scratch *s, void *stream, int *launches);
 // register-strip / shared-memory-row kernels (aim_dp_fast.cu); returns 1 when launch_dp's literal kernel must serve the batch
 int launch_dp_fast(const KernelArgs &a, Scratch *s, void *stream, int *launches);
 

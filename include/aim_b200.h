@@ -23,6 +23,10 @@ extern "C" {
 #define AIM_ALGO_NW 0  /* NW/DPU-{WRAM,MRAM}: linear gap, int16 flat table (NW/DPU-WRAM/dpu/nw.c:109-153)      */
 #define AIM_ALGO_SWG 1 /* SWG/DPU-MRAM: gap-affine, int16 cells, MAX_SCORE borders (SWG/DPU-MRAM/dpu/swg.c:151) */
 #define AIM_ALGO_WFA 2 /* WFA/DPU-{WRAM,MRAM}: gap-affine WFA, +adaptive with reduce=1 (WFA/DPU-MRAM/dpu/wfa.c:356) */
+/* aim-genasm submodule.  max_score = k error levels; results: score = the reference's
+ * "bitmacScore" (DC, genasmDC.c:553) or the minimum error level (filter, genasm_filter.c:226-238; -1 = none). */
+#define AIM_ALGO_GENASM_DC 3     /* GenASM/DPU-{WRAM,MRAM}-DC: Bitap + traceback (aim-genasm/GenASM/DPU-WRAM-DC/dpu/genasmDC.c:338) */
+#define AIM_ALGO_GENASM_FILTER 4 /* GenASM/DPU-{WRAM,MRAM}-filter (aim-genasm/GenASM/DPU-WRAM-filter/dpu/genasm_filter.c:52)        */
 
 /* Return codes (the reference aborts the process through DPU_ASSERT/exit instead). */
 #define AIM_OK 0
@@ -37,6 +41,10 @@ extern "C" {
 #define AIM_STATUS_OK 0
 #define AIM_STATUS_BACKTRACE 1 /* reference would print "No link found"/"No backtrace operation found" and exit(1) */
 #define AIM_STATUS_ARENA 2     /* wavefront history exceeded the per-pair arena (reference: "Out of memory MRAM") */
+#define AIM_STATUS_GENASM_UNDEFINED 3 /* GenASM-DC: the reference's traceback reads rows it never wrote for this pair (a text
+                                       * byte outside ACGTacgt, or the walk reaches text row n): its output is not a function
+                                       * of the pair; no CIGAR is returned                                                     */
+#define AIM_STATUS_GENASM_NOALIGN 4   /* GenASM-DC: "No alignment found!" within max_score errors (genasmDC.c:543-547), score -1 */
 
 /* The compile-time knobs of the reference (-DMAX_SCORE -DREAD_SIZE -DMATCH -DMISMATCH -DGAP_O
  * -DGAP_E [-DGAP_I -DGAP_D] [-DBACKTRACE] [-DREDUCE]; WFA/DPU-MRAM/run-wfa-pim-mram.py:133-139)
@@ -55,7 +63,8 @@ typedef struct aim_params {
     int32_t ngpus;      /* <=1: one device; N: shard pairs contiguously over N devices */
     int32_t device;     /* first device ordinal                                        */
     int32_t arena_mb;   /* long-read WFA history arena per resident pair in MiB (0 = default) */
-    int32_t reserved[4];
+    int32_t variant;    /* GenASM-DC: 0 = DPU-WRAM-DC semantics, 1 = DPU-MRAM-DC ('S' for substitutions, pattern 'N' no wildcard) */
+    int32_t reserved[3];
 } aim_params;
 
 /* result_t of the reference (WFA/DPU-MRAM/common/common.h:179-187; NW/DPU-WRAM/common/common.h:122-130)
@@ -68,6 +77,12 @@ typedef struct aim_result {
     int32_t status;         /* AIM_STATUS_*                                                  */
     uint32_t idx;           /* 0-based pair number                                           */
 } aim_result;
+
+/* GenASM through the same two entry points (aim-genasm/GenASM/DPU-WRAM-DC/host/host.c:150-300 is the same host
+ * skeleton): algo = AIM_ALGO_GENASM_DC writes pair i's CIGAR STRING - the reference's own format, run lengths with
+ * REVERSED decimal digits, NUL-terminated (genasmDC.c:128-135,323-335) - at ops + i*2*read_size and sets
+ * max_operations = strlen + 1 (result_t.max_operations), begin_offset = 0, end_offset = strlen; backtrace is implied.
+ * algo = AIM_ALGO_GENASM_FILTER returns scores only (ops may be NULL). */
 
 /* ---- the device boundary (replaces host.c:186-330) ----------------------------------------
  * Align n pairs held in HOST memory.  Layout is the reference host's own (host.c:126-131,

@@ -24,12 +24,15 @@
 #define ORC_ALGO_NW 0
 #define ORC_ALGO_SWG 1
 #define ORC_ALGO_WFA 2
+#define ORC_ALGO_GENASM_DC 3
+#define ORC_ALGO_GENASM_FILTER 4
 
 #define ORC_OK 0
 #define ORC_ERR_BACKTRACE 1 /* reference would print "No link found"/"No backtrace operation found" and exit(1) */
 
 typedef struct {
     int32_t algo, match, mismatch, gap_open, gap_ext, max_score, read_size, backtrace, reduce;
+    int32_t variant; /* GenASM-DC: 1 = DPU-MRAM-DC ('S' for substitutions, pattern 'N' is no wildcard: genasmDC.c of that directory) */
 } orc_params;
 
 typedef struct {
@@ -433,6 +436,167 @@ static void swg_align(const orc_params *p, const char *pattern, const char *text
 }
 
 /* ------------------------------------------------------------------------------------------
+ * GenASM-DC / GenASM-filter (aim-genasm submodule).
+ * Follows aim-genasm/GenASM/DPU-WRAM-DC/dpu/genasmDC.c: pattern bitmasks :40-88, genasmDC :338-556
+ * (bit-vector fill + traceback matrix), genasmTB :90-336 (traceback, CIGAR with REVERSED count digits),
+ * score :553; filter = aim-genasm/GenASM/DPU-WRAM-filter/dpu/genasm_filter.c:52-239 (same fill, no
+ * traceback, returns the minimum error level).  Bit vectors are `count` 64-bit words, word 0 the MOST
+ * significant, count = (m + 64) / 64; the end test reads word 0 with bit (m % 64 ? m % 64 - 1 : 63)
+ * (genasmDC.c:389-399,530-541) - kept literally, so m % 64 == 0 never finds an alignment.
+ * Where the reference reads memory it never wrote for this pair the result is UNDEFINED there
+ * (it depends on what earlier pairs left in the tasklet's MRAM segment): a text byte outside ACGTacgt skips
+ * the whole step including the traceback rows (genasmDC.c:430-433), and the traceback may step to text row n
+ * (pattern longer than the text consumed).  Those pairs get status ORC_GENASM_UNDEFINED and are excluded
+ * from parity; "No alignment found" (score -1, CIGAR buffer untouched) gets ORC_GENASM_NOALIGN.
+ * ------------------------------------------------------------------------------------------ */
+#define ORC_GENASM_UNDEFINED 3
+#define ORC_GENASM_NOALIGN 4
+typedef unsigned long long u64_t;
+
+static int genasm_code(char c)
+{
+    switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return -1;
+    }
+}
+
+static void genasm_shl1(u64_t *dst, const u64_t *src, int count)
+{   /* genasmDC.c:474-479: word 0 is the most significant */
+    dst[0] = src[0] << 1;
+    for (int a = 1; a < count; a++) { dst[a - 1] |= (src[a] >> 63); dst[a] = src[a] << 1; }
+}
+
+static void genasm_align(const orc_params *p, const char *pattern, const char *text, int m, int n, orc_result *res,
+                         char *cigar, int with_tb)
+{
+    const int k = p->max_score;
+    const int count = (int)((m + 64) / 64.0);
+    const u64_t max = ~0ULL;
+    res->max_operations = m + n;
+    res->begin_offset = 0;
+    res->end_offset = 0;
+    res->score = -1;
+    res->status = ORC_OK;
+    /* pattern bitmasks (genasmDC.c:40-88) */
+    u64_t *pm = (u64_t *)malloc(sizeof(u64_t) * 4 * count);
+    for (int i = 0; i < 4 * count; i++) pm[i] = max;
+    for (int i = 0; i < m; i++) {
+        const int index = count - ((m - i - 1) / 64) - 1;
+        const u64_t bit = ~(1ULL << ((m - i - 1) % 64));
+        const int c = genasm_code(pattern[i]);
+        if (c >= 0) pm[c * count + index] &= bit;
+        else if ((pattern[i] == 'N' || pattern[i] == 'n') && !p->variant) for (int q = 0; q < 4; q++) pm[q * count + index] &= bit;
+    }
+    const int len1 = (k + 1) * count;
+    u64_t *R = (u64_t *)malloc(sizeof(u64_t) * len1), *oldR = (u64_t *)malloc(sizeof(u64_t) * len1);
+    u64_t *sub = (u64_t *)malloc(sizeof(u64_t) * count * 4), *ins = sub + count, *mat = ins + count, *del = mat + count;
+    /* traceback matrix [n][k+1][4][count] (genasmDC.c:386) + which text rows were written */
+    u64_t *tb = with_tb ? (u64_t *)malloc(sizeof(u64_t) * (size_t)(n > 0 ? n : 1) * (k + 1) * 4 * count) : NULL;
+    char *row_written = with_tb ? (char *)calloc((size_t)n + 1, 1) : NULL;
+    const int rem = m % 64;
+    const u64_t max1 = rem == 0 ? (1ULL << 63) : (1ULL << (rem - 1));
+    for (int i = 0; i < len1; i++) R[i] = max;
+    for (int x = 1; x < k + 1; x++) {   /* genasmDC.c:406-425 */
+        if ((x % 64) == 0) {
+            const int ind = count - (x / 64);
+            for (int y = count - 1; y >= ind && y >= 0; y--) R[x * count + y] = 0ULL;
+        } else {
+            const int ind = count - 1 - (x / 64);
+            for (int y = count - 1; y > ind && y >= 0; y--) R[x * count + y] = 0ULL;
+            if (ind >= 0) R[x * count + ind] = max << (x % 64);
+        }
+    }
+    for (int i = n - 1; i >= 0; i--) {   /* genasmDC.c:428-527 */
+        const int c = genasm_code(text[i]);
+        if (c < 0) continue;
+        const u64_t *cur = pm + c * count;
+        memcpy(oldR, R, sizeof(u64_t) * len1);
+        genasm_shl1(R, oldR, count);
+        for (int a = 0; a < count; a++) R[a] |= cur[a];
+        if (with_tb) {
+            row_written[i] = 1;
+            for (int a = 0; a < count; a++) {
+                u64_t *t = tb + (((size_t)i * (k + 1) + 0) * 4) * count;
+                t[0 * count + a] = R[a]; t[1 * count + a] = max; t[2 * count + a] = max; t[3 * count + a] = max;
+            }
+        }
+        for (int d = 1; d <= k; d++) {
+            int index = (d - 1) * count;
+            for (int a = 0; a < count; a++) del[a] = oldR[index + a];
+            genasm_shl1(sub, del, count);
+            genasm_shl1(ins, R + index, count);
+            index += count;
+            genasm_shl1(mat, oldR + index, count);
+            for (int a = 0; a < count; a++) mat[a] |= cur[a];
+            for (int a = 0; a < count; a++) R[index + a] = del[a] & sub[a] & ins[a] & mat[a];
+            if (with_tb) {
+                u64_t *t = tb + (((size_t)i * (k + 1) + d) * 4) * count;
+                for (int a = 0; a < count; a++) {
+                    t[0 * count + a] = mat[a]; t[1 * count + a] = sub[a]; t[2 * count + a] = ins[a]; t[3 * count + a] = del[a];
+                }
+            }
+        }
+    }
+    int minError = -1;
+    for (int t = 0; t <= k; t++) if ((R[t * count] & max1) == 0) { minError = t; break; }   /* genasmDC.c:530-541 */
+    if (!with_tb) { res->score = minError; res->max_operations = 0; goto out; }   /* genasm_filter.c:226-238 */
+    if (minError == -1) { res->status = ORC_GENASM_NOALIGN; goto out; }   /* genasmDC.c:543-547 */
+    for (int i = 0; i < n; i++) if (!row_written[i]) { res->status = ORC_GENASM_UNDEFINED; goto out; }
+    {   /* genasmTB (genasmDC.c:90-336) */
+        int curPattern = m - 1, curText = 0, curError = minError, c = 0;
+        int countM = 0, countS = 0, countOpen = 0, countExtend = 0, charCount = 0, isFirst = 1;
+        char lastChar = '0';
+        const char subChar = p->variant ? 'S' : 'X';
+        u64_t mask = max1;
+#define GENASM_FLUSH() do { if (!isFirst) { int num = charCount; while (num != 0) { cigar[c++] = (char)(num % 10 + '0'); num /= 10; } cigar[c++] = lastChar; } } while (0)
+        while (curPattern >= 0 && curError >= 0) {
+            if (curText >= n) { res->status = ORC_GENASM_UNDEFINED; goto out; }   /* reads rows the pair never wrote */
+            const int ind = count - (curPattern / 64) - 1;
+            const u64_t *t = tb + (((size_t)curText * (k + 1) + curError) * 4) * count;
+            const u64_t t0 = t[0 * count + ind], t1 = t[1 * count + ind], t2 = t[2 * count + ind], t3 = t[3 * count + ind];
+            if (lastChar == 'I' && (t2 & mask) == 0) {          /* affine-insertion: always an extension */
+                curPattern -= 1; curError -= 1;
+                charCount += 1; countExtend += 1;
+            } else if (lastChar == 'D' && (t3 & mask) == 0) {   /* affine-deletion: always an extension */
+                curText += 1; curError -= 1;
+                charCount += 1; countExtend += 1;
+            } else if ((t0 & mask) == 0) {                      /* match */
+                curText += 1; curPattern -= 1;
+                if (lastChar == 'M') charCount += 1;
+                else { GENASM_FLUSH(); charCount = 1; lastChar = 'M'; }
+                countM += 1;
+            } else if ((t1 & mask) == 0) {                      /* substitution */
+                curText += 1; curPattern -= 1; curError -= 1;
+                if (lastChar == subChar) charCount += 1;
+                else { GENASM_FLUSH(); charCount = 1; lastChar = subChar; }
+                countS += 1;
+            } else if ((t3 & mask) == 0) {                      /* deletion (lastChar != 'D' here): opens */
+                curText += 1; curError -= 1;
+                GENASM_FLUSH(); charCount = 1; lastChar = 'D'; countOpen += 1;
+            } else if ((t2 & mask) == 0) {                      /* insertion (lastChar != 'I' here): opens */
+                curPattern -= 1; curError -= 1;
+                GENASM_FLUSH(); charCount = 1; lastChar = 'I'; countOpen += 1;
+            } else { res->status = ORC_GENASM_UNDEFINED; goto out; }   /* the reference would spin forever */
+            if (curPattern >= 0) mask = 1ULL << (curPattern % 64);
+            isFirst = 0;
+        }
+        { int num = charCount; while (num != 0) { cigar[c++] = (char)(num % 10 + '0'); num /= 10; } }
+        cigar[c++] = lastChar;
+        cigar[c] = '\0';
+#undef GENASM_FLUSH
+        res->max_operations = c + 1;
+        res->end_offset = c;
+        res->score = countM * p->match + countS * p->mismatch + countOpen * (p->gap_open + p->gap_ext) + countExtend * p->gap_ext;
+    }
+out:
+    free(pm); free(R); free(oldR); free(sub); free(tb); free(row_written);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Batch driver: contiguous partition of pairs over host threads, like the host's per-DPU split
  * (WFA/DPU-MRAM/host/host.c:191-209).  Buffers are laid out as host.c:126-127 lays them out:
  * pair i's pattern at patterns + i*read_size, ops at ops + i*2*read_size.
@@ -457,7 +621,9 @@ static void *orc_worker(void *arg)
     for (uint32_t i = j->first; i < j->last; ++i) {
         const char *pat = j->patterns + (size_t)i * rs, *txt = j->texts + (size_t)i * rs;
         char *ops = j->ops ? j->ops + (size_t)i * 2 * rs : NULL;
-        if (p->algo == ORC_ALGO_WFA) wfa_align(p, pat, txt, j->plen[i], j->tlen[i], &j->results[i], ops);
+        if (p->algo == ORC_ALGO_GENASM_DC) genasm_align(p, pat, txt, j->plen[i], j->tlen[i], &j->results[i], ops, 1);
+        else if (p->algo == ORC_ALGO_GENASM_FILTER) genasm_align(p, pat, txt, j->plen[i], j->tlen[i], &j->results[i], NULL, 0);
+        else if (p->algo == ORC_ALGO_WFA) wfa_align(p, pat, txt, j->plen[i], j->tlen[i], &j->results[i], ops);
         else if (p->algo == ORC_ALGO_NW) nw_align(p, pat, txt, j->plen[i], j->tlen[i], &j->results[i], ops, (int16_t *)tab);
         else swg_align(p, pat, txt, j->plen[i], j->tlen[i], &j->results[i], ops, (swg_cell *)tab);
     }
@@ -468,7 +634,7 @@ static void *orc_worker(void *arg)
 int orc_align_batch(const orc_params *p, uint32_t n, const int32_t *plen, const int32_t *tlen,
                     const char *patterns, const char *texts, orc_result *results, char *ops, int nthreads)
 {
-    if (!p || p->algo < 0 || p->algo > 2 || p->read_size <= 0) return -1;
+    if (!p || p->algo < 0 || p->algo > 4 || p->read_size <= 0) return -1;
     for (uint32_t i = 0; i < n; ++i)
         if (plen[i] < 0 || tlen[i] < 0 || plen[i] > p->read_size || tlen[i] > p->read_size) return -2;
     if (nthreads < 1) nthreads = 1;
@@ -480,7 +646,7 @@ int orc_align_batch(const orc_params *p, uint32_t n, const int32_t *plen, const 
         uint32_t a = (uint32_t)t * per, b = a + per;
         if (a > n) a = n;
         if (b > n) b = n;
-        orc_job j = { p, a, b, plen, tlen, patterns, texts, results, p->backtrace ? ops : NULL };
+        orc_job j = { p, a, b, plen, tlen, patterns, texts, results, (p->backtrace || p->algo == ORC_ALGO_GENASM_DC) ? ops : NULL };
         jobs[t] = j;
         if (nthreads == 1) orc_worker(&jobs[t]);
         else pthread_create(&th[t], NULL, orc_worker, &jobs[t]);

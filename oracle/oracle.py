@@ -13,7 +13,8 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "libaim_oracle.so"
-_ALGO = {"nw": 0, "swg": 1, "wfa": 2}
+_ALGO = {"nw": 0, "swg": 1, "wfa": 2, "genasm_dc": 3, "genasm_filter": 4}
+GENASM_UNDEFINED, GENASM_NOALIGN = 3, 4  # statuses of pairs whose reference output is not a function of the pair
 
 ORC_RESULT = np.dtype([("max_operations", "<i4"), ("begin_offset", "<i4"), ("end_offset", "<i4"),
                        ("score", "<i4"), ("status", "<i4")])
@@ -21,7 +22,7 @@ ORC_RESULT = np.dtype([("max_operations", "<i4"), ("begin_offset", "<i4"), ("end
 
 class OrcParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("algo", "match", "mismatch", "gap_open", "gap_ext", "max_score",
-                                         "read_size", "backtrace", "reduce")]
+                                         "read_size", "backtrace", "reduce", "variant")]
 
 
 def build(force: bool = False) -> Path:
@@ -46,16 +47,20 @@ def _get():
 
 def align(algo: str, plen, tlen, patterns, texts, *, max_score: int, read_size: int, match: int = 0,
           mismatch: int = 3, gap_open: int = 4, gap_ext: int = 1, backtrace: bool = True, reduce: bool = False,
-          nthreads: int = 1):
+          nthreads: int = 1, variant: int = 0):
     """-> (results[ORC_RESULT], ops[n, 2*read_size] uint8 | None)."""
     n = len(plen)
-    p = OrcParams(_ALGO[algo], match, mismatch, gap_open, gap_ext, max_score, read_size, int(backtrace), int(reduce))
+    p = OrcParams(_ALGO[algo], match, mismatch, gap_open, gap_ext, max_score, read_size, int(backtrace), int(reduce), int(variant))
     plen = np.ascontiguousarray(plen, np.int32)
     tlen = np.ascontiguousarray(tlen, np.int32)
     patterns = np.ascontiguousarray(patterns, np.uint8)
     texts = np.ascontiguousarray(texts, np.uint8)
     assert patterns.shape == (n, read_size) and texts.shape == (n, read_size)
     res = np.zeros(n, ORC_RESULT)
+    if algo == "genasm_dc":
+        backtrace = True   # the ops rows carry the CIGAR string (genasmDC.c:641-676)
+    elif algo == "genasm_filter":
+        backtrace = False
     ops = np.zeros((n, 2 * read_size), np.uint8) if backtrace else None
     rc = _get().orc_align_batch(C.byref(p), n, plen.ctypes.data, tlen.ctypes.data, patterns.ctypes.data,
                                 texts.ctypes.data, res.ctypes.data, ops.ctypes.data if backtrace else None, nthreads)

@@ -29,6 +29,9 @@ _DIRS = {
     ("wfa", "mram"): "WFA/DPU-MRAM", ("wfa", "wram"): "WFA/DPU-WRAM",
     ("nw", "mram"): "NW/DPU-MRAM", ("nw", "wram"): "NW/DPU-WRAM",
     ("swg", "mram"): "SWG/DPU-MRAM", ("swg", "wram"): "SWG/DPU-WRAM",
+    # aim-genasm submodule; the filter prints "idx, score", DC prints "idx, score, CIGAR"
+    ("genasm_dc", "mram"): "aim-genasm/GenASM/DPU-MRAM-DC", ("genasm_dc", "wram"): "aim-genasm/GenASM/DPU-WRAM-DC",
+    ("genasm_filter", "mram"): "aim-genasm/GenASM/DPU-MRAM-filter", ("genasm_filter", "wram"): "aim-genasm/GenASM/DPU-WRAM-filter",
 }
 
 
@@ -89,6 +92,8 @@ def build_ref(alg: str, mem: str, *, max_score: int, read_size: int, match: int 
             dpu_srcs = [s for s in dpu_srcs if not s.endswith("dpu_allocator_wram.c")] + [str(patched)]
         defs.append(f"-DWRAM_SEGMENT={wram_segment}")
         common = ["gcc", "-O2", "-w", "-std=gnu11", f"-I{SHIM}", f"-I{src / 'common'}", f"-I{src / 'dpu'}"] + defs
+        if alg.startswith("genasm"):
+            common += ["-include", "limits.h"]  # genasmDC.c uses ULLONG_MAX; the UPMEM toolchain's headers pull limits.h in
         objs = []
         for i, s in enumerate(dpu_srcs):
             o = Path(tmp) / f"dpu{i}.o"
@@ -100,7 +105,7 @@ def build_ref(alg: str, mem: str, *, max_score: int, read_size: int, match: int 
         so = Path(tmp) / "shim.o"
         subprocess.run(common + ["-c", str(SHIM / "shim.c"), "-o", str(so)], check=True)
         tmp_out = Path(tmp) / "bin"
-        subprocess.run(["gcc", "-O2", "-o", str(tmp_out), str(ho), str(so)] + objs + ["-lpthread"], check=True)
+        subprocess.run(["gcc", "-O2", "-o", str(tmp_out), str(ho), str(so)] + objs + ["-lpthread", "-lm"], check=True)
         shutil.copy2(tmp_out, out)
     return out
 
