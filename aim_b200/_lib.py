@@ -49,6 +49,7 @@ def _load() -> C.CDLL:
         "aim_read_pairs": (C.c_int64, [cp, C.c_uint32, C.c_int32, vp, vp, vp, vp]),
         "aim_count_pairs": (C.c_int64, [cp]),
         "aim_write_results": (C.c_int, [cp, C.c_uint32, C.c_int32, C.c_int32, vp, vp]),
+        "aim_write_results_genasm": (C.c_int, [cp, C.c_uint32, C.c_int32, C.c_int32, vp, vp]),
         "aim_cigar_rle": (C.c_int, [vp, C.c_int32, C.c_int32, vp, C.c_size_t]),
         "aim_generate_pairs": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, C.c_double, C.c_int32,
                                          vp, vp, vp, vp, C.c_int32]),
@@ -64,5 +65,5 @@ def _load() -> C.CDLL:
 lib = _load()
 EXPORTED = ["aim_align_batch", "aim_align_device", "aim_host_alloc", "aim_host_free", "aim_shutdown",
             "aim_device_count", "aim_measure_int_peak", "aim_last_error", "aim_strerror", "aim_abi_version", "aim_derive_knobs",
-            "aim_pairs_to_process", "aim_read_pairs", "aim_count_pairs", "aim_write_results", "aim_cigar_rle",
+            "aim_pairs_to_process", "aim_read_pairs", "aim_count_pairs", "aim_write_results", "aim_write_results_genasm", "aim_cigar_rle",
             "aim_generate_pairs", "aim_write_pairs"]

@@ -199,6 +199,13 @@ def write_results(path, results: np.ndarray, ops: np.ndarray | None, read_size: 
         raise AimError(rc)
 
 
+def write_results_genasm(path, results: np.ndarray, cigars: np.ndarray | None, read_size: int, dc: bool) -> None:
+    """GenASM output lines: "idx, score, CIGAR" (DC) or "idx, score" (filter)."""
+    rc = lib.aim_write_results_genasm(os.fsencode(path), len(results), read_size, int(dc), _ptr(results), _ptr(cigars) if dc else None)
+    if rc != 0:
+        raise AimError(rc)
+
+
 def measure_int_peak(device: int = 0) -> float:
     """Measured INT32 ALU ceiling in ops/s (aim_measure_int_peak)."""
     v = C.c_double(0.0)

@@ -12,14 +12,18 @@
 // per pair, 32/G pairs per warp, persistent warps striding over the pairs.  The pattern bitmasks and the text's
 // 2-bit codes sit in shared memory.  The reference's traceback matrix (4 vectors per text step and level,
 // genasmDC.c:386,461-470,515-525) is not stored: all four are shifts of R, so only R[level][text step] streams to
-// a per-pair-slot HBM arena (one quarter of the bytes) and the traceback - first lane of every sub-warp, side by
-// side - reads the three or four BITS it tests per step (genasmDC.c:107-322) straight from it; row n (the state
-// before any text) is known in closed form.  The CIGAR leaves in the reference's own format: run lengths with
-// their decimal digits REVERSED (genasmDC.c:128-135), NUL-terminated, max_operations = strlen + 1.
+// an HBM arena, batch by batch - and of R only the WINDOW the traceback can touch: its pattern bit cp and text row ct
+// obey |cp + ct - (m - 1)| <= k, so row ti needs bits [m - 2 - k - ti, m + k - ti] (2k + 3 bits: one 32-bit word per
+// level and text step at k = 5 instead of the reference's four 128-bit vectors) -, and the traceback is a SECOND kernel with one pair per
+// THREAD (the walk is serial per pair: inside the fill kernel it ran on 1 lane in G and took 60 % of the time) that
+// reads the four BITS it tests per step (genasmDC.c:107-322) straight from the arena with branch-free, independent
+// loads; row n (the state before any text) is known in closed form and the pattern-mask bit is one byte compare.
+// The CIGAR leaves in the reference's own format: run lengths with their decimal digits REVERSED
+// (genasmDC.c:128-135), NUL-terminated, max_operations = strlen + 1.
 //
 // Pairs whose reference output depends on memory the reference never wrote for them get a status instead
 // (AIM_STATUS_GENASM_UNDEFINED: a text byte outside ACGTacgt skips the traceback rows of that step; the traceback
-// walks to text row n) - see oracle/aim_oracle.c.  "No alignment found" (genasmDC.c:543-547): score -1,
+// walks to text row n); DESIGN.md lists the cases.  "No alignment found" (genasmDC.c:543-547): score -1,
 // AIM_STATUS_GENASM_NOALIGN.  variant 1 = DPU-MRAM-DC: substitutions print as 'S' and a pattern 'N' is no wildcard.
 #include <cuda_runtime.h>
 
@@ -42,9 +46,12 @@ struct GenK {
     const char *texts;
     aim_result *results;
     char *ops;
-    u64 *hist;          // DC only: per pair slot [level][text step][count] words (word 0 = bits 0..63)
-    size_t hist_stride; // words per pair slot
-    uint32_t n, idx_base;
+    uint32_t *hist;     // DC only: per pair of the batch [level][text index][ww] 32-bit words: the WINDOW of R the traceback can touch
+    size_t hist_stride; // 32-bit words per pair
+    int ww;             // window width in 32-bit words: 32 * ww >= 2k + 3
+    int32_t *meta;      // DC only: per pair of the batch, min_error | text_ok << 16 (fill kernel -> traceback kernel)
+    uint32_t first, n;  // pairs [first, first + n) of the launch's batch
+    uint32_t idx_base;
     int k, read_size, G, variant;
     int match, mismatch, gap_oe, gap_e;
     uint32_t slot_bytes; // shared memory per pair slot: 4 * W bitmask words, then read_size text codes
@@ -63,6 +70,19 @@ __device__ __forceinline__ void shl1(u64 (&dst)[W], const u64 (&src)[W])
     for (int w = 0; w < W; ++w) dst[w] = (src[w] << 1) | (w ? src[w - 1] >> 63 : 0ull);
 }
 
+// 32-bit half j of a W-word vector (half 0 = bits 0..31); 0 outside
+template <int W>
+__device__ __forceinline__ uint32_t half_at(const u64 (&v)[W], int j)
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (int q = 0; q < 2 * W; ++q) {
+        const uint32_t hq = (q & 1) ? (uint32_t)(v[q >> 1] >> 32) : (uint32_t)v[q >> 1];
+        r = j == q ? hq : r;
+    }
+    return r;
+}
+
 template <int W, int LPL, bool DC>
 __global__ void __launch_bounds__(128) genasm_kernel(const GenK K)
 {
@@ -76,16 +96,16 @@ __global__ void __launch_bounds__(128) genasm_kernel(const GenK K)
     const uint32_t wpb = blockDim.x >> 5;
     const uint32_t slot_global = (blockIdx.x * wpb + wib) * PPW + sub;
     const uint32_t nslots = gridDim.x * wpb * PPW;
-    u64 *hist = DC ? K.hist + (size_t)slot_global * K.hist_stride : nullptr;
     const int k = K.k, RS = K.read_size;
 
     for (uint32_t base_i = 0; base_i < K.n; base_i += nslots) {  // warp-uniform trip count
-        const uint32_t i = base_i + slot_global;
-        const bool active = i < K.n;
+        const uint32_t li = base_i + slot_global;  // pair of the batch
+        const bool active = li < K.n;
+        const uint32_t i = K.first + (active ? li : 0);
         const int m = active ? min(max(K.plen[i], 0), RS) : 0;
         const int n = active ? min(max(K.tlen[i], 0), RS) : 0;
         const int count = (m + 64) / 64;
-        const char *gp = K.patterns + (size_t)(active ? i : 0) * RS, *gt = K.texts + (size_t)(active ? i : 0) * RS;
+        const char *gp = K.patterns + (size_t)i * RS, *gt = K.texts + (size_t)i * RS;
 
         // ---- stage: text codes, all-ones bitmasks, then clear the pattern's bits (genasmDC.c:40-88) ----
         for (int q = sl; q < 4 * W; q += G) pm[q] = ~0ull;
@@ -123,33 +143,42 @@ __global__ void __launch_bounds__(128) genasm_kernel(const GenK K)
         __syncwarp();
 
         // ---- initial state (genasmDC.c:401-425): level d = all ones shifted left by d ----
-        u64 cur[LPL][W], prev[W];
+        u64 cur[LPL][W], lo_old[W];
 #pragma unroll
         for (int l = 0; l < LPL; ++l) {
             const int d = sl * LPL + l;
 #pragma unroll
             for (int w = 0; w < W; ++w) cur[l][w] = d >= 64 * (w + 1) ? 0ull : (d <= 64 * w ? ~0ull : (~0ull << (d - 64 * w)));
         }
+        {   // what the lane below holds before any step: its top level's initial state
+            const int d = sl * LPL - 1;
 #pragma unroll
-        for (int w = 0; w < W; ++w) prev[w] = cur[LPL - 1][w];
+            for (int w = 0; w < W; ++w) lo_old[w] = d >= 64 * (w + 1) ? 0ull : (d <= 64 * w ? ~0ull : (~0ull << (d - 64 * w)));
+        }
+        // this lane's history rows: level d at hist + (d*RS + ti) * ww; the pointer walks down with the text index
+        const int WWN = K.ww;
+        uint32_t *hrow = DC ? K.hist + (size_t)(active ? li : 0) * K.hist_stride + ((size_t)(sl * LPL) * RS + (n - 1)) * WWN : nullptr;
+        const bool store = DC && active;
+        int wbase = m - 2 - k - (n - 1);  // first bit of the window of text index ti = n - 1 - u: m - 2 - k - ti
 
-        // ---- the fill: tick t, lane j is on text step u = t - j, i.e. text index n - 1 - u (genasmDC.c:428-527) ----
+        // ---- the fill: tick t, lane j is on text step u = t - j, i.e. text index n - 1 - u (genasmDC.c:428-527).
+        // The lane below is one step ahead: its top level after step u arrives by shuffle, and its state after step
+        // u - 1 is what arrived one tick earlier. ----
         const int tmax = __reduce_max_sync(kFullMask, n) + G - 1;
-        for (int t = 0; t < tmax; ++t) {
-            const int u = t - sl;
-            u64 lo_new[W], lo_old[W];  // the level below this lane's first level: after steps u and u - 1
+        int u = -sl;
+        for (int t = 0; t < tmax; ++t, ++u) {
+            u64 lo_new[W];
 #pragma unroll
-            for (int w = 0; w < W; ++w) {
-                lo_new[w] = __shfl_up_sync(kFullMask, cur[LPL - 1][w], 1, G);
-                lo_old[w] = __shfl_up_sync(kFullMask, prev[w], 1, G);
-            }
+            for (int w = 0; w < W; ++w) lo_new[w] = __shfl_up_sync(kFullMask, cur[LPL - 1][w], 1, G);
+            u64 keep[W];
+#pragma unroll
+            for (int w = 0; w < W; ++w) keep[w] = lo_new[w];
             if (u >= 0 && u < n) {
-                const int ti = n - 1 - u;
-                const int c = codes[ti];
-                if (c < 4) {
-                    u64 pmw[W], save[W];
+                const int c = codes[n - 1 - u];
+                if (c < 4) {  // else: the reference skips the step, R is unchanged
+                    u64 pmw[W];
 #pragma unroll
-                    for (int w = 0; w < W; ++w) { pmw[w] = pm[c * W + w]; save[w] = cur[LPL - 1][w]; }
+                    for (int w = 0; w < W; ++w) pmw[w] = pm[c * W + w];
 #pragma unroll
                     for (int l = 0; l < LPL; ++l) {
                         const int d = sl * LPL + l;
@@ -171,19 +200,24 @@ __global__ void __launch_bounds__(128) genasm_kernel(const GenK K)
                         }
 #pragma unroll
                         for (int w = 0; w < W; ++w) { lo_old[w] = old_d[w]; lo_new[w] = nw[w]; cur[l][w] = nw[w]; }
-                        if (DC && d <= k) {
-                            u64 *h = hist + ((size_t)d * RS + ti) * count;
-#pragma unroll
-                            for (int w = 0; w < W; ++w) if (w < count) h[w] = nw[w];
+                        if (store && d <= k) {
+                            uint32_t *h = hrow + (size_t)l * RS * WWN;
+                            const int idx = wbase >> 5, sh = wbase & 31;  // floor / non-negative remainder also below bit 0
+                            uint32_t lo = half_at<W>(nw, idx);
+#pragma unroll 1
+                            for (int q = 0; q < WWN; ++q) {
+                                const uint32_t hi = half_at<W>(nw, idx + q + 1);
+                                h[q] = __funnelshift_r(lo, hi, sh);
+                                lo = hi;
+                            }
                         }
                     }
-#pragma unroll
-                    for (int w = 0; w < W; ++w) prev[w] = save[w];
-                } else {  // the reference skips the step: R is unchanged
-#pragma unroll
-                    for (int w = 0; w < W; ++w) prev[w] = cur[LPL - 1][w];
                 }
+                hrow -= WWN;
+                ++wbase;
             }
+#pragma unroll
+            for (int w = 0; w < W; ++w) lo_old[w] = keep[w];
         }
 
         // ---- lowest level whose end bit is clear (genasmDC.c:389-399,530-541: word 0 of the reference = word count-1) ----
@@ -203,81 +237,112 @@ __global__ void __launch_bounds__(128) genasm_kernel(const GenK K)
             if (off < G) lvl = min(lvl, o);
         }
         const int min_error = lvl > k ? -1 : lvl;
-        __syncwarp();  // the arena stores of every lane are visible to the traceback lane
 
         if (active && sl == 0) {
-            aim_result r;
-            r.max_operations = DC ? m + n : 0;
-            r.begin_offset = 0;
-            r.end_offset = 0;
-            r.score = DC ? -1 : min_error;
-            r.status = AIM_STATUS_OK;
-            r.idx = K.idx_base + i;
-            if (DC) {
-                char *cig = K.ops + (size_t)i * 2 * RS;
-                const int cap = 2 * RS;
-                if (min_error < 0) { r.status = AIM_STATUS_GENASM_NOALIGN; cig[0] = '\0'; }
-                else if (!text_ok) { r.status = AIM_STATUS_GENASM_UNDEFINED; cig[0] = '\0'; }
-                else {
-                    // genasmTB (genasmDC.c:90-336).  bit b of R[d] after text index ti; ti == n is the initial state
-                    auto hbit = [&](int ti, int d, int b) -> unsigned {
-                        if (b < 0) return 0u;
-                        if (ti >= n) return b >= d ? 1u : 0u;
-                        return (unsigned)((hist[((size_t)d * RS + ti) * count + (b >> 6)] >> (b & 63)) & 1ull);
-                    };
-                    int cp = m - 1, ct = 0, ce = min_error, c = 0;
-                    int nM = 0, nS = 0, nOpen = 0, nExt = 0, run = 0;
-                    char last = '0';
-                    bool first = true, undefined = false;
-                    const char sub_ch = K.variant ? 'S' : 'X';
-                    auto flush = [&]() {
-                        if (first) return;
-                        int num = run;
-                        while (num != 0 && c < cap - 2) { cig[c++] = (char)('0' + num % 10); num /= 10; }
-                        if (c < cap - 1) cig[c++] = last;
-                    };
-                    while (cp >= 0 && ce >= 0) {
-                        if (ct >= n) { undefined = true; break; }
-                        unsigned t0, t1 = 1u, t2 = 1u, t3 = 1u;
-                        if (ce == 0) t0 = hbit(ct, 0, cp);
-                        else {
-                            const unsigned a = hbit(ct + 1, ce, cp - 1), s1 = hbit(ct + 1, ce - 1, cp - 1);
-                            const unsigned i1 = hbit(ct, ce - 1, cp - 1), d1 = hbit(ct + 1, ce - 1, cp);
-                            const int cc = codes[ct];
-                            t0 = a | (unsigned)((pm[cc * W + (cp >> 6)] >> (cp & 63)) & 1ull);
-                            t1 = s1; t2 = i1; t3 = d1;
-                        }
-                        if (last == 'I' && t2 == 0) { --cp; --ce; ++run; ++nExt; }
-                        else if (last == 'D' && t3 == 0) { ++ct; --ce; ++run; ++nExt; }
-                        else if (t0 == 0) {
-                            ++ct; --cp;
-                            if (last == 'M') ++run; else { flush(); run = 1; last = 'M'; }
-                            ++nM;
-                        } else if (t1 == 0) {
-                            ++ct; --cp; --ce;
-                            if (last == sub_ch) ++run; else { flush(); run = 1; last = sub_ch; }
-                            ++nS;
-                        } else if (t3 == 0) { ++ct; --ce; flush(); run = 1; last = 'D'; ++nOpen; }
-                        else if (t2 == 0) { --cp; --ce; flush(); run = 1; last = 'I'; ++nOpen; }
-                        else { undefined = true; break; }  // the reference would spin forever
-                        first = false;
-                    }
-                    if (undefined) { r.status = AIM_STATUS_GENASM_UNDEFINED; cig[0] = '\0'; }
-                    else {
-                        int num = run;
-                        while (num != 0 && c < cap - 2) { cig[c++] = (char)('0' + num % 10); num /= 10; }
-                        if (c < cap - 1) cig[c++] = last;
-                        cig[c] = '\0';
-                        r.max_operations = c + 1;
-                        r.end_offset = c;
-                        r.score = nM * K.match + nS * K.mismatch + nOpen * K.gap_oe + nExt * K.gap_e;
-                    }
-                }
+            if (DC) K.meta[li] = (min_error & 0xffff) | ((int)text_ok << 16);
+            else {
+                aim_result r;
+                r.max_operations = 0;
+                r.begin_offset = 0;
+                r.end_offset = 0;
+                r.score = min_error;  // genasm_filter.c:226-238
+                r.status = AIM_STATUS_OK;
+                r.idx = K.idx_base + i;
+                K.results[i] = r;
             }
-            K.results[i] = r;
         }
         __syncwarp();
     }
+}
+
+// genasmTB (genasmDC.c:90-336), one pair per thread.  Bit b of R[d] after text index ti comes from the fill kernel's
+// arena; ti == n is the initial state (closed form), b < 0 is the zero a left shift brings in.
+__global__ void __launch_bounds__(128) genasm_tb_kernel(const GenK K)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= K.n) return;
+    const uint32_t i = K.first + li;
+    const int RS = K.read_size;
+    const int m = min(max(K.plen[i], 0), RS), n = min(max(K.tlen[i], 0), RS);
+    const int count = (m + 64) / 64;
+    const int meta = K.meta[li];
+    const int min_error = (int)(short)(meta & 0xffff);
+    const bool text_ok = (meta >> 16) & 1;
+    const uint32_t *hist = K.hist + (size_t)li * K.hist_stride;
+    const int WWN = K.ww, k = K.k;
+    const char *gp = K.patterns + (size_t)i * RS, *gt = K.texts + (size_t)i * RS;
+    char *cig = K.ops + (size_t)i * 2 * RS;
+    const int cap = 2 * RS;
+
+    aim_result r;
+    r.max_operations = m + n;
+    r.begin_offset = 0;
+    r.end_offset = 0;
+    r.score = -1;
+    r.status = AIM_STATUS_OK;
+    r.idx = K.idx_base + i;
+    if (min_error < 0) { r.status = AIM_STATUS_GENASM_NOALIGN; cig[0] = '\0'; }
+    else if (!text_ok) { r.status = AIM_STATUS_GENASM_UNDEFINED; cig[0] = '\0'; }
+    else {
+        // branch-free: the load always happens (indices clamped into the pair's rows), the special cases are selects
+        auto hbit = [&](int ti, int d, int b) -> unsigned {
+            const int tc = min(ti, n - 1);
+            const int wb = min(max(b - (m - 2 - k - tc), 0), 32 * WWN - 1);  // bit of row tc's window
+            const uint32_t wv = hist[((size_t)d * RS + tc) * WWN + (wb >> 5)];
+            unsigned v = (wv >> (wb & 31)) & 1u;
+            v = ti >= n ? (b >= d ? 1u : 0u) : v;
+            return b < 0 ? 0u : v;
+        };
+        int cp = m - 1, ct = 0, ce = min_error, c = 0;
+        int nM = 0, nS = 0, nOpen = 0, nExt = 0, run = 0;
+        char last = '0';
+        bool first = true, undefined = false;
+        const char sub_ch = K.variant ? 'S' : 'X';
+        auto flush = [&]() {
+            if (first) return;
+            int num = run;
+            while (num != 0 && c < cap - 2) { cig[c++] = (char)('0' + num % 10); num /= 10; }
+            if (c < cap - 1) cig[c++] = last;
+        };
+        while (cp >= 0 && ce >= 0) {
+            if (ct >= n) { undefined = true; break; }
+            const bool z = ce == 0;
+            const int dl = max(ce - 1, 0);
+            // level 0 keeps only R itself (genasmDC.c:461-470): match = its bit, the other three read as set
+            const unsigned a = z ? hbit(ct, 0, cp) : hbit(ct + 1, ce, cp - 1);
+            const unsigned s1 = hbit(ct + 1, dl, cp - 1), i1 = hbit(ct, dl, cp - 1), d1 = hbit(ct + 1, dl, cp);
+            const int pch = gp[m - 1 - cp], tch = gt[ct];
+            const int pc = base_code(pch);
+            const bool hit = pc < 4 ? pc == base_code(tch) : ((pch & ~0x20) == 'N' && K.variant == 0);  // the pattern-mask bit is clear
+            const unsigned t0 = z ? a : (a | (hit ? 0u : 1u));
+            const unsigned t1 = z ? 1u : s1, t2 = z ? 1u : i1, t3 = z ? 1u : d1;
+            if (last == 'I' && t2 == 0) { --cp; --ce; ++run; ++nExt; }
+            else if (last == 'D' && t3 == 0) { ++ct; --ce; ++run; ++nExt; }
+            else if (t0 == 0) {
+                ++ct; --cp;
+                if (last == 'M') ++run; else { flush(); run = 1; last = 'M'; }
+                ++nM;
+            } else if (t1 == 0) {
+                ++ct; --cp; --ce;
+                if (last == sub_ch) ++run; else { flush(); run = 1; last = sub_ch; }
+                ++nS;
+            } else if (t3 == 0) { ++ct; --ce; flush(); run = 1; last = 'D'; ++nOpen; }
+            else if (t2 == 0) { --cp; --ce; flush(); run = 1; last = 'I'; ++nOpen; }
+            else { undefined = true; break; }  // the reference would spin forever
+            first = false;
+        }
+        if (undefined) { r.status = AIM_STATUS_GENASM_UNDEFINED; cig[0] = '\0'; }
+        else {
+            int num = run;
+            while (num != 0 && c < cap - 2) { cig[c++] = (char)('0' + num % 10); num /= 10; }
+            if (c < cap - 1) cig[c++] = last;
+            cig[c] = '\0';
+            r.max_operations = c + 1;
+            r.end_offset = c;
+            r.score = nM * K.match + nS * K.mismatch + nOpen * K.gap_oe + nExt * K.gap_e;
+        }
+    }
+    K.results[i] = r;
 }
 
 template <int W, int LPL>
@@ -304,8 +369,9 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
     const bool dc = p.algo == AIM_ALGO_GENASM_DC;
     const int k = p.max_score;
     const int count_max = (p.read_size + 64) / 64;
-    if (k + 1 > 128) { set_error("GenASM: MAX_SCORE above 127 is not served by the B200 kernel"); return AIM_ERR_ARG; }
+    if (k > 126) { set_error("GenASM: MAX_SCORE above 126 is not served by the B200 kernel"); return AIM_ERR_ARG; }
     if (count_max > 8) { set_error("GenASM: READ_SIZE above 448 is not served by the B200 kernel"); return AIM_ERR_ARG; }
+    if (a.n == 0) return AIM_OK;
     const int lpl = k + 1 <= 32 ? 1 : (k + 1 <= 64 ? 2 : 4);
     int G = 4;
     while (G * lpl < k + 1) G *= 2;
@@ -313,28 +379,43 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
 
     GenK K{};
     K.plen = a.plen; K.tlen = a.tlen; K.patterns = a.patterns; K.texts = a.texts; K.results = a.results; K.ops = a.ops;
-    K.n = a.n; K.idx_base = a.idx_base; K.k = k; K.read_size = p.read_size; K.G = G; K.variant = p.variant;
+    K.idx_base = a.idx_base; K.k = k; K.read_size = p.read_size; K.G = G; K.variant = p.variant;
     K.match = p.match; K.mismatch = p.mismatch; K.gap_oe = p.gap_open + p.gap_ext; K.gap_e = p.gap_ext;
     K.slot_bytes = (uint32_t)(4 * W * 8 + p.read_size);
     const int PPW = 32 / G;
     const size_t smem = (size_t)4 * PPW * K.slot_bytes;
-    int blocks_per_sm = W == 8 || lpl == 4 ? 4 : (W == 4 || lpl == 2 ? 8 : 16);
-    K.hist_stride = dc ? (size_t)(k + 1) * (size_t)p.read_size * (size_t)count_max : 0;
-    while (blocks_per_sm > 1 && (size_t)sc->sm_count * blocks_per_sm * 4 * PPW * K.hist_stride * 8 > ((size_t)6 << 30)) blocks_per_sm /= 2;
-    int grid = sc->sm_count * blocks_per_sm;
-    {
-        const uint64_t per_block = (uint64_t)4 * PPW;
-        if ((uint64_t)grid * per_block > a.n) grid = (int)std::max<uint64_t>(1, (a.n + per_block - 1) / per_block);
-    }
-    if (a.n == 0) return AIM_OK;
-    const size_t hist_bytes = (size_t)grid * 4 * PPW * K.hist_stride * 8;
-    int rc = scratch_reserve(sc, std::max<size_t>(hist_bytes, 256));
+    const int blocks_per_sm = W == 8 || lpl == 4 ? 4 : (W == 4 || lpl == 2 ? 8 : 16);
+    K.ww = 1;
+    while (32 * K.ww < 2 * k + 3) K.ww *= 2;
+    K.hist_stride = dc ? (size_t)(k + 1) * (size_t)p.read_size * (size_t)K.ww : 0;
+
+    // DC: the history of a whole batch lives in the arena between the fill and the traceback kernels
+    size_t budget = (size_t)4 << 30;
+    if (const char *bm = getenv("AIM_GENASM_ARENA_MB")) { const long v = atol(bm); if (v >= 16 && v <= 65536) budget = (size_t)v << 20; }
+    uint32_t batch = a.n;
+    if (dc) batch = (uint32_t)std::max<size_t>(1024, std::min<size_t>(a.n, budget / (K.hist_stride * 4)));
+    batch = std::min(batch, a.n);
+    const size_t meta_bytes = dc ? ((size_t)batch * 4 + 255) / 256 * 256 : 0;
+    int rc = scratch_reserve(sc, std::max<size_t>(meta_bytes + (size_t)batch * K.hist_stride * 4, 256));
     if (rc != AIM_OK) return rc;
-    K.hist = reinterpret_cast<u64 *>(sc->buf);
-    cudaError_t err = W == 2 ? launch_w<2>(K, lpl, dc, grid, smem, stream)
-                             : (W == 4 ? launch_w<4>(K, lpl, dc, grid, smem, stream) : launch_w<8>(K, lpl, dc, grid, smem, stream));
-    if (err != cudaSuccess) { set_error(std::string("genasm launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
-    if (launches) ++*launches;
+    K.meta = reinterpret_cast<int32_t *>(sc->buf);
+    K.hist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sc->buf) + meta_bytes);
+    for (uint32_t first = 0; first < a.n; first += batch) {
+        K.first = first;
+        K.n = std::min(batch, a.n - first);
+        int grid = sc->sm_count * blocks_per_sm;
+        const uint64_t per_block = (uint64_t)4 * PPW;
+        if ((uint64_t)grid * per_block > K.n) grid = (int)std::max<uint64_t>(1, (K.n + per_block - 1) / per_block);
+        cudaError_t err = W == 2 ? launch_w<2>(K, lpl, dc, grid, smem, stream)
+                                 : (W == 4 ? launch_w<4>(K, lpl, dc, grid, smem, stream) : launch_w<8>(K, lpl, dc, grid, smem, stream));
+        if (err == cudaSuccess && launches) ++*launches;
+        if (err == cudaSuccess && dc) {
+            genasm_tb_kernel<<<(K.n + 127) / 128, 128, 0, stream>>>(K);
+            err = cudaGetLastError();
+            if (err == cudaSuccess && launches) ++*launches;
+        }
+        if (err != cudaSuccess) { set_error(std::string("genasm launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
+    }
     return AIM_OK;
 }
 

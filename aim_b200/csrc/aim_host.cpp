@@ -313,6 +313,42 @@ extern "C" int aim_write_results(const char *path, uint32_t n, int32_t read_size
     return rc;
 }
 
+// GenASM printers: DC "%d, %d, %s\n" (idx, score, the DPU's CIGAR string up to its NUL:
+// aim-genasm/GenASM/DPU-WRAM-DC/host/host.c:286-296), filter "%d, %d\n" (DPU-WRAM-filter/host/host.c:272).
+extern "C" int aim_write_results_genasm(const char *path, uint32_t n, int32_t read_size, int32_t dc,
+                                        const aim_result *results, const char *cigars)
+{
+    if (dc && !cigars) { aim::set_error("cigars buffer required for GenASM-DC"); return AIM_ERR_ARG; }
+    FILE *f = fopen(path, "w");
+    if (!f) { aim::set_error(std::string("Output file '") + path + "' couldn't be opened"); return AIM_ERR_IO; }
+    const size_t rs2 = (size_t)read_size * 2;
+    std::vector<char> buf((size_t)1 << 20);
+    size_t pos = 0;
+    int rc = AIM_OK;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (pos + rs2 + 64 > buf.size()) {
+            if (fwrite(buf.data(), 1, pos, f) != pos) { rc = AIM_ERR_IO; break; }
+            pos = 0;
+        }
+        char *o = buf.data();
+        pos += put_int(o + pos, (int32_t)results[i].idx);
+        o[pos++] = ','; o[pos++] = ' ';
+        pos += put_int(o + pos, results[i].score);
+        if (dc) {
+            o[pos++] = ','; o[pos++] = ' ';
+            const char *c = cigars + (size_t)i * rs2;
+            const size_t len = strnlen(c, rs2);
+            memcpy(o + pos, c, len);
+            pos += len;
+        }
+        o[pos++] = '\n';
+    }
+    if (rc == AIM_OK && pos && fwrite(buf.data(), 1, pos, f) != pos) rc = AIM_ERR_IO;
+    if (ferror(f)) rc = AIM_ERR_IO;
+    fclose(f);
+    return rc;
+}
+
 extern "C" int aim_write_pairs(const char *path, uint32_t n, int32_t read_size, const int32_t *plen,
                                const int32_t *tlen, const char *patterns, const char *texts)
 {

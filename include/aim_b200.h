@@ -152,6 +152,10 @@ int64_t aim_count_pairs(const char *path);
  * "%d, %d, \n" (idx, score) and, if backtrace, the run-length CIGAR of ops[begin..end) + "\n". */
 int aim_write_results(const char *path, uint32_t n, int32_t read_size, int32_t backtrace,
                       const aim_result *results, const char *ops);
+/* The GenASM printers: dc != 0 -> "%d, %d, %s\n" (idx, score, pair i's NUL-terminated CIGAR string at cigars + i*2*read_size;
+ * aim-genasm/GenASM/DPU-WRAM-DC/host/host.c:286-296); dc == 0 -> "%d, %d\n" (DPU-WRAM-filter/host/host.c:272). */
+int aim_write_results_genasm(const char *path, uint32_t n, int32_t read_size, int32_t dc,
+                             const aim_result *results, const char *cigars);
 /* RLE one pair's ops into out (capacity cap); returns the length written (no NUL) or -1. */
 int aim_cigar_rle(const char *ops, int32_t begin_offset, int32_t end_offset, char *out, size_t cap);
 

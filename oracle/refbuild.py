@@ -140,6 +140,10 @@ def build_all() -> list[Path]:
     outs = [build_ref(**cfg) for cfg in CONFIGS.values()]
     outs.append(build_ref("nw", "mram", max_score=4, read_size=112, mismatch=3, gap_o=4, backtrace=True))
     outs.append(build_ref("wfa", "mram", max_score=5000, read_size=11008, backtrace=True, reduce=True, big_wram=True))
+    # aim-genasm: bench.py configs 7-9
+    outs.append(build_ref("genasm_dc", "wram", max_score=5, read_size=112, backtrace=True))
+    outs.append(build_ref("genasm_filter", "wram", max_score=1, read_size=112, backtrace=False))
+    outs.append(build_ref("genasm_dc", "wram", max_score=30, read_size=168, backtrace=True))
     return outs
 
 

@@ -144,3 +144,64 @@ def test_gpu_genasm_multichunk_and_device_resident():
                 if ch in "MXI":
                     tot += cnt
         assert tot == arrays[0][i]
+
+
+# ---------------------------------------------------------------------------- host side (CPU)
+def test_genasm_wrapper_knobs():
+    """MAX_SCORE / READ_SIZE as the aim-genasm run scripts derive them (run-genasmdc-pim-wram.py:52-70,
+    run-genasmfilter-pim-wram.py:52-67)."""
+    from aim_b200 import run_pim
+    base = dict(match_cost=0, mismatch_cost=3, gap_opening=4, gap_extending=1, number_reads=10, nr_of_dpus=None, nr_of_tasklets=None, gpus=1)
+    e = run_pim.derive_genasm("dc", dict(base, read_length=100, error=0.01, max_edit=None))
+    assert (e["MAX_SCORE"], e["READ_SIZE"], e["AIM_ALGO"]) == (5, 112, "genasm_dc")
+    e = run_pim.derive_genasm("dc", dict(base, read_length=150, error=0.04, max_edit=None))
+    assert (e["MAX_SCORE"], e["READ_SIZE"]) == (30, 168)
+    e = run_pim.derive_genasm("filter", dict(base, read_length=100, error=0.015, max_edit=None))
+    assert (e["MAX_SCORE"], e["READ_SIZE"], e["AIM_ALGO"]) == (2, 112, "genasm_filter")
+    e = run_pim.derive_genasm("dc", dict(base, read_length=100, error=None, max_edit=7))
+    assert (e["MAX_SCORE"], e["READ_SIZE"]) == (7, 120)
+    e = run_pim.derive_genasm("filter", dict(base, read_length=100, error=0.0, max_edit=None))
+    assert (e["MAX_SCORE"], e["READ_SIZE"]) == (1, 112)
+    with pytest.raises(SystemExit):
+        run_pim.derive_genasm("dc", dict(base, read_length=100, error=None, max_edit=None))
+    with pytest.raises(SystemExit):
+        run_pim.derive_genasm("dc", dict(base, read_length=100, error=0.01, max_edit=None, mismatch_cost=0))
+
+
+def test_genasm_result_writer_format(tmp_path):
+    rs = 16
+    res = np.zeros(3, A.RESULT_DTYPE)
+    res["idx"] = [0, 1, 2]
+    res["score"] = [5, -1, 3]
+    cig = np.zeros((3, 2 * rs), np.uint8)
+    cig[0, :8] = np.frombuffer(b"04M1I95M", np.uint8)
+    cig[2, :4] = np.frombuffer(b"21M\0", np.uint8)
+    out = tmp_path / "o"
+    A.write_results_genasm(out, res, cig, rs, True)
+    assert out.read_bytes() == b"0, 5, 04M1I95M\n1, -1, \n2, 3, 21M\n"
+    A.write_results_genasm(out, res, None, rs, False)
+    assert out.read_bytes() == b"0, 5\n1, -1\n2, 3\n"
+
+
+@pytest.mark.gpu
+def test_gpu_genasm_cli_via_wrappers(tmp_path):
+    """`run-genasm{dc,filter}-pim-*.py` -> build/host: the reference's output lines on its own Dataset."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    f = tmp_path / "sample"
+    f.write_bytes(lzma.open(GOLDEN / "datasets" / "sample-l100-e1-40K.xz").read())
+    for script, case in (("run-genasmdc-pim-wram.py", "dc_wram_sample"), ("run-genasmdc-pim-mram.py", "dc_mram_sample"),
+                         ("run-genasmfilter-pim-wram.py", "filter_wram_sample")):
+        out = tmp_path / "out"
+        r = subprocess.run([sys.executable, str(root / "scripts" / script), "-i", str(f), "-o", str(out), "-l", "100", "-e", "0.01",
+                            "-n", "40000"] + (["-k", "5"] if "filter" in script else []), capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "DPU Kernel:" in r.stdout
+        got = out.read_bytes().decode("latin-1").split("\n")[:-1]
+        ref = lzma.open(GOLDEN / GMAN[case]["output"]).read().decode("latin-1").split("\n")[:-1]
+        assert len(got) == len(ref) == 20000
+        diff = [i for i in range(len(ref)) if got[i] != ref[i]]
+        # only the pairs flagged as undefined in the reference (printed with score -1 and no CIGAR) may differ
+        assert all(got[i].startswith(f"{i}, -1, ") for i in diff) and len(diff) <= 120, diff[:5]

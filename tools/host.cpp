@@ -3,7 +3,7 @@
 // Same argv, same stdout lines, same pair-file parsing, same output bytes.  The knobs the
 // reference bakes in with -D at compile time arrive through the environment, under the same
 // names (the run-*-pim-*.py wrappers set them):
-//   AIM_ALGO=nw|swg|wfa  MAX_SCORE READ_SIZE MATCH MISMATCH GAP_O GAP_E (GAP_I/GAP_D for NW)
+//   AIM_ALGO=nw|swg|wfa|genasm_dc|genasm_filter  MAX_SCORE READ_SIZE MATCH MISMATCH GAP_O GAP_E (GAP_I/GAP_D for NW)
 //   BACKTRACE=0|1  REDUCE=0|1  NR_DPUS (only feeds the pairs-to-process rule, host.c:191)
 //   NR_TASKLETS WRAM_SEGMENT (accepted, ignored)  AIM_NGPUS  AIM_DEVICE  AIM_VARIANT=wram|mram
 #include <sys/time.h>
@@ -45,16 +45,22 @@ int main(int argc, char *argv[])
     std::string variant = variant_s ? variant_s : "mram";
     aim_params p;
     memset(&p, 0, sizeof(p));
-    p.algo = algo == "nw" ? AIM_ALGO_NW : algo == "swg" ? AIM_ALGO_SWG : AIM_ALGO_WFA;
+    p.algo = algo == "nw" ? AIM_ALGO_NW : algo == "swg" ? AIM_ALGO_SWG : algo == "genasm_dc" ? AIM_ALGO_GENASM_DC
+             : algo == "genasm_filter" ? AIM_ALGO_GENASM_FILTER : AIM_ALGO_WFA;
+    // the aim-genasm hosts (aim-genasm/GenASM/DPU-*-{DC,filter}/host/host.c) share this skeleton; they differ in the defaults
+    // (common.h:50-56: MAX_SCORE 5, READ_SIZE 120), in the output line and in having no BACKTRACE knob
+    const bool genasm = p.algo == AIM_ALGO_GENASM_DC || p.algo == AIM_ALGO_GENASM_FILTER;
     // defaults of */common/common.h
     p.match = (int32_t)env_int("MATCH", 0);
     p.mismatch = (int32_t)env_int("MISMATCH", 3);
     p.gap_open = (int32_t)env_int(p.algo == AIM_ALGO_NW ? "GAP_I" : "GAP_O", 4);
     p.gap_ext = (int32_t)env_int("GAP_E", 1);
-    p.max_score = (int32_t)env_int("MAX_SCORE", p.algo == AIM_ALGO_WFA ? 250 : p.algo == AIM_ALGO_SWG ? 400 : 40);
-    p.read_size = (int32_t)env_int("READ_SIZE", p.algo == AIM_ALGO_WFA ? 110 : p.algo == AIM_ALGO_SWG ? 560 : 56);
+    p.max_score = (int32_t)env_int("MAX_SCORE", genasm ? 5 : p.algo == AIM_ALGO_WFA ? 250 : p.algo == AIM_ALGO_SWG ? 400 : 40);
+    p.read_size = (int32_t)env_int("READ_SIZE", genasm ? 120 : p.algo == AIM_ALGO_WFA ? 110 : p.algo == AIM_ALGO_SWG ? 560 : 56);
     p.read_size = (p.read_size + 7) / 8 * 8;
     p.backtrace = (int32_t)env_int("BACKTRACE", 0);
+    if (genasm) p.backtrace = p.algo == AIM_ALGO_GENASM_DC;
+    p.variant = (genasm && variant == "mram") ? 1 : 0;
     p.reduce = (int32_t)env_int("REDUCE", 0);
     p.ngpus = (int32_t)env_int("AIM_NGPUS", 1);
     p.device = (int32_t)env_int("AIM_DEVICE", 0);
@@ -146,7 +152,8 @@ int main(int argc, char *argv[])
             exit(-1);
         }
     }
-    rc = aim_write_results(out, (uint32_t)n, p.read_size, p.backtrace, results, ops);
+    rc = genasm ? aim_write_results_genasm(out, (uint32_t)n, p.read_size, p.algo == AIM_ALGO_GENASM_DC, results, ops)
+                : aim_write_results(out, (uint32_t)n, p.read_size, p.backtrace, results, ops);
     if (rc != AIM_OK) {
         fprintf(stderr, "Output file '%s' couldn't be opened\n", out);
         exit(1);
