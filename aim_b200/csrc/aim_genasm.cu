@@ -166,19 +166,27 @@ __global__ void __launch_bounds__(128) genasm_kernel(const GenK K)
         // u - 1 is what arrived one tick earlier. ----
         const int tmax = __reduce_max_sync(kFullMask, n) + G - 1;
         int u = -sl;
+        // the text code and the bitmask words of a step are fetched one and two ticks ahead (shared-memory latency off the
+        // critical path): c1/pm1 belong to step u, c2 to step u + 1.  Code 4 = skip the step (also outside the text).
+        auto code_at = [&](int uu) -> int { return (uu >= 0 && uu < n) ? (int)codes[n - 1 - uu] : 4; };
+        int c1 = code_at(u), c2 = code_at(u + 1);
+        u64 pm1[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) pm1[w] = pm[(c1 & 3) * W + w];
         for (int t = 0; t < tmax; ++t, ++u) {
             u64 lo_new[W];
 #pragma unroll
             for (int w = 0; w < W; ++w) lo_new[w] = __shfl_up_sync(kFullMask, cur[LPL - 1][w], 1, G);
-            u64 keep[W];
+            u64 keep[W], pmw[W];
 #pragma unroll
-            for (int w = 0; w < W; ++w) keep[w] = lo_new[w];
+            for (int w = 0; w < W; ++w) { keep[w] = lo_new[w]; pmw[w] = pm1[w]; }
+            const int c = c1;
+            c1 = c2;
+#pragma unroll
+            for (int w = 0; w < W; ++w) pm1[w] = pm[(c1 & 3) * W + w];
+            c2 = code_at(u + 2);
             if (u >= 0 && u < n) {
-                const int c = codes[n - 1 - u];
                 if (c < 4) {  // else: the reference skips the step, R is unchanged
-                    u64 pmw[W];
-#pragma unroll
-                    for (int w = 0; w < W; ++w) pmw[w] = pm[c * W + w];
 #pragma unroll
                     for (int l = 0; l < LPL; ++l) {
                         const int d = sl * LPL + l;
@@ -389,32 +397,70 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
     while (32 * K.ww < 2 * k + 3) K.ww *= 2;
     K.hist_stride = dc ? (size_t)(k + 1) * (size_t)p.read_size * (size_t)K.ww : 0;
 
-    // DC: the history of a whole batch lives in the arena between the fill and the traceback kernels
+    // DC: the history of a whole batch lives in the arena between the fill and the traceback kernels.  Two arena halves:
+    // the traceback of batch b (latency-bound, one thread per pair) runs on a side stream under the fill of batch b + 1
+    // (issue-bound), so a launch is cut into at least four batches when it is large enough.
     size_t budget = (size_t)4 << 30;
     if (const char *bm = getenv("AIM_GENASM_ARENA_MB")) { const long v = atol(bm); if (v >= 16 && v <= 65536) budget = (size_t)v << 20; }
     uint32_t batch = a.n;
-    if (dc) batch = (uint32_t)std::max<size_t>(1024, std::min<size_t>(a.n, budget / (K.hist_stride * 4)));
-    batch = std::min(batch, a.n);
+    if (dc) {
+        const size_t fit = std::max<size_t>(1024, budget / 2 / (K.hist_stride * 4));
+        batch = (uint32_t)std::min<size_t>(fit, std::max<size_t>(32768, ((size_t)a.n + 3) / 4));
+        batch = std::min(batch, a.n);
+    }
+    const bool overlap = dc && batch < a.n && !getenv("AIM_GENASM_NO_OVERLAP");
+    const int halves = overlap ? 2 : 1;
     const size_t meta_bytes = dc ? ((size_t)batch * 4 + 255) / 256 * 256 : 0;
-    int rc = scratch_reserve(sc, std::max<size_t>(meta_bytes + (size_t)batch * K.hist_stride * 4, 256));
+    const size_t hist_bytes = ((size_t)batch * K.hist_stride * 4 + 255) / 256 * 256;
+    int rc = scratch_reserve(sc, std::max<size_t>((size_t)halves * (meta_bytes + hist_bytes), 256));
     if (rc != AIM_OK) return rc;
-    K.meta = reinterpret_cast<int32_t *>(sc->buf);
-    K.hist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sc->buf) + meta_bytes);
-    for (uint32_t first = 0; first < a.n; first += batch) {
+    static cudaStream_t side[64] = {};
+    static cudaEvent_t ev_fill[64][2] = {}, ev_tb[64][2] = {};
+    const int dev = sc->device & 63;
+    if (overlap && !side[dev]) {
+        cudaError_t e = cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking);
+        for (int h = 0; h < 2 && e == cudaSuccess; ++h) {
+            e = cudaEventCreateWithFlags(&ev_fill[dev][h], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_tb[dev][h], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) { set_error(std::string("genasm side stream: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
+    }
+    uint32_t nb = 0;
+    for (uint32_t first = 0; first < a.n; first += batch, ++nb) {
+        const int h = overlap ? (int)(nb & 1u) : 0;
+        unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf) + (size_t)h * (meta_bytes + hist_bytes);
+        K.meta = reinterpret_cast<int32_t *>(base);
+        K.hist = reinterpret_cast<uint32_t *>(base + meta_bytes);
         K.first = first;
         K.n = std::min(batch, a.n - first);
         int grid = sc->sm_count * blocks_per_sm;
         const uint64_t per_block = (uint64_t)4 * PPW;
         if ((uint64_t)grid * per_block > K.n) grid = (int)std::max<uint64_t>(1, (K.n + per_block - 1) / per_block);
-        cudaError_t err = W == 2 ? launch_w<2>(K, lpl, dc, grid, smem, stream)
-                                 : (W == 4 ? launch_w<4>(K, lpl, dc, grid, smem, stream) : launch_w<8>(K, lpl, dc, grid, smem, stream));
+        cudaError_t err = cudaSuccess;
+        if (overlap && nb >= 2) err = cudaStreamWaitEvent(stream, ev_tb[dev][h], 0);  // the traceback that read this half is done
+        if (err == cudaSuccess)
+            err = W == 2 ? launch_w<2>(K, lpl, dc, grid, smem, stream)
+                         : (W == 4 ? launch_w<4>(K, lpl, dc, grid, smem, stream) : launch_w<8>(K, lpl, dc, grid, smem, stream));
         if (err == cudaSuccess && launches) ++*launches;
         if (err == cudaSuccess && dc) {
-            genasm_tb_kernel<<<(K.n + 127) / 128, 128, 0, stream>>>(K);
-            err = cudaGetLastError();
+            cudaStream_t ts = stream;
+            if (overlap) {
+                ts = side[dev];
+                err = cudaEventRecord(ev_fill[dev][h], stream);
+                if (err == cudaSuccess) err = cudaStreamWaitEvent(ts, ev_fill[dev][h], 0);
+            }
+            if (err == cudaSuccess) {
+                genasm_tb_kernel<<<(K.n + 127) / 128, 128, 0, ts>>>(K);
+                err = cudaGetLastError();
+            }
+            if (err == cudaSuccess && overlap) err = cudaEventRecord(ev_tb[dev][h], ts);
             if (err == cudaSuccess && launches) ++*launches;
         }
         if (err != cudaSuccess) { set_error(std::string("genasm launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
+    }
+    if (overlap) {  // the caller's stream continues only after the last tracebacks
+        for (int h = 0; h < 2; ++h)
+            if (nb > (uint32_t)h && cudaStreamWaitEvent(stream, ev_tb[dev][h], 0) != cudaSuccess) { set_error("genasm: stream join failed"); return AIM_ERR_CUDA; }
     }
     return AIM_OK;
 }
