@@ -180,6 +180,49 @@ def align_device(params: AlignParams, n: int, d_plen: int, d_tlen: int, d_patter
     return (ms.value if timed else None), nl.value
 
 
+def packed_row_bytes(read_size: int) -> int:
+    return int(lib.aim_packed_row_bytes(read_size))
+
+
+def pack_pairs(plen, tlen, patterns, texts, read_size: int, nthreads: int = 0, out=None):
+    """aim_pack_pairs: ASCII rows -> (packed[n, 2, row_bytes/4] uint32, flags[ceil(n/32)] uint32)."""
+    n = len(plen)
+    words = packed_row_bytes(read_size) // 4
+    if out is None:
+        packed, flags = np.zeros((n, 2, words), np.uint32), np.zeros((n + 31) // 32, np.uint32)
+    else:
+        packed, flags = out
+    rc = lib.aim_pack_pairs(n, read_size, _ptr(np.ascontiguousarray(plen, np.int32)), _ptr(np.ascontiguousarray(tlen, np.int32)),
+                            _ptr(patterns), _ptr(texts), _ptr(packed), _ptr(flags), nthreads)
+    if rc != 0:
+        raise AimError(rc)
+    return packed, flags
+
+
+def align_packed(params: AlignParams, plen, tlen, packed, flags, cigar_pitch: int = 64, idx_base: int = 0, results=None, cigars=None):
+    """aim_align_packed on host arrays -> (results[RESULT_DTYPE], cigars[n, cigar_pitch] uint8, phase_ms[3])."""
+    n = len(plen)
+    plen = np.ascontiguousarray(plen, np.int32)
+    tlen = np.ascontiguousarray(tlen, np.int32)
+    if results is None:
+        results = np.zeros(n, RESULT_DTYPE)
+    if cigars is None:
+        cigars = np.zeros((n, cigar_pitch), np.uint8)
+    phase = (C.c_double * 3)()
+    p = params.to_c()
+    rc = lib.aim_align_packed(C.byref(p), n, idx_base, _ptr(plen), _ptr(tlen), _ptr(packed), _ptr(flags), _ptr(results), _ptr(cigars),
+                              cigar_pitch, phase)
+    if rc != 0:
+        raise AimError(rc)
+    return results, cigars, list(phase)
+
+
+def write_results_packed(path, results: np.ndarray, cigars: np.ndarray) -> None:
+    rc = lib.aim_write_results_packed(os.fsencode(path), len(results), _ptr(results), _ptr(cigars), cigars.shape[1])
+    if rc != 0:
+        raise AimError(rc)
+
+
 def cigar_strings(results: np.ndarray, ops: np.ndarray) -> list[str]:
     """RLE CIGARs as edit_cigar_print writes them (host.c:69-89)."""
     out = []

@@ -287,6 +287,123 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
     return AIM_OK;
 }
 
+// One GPU's share [first, first + n) of a PACKED host batch (aim_align_packed): per chunk, lengths + packed rows + flag
+// words up, kernels, results + CIGAR rows down; same three-stream pipeline as run_shard.  The chunk's device buffers are
+// reused: d_pat holds the packed rows, d_txt the flag words followed by the CIGAR rows, d_ops the op rows the backtrace
+// writes (they never leave the device).
+int run_shard_packed(const aim_params &p, int device, uint32_t first, uint32_t n, uint32_t idx_base, const int32_t *plen,
+                     const int32_t *tlen, const uint32_t *packed, const uint32_t *flags, aim_result *results, char *cigars,
+                     int32_t pitch, double phase_ms[3], std::string *err)
+{
+    auto fail = [&](int rc) { if (err) *err = aim_last_error(); return rc; };
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(device, &ctx);
+    if (rc != AIM_OK) return fail(rc);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(AIM_ERR_CUDA); }
+    if (n == 0) return AIM_OK;
+    const size_t rs = (size_t)p.read_size;
+    const size_t row2 = 2 * (size_t)aim_packed_row_bytes(p.read_size);  // packed bytes per pair
+    if (row2 > rs) { set_error("read_size too small for the packed entry"); return fail(AIM_ERR_ARG); }
+    // chunks start on multiples of 32 pairs so that every chunk owns whole flag words
+    const uint32_t lead = (32u - (first & 31u)) & 31u;  // pairs of a shard that starts inside a flag word: handled by an unaligned first chunk
+    uint32_t chunk_pairs = (uint32_t)std::max<size_t>(16384, std::min<size_t>(((size_t)96 << 20) / (row2 + (size_t)pitch + 32), 1u << 20)) & ~31u;
+    if (const char *cm = getenv("AIM_CHUNK_PAIRS")) { const long v = atol(cm); if (v >= 32) chunk_pairs = (uint32_t)v & ~31u; }
+    if (!ctx->s_h2d) {
+        AIM_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        AIM_CUDA(cudaStreamCreateWithFlags(&ctx->s_kernel, cudaStreamNonBlocking));
+        AIM_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    }
+    // chunk list: an unaligned head (if any), then aligned chunks
+    std::vector<std::pair<uint32_t, uint32_t>> ch;  // (offset inside the shard, pairs)
+    {
+        uint32_t off = 0;
+        if (lead && lead < n) { ch.emplace_back(0u, lead); off = lead; }
+        while (off < n) { const uint32_t m = std::min(chunk_pairs, n - off); ch.emplace_back(off, m); off += m; }
+    }
+    const uint32_t nchunks = (uint32_t)ch.size();
+    const int nbuf = (int)std::min<uint32_t>(kNumBuf, nchunks);
+    const uint32_t cap = std::min(std::max(chunk_pairs, lead), std::max(n, 32u));
+    for (int b = 0; b < nbuf; ++b) {
+        rc = ensure_chunk(ctx->chunk[b], cap, p.read_size, true, false);
+        if (rc != AIM_OK) return fail(rc);
+    }
+    double ph[3] = {0, 0, 0};
+    auto finish = [&](uint32_t c) -> int {
+        ChunkBuf &B = ctx->chunk[c % (uint32_t)nbuf];
+        cudaError_t e = cudaEventSynchronize(B.ev[5]);
+        if (e != cudaSuccess) { set_error(std::string("chunk sync: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
+        float t;
+        for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&t, B.ev[2 * k], B.ev[2 * k + 1]); ph[k] += t; }
+        return AIM_OK;
+    };
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        ChunkBuf &B = ctx->chunk[c % (uint32_t)nbuf];
+        if (c >= (uint32_t)nbuf) { rc = finish(c - (uint32_t)nbuf); if (rc != AIM_OK) return fail(rc); }
+        const uint32_t off = ch[c].first, m = ch[c].second;
+        const uint32_t g0 = first + off;  // first pair of the chunk in the caller's arrays
+        const int32_t *s_plen = plen + g0, *s_tlen = tlen + g0;
+        {   // host.c:119-123 rejects reads longer than READ_SIZE
+            int32_t lo = 0, hi = 0;
+            for (uint32_t i = 0; i < m; ++i) {
+                lo = std::min(lo, std::min(s_plen[i], s_tlen[i]));
+                hi = std::max(hi, std::max(s_plen[i], s_tlen[i]));
+            }
+            if (lo < 0 || hi > p.read_size) {
+                cudaDeviceSynchronize();
+                set_error(lo < 0 ? "negative sequence length" : "READ LENGTH less than length of the input reads");
+                return fail(lo < 0 ? AIM_ERR_ARG : AIM_ERR_LENGTH);
+            }
+        }
+        // flag words of the chunk: the caller's words when the chunk starts on a word boundary, else shifted on the host
+        const uint32_t fwords = (m + 31) / 32;
+        uint32_t *d_flags = reinterpret_cast<uint32_t *>(B.d_txt);
+        const size_t flag_bytes = ((size_t)fwords * 4 + 255) / 256 * 256;
+        char *d_cig = B.d_txt + flag_bytes;
+        if (flag_bytes + (size_t)m * (size_t)pitch > (size_t)B.pairs_cap * rs) { set_error("cigar_pitch too large for the chunk buffers"); return fail(AIM_ERR_ARG); }
+        std::vector<uint32_t> shifted;
+        const uint32_t *s_flags = flags + (g0 >> 5);
+        if (g0 & 31u) {
+            shifted.assign(fwords, 0u);
+            for (uint32_t i = 0; i < m; ++i) {
+                const uint32_t g = g0 + i;
+                if ((flags[g >> 5] >> (g & 31)) & 1u) shifted[i >> 5] |= 1u << (i & 31);
+            }
+            s_flags = shifted.data();
+        }
+        AIM_CUDA(cudaEventRecord(B.ev[0], ctx->s_h2d));
+        AIM_CUDA(cudaMemcpyAsync(B.d_plen, s_plen, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+        AIM_CUDA(cudaMemcpyAsync(B.d_tlen, s_tlen, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+        AIM_CUDA(cudaMemcpyAsync(B.d_pat, reinterpret_cast<const char *>(packed) + (size_t)g0 * row2, (size_t)m * row2, cudaMemcpyHostToDevice, ctx->s_h2d));
+        AIM_CUDA(cudaMemcpyAsync(d_flags, s_flags, (size_t)fwords * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (!shifted.empty()) AIM_CUDA(cudaStreamSynchronize(ctx->s_h2d));  // the temporary must outlive the copy (unaligned head only)
+        AIM_CUDA(cudaEventRecord(B.ev[1], ctx->s_h2d));
+
+        AIM_CUDA(cudaStreamWaitEvent(ctx->s_kernel, B.ev[1], 0));
+        AIM_CUDA(cudaEventRecord(B.ev[2], ctx->s_kernel));
+        KernelArgs a{p, m, idx_base + g0, B.d_plen, B.d_tlen, nullptr, nullptr, B.d_res, B.d_ops};
+        a.packed = reinterpret_cast<const uint32_t *>(B.d_pat);
+        a.pflags = d_flags;
+        a.cigars = d_cig;
+        a.cigar_pitch = pitch;
+        rc = launch(a, &ctx->scratch, ctx->s_kernel, nullptr);
+        if (rc != AIM_OK) { cudaDeviceSynchronize(); return fail(rc); }
+        AIM_CUDA(cudaEventRecord(B.ev[3], ctx->s_kernel));
+
+        AIM_CUDA(cudaStreamWaitEvent(ctx->s_d2h, B.ev[3], 0));
+        AIM_CUDA(cudaEventRecord(B.ev[4], ctx->s_d2h));
+        AIM_CUDA(cudaMemcpyAsync(results + g0, B.d_res, (size_t)m * sizeof(aim_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        AIM_CUDA(cudaMemcpyAsync(cigars + (size_t)g0 * (size_t)pitch, d_cig, (size_t)m * (size_t)pitch, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        AIM_CUDA(cudaEventRecord(B.ev[5], ctx->s_d2h));
+    }
+    for (uint32_t c = (nchunks >= (uint32_t)nbuf ? nchunks - (uint32_t)nbuf : 0); c < nchunks; ++c) {
+        rc = finish(c);
+        if (rc != AIM_OK) return fail(rc);
+    }
+    if (phase_ms) for (int k = 0; k < 3; ++k) phase_ms[k] = ph[k];
+    return AIM_OK;
+}
+
 }  // namespace
 
 int scratch_reserve(Scratch *s, size_t bytes)
@@ -414,6 +531,46 @@ extern "C" int aim_align_batch(const aim_params *params, uint32_t n, uint32_t id
         th.emplace_back([&, d, first, cnt]() {
             rcs[(size_t)d] = run_shard(*params, params->device + d, first, cnt, idx_base, plen, tlen, patterns, texts,
                                        results, ops, &ph[(size_t)d * 3], &errs[(size_t)d]);
+            if (rcs[(size_t)d] != AIM_OK && errs[(size_t)d].empty()) errs[(size_t)d] = aim_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < g; ++d) {
+        if (rcs[(size_t)d] != AIM_OK) { set_error("gpu " + std::to_string(params->device + d) + ": " + errs[(size_t)d]); return rcs[(size_t)d]; }
+        if (phase_ms) for (int k = 0; k < 3; ++k) phase_ms[k] = std::max(phase_ms[k], ph[(size_t)d * 3 + k]);
+    }
+    return AIM_OK;
+}
+
+extern "C" int aim_align_packed(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen, const int32_t *tlen,
+                                const uint32_t *packed, const uint32_t *flags, aim_result *results, char *cigars,
+                                int32_t cigar_pitch, double phase_ms[3])
+{
+    int rc = validate(params, false, nullptr);
+    if (rc != AIM_OK) return rc;
+    if (params->algo != AIM_ALGO_WFA || !params->backtrace) { set_error("aim_align_packed serves WFA with backtrace"); return AIM_ERR_ARG; }
+    if (cigar_pitch < 16 || (cigar_pitch % 16) != 0 || cigar_pitch > 2 * params->read_size || params->read_size < 64) {
+        set_error("cigar_pitch must be a multiple of 16 in 16..2*read_size (read_size >= 64)");
+        return AIM_ERR_ARG;
+    }
+    if (n > 0 && (!plen || !tlen || !packed || !flags || !results || !cigars)) { set_error("NULL host buffer"); return AIM_ERR_ARG; }
+    if (phase_ms) phase_ms[0] = phase_ms[1] = phase_ms[2] = 0.0;
+    int ndev = aim_device_count();
+    if (ndev == 0) { set_error("no CUDA device (aim_b200 has no CPU fallback)"); return AIM_ERR_NO_DEVICE; }
+    const int g = params->ngpus <= 1 ? 1 : params->ngpus;
+    if (params->device < 0 || params->device + g > ndev) { set_error("device range exceeds visible GPUs"); return AIM_ERR_ARG; }
+    if (g == 1) return run_shard_packed(*params, params->device, 0, n, idx_base, plen, tlen, packed, flags, results, cigars, cigar_pitch, phase_ms, nullptr);
+    // contiguous index ranges per GPU on multiples of 32 pairs (whole flag words), one host thread + stream set each
+    const uint32_t per = ((n + (uint32_t)g - 1) / (uint32_t)g + 31u) & ~31u;
+    std::vector<std::thread> th;
+    std::vector<int> rcs((size_t)g, AIM_OK);
+    std::vector<std::string> errs((size_t)g);
+    std::vector<double> ph((size_t)g * 3, 0.0);
+    for (int d = 0; d < g; ++d) {
+        const uint32_t first = std::min<uint64_t>(n, (uint64_t)d * per), cnt = std::min(per, n - first);
+        th.emplace_back([&, d, first, cnt]() {
+            rcs[(size_t)d] = run_shard_packed(*params, params->device + d, first, cnt, idx_base, plen, tlen, packed, flags, results,
+                                              cigars, cigar_pitch, &ph[(size_t)d * 3], &errs[(size_t)d]);
             if (rcs[(size_t)d] != AIM_OK && errs[(size_t)d].empty()) errs[(size_t)d] = aim_last_error();
         });
     }

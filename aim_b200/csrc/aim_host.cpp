@@ -313,6 +313,92 @@ extern "C" int aim_write_results(const char *path, uint32_t n, int32_t read_size
     return rc;
 }
 
+// ---- compact transfers (include/aim_b200.h): host-side 2-bit packing and the printer for CIGAR rows ----
+extern "C" int32_t aim_packed_row_bytes(int32_t read_size)
+{
+    if (read_size <= 0) return 0;
+    const uint32_t words = ((uint32_t)read_size / 16 + 2 + 3) / 4 * 4;  // the short-read kernel's row: one spare word, multiple of 4
+    return (int32_t)(words * 4);
+}
+
+extern "C" int aim_pack_pairs(uint32_t n, int32_t read_size, const int32_t *plen, const int32_t *tlen, const char *patterns,
+                              const char *texts, uint32_t *packed, uint32_t *flags, int32_t nthreads)
+{
+    if (!plen || !tlen || !patterns || !texts || !packed || !flags || read_size <= 0) { aim::set_error("aim_pack_pairs: NULL argument"); return AIM_ERR_ARG; }
+    const size_t rs = (size_t)read_size;
+    const uint32_t words = (uint32_t)aim_packed_row_bytes(read_size) / 4;
+    const uint32_t fwords = (n + 31) / 32;
+    int T = nthreads > 0 ? nthreads : io_threads((size_t)n * rs * 2);
+    T = std::max(1, std::min<int>(T, (int)std::max<uint32_t>(1, fwords)));
+    // threads own whole flag words (32 pairs), so no two threads touch the same word
+    const uint32_t per = (fwords + (uint32_t)T - 1) / (uint32_t)T;
+    std::vector<int> bad((size_t)T, 0);
+    parallel_for(T, [&](int t) {
+        const uint32_t w0 = std::min(fwords, (uint32_t)t * per), w1 = std::min(fwords, w0 + per);
+        for (uint32_t fw = w0; fw < w1; ++fw) {
+            uint32_t fbits = 0;
+            const uint32_t hi = std::min(n, (fw + 1) * 32);
+            for (uint32_t i = fw * 32; i < hi; ++i) {
+                bool ok = true;
+                for (int q = 0; q < 2; ++q) {
+                    const int32_t len = q ? tlen[i] : plen[i];
+                    if (len < 0 || len > read_size) { bad[(size_t)t] = 1; continue; }
+                    const unsigned char *row = reinterpret_cast<const unsigned char *>((q ? texts : patterns) + (size_t)i * rs);
+                    uint32_t *out = packed + ((size_t)i * 2 + (size_t)q) * words;
+                    for (uint32_t w = 0; w < words; ++w) {
+                        uint32_t v = 0;
+                        const int32_t b0 = (int32_t)w * 16;
+                        for (int32_t b = 0; b < 16; ++b) {
+                            uint32_t code = 0;
+                            if (b0 + b < len) {
+                                const unsigned char c = row[b0 + b];
+                                code = (c >> 1) & 3u;
+                                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') ok = false;
+                            }
+                            v = (v << 2) | code;
+                        }
+                        out[w] = v;
+                    }
+                }
+                if (!ok) fbits |= 1u << (i & 31);
+            }
+            flags[fw] = fbits;
+        }
+    });
+    for (int t = 0; t < T; ++t) if (bad[(size_t)t]) { aim::set_error("READ LENGTH less than length of the input reads"); return AIM_ERR_LENGTH; }
+    return AIM_OK;
+}
+
+extern "C" int aim_write_results_packed(const char *path, uint32_t n, const aim_result *results, const char *cigars, int32_t cigar_pitch)
+{
+    if (!cigars || cigar_pitch <= 0) { aim::set_error("cigars buffer required"); return AIM_ERR_ARG; }
+    FILE *f = fopen(path, "w");
+    if (!f) { aim::set_error(std::string("Output file '") + path + "' couldn't be opened"); return AIM_ERR_IO; }
+    std::vector<char> buf((size_t)1 << 20);
+    size_t pos = 0;
+    int rc = AIM_OK;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (pos + (size_t)cigar_pitch + 64 > buf.size()) {
+            if (fwrite(buf.data(), 1, pos, f) != pos) { rc = AIM_ERR_IO; break; }
+            pos = 0;
+        }
+        char *o = buf.data();
+        pos += put_int(o + pos, (int32_t)results[i].idx);
+        o[pos++] = ','; o[pos++] = ' ';
+        pos += put_int(o + pos, results[i].score);
+        o[pos++] = ','; o[pos++] = ' '; o[pos++] = '\n';
+        const char *c = cigars + (size_t)i * (size_t)cigar_pitch;
+        const size_t len = strnlen(c, (size_t)cigar_pitch);
+        memcpy(o + pos, c, len);
+        pos += len;
+        o[pos++] = '\n';
+    }
+    if (rc == AIM_OK && pos && fwrite(buf.data(), 1, pos, f) != pos) rc = AIM_ERR_IO;
+    if (ferror(f)) rc = AIM_ERR_IO;
+    fclose(f);
+    return rc;
+}
+
 // GenASM printers: DC "%d, %d, %s\n" (idx, score, the DPU's CIGAR string up to its NUL:
 // aim-genasm/GenASM/DPU-WRAM-DC/host/host.c:286-296), filter "%d, %d\n" (DPU-WRAM-filter/host/host.c:272).
 extern "C" int aim_write_results_genasm(const char *path, uint32_t n, int32_t read_size, int32_t dc,

@@ -33,6 +33,11 @@ struct KernelArgs {
     const char *texts;
     aim_result *results;
     char *ops;
+    // packed entry (aim_align_packed): sequences arrive 2-bit packed, CIGARs leave run-length encoded
+    const uint32_t *packed = nullptr;  // per pair 2 x aim_packed_row_bytes()/4 words (pattern, then text); patterns/texts are NULL
+    const uint32_t *pflags = nullptr;  // one bit per pair: a byte outside {A,C,G,T} - the pair cannot be served packed
+    char *cigars = nullptr;            // per pair cigar_pitch bytes: the CIGAR as the reference prints it, NUL-terminated
+    int32_t cigar_pitch = 0;
 };
 
 // Per-device scratch owned by the dispatcher and handed to the launchers.

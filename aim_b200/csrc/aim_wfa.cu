@@ -539,6 +539,7 @@ int launch_wfa(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
     {   // short reads: several pairs per warp in lockstep (aim_wfa_sub.cu); falls through when not applicable
         const int rc = launch_wfa_sub(a, sc, stream_v, launches);
         if (rc != 1) return rc;
+        if (a.packed) { set_error("the packed entry serves the short-read WFA kernel only (MAX_SCORE / READ_SIZE too large)"); return AIM_ERR_ARG; }
     }
     {   // long reads, score only: windowed rings in shared memory (aim_wfa_long.cu); its leftovers come back
         // through wfa_warp_launch with a list

@@ -510,6 +510,57 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
+// Packed entry only: the CIGAR of every pair as edit_cigar_print writes it (WFA/DPU-MRAM/host/host.c:69-89: "%d%c" per run of
+// ops[begin_offset .. end_offset), the op at begin_offset always printed), NUL-terminated, in a fixed-pitch row, so that
+// ~30 bytes instead of the 2 * READ_SIZE op row cross PCIe.  One pair per thread.  A pair the lockstep kernel skipped
+// (non-ACGT byte: no ASCII is on the device in this mode) gets AIM_STATUS_NEEDS_ASCII; a CIGAR longer than the row gets
+// AIM_STATUS_CIGAR_OVERFLOW; the caller serves both through aim_align_batch.
+__global__ void __launch_bounds__(128) cigar_rle_kernel(const int32_t *plen, const int32_t *tlen, const uint32_t *flags,
+                                                        aim_result *results, const char *ops, char *cigars, int pitch,
+                                                        uint32_t n, uint32_t idx_base, int RS)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    char *out = cigars + (size_t)i * pitch;
+    if ((flags[i >> 5] >> (i & 31)) & 1u) {
+        aim_result r;
+        r.max_operations = min(max(plen[i], 0), RS) + min(max(tlen[i], 0), RS);
+        r.begin_offset = r.max_operations - 1;
+        r.end_offset = r.max_operations;
+        r.score = 0;
+        r.status = AIM_STATUS_NEEDS_ASCII;
+        r.idx = idx_base + i;
+        results[i] = r;
+        out[0] = '\0';
+        return;
+    }
+    const aim_result r = results[i];
+    if (r.status != AIM_STATUS_OK) { out[0] = '\0'; return; }
+    const char *row = ops + (size_t)i * 2 * RS;
+    const int b = r.begin_offset, e = r.end_offset > b ? r.end_offset : b + 1;
+    int pos = 0;
+    bool over = false;
+    auto emit = [&](int len, char op) {
+        char tmp[10];
+        int k = 0;
+        do { tmp[k++] = (char)('0' + len % 10); len /= 10; } while (len);
+        if (pos + k + 1 >= pitch) { over = true; return; }
+        while (k) out[pos++] = tmp[--k];
+        out[pos++] = op;
+    };
+    // (an empty alignment has b = -1 and the reference prints the byte before its span: an 'M' of the memset, wfa.c:499-501)
+    char last = b >= 0 ? row[b] : 'M';
+    int run = 1;
+    for (int j = b + 1; j < e && !over; ++j) {
+        const char c = row[j];
+        if (c == last) ++run;
+        else { emit(run, last); last = c; run = 1; }
+    }
+    if (!over) emit(run, last);
+    if (over) { results[i].status = AIM_STATUS_CIGAR_OVERFLOW; out[0] = '\0'; }
+    else out[pos] = '\0';
+}
+
 template <int G>
 cudaError_t launch_g(const SubK &K, bool reduce, bool bt, int grid, int block, size_t smem, cudaStream_t st)
 {
@@ -607,6 +658,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     if (arena_cells > 0x0fffffffu) return 1;
 
+    const bool prepacked = a.packed != nullptr;
     K.plen = a.plen; K.tlen = a.tlen; K.patterns = a.patterns; K.texts = a.texts;
     K.results = a.results; K.ops = a.ops; K.n = a.n; K.idx_base = a.idx_base;
     K.x = x; K.o = o; K.e = e; K.max_score = MS; K.read_size = p.read_size;
@@ -679,15 +731,16 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     uint32_t *list = reinterpret_cast<uint32_t *>(base + plan_dev + flags_dev);
     uint32_t *packed = reinterpret_cast<uint32_t *>(base + plan_dev + flags_dev + list_dev);
     K.plan = reinterpret_cast<const uint32_t *>(base);
-    K.flags = flags;
-    K.packed = reinterpret_cast<const uint4 *>(packed);
+    K.flags = prepacked ? a.pflags : flags;
+    K.packed = reinterpret_cast<const uint4 *>(prepacked ? a.packed : packed);
+    if (prepacked && aim_packed_row_bytes(p.read_size) != (int32_t)(K.seq_words * 4)) { set_error("packed row pitch mismatch"); return AIM_ERR_ARG; }
     K.arena = reinterpret_cast<uint2 *>(base + plan_dev + flags_dev + list_dev + packed_dev);
     void *warp_scratch = base + plan_dev + flags_dev + list_dev + packed_dev + arena_bytes;
     cudaError_t err = cudaMemcpyAsync(base, plan.data(), plan_bytes, cudaMemcpyHostToDevice, stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(list_count, 0, flags_dev, stream);
     if (err == cudaSuccess && p.backtrace)  // op rows: 'M' everywhere (wfa.c:499-501); the backtrace overwrites the few edits
         err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * (size_t)p.read_size, stream);
-    if (err == cudaSuccess) {
+    if (err == cudaSuccess && !prepacked) {
         const uint64_t total = (uint64_t)a.n * 2 * K.seq_words;
         const int pgrid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sc->sm_count * 64);
         wfa_prep_kernel<<<pgrid, 256, 0, stream>>>(a.patterns, a.texts, a.plen, a.tlen, a.n, p.read_size, K.seq_words, packed, flags, list, list_count);
@@ -704,6 +757,15 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { set_error(std::string("wfa_sub launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
     if (launches) ++*launches;
+    if (prepacked) {  // no ASCII on the device: flagged pairs are reported, and the CIGARs leave run-length encoded
+        if (a.cigars) {
+            cigar_rle_kernel<<<(a.n + 127) / 128, 128, 0, stream>>>(a.plen, a.tlen, a.pflags, a.results, a.ops, a.cigars, a.cigar_pitch,
+                                                                  a.n, a.idx_base, p.read_size);
+            if (cudaGetLastError() != cudaSuccess) { set_error("cigar_rle launch failed"); return AIM_ERR_CUDA; }
+            if (launches) ++*launches;
+        }
+        return AIM_OK;
+    }
     return wfa_warp_launch(W, warp_scratch, list, list_count, stream_v, launches);
 }
 

@@ -44,6 +44,9 @@ extern "C" {
 #define AIM_STATUS_GENASM_UNDEFINED 3 /* GenASM-DC: the reference's traceback reads rows it never wrote for this pair (a text
                                        * byte outside ACGTacgt, or the walk reaches text row n): its output is not a function
                                        * of the pair; no CIGAR is returned                                                     */
+#define AIM_STATUS_NEEDS_ASCII 5      /* aim_align_packed: the pair holds a byte outside {A,C,G,T} (the reference compares raw bytes, wfa.c:209):
+                                       * serve it through aim_align_batch                                                          */
+#define AIM_STATUS_CIGAR_OVERFLOW 6   /* aim_align_packed: the CIGAR text does not fit cigar_pitch; score is valid                      */
 #define AIM_STATUS_GENASM_NOALIGN 4   /* GenASM-DC: "No alignment found!" within max_score errors (genasmDC.c:543-547), score -1 */
 
 /* The compile-time knobs of the reference (-DMAX_SCORE -DREAD_SIZE -DMATCH -DMISMATCH -DGAP_O
@@ -110,6 +113,29 @@ int aim_align_device(const aim_params *params, int device, uint32_t n, uint32_t 
                      const char *d_patterns, const char *d_texts,
                      aim_result *d_results, char *d_ops,
                      void *stream, float *kernel_ms, int32_t *launches);
+
+/* ---- compact transfers (extension; WFA short reads) -------------------------------------------------
+ * aim_align_batch moves the reference host's own buffers: 2*READ_SIZE ASCII bytes in and the 2*READ_SIZE op row out per
+ * pair (696 B at READ_SIZE 168), which is what bounds it: one PCIe Gen5 x16 link carries ~1.2e8 pairs/s of that layout and
+ * the host's memory ~1.9e8 pairs/s for all GPUs of a box together, while one B200 aligns 3e8 pairs/s.  This entry moves the
+ * information instead: sequences 2 bits per base (aim_pack_pairs: what get_reads would produce, host.c:91-134), and per
+ * pair the CIGAR TEXT the reference prints (edit_cigar_print, host.c:69-89: "40M1D59M", NUL-terminated) in a row of
+ * cigar_pitch bytes, i.e. what the print loop (host.c:340-350) needs, ready to write.  Same scores, same CIGARs.
+ *   packed : n x 2 x aim_packed_row_bytes(read_size) bytes, pair i's pattern row then its text row; 16 bases per 32-bit
+ *            word, first base in the two most significant bits, codes A,C,T,G = 0,1,2,3 ((c >> 1) & 3), 'A' past the end
+ *   flags  : one bit per pair (bit i & 31 of word i >> 5): set by aim_pack_pairs for a pair with a byte outside {A,C,G,T}
+ *            inside its sequences; such pairs come back with AIM_STATUS_NEEDS_ASCII
+ *   cigars : n x cigar_pitch bytes (cigar_pitch a multiple of 16, 16..2*read_size); AIM_STATUS_CIGAR_OVERFLOW if too small
+ * params->algo must be AIM_ALGO_WFA with backtrace; configurations the short-read kernel does not serve return AIM_ERR_ARG.
+ * Buffers from aim_host_alloc() are DMA'd in place. */
+int32_t aim_packed_row_bytes(int32_t read_size);
+int aim_pack_pairs(uint32_t n, int32_t read_size, const int32_t *plen, const int32_t *tlen, const char *patterns,
+                   const char *texts, uint32_t *packed, uint32_t *flags, int32_t nthreads);
+int aim_align_packed(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen, const int32_t *tlen,
+                     const uint32_t *packed, const uint32_t *flags, aim_result *results, char *cigars, int32_t cigar_pitch,
+                     double phase_ms[3]);
+/* "%d, %d, \n" + the CIGAR row + "\n" per pair: the reference's output bytes from aim_align_packed's results. */
+int aim_write_results_packed(const char *path, uint32_t n, const aim_result *results, const char *cigars, int32_t cigar_pitch);
 
 /* Pinned host memory for zero-staging transfers (cudaHostAlloc / cudaFreeHost). */
 void *aim_host_alloc(size_t bytes);

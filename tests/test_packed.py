@@ -1,0 +1,113 @@
+"""Compact transfers (include/aim_b200.h: aim_pack_pairs / aim_align_packed / aim_write_results_packed): same scores and the
+same CIGAR text as the reference prints (edit_cigar_print, WFA/DPU-MRAM/host/host.c:69-89), with 2-bit sequences in and
+run-length CIGAR rows out."""
+import lzma
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, MANIFEST, md5_bytes, oracle_results_to_aim
+import aim_b200 as A
+from oracle import oracle as O
+
+
+def py_pack(row: bytes, length: int, words: int):
+    out = []
+    for w in range(words):
+        v = 0
+        for b in range(16):
+            j = 16 * w + b
+            code = ((row[j] >> 1) & 3) if j < length else 0
+            v = (v << 2) | code
+        out.append(v)
+    return out
+
+
+def test_pack_pairs_matches_restatement_and_flags_non_acgt():
+    rs = 168
+    plen, tlen, pats, txts = A.generate_pairs(4, 300, 150, 0.04, rs, nthreads=1)
+    pats, txts = pats.copy(), txts.copy()
+    pats[5, 10] = ord("N")
+    txts[64, 3] = ord("a")
+    pats[7, plen[7]:] = ord("N")  # bytes beyond the sequence do not count
+    words = A.packed_row_bytes(rs) // 4
+    assert A.packed_row_bytes(rs) == 48 and A.packed_row_bytes(272) == 80
+    for threads in (1, 3):
+        packed, flags = A.pack_pairs(plen, tlen, pats, txts, rs, nthreads=threads)
+        assert packed.shape == (300, 2, words)
+        for i in (0, 5, 7, 64, 299):
+            assert list(packed[i, 0]) == py_pack(bytes(pats[i]), plen[i], words)
+            assert list(packed[i, 1]) == py_pack(bytes(txts[i]), tlen[i], words)
+        set_bits = [i for i in range(300) if (flags[i >> 5] >> (i & 31)) & 1]
+        assert set_bits == [5, 64]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reduce", [True, False])
+def test_packed_path_equals_oracle(reduce, monkeypatch):
+    """Scores, spans and CIGAR text bit-exact vs the oracle; flagged / overflowing pairs reported; odd chunking and idx_base."""
+    monkeypatch.setenv("AIM_CHUNK_PAIRS", "4096")  # several chunks
+    rs, ms = 168, 30
+    n = 20_000
+    plen, tlen, pats, txts = A.generate_pairs(41, n, 150, 0.04, rs)
+    pats, txts = pats.copy(), txts.copy()
+    dirty = [3, 4097, 12_345]
+    for i in dirty:
+        pats[i, 7] = ord("N")
+    plen, tlen = plen.copy(), tlen.copy()
+    plen[10], tlen[11] = 0, 0
+    plen[12] = tlen[12] = 0
+    packed, flags = A.pack_pairs(plen, tlen, pats, txts, rs)
+    params = A.AlignParams(algo="wfa", max_score=ms, read_size=rs, backtrace=True, reduce=reduce)
+    res, cig, phase = A.align_packed(params, plen, tlen, packed, flags, cigar_pitch=64, idx_base=1000)
+    exp, eops = O.align("wfa", plen, tlen, pats, txts, max_score=ms, read_size=rs, backtrace=True, reduce=reduce, nthreads=8)
+    want = A.cigar_strings(oracle_results_to_aim(exp), eops)
+    assert np.array_equal(res["idx"], np.arange(1000, 1000 + n, dtype=np.uint32))
+    ok = np.ones(n, bool)
+    ok[dirty] = False
+    assert np.array_equal(res["status"][dirty], [5, 5, 5])
+    assert int((res["status"][ok] != 0).sum()) == 0
+    for f in ("score", "max_operations", "begin_offset", "end_offset"):
+        assert np.array_equal(res[f][ok], exp[f][ok]), f
+    for i in np.nonzero(ok)[0]:
+        got = bytes(cig[i]).split(b"\0", 1)[0].decode()
+        assert got == want[i], (i, got, want[i])
+    assert all(p >= 0 for p in phase)
+    # a row too small for some CIGARs: those pairs say so, the others are unchanged
+    res2, cig2, _ = A.align_packed(params, plen, tlen, packed, flags, cigar_pitch=16)
+    over = res2["status"] == 6
+    assert over.any() and np.array_equal(res2["score"][ok], exp["score"][ok])
+    for i in np.nonzero(ok & ~over)[0][:2000]:
+        assert bytes(cig2[i]).split(b"\0", 1)[0].decode() == want[i]
+    assert all(len(want[i]) >= 15 for i in np.nonzero(over)[0])
+
+
+@pytest.mark.gpu
+def test_packed_path_writes_the_reference_bytes(tmp_path):
+    """Golden case cfg4 (reference output committed): pack -> aim_align_packed -> aim_write_results_packed == the reference's file."""
+    e = MANIFEST["cfg4_wfa_adaptive_synth"]
+    p = e["params"]
+    f = tmp_path / "in.pairs"
+    f.write_bytes(lzma.open(GOLDEN / e["input"]).read())
+    rs = p["read_size"]
+    plen, tlen, pats, txts = A.read_pairs(f, rs)
+    packed, flags = A.pack_pairs(plen, tlen, pats, txts, rs)
+    params = A.AlignParams(algo="wfa", max_score=p["max_score"], read_size=rs, backtrace=True, reduce=True)
+    res, cig, _ = A.align_packed(params, plen, tlen, packed, flags, cigar_pitch=96)
+    out = tmp_path / "out"
+    A.write_results_packed(out, res, cig)
+    assert md5_bytes(out.read_bytes()) == e["md5"]
+
+
+@pytest.mark.gpu
+def test_packed_entry_rejects_what_it_does_not_serve():
+    rs = 168
+    plen, tlen, pats, txts = A.generate_pairs(4, 64, 150, 0.04, rs)
+    packed, flags = A.pack_pairs(plen, tlen, pats, txts, rs)
+    with pytest.raises(A.AimError):
+        A.align_packed(A.AlignParams(algo="nw", max_score=30, read_size=rs, backtrace=True), plen, tlen, packed, flags)
+    with pytest.raises(A.AimError):
+        A.align_packed(A.AlignParams(algo="wfa", max_score=30, read_size=rs, backtrace=False), plen, tlen, packed, flags)
+    with pytest.raises(A.AimError):
+        A.align_packed(A.AlignParams(algo="wfa", max_score=30, read_size=rs, backtrace=True), plen, tlen, packed, flags, cigar_pitch=20)
