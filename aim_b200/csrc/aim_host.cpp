@@ -314,6 +314,27 @@ extern "C" int aim_write_results(const char *path, uint32_t n, int32_t read_size
 }
 
 // ---- compact transfers (include/aim_b200.h): host-side 2-bit packing and the printer for CIGAR rows ----
+namespace {
+// c = eight 2-bit codes, one in the low bits of each byte (byte j = base j) -> 16 bits, base 0 in the two most significant bits
+uint32_t gather_swar(uint64_t c)
+{
+    uint64_t g = c | (c >> 6);  // two bases in the low nibble of every even byte (base j low, j + 1 high)
+    g = (g & 0x000f000f000f000full) | ((g >> 12) & 0x00f000f000f000f0ull);  // four bases in the low byte of every 16-bit lane
+    const uint32_t lo = (uint32_t)g, hi = (uint32_t)(g >> 32);
+    const uint32_t b8 = (lo & 0xffu) | ((hi & 0xffu) << 8);  // base j at bits [2j + 1, 2j]
+    uint32_t r = ((b8 & 0x3333u) << 2) | ((b8 >> 2) & 0x3333u);  // reverse the order of the eight 2-bit fields
+    r = ((r & 0x0f0fu) << 4) | ((r >> 4) & 0x0f0fu);
+    r = ((r & 0x00ffu) << 8) | ((r >> 8) & 0x00ffu);
+    return r;
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("bmi2"))) uint32_t gather_bmi2(uint64_t c)
+{
+    return (uint32_t)__builtin_ia32_pext_di(__builtin_bswap64(c), 0x0303030303030303ull);
+}
+#endif
+}  // namespace
+
 extern "C" int32_t aim_packed_row_bytes(int32_t read_size)
 {
     if (read_size <= 0) return 0;
@@ -328,6 +349,10 @@ extern "C" int aim_pack_pairs(uint32_t n, int32_t read_size, const int32_t *plen
     const size_t rs = (size_t)read_size;
     const uint32_t words = (uint32_t)aim_packed_row_bytes(read_size) / 4;
     const uint32_t fwords = (n + 31) / 32;
+    uint32_t (*gather)(uint64_t) = gather_swar;
+#if defined(__x86_64__) && defined(__GNUC__)
+    if (__builtin_cpu_supports("bmi2") && !getenv("AIM_NO_BMI2")) gather = gather_bmi2;
+#endif
     int T = nthreads > 0 ? nthreads : io_threads((size_t)n * rs * 2);
     T = std::max(1, std::min<int>(T, (int)std::max<uint32_t>(1, fwords)));
     // threads own whole flag words (32 pairs), so no two threads touch the same word
@@ -346,16 +371,25 @@ extern "C" int aim_pack_pairs(uint32_t n, int32_t read_size, const int32_t *plen
                     const unsigned char *row = reinterpret_cast<const unsigned char *>((q ? texts : patterns) + (size_t)i * rs);
                     uint32_t *out = packed + ((size_t)i * 2 + (size_t)q) * words;
                     for (uint32_t w = 0; w < words; ++w) {
-                        uint32_t v = 0;
                         const int32_t b0 = (int32_t)w * 16;
-                        for (int32_t b = 0; b < 16; ++b) {
-                            uint32_t code = 0;
-                            if (b0 + b < len) {
-                                const unsigned char c = row[b0 + b];
-                                code = (c >> 1) & 3u;
-                                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') ok = false;
+                        uint32_t v = 0;
+                        for (int hlf = 0; hlf < 2; ++hlf) {  // 8 bases -> 16 bits, first base in the two most significant bits
+                            const int32_t bb = b0 + 8 * hlf;
+                            uint32_t h16 = 0;
+                            if (bb < len) {
+                                uint64_t x;
+                                memcpy(&x, row + bb, 8);  // rows are READ_SIZE (multiple of 8) bytes: never past the row
+                                const int32_t nv = len - bb;  // bytes of this group that belong to the sequence
+                                if (nv < 8) {
+                                    const uint64_t keep = (1ull << (8 * nv)) - 1ull;
+                                    x = (x & keep) | (0x4141414141414141ull & ~keep);  // pad with 'A'
+                                }
+                                const uint64_t c = (x >> 1) & 0x0303030303030303ull;
+                                const uint64_t is2 = (c >> 1) & ~c & 0x0101010101010101ull;  // code 2 <=> 'T' (0x54 = 0x41 + 2*2 + 15)
+                                if (0x4141414141414141ull + 2ull * c + 15ull * is2 != x) ok = false;
+                                h16 = gather(c);
                             }
-                            v = (v << 2) | code;
+                            v = (v << 16) | h16;
                         }
                         out[w] = v;
                     }

@@ -548,15 +548,32 @@ __global__ void __launch_bounds__(128) cigar_rle_kernel(const int32_t *plen, con
         while (k) out[pos++] = tmp[--k];
         out[pos++] = op;
     };
-    // (an empty alignment has b = -1 and the reference prints the byte before its span: an 'M' of the memset, wfa.c:499-501)
-    char last = b >= 0 ? row[b] : 'M';
-    int run = 1;
-    for (int j = b + 1; j < e && !over; ++j) {
-        const char c = row[j];
-        if (c == last) ++run;
-        else { emit(run, last); last = c; run = 1; }
+    if (b < 0) {  // an empty alignment has b = -1 and the reference prints the byte before its span: an 'M' of the memset (wfa.c:499-501)
+        emit(1, 'M');
+    } else {
+        // run boundaries eight ops at a time: byte k of (x ^ x shifted down one op) is non-zero where op 8w+k differs from op 8w+k+1
+        const unsigned long long *row64 = reinterpret_cast<const unsigned long long *>(row);
+        const int w0 = b >> 3, w1 = (e - 1) >> 3;
+        int run_start = b;
+        unsigned long long x = row64[w0];
+        for (int w = w0; w <= w1 && !over; ++w) {
+            const unsigned long long nx = w < w1 ? row64[w + 1] : x;
+            unsigned long long diff = x ^ ((x >> 8) | (nx << 56));
+            // only boundaries between ops j and j + 1 with b <= j and j + 1 <= e - 1 count
+            const int lo_k = max(b - 8 * w, 0), hi_k = min(e - 1 - 8 * w, 8);  // bytes [lo_k, hi_k)
+            if (lo_k > 0) diff &= ~0ull << (8 * lo_k);
+            if (hi_k < 8) diff &= hi_k > 0 ? ~(~0ull << (8 * hi_k)) : 0ull;
+            while (diff && !over) {
+                const int k = (__ffsll((long long)diff) - 1) >> 3;
+                const int j = 8 * w + k;
+                emit(j - run_start + 1, (char)((x >> (8 * k)) & 0xffull));
+                run_start = j + 1;
+                diff &= ~(0xffull << (8 * k));
+            }
+            x = nx;
+        }
+        if (!over) emit(e - run_start, row[e - 1]);
     }
-    if (!over) emit(run, last);
     if (over) { results[i].status = AIM_STATUS_CIGAR_OVERFLOW; out[0] = '\0'; }
     else out[pos] = '\0';
 }

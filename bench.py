@@ -306,6 +306,37 @@ def main() -> None:
                "ms_per_step": te_s * 1e3,
                "api": "aim_align_batch (C ABI), pinned host buffers, H2D+kernel+D2H double-buffered inside"}
 
+    # ---- end-to-end arm with COMPACT transfers (aim_align_packed: 2-bit sequences in, run-length CIGAR rows out) ----
+    e2e_packed = None
+    if not args.no_e2e and cfg["algo"] == "wfa" and bt and rs < 2048:
+        pitch = 64
+        words = A.packed_row_bytes(rs) // 4
+        h_packed = A.PinnedArray((P, 2, words), np.uint32)
+        h_flags = A.PinnedArray(((P + 31) // 32,), np.uint32)
+        h_cig = A.PinnedArray((P, pitch), np.uint8)
+        h_res2 = A.PinnedArray((P,), A.RESULT_DTYPE)
+        tp0 = time.perf_counter()
+        A.pack_pairs(h_plen.array, h_tlen.array, h_pat.array, h_txt.array, rs, nthreads=threads, out=(h_packed.array, h_flags.array))
+        pack_s = time.perf_counter() - tp0  # host-side, outside the timed region (the reference parses its pair file outside its timers too)
+
+        def packed_step():
+            A.align_packed(params, h_plen.array, h_tlen.array, h_packed.array, h_flags.array, cigar_pitch=pitch,
+                           results=h_res2.array, cigars=h_cig.array)
+        packed_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            packed_step()
+        torch.cuda.synchronize(dev)
+        tp_s = shard.max_over_ranks((time.perf_counter() - t0) / args.steps, dev)
+        assert np.array_equal(h_res2.array["score"], res_dev["score"]), "bench: packed e2e and device-resident scores differ"
+        assert int((h_res2.array["status"] != 0).sum()) == 0, "bench: packed e2e reported flagged / overflowing pairs"
+        e2e_packed = {"value": world * P / tp_s, "unit": "pairs/s", "h2d_bytes_per_step": int(P * (2 * words * 4 + 8) + (P + 31) // 32 * 4),
+                      "d2h_bytes_per_step": int(P * (A.RESULT_DTYPE.itemsize + pitch)), "ms_per_step": tp_s * 1e3,
+                      "api": "aim_align_packed (C ABI extension): 2-bit packed sequences in, run-length CIGAR rows out, pinned host buffers",
+                      "host_pack_pairs_per_s": P / pack_s, "host_pack_threads": threads,
+                      "note": "same scores and CIGAR text; packing happens on the host before the timed region, like the reference's pair-file parse"}
+
     if rank == 0:
         # ---- rooflines for the dominant kernel (one launch = one step on one GPU) ----
         peaks = {}
@@ -366,7 +397,7 @@ def main() -> None:
                        "l2": f"inputs {P * 2 * rs / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                        "generator": f"seed {cfg['seed']}, generate_dataset semantics", "mean_score": mean_score},
             "gcups_equiv": pl_mean * tl_mean * world * P / (ms_per_step * 1e-3) / 1e9,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "gpu_launches": launches,
             "roofline": roofline, "int_roofline": int_roofline, "cpu_baseline": cpu_baseline,
             "step_ms": step_ms,
         }
