@@ -42,16 +42,19 @@ struct DpK {
     uint32_t wpr;          // flag words per row
 };
 
-__device__ __forceinline__ int s16(int v) { return (int)(short)v; }
+// cell truncation: int16 (NW/*, SWG/DPU-MRAM: common.h:91-99) or int8 (SWG/DPU-WRAM with MAX_SCORE < 127: common.h:71-79)
+template <int BITS>
+__device__ __forceinline__ int trunc_cell(int v) { return BITS == 8 ? (int)(signed char)v : (int)(short)v; }
 
 // NW predicate byte: 3 = 'D' (left + GAP_D), 2 = 'I' (up + GAP_I), 1 = 'X', 0 = 'M'; tested in the
 // reference's order (nw.c:78-94).
 // SWG predicate byte: bits 0-2 = M-layer decision in the reference's order (swg.c:106-133):
 // 0 -> D layer, 1 -> I layer, 2 'M', 3 'X', 4 dead end; bit 3 = D opened here (swg.c:88);
 // bit 4 = I opened here (swg.c:97).
-template <int ALGO>
+template <int ALGO, int BITS>
 __global__ void __launch_bounds__(128) dp_kernel(const DpK K)
 {
+    auto s16 = [](int v) { return trunc_cell<BITS>(v); };  // every "int16" assignment below is a cell-type assignment
     const int lane = threadIdx.x & 31;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nthreads = gridDim.x * blockDim.x;
@@ -190,7 +193,10 @@ int launch_dp(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
     cudaStream_t stream = (cudaStream_t)stream_v;
     const aim_params &p = a.p;
     if (a.n == 0) return AIM_OK;
-    {
+    // SWG/DPU-WRAM semantics (variant 1): int8 cells when MAX_SCORE < 127 - the literal kernel with 8-bit truncation serves it
+    // (the 32-bit fast kernels are exact only where no truncation can occur)
+    const bool w8 = p.algo == AIM_ALGO_SWG && p.variant == 1 && p.max_score < 127;
+    if (!w8) {
         const int rc = launch_dp_fast(a, sc, stream_v, launches);
         if (rc != 1) return rc;
     }
@@ -222,8 +228,9 @@ int launch_dp(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
         err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * RS, stream);
     }
     if (err == cudaSuccess) {
-        if (p.algo == AIM_ALGO_NW) dp_kernel<AIM_ALGO_NW><<<grid, block, 0, stream>>>(K);
-        else dp_kernel<AIM_ALGO_SWG><<<grid, block, 0, stream>>>(K);
+        if (p.algo == AIM_ALGO_NW) dp_kernel<AIM_ALGO_NW, 16><<<grid, block, 0, stream>>>(K);
+        else if (w8) dp_kernel<AIM_ALGO_SWG, 8><<<grid, block, 0, stream>>>(K);
+        else dp_kernel<AIM_ALGO_SWG, 16><<<grid, block, 0, stream>>>(K);
         err = cudaGetLastError();
     }
     if (err != cudaSuccess) { set_error(std::string("dp launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }

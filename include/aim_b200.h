@@ -66,7 +66,8 @@ typedef struct aim_params {
     int32_t ngpus;      /* <=1: one device; N: shard pairs contiguously over N devices */
     int32_t device;     /* first device ordinal                                        */
     int32_t arena_mb;   /* long-read WFA history arena per resident pair in MiB (0 = default) */
-    int32_t variant;    /* GenASM-DC: 0 = DPU-WRAM-DC semantics, 1 = DPU-MRAM-DC ('S' for substitutions, pattern 'N' no wildcard) */
+    int32_t variant;    /* GenASM-DC: 0 = DPU-WRAM-DC semantics, 1 = DPU-MRAM-DC ('S' for substitutions, pattern 'N' no wildcard);
+                         * SWG: 0 = DPU-MRAM (int16 cells), 1 = DPU-WRAM (int8 cells when max_score < 127, SWG/DPU-WRAM/common/common.h:71-79) */
     int32_t reserved[3];
 } aim_params;
 

@@ -357,6 +357,10 @@ typedef struct { int16_t M, I, D, pad; } swg_cell;
 static void swg_align(const orc_params *p, const char *pattern, const char *text, int plen, int tlen,
                       orc_result *res, char *ops, swg_cell *tab)
 {
+    /* SWG/DPU-WRAM (variant 1): cell_size_t is int8 when MAX_SCORE < 127 (SWG/DPU-WRAM/common/common.h:71-79), truncation at the
+     * same assignments (SWG/DPU-WRAM/dpu/swg.c:128-165) */
+    const int w8 = p->variant == 1 && p->max_score < 127;
+#define CT(x) ((int16_t)(w8 ? (int)(int8_t)(x) : (int)(int16_t)(x)))
     const int GAP_O = p->gap_open, GAP_E = p->gap_ext, MATCH = p->match, MISMATCH = p->mismatch, MAX_SCORE = p->max_score;
     res->max_operations = plen + tlen;
     res->begin_offset = res->max_operations - 1;
@@ -365,16 +369,16 @@ static void swg_align(const orc_params *p, const char *pattern, const char *text
     res->status = ORC_OK;
     if (p->backtrace && ops) memset(ops, 'M', 2 * (size_t)p->read_size);
     int num_cols = tlen + 1;
-    tab[0].D = (int16_t)MAX_SCORE; tab[0].I = (int16_t)MAX_SCORE; tab[0].M = 0;
+    tab[0].D = CT(MAX_SCORE); tab[0].I = CT(MAX_SCORE); tab[0].M = 0;
     for (int v = 1; v <= plen; ++v) {
-        tab[v].D = (int16_t)(GAP_O + v * GAP_E);
-        tab[v].I = (int16_t)MAX_SCORE;
+        tab[v].D = CT(GAP_O + v * GAP_E);
+        tab[v].I = CT(MAX_SCORE);
         tab[v].M = tab[v].D;
     }
     for (int h = 1; h <= tlen; ++h) {
         swg_cell *c = &tab[num_cols * h];
-        c->D = (int16_t)MAX_SCORE;
-        c->I = (int16_t)(GAP_O + h * GAP_E);
+        c->D = CT(MAX_SCORE);
+        c->I = CT(GAP_O + h * GAP_E);
         c->M = c->I;
     }
     int score = 0;
@@ -384,15 +388,15 @@ static void swg_align(const orc_params *p, const char *pattern, const char *text
             swg_cell diag = tab[num_cols * (h - 1) + v - 1];
             swg_cell left = tab[num_cols * (h - 1) + v];
             swg_cell cur;
-            int16_t del_new = (int16_t)(upper.M + GAP_O + GAP_E);
-            int16_t del_ext = (int16_t)(upper.D + GAP_E);
+            int16_t del_new = CT(upper.M + GAP_O + GAP_E);
+            int16_t del_ext = CT(upper.D + GAP_E);
             int16_t del = MINI(del_new, del_ext);
             cur.D = del;
-            int16_t ins_new = (int16_t)(left.M + GAP_O + GAP_E);
-            int16_t ins_ext = (int16_t)(left.I + GAP_E);
+            int16_t ins_new = CT(left.M + GAP_O + GAP_E);
+            int16_t ins_ext = CT(left.I + GAP_E);
             int16_t ins = MINI(ins_new, ins_ext);
             cur.I = ins;
-            int16_t m_match = (int16_t)(diag.M + ((pattern[v - 1] == text[h - 1]) ? MATCH : MISMATCH));
+            int16_t m_match = CT(diag.M + ((pattern[v - 1] == text[h - 1]) ? MATCH : MISMATCH));
             cur.M = MINI(m_match, MINI(ins, del));
             cur.pad = 0;
             score = cur.M;

@@ -61,6 +61,7 @@ int main(int argc, char *argv[])
     p.backtrace = (int32_t)env_int("BACKTRACE", 0);
     if (genasm) p.backtrace = p.algo == AIM_ALGO_GENASM_DC;
     p.variant = (genasm && variant == "mram") ? 1 : 0;
+    if (p.algo == AIM_ALGO_SWG && variant == "wram") p.variant = 1;  // SWG/DPU-WRAM: int8 cells when MAX_SCORE < 127
     p.reduce = (int32_t)env_int("REDUCE", 0);
     p.ngpus = (int32_t)env_int("AIM_NGPUS", 1);
     p.device = (int32_t)env_int("AIM_DEVICE", 0);
