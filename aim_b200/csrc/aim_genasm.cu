@@ -48,13 +48,18 @@ struct GenK {
     char *ops;
     uint32_t *hist;     // DC only: per pair of the batch [level][text index][ww] 32-bit words: the WINDOW of R the traceback can touch
     size_t hist_stride; // 32-bit words per pair
-    int ww;             // window width in 32-bit words: 32 * ww >= 2k + 3
+    int ww;             // window width in 32-bit words: 32 * ww >= 2k + 3 (banded fill: the band, 32 * ww >= 4k + 3)
+    int tmode;          // banded fill: a level's history row is indexed by the TICK (t = n - 1 - ti + level) so that a warp stores eight ticks of
+                        // every lane as one aligned 32-byte piece; 0: indexed by the text index ti
+    int row_len;        // entries per level row
+    int kk;             // row ti of the history starts at bit m - 2 - kk - ti: k (windows cut from full vectors) or 2k (banded fill)
     int32_t *meta;      // DC only: per pair of the batch, min_error | text_ok << 16 (fill kernel -> traceback kernel)
     uint32_t first, n;  // pairs [first, first + n) of the launch's batch
     uint32_t idx_base;
     int k, read_size, G, variant;
     int match, mismatch, gap_oe, gap_e;
     uint32_t slot_bytes; // shared memory per pair slot: 4 * W bitmask words, then read_size text codes
+    int pm_words;        // banded fill: 32-bit words per base row (ones padding on both sides of the bitmask)
 };
 
 __device__ __forceinline__ int base_code(int c)
@@ -263,6 +268,207 @@ __global__ void __launch_bounds__(128) genasm_kernel(const GenK K)
     }
 }
 
+// ---- banded fill (k <= 31) ----------------------------------------------------------------------------------------
+// Every bit of R moves along a DIAGONAL: bit b after tau steps depends on bit b-1 after tau-1 steps of the same level (match)
+// and of the level below (substitution), on bit b-1 after tau steps of the level below (insertion) and on bit b after tau-1
+// steps of the level below (deletion).  With q = b - tau: same q, same q, q-1, q+1.  So a level-d bit depends only on the
+// level-0 bits within d diagonals of its own, and a level-0 bit only on its own diagonal (its start is known: the initial
+// ones << d, or the zero a shift brings in at bit 0).  The bits the reference's OUTPUT depends on - the end test at bit m-1
+// after n steps and the traceback's 2k+3-wide window - lie within k+1 diagonals of q = m-1-n; hence a band of 4k+3
+// diagonals, bits outside it taken as anything, reproduces them EXACTLY at every level (an error entering at the band's edge
+// moves in by one diagonal per level and needs k+1 levels to reach the window), with one 32-bit word per level at k <= 7
+// instead of count 64-bit words with carries.  Band bit j <-> diagonal Q0 + j, Q0 = m - n - 2 - 2k; at time tau it is
+// vector bit b = Q0 + j + tau; b < 0 reads as 0 (what `<< 1` shifts in), the bitmask window of a step is cut from the
+// pattern bitmasks in shared memory (padded with all-ones words) by one funnel shift per word.
+// A text byte outside ACGTacgt is skipped by the reference without advancing tau (genasmDC.c:430-433), so such texts are
+// compacted first (filter only: DC reports those pairs as undefined).
+template <int BW, int LPL, bool DC>
+__global__ void __launch_bounds__(128) genasm_band_kernel(const GenK K)
+{
+    extern __shared__ __align__(16) unsigned char smem_g[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int G = K.G, PPW = 32 / G;
+    const int sub = lane / G, sl = lane - sub * G;
+    unsigned char *slot = smem_g + (size_t)(wib * PPW + sub) * K.slot_bytes;
+    const int PW = K.pm_words;  // 32-bit words per base: BW ones words, the bitmask, BW + 1 ones words
+    uint32_t *pm = reinterpret_cast<uint32_t *>(slot);
+    unsigned char *codes = slot + 4 * PW * 4;
+    const uint32_t wpb = blockDim.x >> 5;
+    const uint32_t slot_global = (blockIdx.x * wpb + wib) * PPW + sub;
+    const uint32_t nslots = gridDim.x * wpb * PPW;
+    const int k = K.k, RS = K.read_size;
+
+    auto ones_from = [](int pos, int w) -> uint32_t {  // word w of "bits >= pos set"
+        const int p = pos - 32 * w;
+        return p <= 0 ? ~0u : (p >= 32 ? 0u : (~0u << p));
+    };
+
+    for (uint32_t base_i = 0; base_i < K.n; base_i += nslots) {  // warp-uniform trip count
+        const uint32_t li = base_i + slot_global;
+        const bool active = li < K.n;
+        const uint32_t i = K.first + (active ? li : 0);
+        const int m = active ? min(max(K.plen[i], 0), RS) : 0;
+        int n = active ? min(max(K.tlen[i], 0), RS) : 0;
+        const char *gp = K.patterns + (size_t)i * RS, *gt = K.texts + (size_t)i * RS;
+
+        // ---- stage: text codes, all-ones bitmask rows, then clear the pattern's bits (genasmDC.c:40-88) ----
+        for (int q = sl; q < 4 * PW; q += G) pm[q] = ~0u;
+        bool text_ok = true;
+        for (int j8 = sl; j8 * 8 < n; j8 += G) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(gt + j8 * 8));
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c0 = base_code((int)((v.x >> (8 * b)) & 0xffu)), c1 = base_code((int)((v.y >> (8 * b)) & 0xffu));
+                if (j8 * 8 + b < n && c0 > 3) text_ok = false;
+                if (j8 * 8 + 4 + b < n && c1 > 3) text_ok = false;
+                lo |= (uint32_t)c0 << (8 * b);
+                hi |= (uint32_t)c1 << (8 * b);
+            }
+            *reinterpret_cast<uint2 *>(codes + j8 * 8) = make_uint2(lo, hi);
+        }
+        __syncwarp();
+        for (int j = sl; j < m; j += G) {
+            const int ch = gp[j], c = base_code(ch), b = m - 1 - j;
+            uint32_t *w32 = pm + BW + (b >> 5);
+            const unsigned clr = ~(1u << (b & 31));
+            if (c < 4) atomicAnd(w32 + c * PW, clr);
+            else if ((ch & ~0x20) == 'N' && K.variant == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) atomicAnd(w32 + q * PW, clr);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int o = __shfl_xor_sync(kFullMask, (int)text_ok, off);
+            if (off < G) text_ok = text_ok && o;
+        }
+        __syncwarp();
+        if (__any_sync(kFullMask, !text_ok)) {  // (warp-uniform branch) the reference skips those steps: drop the bytes, tau counts the steps that happen
+            int kept = n;
+            if (!text_ok && sl == 0) {
+                kept = 0;
+                for (int j = 0; j < n; ++j) { const int c = codes[j]; if (c < 4) codes[kept++] = (unsigned char)c; }
+            }
+            kept = __shfl_sync(kFullMask, kept, sub * G);
+            if (!text_ok) n = kept;
+            __syncwarp();
+        }
+
+        const int Q0 = m - n - 2 - 2 * k;
+        // ---- initial state (genasmDC.c:401-425): vector bit b of level d is (b >= d) ----
+        uint32_t cur[LPL][BW], lo_old[BW];
+#pragma unroll
+        for (int l = 0; l < LPL; ++l)
+#pragma unroll
+            for (int w = 0; w < BW; ++w) cur[l][w] = ones_from(sl * LPL + l - Q0, w);
+#pragma unroll
+        for (int w = 0; w < BW; ++w) lo_old[w] = ones_from(sl * LPL - 1 - Q0, w);
+        // history rows are indexed by the tick: all lanes store the same eight ticks as one aligned 32 BW-byte piece (a 4-byte store
+        // per lane and tick costs a whole 32-byte sector write between L1 and L2, which is what bounded the fill before)
+        uint32_t *hrow = DC ? K.hist + (size_t)(active ? li : 0) * K.hist_stride + (size_t)(sl * LPL) * K.row_len * BW : nullptr;
+        const bool store = DC && active && text_ok;
+
+        const int tmax = (__reduce_max_sync(kFullMask, n) + G - 1 + 7) & ~7;
+        int u = -sl;
+        const int b0_min = -32 * BW, b0_max = (PW - 2 * BW - 1) * 32;  // window starts the padded rows can serve
+        for (int t0 = 0; t0 < tmax; t0 += 8) {
+            uint32_t buf[LPL][8][BW];
+#pragma unroll
+            for (int tj = 0; tj < 8; ++tj, ++u) {
+                uint32_t lo_new[BW], keep[BW];
+#pragma unroll
+                for (int w = 0; w < BW; ++w) { lo_new[w] = __shfl_up_sync(kFullMask, cur[LPL - 1][w], 1, G); keep[w] = lo_new[w]; }
+                if (u >= 0 && u < n) {
+                    const int tau = u + 1;
+                    const int c = codes[n - 1 - u];
+                    // bitmask bits b0 .. b0 + 32 BW - 1 of the step's character; below b0_min everything is virtual, above b0_max all ones
+                    const int b0 = min(max(Q0 + tau, b0_min), b0_max);
+                    const uint32_t *pw = pm + c * PW + BW + (b0 >> 5);
+                    const int sh = b0 & 31;
+                    uint32_t mw[BW];
+                    uint32_t plo = pw[0];
+#pragma unroll
+                    for (int w = 0; w < BW; ++w) { const uint32_t phi = pw[w + 1]; mw[w] = __funnelshift_r(plo, phi, sh); plo = phi; }
+#pragma unroll
+                    for (int l = 0; l < LPL; ++l) {
+                        const int d = sl * LPL + l;
+                        uint32_t old_d[BW], nw[BW];
+#pragma unroll
+                        for (int w = 0; w < BW; ++w) { old_d[w] = cur[l][w]; nw[w] = old_d[w] | mw[w]; }  // match: same diagonal
+                        if (d > 0) {
+#pragma unroll
+                            for (int w = 0; w < BW; ++w) {
+                                const uint32_t ins = (lo_new[w] << 1) | (w ? lo_new[w - 1] >> 31 : 1u);           // diagonal q - 1, new
+                                const uint32_t del = (lo_old[w] >> 1) | (w + 1 < BW ? lo_old[w + 1] << 31 : 0x80000000u);  // diagonal q + 1, old
+                                nw[w] &= lo_old[w] & ins & del;                                                     // substitution: same diagonal, old
+                            }
+                        }
+#pragma unroll
+                        for (int w = 0; w < BW; ++w) {
+                            nw[w] &= ones_from(-Q0 - tau, w);  // vector bits below 0 do not exist: they read as the 0 a shift brings in
+                            lo_old[w] = old_d[w]; lo_new[w] = nw[w]; cur[l][w] = nw[w];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int l = 0; l < LPL; ++l)
+#pragma unroll
+                    for (int w = 0; w < BW; ++w) buf[l][tj][w] = cur[l][w];
+#pragma unroll
+                for (int w = 0; w < BW; ++w) lo_old[w] = keep[w];
+            }
+            if (store) {
+#pragma unroll
+                for (int l = 0; l < LPL; ++l) {
+                    if (sl * LPL + l <= k) {
+                        uint4 *h4 = reinterpret_cast<uint4 *>(hrow + ((size_t)l * K.row_len + t0) * BW);
+                        const uint32_t *bf = &buf[l][0][0];
+#pragma unroll
+                        for (int q = 0; q < 2 * BW; ++q) h4[q] = make_uint4(bf[4 * q], bf[4 * q + 1], bf[4 * q + 2], bf[4 * q + 3]);
+                    }
+                }
+            }
+        }
+
+        // ---- lowest level whose end bit is clear (genasmDC.c:389-399,530-541).  The reference tests bit m-1 of the vector, except
+        // when m % 64 == 0, where it tests bit m+63, which no step ever clears: no alignment is found then. ----
+        const int jend = 2 * k + 1;  // (m - 1) - n - Q0
+        int lvl = 1 << 20;
+        if ((m & 63) != 0) {
+#pragma unroll
+            for (int l = LPL - 1; l >= 0; --l) {
+                const int d = sl * LPL + l;
+                uint32_t word = 0;
+#pragma unroll
+                for (int w = 0; w < BW; ++w) if (w == (jend >> 5)) word = cur[l][w];
+                if (d <= k && !((word >> (jend & 31)) & 1u)) lvl = d;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int o = __shfl_xor_sync(kFullMask, lvl, off);
+            if (off < G) lvl = min(lvl, o);
+        }
+        const int min_error = lvl > k ? -1 : lvl;
+
+        if (active && sl == 0) {
+            if (DC) K.meta[li] = (min_error & 0xffff) | ((int)text_ok << 16);
+            else {
+                aim_result r;
+                r.max_operations = 0;
+                r.begin_offset = 0;
+                r.end_offset = 0;
+                r.score = min_error;  // genasm_filter.c:226-238
+                r.status = AIM_STATUS_OK;
+                r.idx = K.idx_base + i;
+                K.results[i] = r;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // genasmTB (genasmDC.c:90-336), one pair per thread.  Bit b of R[d] after text index ti comes from the fill kernel's
 // arena; ti == n is the initial state (closed form), b < 0 is the zero a left shift brings in.
 __global__ void __launch_bounds__(128) genasm_tb_kernel(const GenK K)
@@ -295,8 +501,9 @@ __global__ void __launch_bounds__(128) genasm_tb_kernel(const GenK K)
         // branch-free: the load always happens (indices clamped into the pair's rows), the special cases are selects
         auto hbit = [&](int ti, int d, int b) -> unsigned {
             const int tc = min(ti, n - 1);
-            const int wb = min(max(b - (m - 2 - k - tc), 0), 32 * WWN - 1);  // bit of row tc's window
-            const uint32_t wv = hist[((size_t)d * RS + tc) * WWN + (wb >> 5)];
+            const int wb = min(max(b - (m - 2 - K.kk - tc), 0), 32 * WWN - 1);  // bit of row tc's window
+            const int row = K.tmode ? n - 1 - tc + d : tc;  // banded fill: rows are indexed by the tick
+            const uint32_t wv = hist[((size_t)d * K.row_len + row) * WWN + (wb >> 5)];
             unsigned v = (wv >> (wb & 31)) & 1u;
             v = ti >= n ? (b >= d ? 1u : 0u) : v;
             return b < 0 ? 0u : v;
@@ -368,6 +575,20 @@ cudaError_t launch_w(const GenK &K, int lpl, bool dc, int grid, size_t smem, cud
     return launch_wl<W, 4>(K, dc, grid, smem, st);
 }
 
+template <int BW, int LPL>
+cudaError_t launch_bl(const GenK &K, bool dc, int grid, size_t smem, cudaStream_t st)
+{
+    if (dc) genasm_band_kernel<BW, LPL, true><<<grid, 128, smem, st>>>(K);
+    else genasm_band_kernel<BW, LPL, false><<<grid, 128, smem, st>>>(K);
+    return cudaGetLastError();
+}
+cudaError_t launch_band(const GenK &K, int bw, bool dc, int grid, size_t smem, cudaStream_t st)
+{   // k <= 31: one level per lane
+    if (bw == 1) return launch_bl<1, 1>(K, dc, grid, smem, st);
+    if (bw == 2) return launch_bl<2, 1>(K, dc, grid, smem, st);
+    return launch_bl<4, 1>(K, dc, grid, smem, st);
+}
+
 }  // namespace
 
 int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launches)
@@ -393,9 +614,18 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
     const int PPW = 32 / G;
     const size_t smem = (size_t)4 * PPW * K.slot_bytes;
     const int blocks_per_sm = W == 8 || lpl == 4 ? 4 : (W == 4 || lpl == 2 ? 8 : 16);
+    // banded fill (k <= 31: 4k + 3 <= 128 bits) unless switched off; else full vectors with the traceback window cut out of them
+    const bool band = k <= 31 && !getenv("AIM_GENASM_FULL");
     K.ww = 1;
-    while (32 * K.ww < 2 * k + 3) K.ww *= 2;
-    K.hist_stride = dc ? (size_t)(k + 1) * (size_t)p.read_size * (size_t)K.ww : 0;
+    K.kk = band ? 2 * k : k;
+    while (32 * K.ww < 2 * K.kk + 3) K.ww *= 2;
+    if (band) {
+        K.pm_words = 2 * K.ww + 1 + 2 * count_max;
+        K.slot_bytes = (uint32_t)(4 * K.pm_words * 4 + p.read_size);
+    }
+    K.tmode = band ? 1 : 0;
+    K.row_len = band ? ((p.read_size + G + 7) & ~7) + 8 : p.read_size;
+    K.hist_stride = dc ? (size_t)(k + 1) * (size_t)K.row_len * (size_t)K.ww : 0;
 
     // DC: the history of a whole batch lives in the arena between the fill and the traceback kernels.  Two arena halves:
     // the traceback of batch b (latency-bound, one thread per pair) runs on a side stream under the fill of batch b + 1
@@ -438,7 +668,8 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
         if ((uint64_t)grid * per_block > K.n) grid = (int)std::max<uint64_t>(1, (K.n + per_block - 1) / per_block);
         cudaError_t err = cudaSuccess;
         if (overlap && nb >= 2) err = cudaStreamWaitEvent(stream, ev_tb[dev][h], 0);  // the traceback that read this half is done
-        if (err == cudaSuccess)
+        if (err == cudaSuccess && band) err = launch_band(K, K.ww, dc, grid, (size_t)4 * PPW * K.slot_bytes, stream);
+        else if (err == cudaSuccess)
             err = W == 2 ? launch_w<2>(K, lpl, dc, grid, smem, stream)
                          : (W == 4 ? launch_w<4>(K, lpl, dc, grid, smem, stream) : launch_w<8>(K, lpl, dc, grid, smem, stream));
         if (err == cudaSuccess && launches) ++*launches;
