@@ -655,6 +655,13 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
         }
         if (e != cudaSuccess) { set_error(std::string("genasm side stream: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
     }
+    // (tuning knob: dummy dynamic shared memory caps the traceback kernel's blocks per SM.  Measured at config 7: 0 KB 293 M pairs/s,
+    // 24 KB 157 M, 48 KB 212 M, 100 KB 136 M - the shared-memory carve-out shrinks L1 and the walk needs the threads.)
+    size_t tb_smem = 0;
+    if (const char *e = getenv("AIM_GENASM_TB_SMEM_KB")) { const long v = atol(e); if (v >= 0 && v <= 200) tb_smem = (size_t)v << 10; }
+    if (dc && tb_smem > (48u << 10)) {
+        if (cudaFuncSetAttribute(genasm_tb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem) != cudaSuccess) { set_error("genasm tb smem attribute"); return AIM_ERR_CUDA; }
+    }
     uint32_t nb = 0;
     for (uint32_t first = 0; first < a.n; first += batch, ++nb) {
         const int h = overlap ? (int)(nb & 1u) : 0;
@@ -681,7 +688,7 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
                 if (err == cudaSuccess) err = cudaStreamWaitEvent(ts, ev_fill[dev][h], 0);
             }
             if (err == cudaSuccess) {
-                genasm_tb_kernel<<<(K.n + 127) / 128, 128, 0, ts>>>(K);
+                genasm_tb_kernel<<<(K.n + 127) / 128, 128, tb_smem, ts>>>(K);
                 err = cudaGetLastError();
             }
             if (err == cudaSuccess && overlap) err = cudaEventRecord(ev_tb[dev][h], ts);
