@@ -52,7 +52,7 @@ struct GenK {
     int tmode;          // banded fill: a level's history row is indexed by the TICK (t = n - 1 - ti + level) so that a warp stores eight ticks of
                         // every lane as one aligned 32-byte piece; 0: indexed by the text index ti
     int row_len;        // entries per level row
-    int kk;             // row ti of the history starts at bit m - 2 - kk - ti: k (windows cut from full vectors) or 2k (banded fill)
+    int kk;             // row ti of the history starts at vector bit m - 2 - kk - ti (kk = k: the traceback's window)
     int32_t *meta;      // DC only: per pair of the batch, min_error | text_ok << 16 (fill kernel -> traceback kernel)
     uint32_t first, n;  // pairs [first, first + n) of the launch's batch
     uint32_t idx_base;
@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(128) genasm_kernel(const GenK K)
 template <int BW, int LPL, bool DC>
 __global__ void __launch_bounds__(128) genasm_band_kernel(const GenK K)
 {
+    constexpr int WS = BW >= 4 ? BW / 2 : 1;  // history words per level and tick: the traceback's 2k+3-bit window, band bits k .. k + 32 WS - 1
     extern __shared__ __align__(16) unsigned char smem_g[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int G = K.G, PPW = 32 / G;
@@ -366,14 +367,14 @@ __global__ void __launch_bounds__(128) genasm_band_kernel(const GenK K)
         for (int w = 0; w < BW; ++w) lo_old[w] = ones_from(sl * LPL - 1 - Q0, w);
         // history rows are indexed by the tick: all lanes store the same eight ticks as one aligned 32 BW-byte piece (a 4-byte store
         // per lane and tick costs a whole 32-byte sector write between L1 and L2, which is what bounded the fill before)
-        uint32_t *hrow = DC ? K.hist + (size_t)(active ? li : 0) * K.hist_stride + (size_t)(sl * LPL) * K.row_len * BW : nullptr;
+        uint32_t *hrow = DC ? K.hist + (size_t)(active ? li : 0) * K.hist_stride + (size_t)(sl * LPL) * K.row_len * WS : nullptr;
         const bool store = DC && active && text_ok;
 
         const int tmax = (__reduce_max_sync(kFullMask, n) + G - 1 + 7) & ~7;
         int u = -sl;
         const int b0_min = -32 * BW, b0_max = (PW - 2 * BW - 1) * 32;  // window starts the padded rows can serve
         for (int t0 = 0; t0 < tmax; t0 += 8) {
-            uint32_t buf[LPL][8][BW];
+            uint32_t buf[LPL][8][WS];
 #pragma unroll
             for (int tj = 0; tj < 8; ++tj, ++u) {
                 uint32_t lo_new[BW], keep[BW];
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(128) genasm_band_kernel(const GenK K)
 #pragma unroll
                 for (int l = 0; l < LPL; ++l)
 #pragma unroll
-                    for (int w = 0; w < BW; ++w) buf[l][tj][w] = cur[l][w];
+                    for (int w = 0; w < WS; ++w) buf[l][tj][w] = __funnelshift_r(cur[l][w], w + 1 < BW ? cur[l][w + 1] : 0u, k);  // k < 32
 #pragma unroll
                 for (int w = 0; w < BW; ++w) lo_old[w] = keep[w];
             }
@@ -422,10 +423,10 @@ __global__ void __launch_bounds__(128) genasm_band_kernel(const GenK K)
 #pragma unroll
                 for (int l = 0; l < LPL; ++l) {
                     if (sl * LPL + l <= k) {
-                        uint4 *h4 = reinterpret_cast<uint4 *>(hrow + ((size_t)l * K.row_len + t0) * BW);
+                        uint4 *h4 = reinterpret_cast<uint4 *>(hrow + ((size_t)l * K.row_len + t0) * WS);
                         const uint32_t *bf = &buf[l][0][0];
 #pragma unroll
-                        for (int q = 0; q < 2 * BW; ++q) h4[q] = make_uint4(bf[4 * q], bf[4 * q + 1], bf[4 * q + 2], bf[4 * q + 3]);
+                        for (int q = 0; q < 2 * WS; ++q) h4[q] = make_uint4(bf[4 * q], bf[4 * q + 1], bf[4 * q + 2], bf[4 * q + 3]);
                     }
                 }
             }
@@ -583,7 +584,7 @@ cudaError_t launch_bl(const GenK &K, bool dc, int grid, size_t smem, cudaStream_
     return cudaGetLastError();
 }
 cudaError_t launch_band(const GenK &K, int bw, bool dc, int grid, size_t smem, cudaStream_t st)
-{   // k <= 31: one level per lane
+{   // k <= 30: one level per lane
     if (bw == 1) return launch_bl<1, 1>(K, dc, grid, smem, st);
     if (bw == 2) return launch_bl<2, 1>(K, dc, grid, smem, st);
     return launch_bl<4, 1>(K, dc, grid, smem, st);
@@ -614,13 +615,16 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
     const int PPW = 32 / G;
     const size_t smem = (size_t)4 * PPW * K.slot_bytes;
     const int blocks_per_sm = W == 8 || lpl == 4 ? 4 : (W == 4 || lpl == 2 ? 8 : 16);
-    // banded fill (k <= 31: 4k + 3 <= 128 bits) unless switched off; else full vectors with the traceback window cut out of them
-    const bool band = k <= 31 && !getenv("AIM_GENASM_FULL");
+    // banded fill unless switched off: band of 4k + 3 bits in BW words, of which the traceback's 2k + 3-bit window (band bits k ..)
+    // goes to the history in WS words: k <= 7: 1 / 1, k <= 14: 2 / 1, k <= 30: 4 / 2; beyond, full vectors with the window cut out
+    const bool band = k <= 30 && !getenv("AIM_GENASM_FULL");
+    const int bw = k <= 7 ? 1 : (k <= 14 ? 2 : 4);
+    K.kk = k;
     K.ww = 1;
-    K.kk = band ? 2 * k : k;
-    while (32 * K.ww < 2 * K.kk + 3) K.ww *= 2;
+    if (band) K.ww = bw >= 4 ? bw / 2 : 1;
+    else while (32 * K.ww < 2 * k + 3) K.ww *= 2;
     if (band) {
-        K.pm_words = 2 * K.ww + 1 + 2 * count_max;
+        K.pm_words = 2 * bw + 1 + 2 * count_max;
         K.slot_bytes = (uint32_t)(4 * K.pm_words * 4 + p.read_size);
     }
     K.tmode = band ? 1 : 0;
@@ -675,7 +679,7 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
         if ((uint64_t)grid * per_block > K.n) grid = (int)std::max<uint64_t>(1, (K.n + per_block - 1) / per_block);
         cudaError_t err = cudaSuccess;
         if (overlap && nb >= 2) err = cudaStreamWaitEvent(stream, ev_tb[dev][h], 0);  // the traceback that read this half is done
-        if (err == cudaSuccess && band) err = launch_band(K, K.ww, dc, grid, (size_t)4 * PPW * K.slot_bytes, stream);
+        if (err == cudaSuccess && band) err = launch_band(K, bw, dc, grid, (size_t)4 * PPW * K.slot_bytes, stream);
         else if (err == cudaSuccess)
             err = W == 2 ? launch_w<2>(K, lpl, dc, grid, smem, stream)
                          : (W == 4 ? launch_w<4>(K, lpl, dc, grid, smem, stream) : launch_w<8>(K, lpl, dc, grid, smem, stream));
