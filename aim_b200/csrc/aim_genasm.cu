@@ -526,12 +526,19 @@ __global__ void __launch_bounds__(128) genasm_tb_kernel(const GenK K)
             const int dl = max(ce - 1, 0);
             // level 0 keeps only R itself (genasmDC.c:461-470): match = its bit, the other three read as set
             const unsigned a = z ? hbit(ct, 0, cp) : hbit(ct + 1, ce, cp - 1);
-            const unsigned s1 = hbit(ct + 1, dl, cp - 1), i1 = hbit(ct, dl, cp - 1), d1 = hbit(ct + 1, dl, cp);
             const int pch = gp[m - 1 - cp], tch = gt[ct];
             const int pc = base_code(pch);
             const bool hit = pc < 4 ? pc == base_code(tch) : ((pch & ~0x20) == 'N' && K.variant == 0);  // the pattern-mask bit is clear
             const unsigned t0 = z ? a : (a | (hit ? 0u : 1u));
-            const unsigned t1 = z ? 1u : s1, t2 = z ? 1u : i1, t3 = z ? 1u : d1;
+            // 19 steps in 20 are matches after a match or a substitution: the reference's first two tests (affine insertion /
+            // deletion, :107,:142) need `last` to be I / D, so the match bit alone decides and the other three bits are not
+            // fetched (each fetch is a 32-byte sector for one bit)
+            unsigned t1 = 1u, t2 = 1u, t3 = 1u;
+            if (!z && (t0 != 0 || last == 'I' || last == 'D')) {
+                t1 = hbit(ct + 1, dl, cp - 1);
+                t2 = hbit(ct, dl, cp - 1);
+                t3 = hbit(ct + 1, dl, cp);
+            }
             if (last == 'I' && t2 == 0) { --cp; --ce; ++run; ++nExt; }
             else if (last == 'D' && t3 == 0) { ++ct; --ce; ++run; ++nExt; }
             else if (t0 == 0) {
