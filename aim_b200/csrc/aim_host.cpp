@@ -327,10 +327,69 @@ uint32_t gather_swar(uint64_t c)
     r = ((r & 0x00ffu) << 8) | ((r >> 8) & 0x00ffu);
     return r;
 }
-#if defined(__x86_64__) && defined(__GNUC__)
-__attribute__((target("bmi2"))) uint32_t gather_bmi2(uint64_t c)
+// one sequence row -> its packed words; returns false if a byte below len is not one of A, C, G, T.  The gather is a template
+// argument so that the BMI2 variant inlines pext
+template <typename Gather>
+inline __attribute__((always_inline)) bool pack_row(const unsigned char *row, int32_t len, uint32_t words, uint32_t *out, uint16_t *h16, Gather gather)
 {
-    return (uint32_t)__builtin_ia32_pext_di(__builtin_bswap64(c), 0x0303030303030303ull);
+    const int32_t groups = (len + 7) / 8, full = len / 8;
+    uint64_t badacc = 0;
+    auto code = [&](uint64_t x) -> uint64_t {
+        const uint64_t c = (x >> 1) & 0x0303030303030303ull;
+        const uint64_t is2 = (c >> 1) & ~c & 0x0101010101010101ull;  // code 2 <=> 'T' (0x54 = 0x41 + 2*2 + 15)
+        badacc |= (0x4141414141414141ull + 2ull * c + 15ull * is2) ^ x;
+        return c;
+    };
+    for (int32_t g = 0; g < full; ++g) {
+        uint64_t x;
+        memcpy(&x, row + 8 * g, 8);
+        h16[g] = (uint16_t)gather(code(x));
+    }
+    if (groups > full) {  // last, partial group: pad with 'A' (rows are READ_SIZE, a multiple of 8, bytes: never read past the row)
+        uint64_t x;
+        memcpy(&x, row + 8 * full, 8);
+        const uint64_t keep = (1ull << (8 * (len - 8 * full))) - 1ull;
+        x = (x & keep) | (0x4141414141414141ull & ~keep);
+        h16[full] = (uint16_t)gather(code(x));
+    }
+    for (uint32_t w = 0; w < words; ++w) {
+        const uint32_t hi = (int32_t)(2 * w) < groups ? h16[2 * w] : 0u, lo = (int32_t)(2 * w + 1) < groups ? h16[2 * w + 1] : 0u;
+        out[w] = (hi << 16) | lo;
+    }
+    return badacc == 0;
+}
+struct PackJob {
+    uint32_t n; int32_t read_size; const int32_t *plen, *tlen; const char *patterns, *texts; uint32_t *packed, *flags; uint32_t words;
+};
+// flag words [w0, w1): threads own whole flag words (32 pairs), so no two threads touch the same word
+template <typename Gather>
+inline __attribute__((always_inline)) bool pack_range(const PackJob &J, uint32_t w0, uint32_t w1, Gather gather)
+{
+    const size_t rs = (size_t)J.read_size;
+    std::vector<uint16_t> h16(rs / 8 + 2);
+    bool lengths_ok = true;
+    for (uint32_t fw = w0; fw < w1; ++fw) {
+        uint32_t fbits = 0;
+        const uint32_t hi = std::min(J.n, (fw + 1) * 32);
+        for (uint32_t i = fw * 32; i < hi; ++i) {
+            bool ok = true;
+            for (int q = 0; q < 2; ++q) {
+                const int32_t len = q ? J.tlen[i] : J.plen[i];
+                if (len < 0 || len > J.read_size) { lengths_ok = false; continue; }
+                const unsigned char *row = reinterpret_cast<const unsigned char *>((q ? J.texts : J.patterns) + (size_t)i * rs);
+                ok &= pack_row(row, len, J.words, J.packed + ((size_t)i * 2 + (size_t)q) * J.words, h16.data(), gather);
+            }
+            if (!ok) fbits |= 1u << (i & 31);
+        }
+        J.flags[fw] = fbits;
+    }
+    return lengths_ok;
+}
+bool pack_range_swar(const PackJob &J, uint32_t w0, uint32_t w1) { return pack_range(J, w0, w1, [](uint64_t c) { return gather_swar(c); }); }
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("bmi2"))) bool pack_range_bmi2(const PackJob &J, uint32_t w0, uint32_t w1)
+{
+    return pack_range(J, w0, w1, [](uint64_t c) __attribute__((target("bmi2"))) { return (uint32_t)__builtin_ia32_pext_di(__builtin_bswap64(c), 0x0303030303030303ull); });
 }
 #endif
 }  // namespace
@@ -347,57 +406,19 @@ extern "C" int aim_pack_pairs(uint32_t n, int32_t read_size, const int32_t *plen
 {
     if (!plen || !tlen || !patterns || !texts || !packed || !flags || read_size <= 0) { aim::set_error("aim_pack_pairs: NULL argument"); return AIM_ERR_ARG; }
     const size_t rs = (size_t)read_size;
-    const uint32_t words = (uint32_t)aim_packed_row_bytes(read_size) / 4;
+    PackJob J{n, read_size, plen, tlen, patterns, texts, packed, flags, (uint32_t)aim_packed_row_bytes(read_size) / 4};
     const uint32_t fwords = (n + 31) / 32;
-    uint32_t (*gather)(uint64_t) = gather_swar;
+    bool (*range)(const PackJob &, uint32_t, uint32_t) = pack_range_swar;
 #if defined(__x86_64__) && defined(__GNUC__)
-    if (__builtin_cpu_supports("bmi2") && !getenv("AIM_NO_BMI2")) gather = gather_bmi2;
+    if (__builtin_cpu_supports("bmi2") && !getenv("AIM_NO_BMI2")) range = pack_range_bmi2;
 #endif
     int T = nthreads > 0 ? nthreads : io_threads((size_t)n * rs * 2);
     T = std::max(1, std::min<int>(T, (int)std::max<uint32_t>(1, fwords)));
-    // threads own whole flag words (32 pairs), so no two threads touch the same word
     const uint32_t per = (fwords + (uint32_t)T - 1) / (uint32_t)T;
     std::vector<int> bad((size_t)T, 0);
     parallel_for(T, [&](int t) {
         const uint32_t w0 = std::min(fwords, (uint32_t)t * per), w1 = std::min(fwords, w0 + per);
-        for (uint32_t fw = w0; fw < w1; ++fw) {
-            uint32_t fbits = 0;
-            const uint32_t hi = std::min(n, (fw + 1) * 32);
-            for (uint32_t i = fw * 32; i < hi; ++i) {
-                bool ok = true;
-                for (int q = 0; q < 2; ++q) {
-                    const int32_t len = q ? tlen[i] : plen[i];
-                    if (len < 0 || len > read_size) { bad[(size_t)t] = 1; continue; }
-                    const unsigned char *row = reinterpret_cast<const unsigned char *>((q ? texts : patterns) + (size_t)i * rs);
-                    uint32_t *out = packed + ((size_t)i * 2 + (size_t)q) * words;
-                    for (uint32_t w = 0; w < words; ++w) {
-                        const int32_t b0 = (int32_t)w * 16;
-                        uint32_t v = 0;
-                        for (int hlf = 0; hlf < 2; ++hlf) {  // 8 bases -> 16 bits, first base in the two most significant bits
-                            const int32_t bb = b0 + 8 * hlf;
-                            uint32_t h16 = 0;
-                            if (bb < len) {
-                                uint64_t x;
-                                memcpy(&x, row + bb, 8);  // rows are READ_SIZE (multiple of 8) bytes: never past the row
-                                const int32_t nv = len - bb;  // bytes of this group that belong to the sequence
-                                if (nv < 8) {
-                                    const uint64_t keep = (1ull << (8 * nv)) - 1ull;
-                                    x = (x & keep) | (0x4141414141414141ull & ~keep);  // pad with 'A'
-                                }
-                                const uint64_t c = (x >> 1) & 0x0303030303030303ull;
-                                const uint64_t is2 = (c >> 1) & ~c & 0x0101010101010101ull;  // code 2 <=> 'T' (0x54 = 0x41 + 2*2 + 15)
-                                if (0x4141414141414141ull + 2ull * c + 15ull * is2 != x) ok = false;
-                                h16 = gather(c);
-                            }
-                            v = (v << 16) | h16;
-                        }
-                        out[w] = v;
-                    }
-                }
-                if (!ok) fbits |= 1u << (i & 31);
-            }
-            flags[fw] = fbits;
-        }
+        if (!range(J, w0, w1)) bad[(size_t)t] = 1;
     });
     for (int t = 0; t < T; ++t) if (bad[(size_t)t]) { aim::set_error("READ LENGTH less than length of the input reads"); return AIM_ERR_LENGTH; }
     return AIM_OK;
