@@ -36,6 +36,7 @@ def _load() -> C.CDLL:
         "aim_align_batch": (C.c_int, [P(AimParams), C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, P(C.c_double)]),
         "aim_align_device": (C.c_int, [P(AimParams), C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp,
                                        P(C.c_float), P(C.c_int32)]),
+        "aim_align_batch_cigars": (C.c_int, [P(AimParams), C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_int32, P(C.c_double)]),
         "aim_align_packed": (C.c_int, [P(AimParams), C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_int32, P(C.c_double)]),
         "aim_pack_pairs": (C.c_int, [C.c_uint32, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int32]),
         "aim_packed_row_bytes": (C.c_int32, [C.c_int32]),
@@ -67,7 +68,7 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
-EXPORTED = ["aim_align_batch", "aim_align_device", "aim_align_packed", "aim_pack_pairs", "aim_packed_row_bytes", "aim_write_results_packed", "aim_host_alloc", "aim_host_free", "aim_shutdown",
+EXPORTED = ["aim_align_batch", "aim_align_device", "aim_align_batch_cigars", "aim_align_packed", "aim_pack_pairs", "aim_packed_row_bytes", "aim_write_results_packed", "aim_host_alloc", "aim_host_free", "aim_shutdown",
             "aim_device_count", "aim_measure_int_peak", "aim_last_error", "aim_strerror", "aim_abi_version", "aim_derive_knobs",
             "aim_pairs_to_process", "aim_read_pairs", "aim_count_pairs", "aim_write_results", "aim_write_results_genasm", "aim_cigar_rle",
             "aim_generate_pairs", "aim_write_pairs"]

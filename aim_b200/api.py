@@ -180,6 +180,26 @@ def align_device(params: AlignParams, n: int, d_plen: int, d_tlen: int, d_patter
     return (ms.value if timed else None), nl.value
 
 
+def align_batch_cigars(params: AlignParams, plen, tlen, patterns, texts, cigar_pitch: int = 64, idx_base: int = 0, results=None, cigars=None):
+    """aim_align_batch_cigars: reference-layout inputs, CIGAR text rows out -> (results, cigars[n, cigar_pitch] uint8, phase_ms[3])."""
+    n = len(plen)
+    plen = np.ascontiguousarray(plen, np.int32)
+    tlen = np.ascontiguousarray(tlen, np.int32)
+    patterns = np.ascontiguousarray(patterns, np.uint8)
+    texts = np.ascontiguousarray(texts, np.uint8)
+    if results is None:
+        results = np.zeros(n, RESULT_DTYPE)
+    if cigars is None:
+        cigars = np.zeros((n, cigar_pitch), np.uint8)
+    phase = (C.c_double * 3)()
+    p = params.to_c()
+    rc = lib.aim_align_batch_cigars(C.byref(p), n, idx_base, _ptr(plen), _ptr(tlen), _ptr(patterns), _ptr(texts), _ptr(results),
+                                    _ptr(cigars), cigar_pitch, phase)
+    if rc != 0:
+        raise AimError(rc)
+    return results, cigars, list(phase)
+
+
 def packed_row_bytes(read_size: int) -> int:
     return int(lib.aim_packed_row_bytes(read_size))
 

@@ -36,7 +36,8 @@ constexpr int kNumBuf = 4;  // chunk buffers in flight: upload / align / downloa
 struct ChunkBuf {
     // device
     int32_t *d_plen = nullptr, *d_tlen = nullptr;
-    char *d_pat = nullptr, *d_txt = nullptr, *d_ops = nullptr;
+    char *d_pat = nullptr, *d_txt = nullptr, *d_ops = nullptr, *d_cig = nullptr;
+    size_t cig_cap = 0;  // bytes of d_cig (aim_align_batch_cigars only)
     aim_result *d_res = nullptr;
     // pinned staging (used only for caller buffers that are not pinned)
     int32_t *h_plen = nullptr, *h_tlen = nullptr;
@@ -94,7 +95,7 @@ int get_ctx(int device, DeviceCtx **out)
 
 void free_chunk(ChunkBuf &b)
 {
-    cudaFree(b.d_plen); cudaFree(b.d_tlen); cudaFree(b.d_pat); cudaFree(b.d_txt); cudaFree(b.d_ops); cudaFree(b.d_res);
+    cudaFree(b.d_plen); cudaFree(b.d_tlen); cudaFree(b.d_pat); cudaFree(b.d_txt); cudaFree(b.d_ops); cudaFree(b.d_res); cudaFree(b.d_cig);
     cudaFreeHost(b.h_plen); cudaFreeHost(b.h_tlen); cudaFreeHost(b.h_pat); cudaFreeHost(b.h_txt);
     cudaFreeHost(b.h_ops); cudaFreeHost(b.h_res);
     for (auto &e : b.ev) if (e) cudaEventDestroy(e);
@@ -169,9 +170,10 @@ int launch(const KernelArgs &a, Scratch *s, cudaStream_t stream, int *launches)
 }
 
 // One GPU's share [first, first + n) of a host batch.
+// cigars != NULL (aim_align_batch_cigars): the op rows stay on the device and pitch-byte CIGAR text rows come back instead.
 int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint32_t idx_base,
               const int32_t *plen, const int32_t *tlen, const char *patterns, const char *texts,
-              aim_result *results, char *ops, double phase_ms[3], std::string *err)
+              aim_result *results, char *ops, double phase_ms[3], std::string *err, char *cigars = nullptr, int32_t pitch = 0)
 {
     auto fail = [&](int rc) { if (err) *err = aim_last_error(); return rc; };
     DeviceCtx *ctx = nullptr;
@@ -187,11 +189,13 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
     patterns += (size_t)first * rs; texts += (size_t)first * rs;
     results += first;
     if (ops) ops += (size_t)first * 2 * rs;
+    if (cigars) cigars += (size_t)first * (size_t)pitch;
     const bool pin_in = is_pinned(plen) && is_pinned(tlen) && is_pinned(patterns) && is_pinned(texts);
-    const bool pin_out = is_pinned(results) && (!bt || is_pinned(ops));
+    // (CIGAR rows are copied straight into the caller's buffer, pinned or not: no staging copy for them)
+    const bool pin_out = cigars ? true : (is_pinned(results) && (!bt || is_pinned(ops)));
     const bool staging = !(pin_in && pin_out);
 
-    const size_t per_pair = 2 * rs + (bt ? 2 * rs : 0) + sizeof(aim_result) + 8;
+    const size_t per_pair = 2 * rs + (cigars ? (size_t)pitch : (bt ? 2 * rs : 0)) + sizeof(aim_result) + 8;
     // chunk: big enough to fill the GPU many times over, small enough that pipeline fill/drain is short
     // (the full-table DP kernels hold one pair per thread for milliseconds: give them several times the
     // resident thread count per chunk so the last, partially filled pass stays short)
@@ -210,6 +214,14 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
     for (int b = 0; b < nbuf; ++b) {
         rc = ensure_chunk(ctx->chunk[b], chunk_pairs, p.read_size, bt, staging);
         if (rc != AIM_OK) return fail(rc);
+        ChunkBuf &B = ctx->chunk[b];
+        if (cigars && B.cig_cap < (size_t)chunk_pairs * (size_t)pitch) {
+            cudaFree(B.d_cig);
+            B.d_cig = nullptr;
+            B.cig_cap = 0;
+            AIM_CUDA(cudaMalloc(&B.d_cig, (size_t)chunk_pairs * (size_t)pitch));
+            B.cig_cap = (size_t)chunk_pairs * (size_t)pitch;
+        }
     }
     double ph[3] = {0, 0, 0};
     std::vector<uint32_t> cn(nchunks);
@@ -267,13 +279,21 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
         KernelArgs a{p, m, idx_base + first + off, B.d_plen, B.d_tlen, B.d_pat, B.d_txt, B.d_res, bt ? B.d_ops : nullptr};
         rc = launch(a, &ctx->scratch, ctx->s_kernel, nullptr);
         if (rc != AIM_OK) return fail(rc);
+        if (cigars) {
+            a.cigars = B.d_cig;
+            a.cigar_pitch = pitch;
+            rc = launch_cigar_rows(a, ctx->s_kernel, nullptr);
+            if (rc != AIM_OK) return fail(rc);
+        }
         AIM_CUDA(cudaEventRecord(B.ev[3], ctx->s_kernel));
 
         AIM_CUDA(cudaStreamWaitEvent(ctx->s_d2h, B.ev[3], 0));
         AIM_CUDA(cudaEventRecord(B.ev[4], ctx->s_d2h));
         aim_result *o_res = pin_out ? results + off : B.h_res;
         AIM_CUDA(cudaMemcpyAsync(o_res, B.d_res, (size_t)m * sizeof(aim_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
-        if (bt) {
+        if (cigars) {
+            AIM_CUDA(cudaMemcpyAsync(cigars + (size_t)off * (size_t)pitch, B.d_cig, (size_t)m * (size_t)pitch, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        } else if (bt) {
             char *o_ops = pin_out ? ops + (size_t)off * 2 * rs : B.h_ops;
             AIM_CUDA(cudaMemcpyAsync(o_ops, B.d_ops, (size_t)m * 2 * rs, cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
@@ -502,14 +522,14 @@ extern "C" int aim_align_device(const aim_params *params, int device, uint32_t n
     return rc;
 }
 
-extern "C" int aim_align_batch(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen,
-                               const int32_t *tlen, const char *patterns, const char *texts,
-                               aim_result *results, char *ops, double phase_ms[3])
+static int align_batch_impl(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen,
+                            const int32_t *tlen, const char *patterns, const char *texts,
+                            aim_result *results, char *ops, double phase_ms[3], char *cigars, int32_t pitch)
 {
     if (!params) { set_error("params is NULL"); return AIM_ERR_ARG; }
     const aim_params norm = normalized(params);
     params = &norm;
-    int rc = validate(params, true, ops);
+    int rc = validate(params, cigars == nullptr, ops);
     if (rc != AIM_OK) return rc;
     if (n > 0 && (!plen || !tlen || !patterns || !texts || !results)) { set_error("NULL host buffer"); return AIM_ERR_ARG; }
     // (sequence lengths are validated chunk by chunk inside run_shard, overlapped with the GPU's work)
@@ -518,7 +538,7 @@ extern "C" int aim_align_batch(const aim_params *params, uint32_t n, uint32_t id
     if (ndev == 0) { set_error("no CUDA device (aim_b200 has no CPU fallback)"); return AIM_ERR_NO_DEVICE; }
     int g = params->ngpus <= 1 ? 1 : params->ngpus;
     if (params->device < 0 || params->device + g > ndev) { set_error("device range exceeds visible GPUs"); return AIM_ERR_ARG; }
-    if (g == 1) return run_shard(*params, params->device, 0, n, idx_base, plen, tlen, patterns, texts, results, ops, phase_ms, nullptr);
+    if (g == 1) return run_shard(*params, params->device, 0, n, idx_base, plen, tlen, patterns, texts, results, ops, phase_ms, nullptr, cigars, pitch);
 
     // contiguous index ranges per GPU, one host thread + stream set each (host.c:201-209 per DPU)
     const uint32_t per = (n + (uint32_t)g - 1) / (uint32_t)g;
@@ -530,7 +550,7 @@ extern "C" int aim_align_batch(const aim_params *params, uint32_t n, uint32_t id
         const uint32_t first = std::min(n, (uint32_t)d * per), cnt = std::min(per, n - first);
         th.emplace_back([&, d, first, cnt]() {
             rcs[(size_t)d] = run_shard(*params, params->device + d, first, cnt, idx_base, plen, tlen, patterns, texts,
-                                       results, ops, &ph[(size_t)d * 3], &errs[(size_t)d]);
+                                       results, ops, &ph[(size_t)d * 3], &errs[(size_t)d], cigars, pitch);
             if (rcs[(size_t)d] != AIM_OK && errs[(size_t)d].empty()) errs[(size_t)d] = aim_last_error();
         });
     }
@@ -540,6 +560,28 @@ extern "C" int aim_align_batch(const aim_params *params, uint32_t n, uint32_t id
         if (phase_ms) for (int k = 0; k < 3; ++k) phase_ms[k] = std::max(phase_ms[k], ph[(size_t)d * 3 + k]);
     }
     return AIM_OK;
+}
+
+extern "C" int aim_align_batch(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen,
+                               const int32_t *tlen, const char *patterns, const char *texts,
+                               aim_result *results, char *ops, double phase_ms[3])
+{
+    return align_batch_impl(params, n, idx_base, plen, tlen, patterns, texts, results, ops, phase_ms, nullptr, 0);
+}
+
+extern "C" int aim_align_batch_cigars(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen,
+                                      const int32_t *tlen, const char *patterns, const char *texts,
+                                      aim_result *results, char *cigars, int32_t cigar_pitch, double phase_ms[3])
+{
+    if (!params) { set_error("params is NULL"); return AIM_ERR_ARG; }
+    aim_params q = *params;
+    if (q.algo != AIM_ALGO_GENASM_DC && q.algo != AIM_ALGO_GENASM_FILTER) q.backtrace = 1;  // the CIGAR is the point
+    if (q.algo == AIM_ALGO_GENASM_FILTER) { set_error("GenASM-filter has no CIGAR"); return AIM_ERR_ARG; }
+    if (!cigars || cigar_pitch < 16 || (cigar_pitch % 16) != 0 || cigar_pitch > 2 * q.read_size) {
+        set_error("cigars required; cigar_pitch must be a multiple of 16 in 16..2*read_size");
+        return AIM_ERR_ARG;
+    }
+    return align_batch_impl(&q, n, idx_base, plen, tlen, patterns, texts, results, nullptr, phase_ms, cigars, cigar_pitch);
 }
 
 extern "C" int aim_align_packed(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen, const int32_t *tlen,

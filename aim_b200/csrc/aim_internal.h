@@ -73,6 +73,8 @@ int launch_wfa(const KernelArgs &a, Scratch *s, void *stream, int *launches);
 // lockstep short-read kernel; returns 1 when the configuration must go to launch_wfa's warp-per-pair kernel
 int launch_wfa_sub(const KernelArgs &a, Scratch *s, void *stream, int *launches);
 int launch_dp(const KernelArgs &a, Scratch *s, void *stream, int *launches);
+// CIGAR text rows (a.cigars, a.cigar_pitch) from the op rows the alignment kernels wrote (aim_wfa_sub.cu)
+int launch_cigar_rows(const KernelArgs &a, void *stream, int *launches);
 // GenASM-DC / GenASM-filter (aim_genasm.cu)
 int launch_genasm(const KernelArgs &a, Scratch *s, void *stream, int *launches);
 // register-strip / shared-memory-row kernels (aim_dp_fast.cu); returns 1 when launch_dp's literal kernel must serve the batch

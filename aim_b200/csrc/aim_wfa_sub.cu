@@ -515,14 +515,23 @@ inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 // ~30 bytes instead of the 2 * READ_SIZE op row cross PCIe.  One pair per thread.  A pair the lockstep kernel skipped
 // (non-ACGT byte: no ASCII is on the device in this mode) gets AIM_STATUS_NEEDS_ASCII; a CIGAR longer than the row gets
 // AIM_STATUS_CIGAR_OVERFLOW; the caller serves both through aim_align_batch.
+// mode 1 (GenASM-DC: the op row already holds the reference's CIGAR string): copy the string into the row.
 __global__ void __launch_bounds__(128) cigar_rle_kernel(const int32_t *plen, const int32_t *tlen, const uint32_t *flags,
                                                         aim_result *results, const char *ops, char *cigars, int pitch,
-                                                        uint32_t n, uint32_t idx_base, int RS)
+                                                        uint32_t n, uint32_t idx_base, int RS, int mode)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     char *out = cigars + (size_t)i * pitch;
-    if ((flags[i >> 5] >> (i & 31)) & 1u) {
+    if (mode == 1) {
+        const int len = results[i].end_offset;
+        const char *row = ops + (size_t)i * 2 * RS;
+        if (len + 1 > pitch) { results[i].status = AIM_STATUS_CIGAR_OVERFLOW; out[0] = '\0'; return; }
+        for (int j = 0; j < len; ++j) out[j] = row[j];
+        out[len] = '\0';
+        return;
+    }
+    if (flags && ((flags[i >> 5] >> (i & 31)) & 1u)) {
         aim_result r;
         r.max_operations = min(max(plen[i], 0), RS) + min(max(tlen[i], 0), RS);
         r.begin_offset = r.max_operations - 1;
@@ -605,6 +614,18 @@ cudaError_t launch_g(const SubK &K, bool reduce, bool bt, int grid, int block, s
 }
 
 }  // namespace
+
+// CIGAR rows from the op rows of ANY algorithm (aim_align_batch_cigars): the text edit_cigar_print would print, or a copy of
+// GenASM-DC's string; enqueued after the alignment kernels on the same stream.
+int launch_cigar_rows(const KernelArgs &a, void *stream_v, int *launches)
+{
+    if (a.n == 0) return AIM_OK;
+    cigar_rle_kernel<<<(a.n + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(a.plen, a.tlen, nullptr, a.results, a.ops, a.cigars, a.cigar_pitch, a.n,
+                                                                          a.idx_base, a.p.read_size, a.p.algo == AIM_ALGO_GENASM_DC ? 1 : 0);
+    if (cudaGetLastError() != cudaSuccess) { set_error("cigar rows launch failed"); return AIM_ERR_CUDA; }
+    if (launches) ++*launches;
+    return AIM_OK;
+}
 
 // Returns AIM_OK after enqueueing, 1 if this configuration is not served by the lockstep kernel
 // (long reads / very large MAX_SCORE: the rings or the packed sequences do not fit), or an AIM_ERR_*.
@@ -777,7 +798,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     if (prepacked) {  // no ASCII on the device: flagged pairs are reported, and the CIGARs leave run-length encoded
         if (a.cigars) {
             cigar_rle_kernel<<<(a.n + 127) / 128, 128, 0, stream>>>(a.plen, a.tlen, a.pflags, a.results, a.ops, a.cigars, a.cigar_pitch,
-                                                                  a.n, a.idx_base, p.read_size);
+                                                                  a.n, a.idx_base, p.read_size, 0);
             if (cudaGetLastError() != cudaSuccess) { set_error("cigar_rle launch failed"); return AIM_ERR_CUDA; }
             if (launches) ++*launches;
         }

@@ -337,6 +337,29 @@ def main() -> None:
                       "host_pack_pairs_per_s": P / pack_s, "host_pack_threads": threads,
                       "note": "same scores and CIGAR text; packing happens on the host before the timed region, like the reference's pair-file parse"}
 
+    # ---- end-to-end arm with the reference's INPUT layout and CIGAR TEXT rows out (aim_align_batch_cigars) ----
+    e2e_cigars = None
+    if not args.no_e2e and bt and rs < 2048:
+        cpitch = 32 if cfg["algo"] == "genasm_dc" and ms <= 8 else (64 if rs <= 200 else 96)
+        h_cig2 = A.PinnedArray((P, cpitch), np.uint8)
+        h_res3 = A.PinnedArray((P,), A.RESULT_DTYPE)
+
+        def cig_step():
+            A.align_batch_cigars(params, h_plen.array, h_tlen.array, h_pat.array, h_txt.array, cigar_pitch=cpitch,
+                                 results=h_res3.array, cigars=h_cig2.array)
+        cig_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cig_step()
+        torch.cuda.synchronize(dev)
+        tc_s = shard.max_over_ranks((time.perf_counter() - t0) / args.steps, dev)
+        assert np.array_equal(h_res3.array["score"], res_dev["score"]), "bench: cigar-row e2e and device-resident scores differ"
+        assert int((h_res3.array["status"] == 6).sum()) == 0, "bench: CIGAR rows overflowed"
+        e2e_cigars = {"value": world * P / tc_s, "unit": "pairs/s", "h2d_bytes_per_step": int(P * (2 * rs + 8)),
+                      "d2h_bytes_per_step": int(P * (A.RESULT_DTYPE.itemsize + cpitch)), "ms_per_step": tc_s * 1e3,
+                      "api": "aim_align_batch_cigars (C ABI extension): the reference's input buffers, CIGAR text rows out, pinned host buffers"}
+
     if rank == 0:
         # ---- rooflines for the dominant kernel (one launch = one step on one GPU) ----
         peaks = {}
@@ -397,7 +420,7 @@ def main() -> None:
                        "l2": f"inputs {P * 2 * rs / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                        "generator": f"seed {cfg['seed']}, generate_dataset semantics", "mean_score": mean_score},
             "gcups_equiv": pl_mean * tl_mean * world * P / (ms_per_step * 1e-3) / 1e9,
-            "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "e2e_cigars": e2e_cigars, "gpu_launches": launches,
             "roofline": roofline, "int_roofline": int_roofline, "cpu_baseline": cpu_baseline,
             "step_ms": step_ms,
         }

@@ -129,6 +129,12 @@ int aim_align_device(const aim_params *params, int device, uint32_t n, uint32_t 
  *   cigars : n x cigar_pitch bytes (cigar_pitch a multiple of 16, 16..2*read_size); AIM_STATUS_CIGAR_OVERFLOW if too small
  * params->algo must be AIM_ALGO_WFA with backtrace; configurations the short-read kernel does not serve return AIM_ERR_ARG.
  * Buffers from aim_host_alloc() are DMA'd in place. */
+/* Half of that without touching the caller's input layout: aim_align_batch with the op rows kept on the device and the CIGAR
+ * TEXT returned instead (any algorithm with a CIGAR; GenASM-DC: its own string).  Inputs exactly as aim_align_batch; cigars =
+ * n x cigar_pitch bytes, NUL-terminated rows; AIM_STATUS_CIGAR_OVERFLOW marks a pair whose text does not fit. */
+int aim_align_batch_cigars(const aim_params *params, uint32_t n, uint32_t idx_base,
+                           const int32_t *plen, const int32_t *tlen, const char *patterns, const char *texts,
+                           aim_result *results, char *cigars, int32_t cigar_pitch, double phase_ms[3]);
 int32_t aim_packed_row_bytes(int32_t read_size);
 int aim_pack_pairs(uint32_t n, int32_t read_size, const int32_t *plen, const int32_t *tlen, const char *patterns,
                    const char *texts, uint32_t *packed, uint32_t *flags, int32_t nthreads);

@@ -111,3 +111,41 @@ def test_packed_entry_rejects_what_it_does_not_serve():
         A.align_packed(A.AlignParams(algo="wfa", max_score=30, read_size=rs, backtrace=False), plen, tlen, packed, flags)
     with pytest.raises(A.AimError):
         A.align_packed(A.AlignParams(algo="wfa", max_score=30, read_size=rs, backtrace=True), plen, tlen, packed, flags, cigar_pitch=20)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo,kw,length,error", [
+    ("wfa", dict(max_score=30, read_size=168, reduce=True), 150, 0.04),
+    ("nw", dict(max_score=8, read_size=112), 100, 0.02),
+    ("swg", dict(max_score=40, read_size=112, mismatch=4, gap_open=6, gap_ext=2), 100, 0.04),
+    ("genasm_dc", dict(max_score=5, read_size=112), 100, 0.01),
+])
+def test_cigar_rows_from_reference_layout_inputs(algo, kw, length, error, monkeypatch):
+    """aim_align_batch_cigars: the reference's input layout, the CIGAR text it prints out - every algorithm, several chunks,
+    pairs with bytes outside ACGT served like in aim_align_batch."""
+    monkeypatch.setenv("AIM_CHUNK_MB", "1")
+    rs = kw["read_size"]
+    n = 40_000
+    plen, tlen, pats, txts = A.generate_pairs(55, n, length, error, rs)
+    pats = pats.copy()
+    if algo != "genasm_dc":
+        pats[[9, 20_001], 5] = ord("N")
+    params = A.AlignParams(algo=algo, backtrace=True, **kw)
+    res, cig, _ = A.align_batch_cigars(params, plen, tlen, pats, txts, cigar_pitch=96, idx_base=3)
+    okw = {k: v for k, v in kw.items()}
+    exp, eops = O.align(algo, plen, tlen, pats, txts, backtrace=True, nthreads=8, **okw)
+    assert np.array_equal(res["idx"], np.arange(3, 3 + n, dtype=np.uint32))
+    for f in ("score", "status", "max_operations", "begin_offset", "end_offset"):
+        assert np.array_equal(res[f], exp[f]), f
+    if algo == "genasm_dc":
+        want = [bytes(eops[i, :exp["end_offset"][i]]).decode() for i in range(n)]
+    else:
+        want = A.cigar_strings(oracle_results_to_aim(exp), eops)
+    for i in range(n):
+        got = bytes(cig[i]).split(b"\0", 1)[0].decode()
+        assert got == want[i], (i, got, want[i])
+    # a row too small: flagged, scores intact
+    res2, cig2, _ = A.align_batch_cigars(params, plen, tlen, pats, txts, cigar_pitch=16)
+    over = res2["status"] == 6
+    assert np.array_equal(res2["score"], exp["score"]) and all(len(want[i]) >= 16 for i in np.nonzero(over)[0])
+    assert all(len(want[i]) < 16 for i in np.nonzero((res2["status"] == 0) & (exp["status"] == 0))[0])
