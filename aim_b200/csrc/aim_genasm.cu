@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(128) genasm_band_kernel(const GenK K)
 
 // genasmTB (genasmDC.c:90-336), one pair per thread.  Bit b of R[d] after text index ti comes from the fill kernel's
 // arena; ti == n is the initial state (closed form), b < 0 is the zero a left shift brings in.
-__global__ void __launch_bounds__(128) genasm_tb_kernel(const GenK K)
+__global__ void __launch_bounds__(128, 12) genasm_tb_kernel(const GenK K)
 {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= K.n) return;
