@@ -56,3 +56,21 @@ def test_read_longer_than_read_size_exits_zero(tmp_path):  # host.c:119-123
     r = subprocess.run([sys.executable, str(ROOT / "scripts" / "run-wfa-pim-wram.py"), "-i", str(f), "-o", str(tmp_path / "o"),
                         "-l", "50", "-e", "0.01", "-n", "100"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0 and "READ LENGTH less than length of the input reads" in r.stdout
+
+
+def test_cigar_rows_and_op_row_fallback_write_the_same_bytes(tmp_path):
+    """build/host prints GPU-built CIGAR rows when they fit (config-4 golden case) and falls back to the op rows when some CIGAR is
+    longer than a row (l=1000 golden case: ~50 edits per pair); AIM_CIGAR_ROWS=0 forces the op rows.  Same bytes every way."""
+    import os
+    for name, args in (("cfg4_wfa_adaptive_synth", ["-l", "150", "-e", "0.04", "-b", "-r"]),
+                       ("wfa_l1000_e5_bt", ["-l", "1000", "-e", "0.05", "-b", "-r"])):
+        e = MANIFEST[name]
+        f = tmp_path / (name + ".pairs")
+        f.write_bytes(lzma.open(GOLDEN / e["input"]).read())
+        for env_extra in ({}, {"AIM_CIGAR_ROWS": "0"}):
+            out = tmp_path / "out"
+            r = subprocess.run([sys.executable, str(ROOT / "scripts" / "run-wfa-pim-mram.py"), "-i", str(f), "-o", str(out),
+                                "-n", str(e["n_arg"])] + args, capture_output=True, text=True, cwd=tmp_path,
+                               env=dict(os.environ, **env_extra))
+            assert r.returncode == 0, r.stdout + r.stderr
+            assert md5_bytes(out.read_bytes()) == e["md5"], (name, env_extra)

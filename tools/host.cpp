@@ -8,6 +8,7 @@
 //   NR_TASKLETS WRAM_SEGMENT (accepted, ignored)  AIM_NGPUS  AIM_DEVICE  AIM_VARIANT=wram|mram
 #include <sys/time.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -109,8 +110,9 @@ int main(int argc, char *argv[])
     char *patterns = (char *)aim_host_alloc(alloc_n * rs);
     char *texts = (char *)aim_host_alloc(alloc_n * rs);
     aim_result *results = (aim_result *)aim_host_alloc(alloc_n * sizeof(aim_result));
-    char *ops = p.backtrace ? (char *)aim_host_alloc(alloc_n * 2 * rs) : nullptr;
-    if (!plen || !tlen || !patterns || !texts || !results || (p.backtrace && !ops)) {
+    // (the op rows are allocated only if they are fetched: GenASM-DC's CIGAR strings, or the fallback below)
+    char *ops = (p.backtrace && genasm) ? (char *)aim_host_alloc(alloc_n * 2 * rs) : nullptr;
+    if (!plen || !tlen || !patterns || !texts || !results || (p.backtrace && genasm && !ops)) {
         fprintf(stderr, "aim_b200: %s\n", aim_last_error());
         exit(1);
     }
@@ -126,7 +128,26 @@ int main(int argc, char *argv[])
 
     double phase[3] = {0, 0, 0};
     double t0 = now_s();
-    int rc = aim_align_batch(&p, (uint32_t)n, 0, plen, tlen, patterns, texts, results, ops, phase);
+    int rc;
+    // With a CIGAR to print, the text edit_cigar_print (host.c:69-89) would write is built on the GPU and only that crosses
+    // PCIe (aim_align_batch_cigars); the op rows are fetched instead when some CIGAR does not fit the row (AIM_CIGAR_ROWS=0 forces that).
+    char *cigars = nullptr;
+    int32_t cigar_pitch = 0;
+    if (p.backtrace && !genasm && env_int("AIM_CIGAR_ROWS", 1) != 0) {
+        cigar_pitch = (int32_t)std::min<size_t>(2 * rs, 128) / 16 * 16;
+        if (cigar_pitch >= 16) cigars = (char *)aim_host_alloc(alloc_n * (size_t)cigar_pitch);
+    }
+    if (cigars) {
+        rc = aim_align_batch_cigars(&p, (uint32_t)n, 0, plen, tlen, patterns, texts, results, cigars, cigar_pitch, phase);
+        bool overflow = false;
+        for (int64_t i = 0; rc == AIM_OK && i < n; ++i) overflow |= results[i].status == AIM_STATUS_CIGAR_OVERFLOW;
+        if (rc != AIM_OK || overflow) { aim_host_free(cigars); cigars = nullptr; }
+    }
+    if (!cigars) {
+        if (p.backtrace && !ops) ops = (char *)aim_host_alloc(alloc_n * 2 * rs);
+        if (p.backtrace && !ops) { fprintf(stderr, "aim_b200: %s\n", aim_last_error()); exit(1); }
+        rc = aim_align_batch(&p, (uint32_t)n, 0, plen, tlen, patterns, texts, results, ops, phase);
+    }
     double wall_ms = (now_s() - t0) * 1e3;
     if (rc != AIM_OK) {
         fprintf(stderr, "aim_b200: %s: %s\n", aim_strerror(rc), aim_last_error());
@@ -154,14 +175,15 @@ int main(int argc, char *argv[])
         }
     }
     rc = genasm ? aim_write_results_genasm(out, (uint32_t)n, p.read_size, p.algo == AIM_ALGO_GENASM_DC, results, ops)
-                : aim_write_results(out, (uint32_t)n, p.read_size, p.backtrace, results, ops);
+         : cigars ? aim_write_results_packed(out, (uint32_t)n, results, cigars, cigar_pitch)
+                  : aim_write_results(out, (uint32_t)n, p.read_size, p.backtrace, results, ops);
     if (rc != AIM_OK) {
         fprintf(stderr, "Output file '%s' couldn't be opened\n", out);
         exit(1);
     }
     if (dpu_file) fclose(dpu_file);
     aim_host_free(plen); aim_host_free(tlen); aim_host_free(patterns); aim_host_free(texts);
-    aim_host_free(results); aim_host_free(ops);
+    aim_host_free(results); aim_host_free(ops); aim_host_free(cigars);
     aim_shutdown();
     return 0;
 }
