@@ -520,19 +520,38 @@ __global__ void __launch_bounds__(128, 12) genasm_tb_kernel(const GenK K)
             while (num != 0 && c < cap - 2) { cig[c++] = (char)('0' + num % 10); num /= 10; }
             if (c < cap - 1) cig[c++] = last;
         };
+        // the pattern-mask bit of (pattern position, text character) is clear: same base in either case (the text is ACGTacgt
+        // here), or a pattern 'N' (genasmDC.c:75-81)
+        auto mask_hit = [&](int pch, int tch) -> bool { return (((pch ^ tch) & ~0x20) == 0) || ((pch & ~0x20) == 'N' && K.variant == 0); };
         while (cp >= 0 && ce >= 0) {
             if (ct >= n) { undefined = true; break; }
+            // ---- a RUN of matches.  After a match, a substitution or at the start the reference's first two tests (affine insertion /
+            // deletion, :107,:142) cannot fire (they need last == I / D), so the match bit alone decides: one history bit and two
+            // bytes per step, in a loop of its own - the threads of a warp reach their edits at different steps, and inside one
+            // common loop every step paid for the (rare) edit path of some other thread ----
+            if (last != 'I' && last != 'D') {
+                int cnt = 0;
+                while (cp >= 0 && ct < n) {
+                    const unsigned a = ce == 0 ? hbit(ct, 0, cp) : hbit(ct + 1, ce, cp - 1);
+                    const unsigned t0r = ce == 0 ? a : (a | (mask_hit(gp[m - 1 - cp], gt[ct]) ? 0u : 1u));
+                    if (t0r != 0) break;
+                    ++ct; --cp; ++cnt;
+                }
+                if (cnt) {
+                    if (last == 'M') run += cnt; else { flush(); run = cnt; last = 'M'; }
+                    nM += cnt;
+                    first = false;
+                }
+                if (cp < 0) break;
+                if (ct >= n) { undefined = true; break; }
+            }
+            // ---- one general step: an edit, or anything after an insertion / deletion ----
             const bool z = ce == 0;
             const int dl = max(ce - 1, 0);
             // level 0 keeps only R itself (genasmDC.c:461-470): match = its bit, the other three read as set
             const unsigned a = z ? hbit(ct, 0, cp) : hbit(ct + 1, ce, cp - 1);
-            const int pch = gp[m - 1 - cp], tch = gt[ct];
-            const int pc = base_code(pch);
-            const bool hit = pc < 4 ? pc == base_code(tch) : ((pch & ~0x20) == 'N' && K.variant == 0);  // the pattern-mask bit is clear
+            const bool hit = mask_hit(gp[m - 1 - cp], gt[ct]);
             const unsigned t0 = z ? a : (a | (hit ? 0u : 1u));
-            // 19 steps in 20 are matches after a match or a substitution: the reference's first two tests (affine insertion /
-            // deletion, :107,:142) need `last` to be I / D, so the match bit alone decides and the other three bits are not
-            // fetched (each fetch is a 32-byte sector for one bit)
             unsigned t1 = 1u, t2 = 1u, t3 = 1u;
             if (!z && (t0 != 0 || last == 'I' || last == 'D')) {
                 t1 = hbit(ct + 1, dl, cp - 1);
