@@ -52,6 +52,7 @@ struct GenK {
     int tmode;          // banded fill: a level's history row is indexed by the TICK (t = n - 1 - ti + level) so that a warp stores eight ticks of
                         // every lane as one aligned 32-byte piece; 0: indexed by the text index ti
     int row_len;        // entries per level row
+    int lpl;            // levels per lane of the fill kernel (tick of (ti, level) = n - 1 - ti + level / lpl)
     int kk;             // row ti of the history starts at vector bit m - 2 - kk - ti (kk = k: the traceback's window)
     int32_t *meta;      // DC only: per pair of the batch, min_error | text_ok << 16 (fill kernel -> traceback kernel)
     uint32_t first, n;  // pairs [first, first + n) of the launch's batch
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(128, 12) genasm_tb_kernel(const GenK K)
         auto hbit = [&](int ti, int d, int b) -> unsigned {
             const int tc = min(ti, n - 1);
             const int wb = min(max(b - (m - 2 - K.kk - tc), 0), 32 * WWN - 1);  // bit of row tc's window
-            const int row = K.tmode ? n - 1 - tc + d : tc;  // banded fill: rows are indexed by the tick
+            const int row = K.tmode ? n - 1 - tc + d / K.lpl : tc;  // banded fill: rows are indexed by the tick
             const uint32_t wv = hist[((size_t)d * K.row_len + row) * WWN + (wb >> 5)];
             unsigned v = (wv >> (wb & 31)) & 1u;
             v = ti >= n ? (b >= d ? 1u : 0u) : v;
@@ -609,8 +610,13 @@ cudaError_t launch_bl(const GenK &K, bool dc, int grid, size_t smem, cudaStream_
     else genasm_band_kernel<BW, LPL, false><<<grid, 128, smem, st>>>(K);
     return cudaGetLastError();
 }
-cudaError_t launch_band(const GenK &K, int bw, bool dc, int grid, size_t smem, cudaStream_t st)
-{   // k <= 30: one level per lane
+cudaError_t launch_band(const GenK &K, int bw, int lpl, bool dc, int grid, size_t smem, cudaStream_t st)
+{   // k <= 30: one or two levels per lane
+    if (lpl == 2) {
+        if (bw == 1) return launch_bl<1, 2>(K, dc, grid, smem, st);
+        if (bw == 2) return launch_bl<2, 2>(K, dc, grid, smem, st);
+        return launch_bl<4, 2>(K, dc, grid, smem, st);
+    }
     if (bw == 1) return launch_bl<1, 1>(K, dc, grid, smem, st);
     if (bw == 2) return launch_bl<2, 1>(K, dc, grid, smem, st);
     return launch_bl<4, 1>(K, dc, grid, smem, st);
@@ -628,9 +634,13 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
     if (k > 126) { set_error("GenASM: MAX_SCORE above 126 is not served by the B200 kernel"); return AIM_ERR_ARG; }
     if (count_max > 8) { set_error("GenASM: READ_SIZE above 448 is not served by the B200 kernel"); return AIM_ERR_ARG; }
     if (a.n == 0) return AIM_OK;
-    const int lpl = k + 1 <= 32 ? 1 : (k + 1 <= 64 ? 2 : 4);
+    // banded fill (k <= 30) unless switched off; it takes two levels per lane when that halves the lanes per pair (a lane's second
+    // level costs a fifth of a tick: the shuffle, the bitmask window and the loop are shared)
+    const bool band = k <= 30 && !getenv("AIM_GENASM_FULL");
+    int lpl = k + 1 <= 32 ? 1 : (k + 1 <= 64 ? 2 : 4);
     int G = 4;
     while (G * lpl < k + 1) G *= 2;
+    if (band && G > 4 && !getenv("AIM_GENASM_LPL1")) { lpl = 2; G = 4; while (G * lpl < k + 1) G *= 2; }
     const int W = count_max <= 2 ? 2 : (count_max <= 4 ? 4 : 8);
 
     GenK K{};
@@ -640,10 +650,9 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
     K.slot_bytes = (uint32_t)(4 * W * 8 + p.read_size);
     const int PPW = 32 / G;
     const size_t smem = (size_t)4 * PPW * K.slot_bytes;
-    const int blocks_per_sm = W == 8 || lpl == 4 ? 4 : (W == 4 || lpl == 2 ? 8 : 16);
+    const int blocks_per_sm = band ? 16 : (W == 8 || lpl == 4 ? 4 : (W == 4 || lpl == 2 ? 8 : 16));
     // banded fill unless switched off: band of 4k + 3 bits in BW words, of which the traceback's 2k + 3-bit window (band bits k ..)
     // goes to the history in WS words: k <= 7: 1 / 1, k <= 14: 2 / 1, k <= 30: 4 / 2; beyond, full vectors with the window cut out
-    const bool band = k <= 30 && !getenv("AIM_GENASM_FULL");
     const int bw = k <= 7 ? 1 : (k <= 14 ? 2 : 4);
     K.kk = k;
     K.ww = 1;
@@ -654,6 +663,7 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
         K.slot_bytes = (uint32_t)(4 * K.pm_words * 4 + p.read_size);
     }
     K.tmode = band ? 1 : 0;
+    K.lpl = lpl;
     K.row_len = band ? ((p.read_size + G + 7) & ~7) + 8 : p.read_size;
     K.hist_stride = dc ? (size_t)(k + 1) * (size_t)K.row_len * (size_t)K.ww : 0;
 
@@ -705,7 +715,7 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
         if ((uint64_t)grid * per_block > K.n) grid = (int)std::max<uint64_t>(1, (K.n + per_block - 1) / per_block);
         cudaError_t err = cudaSuccess;
         if (overlap && nb >= 2) err = cudaStreamWaitEvent(stream, ev_tb[dev][h], 0);  // the traceback that read this half is done
-        if (err == cudaSuccess && band) err = launch_band(K, bw, dc, grid, (size_t)4 * PPW * K.slot_bytes, stream);
+        if (err == cudaSuccess && band) err = launch_band(K, bw, lpl, dc, grid, (size_t)4 * PPW * K.slot_bytes, stream);
         else if (err == cudaSuccess)
             err = W == 2 ? launch_w<2>(K, lpl, dc, grid, smem, stream)
                          : (W == 4 ? launch_w<4>(K, lpl, dc, grid, smem, stream) : launch_w<8>(K, lpl, dc, grid, smem, stream));
