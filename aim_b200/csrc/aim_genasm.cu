@@ -611,7 +611,8 @@ cudaError_t launch_bl(const GenK &K, bool dc, int grid, size_t smem, cudaStream_
     return cudaGetLastError();
 }
 cudaError_t launch_band(const GenK &K, int bw, int lpl, bool dc, int grid, size_t smem, cudaStream_t st)
-{   // k <= 30: one or two levels per lane
+{   // k <= 30: one, two or (one-word bands) four levels per lane
+    if (lpl == 4) return launch_bl<1, 4>(K, dc, grid, smem, st);
     if (lpl == 2) {
         if (bw == 1) return launch_bl<1, 2>(K, dc, grid, smem, st);
         if (bw == 2) return launch_bl<2, 2>(K, dc, grid, smem, st);
@@ -640,7 +641,14 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
     int lpl = k + 1 <= 32 ? 1 : (k + 1 <= 64 ? 2 : 4);
     int G = 4;
     while (G * lpl < k + 1) G *= 2;
-    if (band && G > 4 && !getenv("AIM_GENASM_LPL1")) { lpl = 2; G = 4; while (G * lpl < k + 1) G *= 2; }
+    if (band && !getenv("AIM_GENASM_LPL1")) {
+        // two levels per lane, two lanes per pair at least (measured at k = 5: 2 levels x 4 lanes 482 M pairs/s, 4 levels x 2 lanes 470 M,
+        // 1 level x 8 lanes 420 M; at k = 1: 1 level x 2 lanes 1.73 G against 1.13 G with 4 lanes)
+        lpl = k + 1 <= 2 ? 1 : 2;
+        G = 2;
+        while (G * lpl < k + 1) G *= 2;
+        if (k > 7 && G < 4) G = 4;
+    }
     const int W = count_max <= 2 ? 2 : (count_max <= 4 ? 4 : 8);
 
     GenK K{};
