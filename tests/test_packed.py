@@ -149,3 +149,27 @@ def test_cigar_rows_from_reference_layout_inputs(algo, kw, length, error, monkey
     over = res2["status"] == 6
     assert np.array_equal(res2["score"], exp["score"]) and all(len(want[i]) >= 16 for i in np.nonzero(over)[0])
     assert all(len(want[i]) < 16 for i in np.nonzero((res2["status"] == 0) & (exp["status"] == 0))[0])
+
+
+def test_packed_writer_format_and_length_check(tmp_path):
+    """aim_write_results_packed = the reference's output lines from CIGAR rows; aim_pack_pairs rejects lengths beyond READ_SIZE
+    like get_reads does (host.c:119-123)."""
+    res = np.zeros(3, A.RESULT_DTYPE)
+    res["idx"] = [10, 11, 12]
+    res["score"] = [5, 0, 31]
+    cig = np.zeros((3, 16), np.uint8)
+    for i, t in enumerate((b"40M1D59M", b"100M", b"1M")):
+        cig[i, :len(t)] = np.frombuffer(t, np.uint8)
+    out = tmp_path / "o"
+    A.write_results_packed(out, res, cig)
+    assert out.read_bytes() == b"10, 5, \n40M1D59M\n11, 0, \n100M\n12, 31, \n1M\n"
+    rs = 64
+    plen, tlen, pats, txts = A.generate_pairs(1, 40, 50, 0.04, rs, nthreads=1)
+    bad = plen.copy()
+    bad[33] = rs + 1
+    with pytest.raises(A.AimError) as ei:
+        A.pack_pairs(bad, tlen, pats, txts, rs)
+    assert ei.value.code == -2  # AIM_ERR_LENGTH
+    # the last flag word covers fewer than 32 pairs
+    packed, flags = A.pack_pairs(plen, tlen, pats, txts, rs)
+    assert flags.shape == (2,) and int(flags.sum()) == 0
