@@ -429,26 +429,39 @@ extern "C" int aim_write_results_packed(const char *path, uint32_t n, const aim_
     if (!cigars || cigar_pitch <= 0) { aim::set_error("cigars buffer required"); return AIM_ERR_ARG; }
     FILE *f = fopen(path, "w");
     if (!f) { aim::set_error(std::string("Output file '") + path + "' couldn't be opened"); return AIM_ERR_IO; }
-    std::vector<char> buf((size_t)1 << 20);
-    size_t pos = 0;
+    // blocks of pairs formatted by the I/O threads into their own buffers, written in order (as aim_write_results)
+    const uint32_t block = 32768;
+    const int T = io_threads((size_t)n * ((size_t)cigar_pitch + 24));
+    const size_t per_pair_cap = 40 + (size_t)cigar_pitch;
+    std::vector<std::vector<char>> buf((size_t)T);
+    std::vector<size_t> len((size_t)T, 0);
     int rc = AIM_OK;
-    for (uint32_t i = 0; i < n; ++i) {
-        if (pos + (size_t)cigar_pitch + 64 > buf.size()) {
-            if (fwrite(buf.data(), 1, pos, f) != pos) { rc = AIM_ERR_IO; break; }
-            pos = 0;
+    for (uint64_t base = 0; base < n && rc == AIM_OK; base += (uint64_t)block * (uint64_t)T) {
+        parallel_for(T, [&](int t) {
+            const uint64_t lo = base + (uint64_t)t * block, hi = std::min<uint64_t>(n, lo + block);
+            len[(size_t)t] = 0;
+            if (lo >= hi) return;
+            std::vector<char> &b = buf[(size_t)t];
+            if (b.size() < (size_t)(hi - lo) * per_pair_cap) b.resize((size_t)(hi - lo) * per_pair_cap);
+            char *o = b.data();
+            size_t pos = 0;
+            for (uint64_t i = lo; i < hi; ++i) {
+                pos += put_int(o + pos, (int32_t)results[i].idx);
+                o[pos++] = ','; o[pos++] = ' ';
+                pos += put_int(o + pos, results[i].score);
+                o[pos++] = ','; o[pos++] = ' '; o[pos++] = '\n';
+                const char *c = cigars + (size_t)i * (size_t)cigar_pitch;
+                const size_t l = strnlen(c, (size_t)cigar_pitch);
+                memcpy(o + pos, c, l);
+                pos += l;
+                o[pos++] = '\n';
+            }
+            len[(size_t)t] = pos;
+        });
+        for (int t = 0; t < T; ++t) {
+            if (len[(size_t)t] && fwrite(buf[(size_t)t].data(), 1, len[(size_t)t], f) != len[(size_t)t]) { rc = AIM_ERR_IO; break; }
         }
-        char *o = buf.data();
-        pos += put_int(o + pos, (int32_t)results[i].idx);
-        o[pos++] = ','; o[pos++] = ' ';
-        pos += put_int(o + pos, results[i].score);
-        o[pos++] = ','; o[pos++] = ' '; o[pos++] = '\n';
-        const char *c = cigars + (size_t)i * (size_t)cigar_pitch;
-        const size_t len = strnlen(c, (size_t)cigar_pitch);
-        memcpy(o + pos, c, len);
-        pos += len;
-        o[pos++] = '\n';
     }
-    if (rc == AIM_OK && pos && fwrite(buf.data(), 1, pos, f) != pos) rc = AIM_ERR_IO;
     if (ferror(f)) rc = AIM_ERR_IO;
     fclose(f);
     return rc;

@@ -173,3 +173,20 @@ def test_packed_writer_format_and_length_check(tmp_path):
     # the last flag word covers fewer than 32 pairs
     packed, flags = A.pack_pairs(plen, tlen, pats, txts, rs)
     assert flags.shape == (2,) and int(flags.sum()) == 0
+
+
+@pytest.mark.parametrize("threads", ["1", "3"])
+def test_packed_writer_blocks_stay_in_order(tmp_path, monkeypatch, threads):
+    monkeypatch.setenv("AIM_IO_THREADS", threads)
+    n = 100_003  # several 32 K blocks, the last one partial
+    res = np.zeros(n, A.RESULT_DTYPE)
+    res["idx"] = np.arange(n)
+    res["score"] = np.arange(n) % 31
+    cig = np.zeros((n, 16), np.uint8)
+    rows = [(b"%dM1X%dM" % (i % 90 + 1, i % 7 + 1)) for i in range(n)]
+    for i, t in enumerate(rows):
+        cig[i, :len(t)] = np.frombuffer(t, np.uint8)
+    out = tmp_path / "o"
+    A.write_results_packed(out, res, cig)
+    want = b"".join(b"%d, %d, \n%s\n" % (i, i % 31, rows[i]) for i in range(n))
+    assert out.read_bytes() == want
