@@ -12,7 +12,7 @@ CXX_SRCS  := $(CSRC)/aim_host.cpp
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CXX_SRCS))
 HDRS      := include/aim_b200.h $(CSRC)/aim_internal.h $(CSRC)/aim_wfa_common.cuh
 
-all: aim_b200/libaim_b200.so build/host oracle/libaim_oracle.so
+all: aim_b200/libaim_b200.so build/host build/aim_genpairs oracle/libaim_oracle.so
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -28,6 +28,11 @@ aim_b200/libaim_b200.so: $(OBJS)
 build/host: tools/host.cpp aim_b200/libaim_b200.so include/aim_b200.h
 	@mkdir -p build
 	$(CXX) -O2 -std=c++17 -Wall -Iinclude tools/host.cpp -o $@ -Laim_b200 -laim_b200 -Wl,-rpath,'$$ORIGIN/../aim_b200' -lpthread -ldl
+
+# stand-alone pair-file generator for bench.py's reference arm (host-only code, no CUDA, no libaim_b200.so)
+build/aim_genpairs: tools/genpairs.cpp $(CSRC)/aim_host.cpp $(HDRS)
+	@mkdir -p build
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -I$(CSRC) tools/genpairs.cpp $(CSRC)/aim_host.cpp -o $@ -lpthread
 
 oracle/libaim_oracle.so: oracle/aim_oracle.c
 	$(CC) -O2 -std=gnu11 -fPIC -shared -Wall -o $@ $< -lpthread

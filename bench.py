@@ -68,16 +68,33 @@ INT_OPS_PER_GENASM_WORD = 14  # one (text step, level, 64-bit word): 3 shifts wi
 
 
 def knobs(cfg):
-    """(MAX_SCORE, READ_SIZE) of a config as the reference's run script derives them."""
+    """(MAX_SCORE, READ_SIZE) of a config as the reference's run scripts derive them, in the same Python float
+    arithmetic (run-wfa-pim-mram.py:58-67, run-nw-pim-mram.py:51-60).  Pure Python: the reference arm must not load
+    product code; the GPU arm asserts that aim_derive_knobs (C ABI) agrees."""
     import math
-    import aim_b200 as A
+    l, e = cfg["length"], cfg["error"]
     if cfg["algo"] == "genasm_filter":  # run-genasmfilter-pim-wram.py:57-67
-        w = math.ceil(cfg["length"] * cfg["error"]) or 1
-        return w, math.ceil((cfg["length"] + w + 7) / 8) * 8
-    algo = "wfa" if cfg["algo"] == "genasm_dc" else cfg["algo"]  # run-genasmdc-pim-wram.py:57-70 = the WFA script's formula
-    return A.derive_knobs(algo, cfg["length"], cfg["error"], cfg["mismatch"], cfg["gap_open"], cfg["gap_ext"])
+        w = math.ceil(l * e) or 1
+        return w, math.ceil((l + w + 7) / 8) * 8
+    w = l * e
+    gap = w * cfg["gap_open"] if cfg["algo"] == "nw" else w * (cfg["gap_open"] + cfg["gap_ext"])
+    # run-genasmdc-pim-wram.py:57-70 = the WFA script's formula
+    return math.ceil(max(w * cfg["mismatch"], gap)), math.ceil((l + w + 7) / 8) * 8
+
+
+def config_dict(cfg, P, world):
+    """`config` of the JSON line: identical for the GPU arm and the reference arm (the driver compares them)."""
+    ms, rs = knobs(cfg)
+    return {"workload": cfg["name"], "pairs_per_gpu_per_step": P, "algo": cfg["algo"], "max_score": ms, "read_size": rs,
+            "penalties": {"x": cfg["mismatch"], "o": cfg["gap_open"], "e": cfg["gap_ext"]}, "backtrace": cfg["backtrace"],
+            "adaptive": cfg["reduce"], "parallelism": f"pairs sharded by index over {world} GPU(s), no collective",
+            "l2": f"inputs {P * 2 * rs / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+            "generator": f"seed {cfg['seed']}, generate_dataset semantics"}
 # bounded CPU-reference sample per config (about 10-30 s of CPU work on 16 threads)
 REF_SAMPLE = {4: 2_000_000, 2: 400_000, 3: 16_000, 5: 160, 6: 160, 7: 1_000_000, 8: 2_000_000, 9: 100_000}
+# pairs per rank checked bit-exact against the oracle after the timed region (0 = every pair of the step); long reads and
+# GenASM take a bounded, evenly spread sample (the oracle does ~1e2 long-read pairs/s per core)
+PARITY_SAMPLE = {2: 0, 3: 0, 4: 0, 5: 20_000, 6: 2_000, 7: 1_000_000, 8: 2_000_000, 9: 100_000}
 # algorithmic work per pair (SURVEY.md 8d; restated in DESIGN.md "Measurement")
 INT_OPS_PER_OFFSET = 11   # one computed (score, diagonal) offset: I, D, M recurrences
 INT_OPS_PER_EXTEND = 4    # xor, clz, add, cmp per 16-base word step
@@ -122,7 +139,6 @@ def cpu_reference_run(cfg: dict, pairs: int, threads: int, repeats: int = 1, war
     """Time the UNMODIFIED reference (native build of its DPU + host C sources, oracle/_ref) on the host
     cores: one simulated DPU per chunk of pairs, `threads` host threads.  The pair file is written once;
     the reference host is run warmup + repeats times and the phase timers it prints are averaged."""
-    import aim_b200 as A
     from oracle import refbuild as rb
     ms, rs = knobs(cfg)
     kw = dict(max_score=ms, read_size=rs, mismatch=cfg["mismatch"], gap_o=cfg["gap_open"], gap_e=cfg["gap_ext"],
@@ -140,9 +156,9 @@ def cpu_reference_run(cfg: dict, pairs: int, threads: int, repeats: int = 1, war
     ph_sum, runs, lines, wall = [0.0, 0.0, 0.0], 0, 0, 0.0
     with tempfile.TemporaryDirectory(prefix="aimbench") as tmp:
         pairs_file = Path(tmp) / "in.pairs"
-        plen, tlen, pats, txts = A.generate_pairs(cfg["seed"], pairs, cfg["length"], cfg["error"], rs)
-        A.write_pairs(pairs_file, plen, tlen, pats, txts)
-        del pats, txts
+        # the stand-alone generator (tools/genpairs.cpp, host-only code): no product library in this process tree
+        subprocess.run([str(ROOT / "build" / "aim_genpairs"), str(cfg["seed"]), "0", str(pairs), str(cfg["length"]), repr(cfg["error"]),
+                        str(rs), str(pairs_file)], check=True)
         for it in range(warmup + repeats):
             t0 = time.perf_counter()
             out = rb.run_ref(binary, pairs_file, Path(tmp) / "out", pairs + 8 * nr_dpus, nr_dpus=nr_dpus, threads=threads)
@@ -162,7 +178,6 @@ def run_reference_arm(args, cfg) -> None:
     rank, _, world = dist_env()
     if rank != 0:
         return
-    import aim_b200 as A
     threads = os.cpu_count() or 1
     sample = args.ref_pairs or REF_SAMPLE[args.config]
     last = cpu_reference_run(cfg, sample, threads, repeats=args.steps, warmup=args.warmup)
@@ -174,11 +189,12 @@ def run_reference_arm(args, cfg) -> None:
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64" if cfg["algo"].startswith("genasm") else "int16", "data": "synthetic",
-        "config": {"workload": cfg["name"], "pairs_per_step": last["pairs"], "max_score": ms, "read_size": rs,
-                   "note": "reference DPU C sources compiled natively (UPMEM SDK stand-in), one host thread per simulated DPU; "
-                           "time = its own CPU-DPU + DPU Kernel + DPU-CPU phases; UPMEM functional simulator unavailable (not installed)"},
+        "config": config_dict(cfg, args.pairs or cfg["pairs"], max(1, world)),
+        "sample_pairs_per_step": last["pairs"],
+        "note": "reference DPU C sources compiled natively (UPMEM SDK stand-in), one host thread per simulated DPU; "
+                "time = its own CPU-DPU + DPU Kernel + DPU-CPU phases; UPMEM functional simulator unavailable (not installed)",
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "reference",
-                         "sample": f"{last['pairs']} pairs of the workload, {last['nr_dpus']} simulated DPUs on {threads} threads",
+                         "sample": f"{last['pairs']} pairs of the workload per step, {last['nr_dpus']} simulated DPUs on {threads} threads",
                          "kernel_only_value": last["pairs"] / (last["kernel_ms"] * 1e-3)},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -197,6 +213,11 @@ def main() -> None:
     ap.add_argument("--ref-pairs", type=int, default=0, help="CPU reference sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--parity", default="auto", choices=["auto", "full", "off"],
+                    help="bit-exact check of the step's results against the CPU oracle, outside the timed region "
+                         "(auto: every pair for configs 2-4, a bounded sample for long reads / GenASM)")
+    ap.add_argument("--parity-pairs", type=int, default=-1, help="pairs per rank to check (0 = all)")
+    ap.add_argument("--no-inproc", action="store_true", help="skip the one-process aim_align_batch(ngpus=N) leg at N>1")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -223,6 +244,8 @@ def main() -> None:
 
     P = args.pairs or cfg["pairs"]
     ms, rs = knobs(cfg)
+    if not cfg["algo"].startswith("genasm"):
+        assert (ms, rs) == A.derive_knobs(cfg["algo"], cfg["length"], cfg["error"], cfg["mismatch"], cfg["gap_open"], cfg["gap_ext"])
     params = A.AlignParams(algo=cfg["algo"], mismatch=cfg["mismatch"], gap_open=cfg["gap_open"], gap_ext=cfg["gap_ext"],
                            max_score=ms, read_size=rs, backtrace=cfg["backtrace"], reduce=cfg["reduce"], device=local_rank)
     bt = cfg["backtrace"]
@@ -360,6 +383,78 @@ def main() -> None:
                       "d2h_bytes_per_step": int(P * (A.RESULT_DTYPE.itemsize + cpitch)), "ms_per_step": tc_s * 1e3,
                       "api": "aim_align_batch_cigars (C ABI extension): the reference's input buffers, CIGAR text rows out, pinned host buffers"}
 
+    # ---- parity: this step's results against the CPU oracle, bit-exact, OUTSIDE every timed region ----
+    # Checked: the end-to-end arm's output (scores, spans and op bytes as they arrive in the caller's host buffers through
+    # the C ABI); the device-resident arm's buffers must then be byte-identical to those.  Every rank checks its own pairs.
+    parity = None
+    if args.parity != "off":
+        from oracle import oracle as O
+        want = args.parity_pairs if args.parity_pairs >= 0 else (0 if args.parity == "full" else PARITY_SAMPLE[args.config])
+        stride = 1 if want <= 0 or want >= P else max(1, P // want)
+        tpar0 = time.perf_counter()
+        if args.no_e2e:  # no host-side output yet: fetch the device-resident arm's
+            h_res.array[:] = res_dev
+            if bt:
+                torch.from_numpy(h_ops.array).copy_(d_ops)
+        kw = dict(max_score=ms, read_size=rs, mismatch=cfg["mismatch"], gap_open=cfg["gap_open"], gap_ext=cfg["gap_ext"],
+                  backtrace=bt, reduce=cfg["reduce"], nthreads=threads, stride=stride, offset=(stride // 2))
+        pr = O.check(cfg["algo"], h_plen.array, h_tlen.array, h_pat.array, h_txt.array, h_res.array, h_ops.array if bt else None, **kw)
+        # device-resident arm == end-to-end arm, byte for byte (results incl. idx and status; op rows over the whole row)
+        dev_same = bool(np.array_equal(res_dev.view(np.uint8), h_res.array.view(np.uint8)))
+        if bt and dev_same:
+            step_rows = max(1, (256 << 20) // (2 * rs))
+            for a0 in range(0, P, step_rows):
+                a1 = min(P, a0 + step_rows)
+                if not torch.equal(d_ops[a0:a1], torch.from_numpy(h_ops.array[a0:a1]).to(dev, non_blocking=False)):
+                    dev_same = False
+                    break
+        cig_checked = 0
+        if e2e_cigars is not None and not genasm:  # CIGAR text rows (aim_align_batch_cigars / aim_align_packed) against the run-length text of the checked op rows
+            samp = np.random.default_rng(1).choice(P, size=min(P, 200_000), replace=False)
+            samp.sort()
+            exp = A.cigar_strings(h_res.array[samp], h_ops.array[samp])
+            for arr in [h_cig2.array] + ([h_cig.array] if e2e_packed is not None else []):
+                got = [bytes(r).split(b"\0", 1)[0].decode() for r in arr[samp]]
+                assert got == exp, "bench: CIGAR text rows differ from the run-length text of the op rows"
+            if e2e_packed is not None:
+                assert np.array_equal(h_res2.array["score"], h_res.array["score"]) and np.array_equal(h_res3.array["begin_offset"], h_res.array["begin_offset"])
+            cig_checked = len(samp)
+        tot = torch.tensor([pr["pairs_checked"], pr["mismatches"], 0 if dev_same else 1], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        parity = {"pairs_checked": int(tot[0]), "mismatches": int(tot[1]), "device_arm_differs_on_ranks": int(tot[2]),
+                  "against": "oracle/aim_oracle.c (C restatement pinned on the reference's outputs), score + status + begin/end offsets + op bytes of the span",
+                  "checked_output": "aim_align_batch host buffers (e2e arm); device-resident buffers byte-compared to them",
+                  "stride": stride, "cigar_text_rows_checked_per_rank": cig_checked, "oracle_threads_per_rank": threads,
+                  "seconds": time.perf_counter() - tpar0, "first_bad_rank0": pr["first_bad"]}
+        assert parity["mismatches"] == 0 and parity["device_arm_differs_on_ranks"] == 0, f"bench: PARITY FAILURE {parity}"
+
+    # ---- one process, N GPUs: aim_align_batch(ngpus = N) on rank 0's batch while the other ranks wait (N > 1 only) ----
+    inproc = None
+    if world > 1 and not args.no_inproc and not args.no_e2e:
+        gwait = dist.new_group(backend="gloo")
+        barrier()
+        if rank == 0:
+            p_all = A.AlignParams(algo=cfg["algo"], mismatch=cfg["mismatch"], gap_open=cfg["gap_open"], gap_ext=cfg["gap_ext"], max_score=ms,
+                                  read_size=rs, backtrace=bt, reduce=cfg["reduce"], device=0, ngpus=world)
+            h_resN = A.PinnedArray((P,), A.RESULT_DTYPE)
+            h_opsN = A.PinnedArray((P, 2 * rs), np.uint8) if bt else None
+
+            def inproc_step():
+                A.align_batch(p_all, h_plen.array, h_tlen.array, h_pat.array, h_txt.array, results=h_resN.array, ops=h_opsN.array if bt else None)
+            inproc_step()
+            t0 = time.perf_counter()
+            nst = max(2, min(args.steps, 5))
+            for _ in range(nst):
+                inproc_step()
+            ti_s = (time.perf_counter() - t0) / nst
+            same = bool(np.array_equal(h_resN.array.view(np.uint8), h_res.array.view(np.uint8))) and (not bt or bool(np.array_equal(h_opsN.array, h_ops.array)))
+            inproc = {"api": f"aim_align_batch(ngpus={world}) from ONE process: rank 0's {P} pairs split over {world} GPUs by index, pinned host buffers",
+                      "value": P / ti_s, "unit": "pairs/s", "ms_per_step": ti_s * 1e3, "identical_to_one_gpu_output": same}
+            assert same, "bench: aim_align_batch(ngpus=N) output differs from the one-GPU output"
+            del h_resN, h_opsN
+        dist.barrier(group=gwait)
+
     if rank == 0:
         # ---- rooflines for the dominant kernel (one launch = one step on one GPU) ----
         peaks = {}
@@ -379,8 +474,11 @@ def main() -> None:
         elif cfg["algo"] == "wfa":
             # bytes: 2-bit sequences + lengths in, result + 2-bit ops out
             bytes_pair = (pl_mean / 4 + tl_mean / 4 + 8) + (8 + ((pl_mean + tl_mean) / 4 if bt else 0))
+            # 11 int-ops per computed (score, diagonal) cell (its I, D and M recurrences together) + one 4-op extend
+            # group per live diagonal and score and per 16 matched bases
             sched = _wfa_work(res_dev["score"], cfg, ms)
-            int_ops_pair = sched["offsets"] * INT_OPS_PER_OFFSET + (sched["diag_steps"] + pl_mean / 16) * INT_OPS_PER_EXTEND
+            int_ops_pair = sched["diag_steps"] * INT_OPS_PER_OFFSET + (sched["diag_steps"] + pl_mean / 16) * INT_OPS_PER_EXTEND
+            int_ops_pair_components = sched["offsets"] * INT_OPS_PER_OFFSET + (sched["diag_steps"] + pl_mean / 16) * INT_OPS_PER_EXTEND
         else:
             cells = pl_mean * tl_mean
             bytes_pair = (pl_mean / 4 + tl_mean / 4 + 8) + (8 + ((pl_mean + tl_mean) / 4 if bt else 0))
@@ -394,8 +492,14 @@ def main() -> None:
         int_peak = A.measure_int_peak(local_rank)
         int_roofline = {"bound": "int32_alu", "achieved": int_ops_pair * P / kernel_s / 1e12, "peak": int_peak / 1e12, "unit": "Tops/s",
                         "frac": int_ops_pair * P / kernel_s / int_peak, "algorithmic_int_ops_per_pair": int_ops_pair,
+                        "convention": "SURVEY 8d per-unit figures x units: WFA 11 ops per computed (score, diagonal) cell + 4 per extend group; "
+                                      "NW 8 / SWG 14 ops per DP cell with backtrace flags",
                         "peak_source": "aim_measure_int_peak: dependent-free add/logic/min-max mix, this GPU, this run",
                         "gcups_equiv": pl_mean * tl_mean * P / kernel_s / 1e9}
+        if cfg["algo"] == "wfa":
+            int_roofline["frac_counting_each_component_offset"] = int_ops_pair_components * P / kernel_s / int_peak
+            int_roofline["cells_per_pair"] = sched["diag_steps"]
+            int_roofline["component_offsets_per_pair"] = sched["offsets"]
         cpu_baseline = None
         if not args.no_cpu_baseline:
             try:
@@ -414,11 +518,7 @@ def main() -> None:
             "metric": "aligned pairs/sec (score+CIGAR)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64" if genasm else "int16", "data": "synthetic",
-            "config": {"workload": cfg["name"], "pairs_per_gpu_per_step": P, "algo": cfg["algo"], "max_score": ms, "read_size": rs,
-                       "penalties": {"x": cfg["mismatch"], "o": cfg["gap_open"], "e": cfg["gap_ext"]}, "backtrace": bt,
-                       "adaptive": cfg["reduce"], "parallelism": f"pairs sharded by index over {world} GPU(s), no collective",
-                       "l2": f"inputs {P * 2 * rs / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                       "generator": f"seed {cfg['seed']}, generate_dataset semantics", "mean_score": mean_score},
+            "config": config_dict(cfg, P, world), "mean_score": mean_score, "parity": parity, "inproc_ngpus": inproc,
             "gcups_equiv": pl_mean * tl_mean * world * P / (ms_per_step * 1e-3) / 1e9,
             "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "e2e_cigars": e2e_cigars, "gpu_launches": launches,
             "roofline": roofline, "int_roofline": int_roofline, "cpu_baseline": cpu_baseline,

@@ -659,3 +659,101 @@ int orc_align_batch(const orc_params *p, uint32_t n, const int32_t *plen, const 
     free(jobs); free(th);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Checker for full-size parity runs (bench.py "parity", tests/test_gpu_fullsize.py): align every
+ * pair here and compare with a candidate's output in place - score, begin/end offsets,
+ * max_operations and the op bytes of the valid span [begin_offset, end_offset) - without a second
+ * n x 2*read_size op array.  `cand_results` uses the product's 24-byte result layout
+ * (include/aim_b200.h aim_result: the reference's result_t with status in the pad word + idx).
+ * Returns the number of mismatching pairs through *mismatches and the lowest mismatching index
+ * through *first_bad (UINT32_MAX when none).  stride/offset select pairs offset, offset+stride, ...
+ * (stride 1 = all) so a bounded sample can be spread over the whole batch.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t max_operations, begin_offset, end_offset, score, status;
+    uint32_t idx;
+} orc_cand_result;
+
+typedef struct {
+    orc_job job;
+    const orc_cand_result *cand;
+    const char *cand_ops;
+    uint32_t stride, offset;
+    uint64_t mismatches, checked;
+    uint32_t first_bad;
+} orc_check_job;
+
+static void *orc_check_worker(void *arg)
+{
+    orc_check_job *c = (orc_check_job *)arg;
+    orc_job *j = &c->job;
+    const orc_params *p = j->p;
+    size_t rs = (size_t)p->read_size;
+    const int has_ops = (p->backtrace || p->algo == ORC_ALGO_GENASM_DC) && c->cand_ops;
+    void *tab = NULL;
+    char *row = (char *)malloc(2 * rs + 16);
+    if (p->algo == ORC_ALGO_NW) tab = malloc(sizeof(int16_t) * (rs + 2) * (rs + 2));
+    else if (p->algo == ORC_ALGO_SWG) tab = malloc(sizeof(swg_cell) * (rs + 2) * (rs + 2));
+    c->first_bad = UINT32_MAX;
+    uint32_t i = j->first;
+    if (c->stride > 1) { uint32_t r = i % c->stride; i += (c->offset + c->stride - r) % c->stride; }
+    for (; i < j->last; i += c->stride) {
+        const char *pat = j->patterns + (size_t)i * rs, *txt = j->texts + (size_t)i * rs;
+        orc_result r;
+        memset(&r, 0, sizeof r);
+        char *ops = has_ops || p->backtrace ? row : NULL;
+        if (p->algo == ORC_ALGO_GENASM_DC) genasm_align(p, pat, txt, j->plen[i], j->tlen[i], &r, row, 1);
+        else if (p->algo == ORC_ALGO_GENASM_FILTER) genasm_align(p, pat, txt, j->plen[i], j->tlen[i], &r, NULL, 0);
+        else if (p->algo == ORC_ALGO_WFA) wfa_align(p, pat, txt, j->plen[i], j->tlen[i], &r, ops);
+        else if (p->algo == ORC_ALGO_NW) nw_align(p, pat, txt, j->plen[i], j->tlen[i], &r, ops, (int16_t *)tab);
+        else swg_align(p, pat, txt, j->plen[i], j->tlen[i], &r, ops, (swg_cell *)tab);
+        const orc_cand_result *g = &c->cand[i];
+        int bad = g->score != r.score || g->status != r.status;
+        if (p->backtrace || p->algo == ORC_ALGO_GENASM_DC)
+            bad |= g->begin_offset != r.begin_offset || g->end_offset != r.end_offset || g->max_operations != r.max_operations;
+        if (!bad && has_ops && r.status == ORC_OK && r.end_offset > r.begin_offset && r.begin_offset >= 0)
+            bad = memcmp(c->cand_ops + (size_t)i * 2 * rs + r.begin_offset, row + r.begin_offset, (size_t)(r.end_offset - r.begin_offset)) != 0;
+        ++c->checked;
+        if (bad) { ++c->mismatches; if (i < c->first_bad) c->first_bad = i; }
+    }
+    free(tab); free(row);
+    return NULL;
+}
+
+int orc_check_batch(const orc_params *p, uint32_t n, const int32_t *plen, const int32_t *tlen, const char *patterns,
+                    const char *texts, const void *cand_results, const char *cand_ops, uint32_t stride, uint32_t offset,
+                    int nthreads, uint64_t *checked, uint64_t *mismatches, uint32_t *first_bad)
+{
+    if (!p || p->algo < 0 || p->algo > 4 || p->read_size <= 0 || !cand_results) return -1;
+    for (uint32_t i = 0; i < n; ++i)
+        if (plen[i] < 0 || tlen[i] < 0 || plen[i] > p->read_size || tlen[i] > p->read_size) return -2;
+    if (stride < 1) stride = 1;
+    if (nthreads < 1) nthreads = 1;
+    if ((uint32_t)nthreads > n) nthreads = n ? (int)n : 1;
+    orc_check_job *jobs = (orc_check_job *)calloc((size_t)nthreads, sizeof(orc_check_job));
+    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+    uint32_t per = (n + (uint32_t)nthreads - 1) / (uint32_t)nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        uint32_t a = (uint32_t)t * per, b = a + per;
+        if (a > n) a = n;
+        if (b > n) b = n;
+        orc_job j = { p, a, b, plen, tlen, patterns, texts, NULL, NULL };
+        jobs[t].job = j;
+        jobs[t].cand = (const orc_cand_result *)cand_results;
+        jobs[t].cand_ops = cand_ops;
+        jobs[t].stride = stride;
+        jobs[t].offset = offset % stride;
+        if (nthreads == 1) orc_check_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, orc_check_worker, &jobs[t]);
+    }
+    if (nthreads > 1) for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    uint64_t mm = 0, ck = 0;
+    uint32_t fb = UINT32_MAX;
+    for (int t = 0; t < nthreads; ++t) { mm += jobs[t].mismatches; ck += jobs[t].checked; if (jobs[t].first_bad < fb) fb = jobs[t].first_bad; }
+    if (checked) *checked = ck;
+    if (mismatches) *mismatches = mm;
+    if (first_bad) *first_bad = fb;
+    free(jobs); free(th);
+    return 0;
+}

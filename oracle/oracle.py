@@ -42,6 +42,9 @@ def _get():
         _lib = C.CDLL(str(LIB))
         _lib.orc_align_batch.restype = C.c_int
         _lib.orc_align_batch.argtypes = [C.POINTER(OrcParams), C.c_uint32] + [C.c_void_p] * 6 + [C.c_int]
+        _lib.orc_check_batch.restype = C.c_int
+        _lib.orc_check_batch.argtypes = ([C.POINTER(OrcParams), C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32, C.c_uint32, C.c_int] +
+                                         [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)])
     return _lib
 
 
@@ -67,3 +70,27 @@ def align(algo: str, plen, tlen, patterns, texts, *, max_score: int, read_size: 
     if rc != 0:
         raise RuntimeError(f"orc_align_batch rc={rc}")
     return res, ops
+
+
+def check(algo: str, plen, tlen, patterns, texts, cand_results, cand_ops, *, max_score: int, read_size: int, match: int = 0,
+          mismatch: int = 3, gap_open: int = 4, gap_ext: int = 1, backtrace: bool = True, reduce: bool = False,
+          nthreads: int = 1, variant: int = 0, stride: int = 1, offset: int = 0) -> dict:
+    """Full-size parity: align pairs offset, offset+stride, ... here and compare each with the candidate's
+    24-byte result (score, status, and with backtrace begin/end/max_operations) and the op bytes of its valid
+    span, in place.  -> {"pairs_checked", "mismatches", "first_bad"}."""
+    n = len(plen)
+    p = OrcParams(_ALGO[algo], match, mismatch, gap_open, gap_ext, max_score, read_size, int(backtrace), int(reduce), int(variant))
+    plen = np.ascontiguousarray(plen, np.int32)
+    tlen = np.ascontiguousarray(tlen, np.int32)
+    assert patterns.flags.c_contiguous and texts.flags.c_contiguous and cand_results.flags.c_contiguous
+    assert patterns.shape == (n, read_size) and texts.shape == (n, read_size)
+    assert cand_results.dtype.itemsize == 24 and len(cand_results) == n
+    if cand_ops is not None:
+        assert cand_ops.flags.c_contiguous and cand_ops.shape == (n, 2 * read_size)
+    ck, mm, fb = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+    rc = _get().orc_check_batch(C.byref(p), n, plen.ctypes.data, tlen.ctypes.data, patterns.ctypes.data, texts.ctypes.data,
+                                cand_results.ctypes.data, cand_ops.ctypes.data if cand_ops is not None else None,
+                                int(stride), int(offset), int(nthreads), C.byref(ck), C.byref(mm), C.byref(fb))
+    if rc != 0:
+        raise RuntimeError(f"orc_check_batch rc={rc}")
+    return {"pairs_checked": int(ck.value), "mismatches": int(mm.value), "first_bad": None if fb.value == 0xFFFFFFFF else int(fb.value)}

@@ -1,12 +1,23 @@
-"""GPU: size-independent properties at (a slice of) BASELINE.json's full sizes, where the oracle
-would take too long: every CIGAR is a valid edit script of its pair, consumes exactly plen/tlen,
-and re-scores to the reported score under the run's penalties."""
+"""GPU, at (a slice of) BASELINE.json's full sizes: bit-exact equality with the CPU oracle (score, span, op bytes:
+oracle.check aligns every pair on all host threads and compares in place - a tie-break difference in the backtrace
+fails here), plus the size-independent properties: every CIGAR is a valid edit script of its pair, consumes exactly
+plen/tlen, and re-scores to the reported score under the run's penalties."""
+import os
+
 import numpy as np
 import pytest
 
 import aim_b200 as A
+from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
+THREADS = os.cpu_count() or 1
+
+
+def _oracle_equal(algo, res, ops, plen, tlen, pats, txts, stride=1, **kw):
+    r = O.check(algo, plen, tlen, pats, txts, np.ascontiguousarray(res), ops, nthreads=THREADS, stride=stride, **kw)
+    assert r["mismatches"] == 0, f"{r['mismatches']} of {r['pairs_checked']} pairs differ from the oracle, first at pair {r['first_bad']}"
+    return r["pairs_checked"]
 
 
 def _check_cigars(res, ops, plen, tlen, pats, txts, x, o, e, linear_gap=None, sample=4000, seed=0):
@@ -48,6 +59,7 @@ def test_cfg4_wfa_adaptive_1m_pairs():
     assert int((res["status"] != 0).sum()) == 0
     assert int((res["score"] > ms).sum()) == 0  # 6 edits cost at most 6*5 = 30
     _check_cigars(res, ops, plen, tlen, pats, txts, 3, 4, 1)
+    assert _oracle_equal("wfa", res, ops, plen, tlen, pats, txts, max_score=ms, read_size=rs, backtrace=True, reduce=True) == n
     # score-only run agrees on scores
     res2, _, _ = A.align_batch(A.AlignParams(algo="wfa", max_score=ms, read_size=rs, backtrace=False, reduce=True), plen, tlen, pats, txts)
     assert np.array_equal(res["score"], res2["score"])
@@ -60,12 +72,36 @@ def test_cfg5_long_reads_scores_and_cigars():
     res, _, _ = A.align_batch(A.AlignParams(algo="wfa", max_score=ms, read_size=rs, backtrace=False, reduce=True), plen, tlen, pats, txts)
     assert int((res["status"] != 0).sum()) == 0
     assert res["score"].min() > 2500 and res["score"].max() <= ms
+    assert _oracle_equal("wfa", res, None, plen, tlen, pats, txts, max_score=ms, read_size=rs, backtrace=False, reduce=True) == n
     resb, ops, _ = A.align_batch(A.AlignParams(algo="wfa", max_score=ms, read_size=rs, backtrace=True, reduce=True), plen, tlen, pats, txts)
     assert np.array_equal(res["score"], resb["score"])
     _check_cigars(resb, ops, plen, tlen, pats, txts, 3, 4, 1, sample=16)
+    # with backtrace (beyond what the reference can run at this size): the oracle has no WRAM guard
+    assert _oracle_equal("wfa", resb, ops, plen, tlen, pats, txts, stride=4, max_score=ms, read_size=rs, backtrace=True, reduce=True) == n // 4
+
+
+def test_cfg3_swg_200k_pairs_oracle_equal():
+    ms, rs = A.derive_knobs("swg", 250, 0.04, 4, 6, 2)
+    n = 200_000
+    plen, tlen, pats, txts = A.generate_pairs(3, n, 250, 0.04, rs)
+    kw = dict(max_score=ms, read_size=rs, mismatch=4, gap_open=6, gap_ext=2, backtrace=True)
+    res, ops, _ = A.align_batch(A.AlignParams(algo="swg", **kw), plen, tlen, pats, txts)
+    assert int((res["status"] != 0).sum()) == 0
+    assert _oracle_equal("swg", res, ops, plen, tlen, pats, txts, **kw) == n
+
+
+def test_cfg2_nw_1m_pairs_oracle_equal():
+    ms, rs = A.derive_knobs("nw", 100, 0.01)
+    n = 1_000_000
+    plen, tlen, pats, txts = A.generate_pairs(2, n, 100, 0.01, rs)
+    kw = dict(max_score=ms, read_size=rs, backtrace=True)
+    res, ops, _ = A.align_batch(A.AlignParams(algo="nw", **kw), plen, tlen, pats, txts)
+    assert _oracle_equal("nw", res, ops, plen, tlen, pats, txts, **kw) == n
 
 
 def test_cfg2_nw_linear_gap_cigars_on_dataset(golden_case):
     e, kw, (plen, tlen, pats, txts) = golden_case("cfg2_nw_err")
     res, ops, _ = A.align_batch(A.AlignParams(**kw), plen, tlen, pats, txts)
     _check_cigars(res, ops, plen, tlen, pats, txts, 3, 0, 0, linear_gap=4, sample=2000)
+    okw = {k: v for k, v in kw.items() if k in ("max_score", "read_size", "match", "mismatch", "gap_open", "gap_ext", "backtrace", "reduce")}
+    assert _oracle_equal(kw["algo"], res, ops, plen, tlen, pats, txts, **okw) == len(plen)
