@@ -12,7 +12,7 @@ CXX_SRCS  := $(CSRC)/aim_host.cpp
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CXX_SRCS))
 HDRS      := include/aim_b200.h $(CSRC)/aim_internal.h $(CSRC)/aim_wfa_common.cuh
 
-all: aim_b200/libaim_b200.so build/host build/aim_genpairs oracle/libaim_oracle.so
+all: aim_b200/libaim_b200.so aim_b200/libaim_dpu.so build/host build/aim_genpairs oracle/libaim_oracle.so
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -24,6 +24,10 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDRS)
 
 aim_b200/libaim_b200.so: $(OBJS)
 	$(NVCC) -shared $(ARCH) -cudart static -o $@ $(OBJS) -lpthread
+
+# UPMEM host-API adapter (include/dpu.h): the reference's host.c files compile unchanged against it (host-only code)
+aim_b200/libaim_dpu.so: $(CSRC)/aim_dpu.cpp include/dpu.h include/aim_b200.h aim_b200/libaim_b200.so
+	$(CXX) -O2 -std=c++17 -fPIC -shared -Wall -Wextra -Iinclude $(CSRC)/aim_dpu.cpp -o $@ -Laim_b200 -laim_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
 
 build/host: tools/host.cpp aim_b200/libaim_b200.so include/aim_b200.h
 	@mkdir -p build
@@ -38,6 +42,6 @@ oracle/libaim_oracle.so: oracle/aim_oracle.c
 	$(CC) -O2 -std=gnu11 -fPIC -shared -Wall -o $@ $< -lpthread
 
 clean:
-	rm -rf build aim_b200/libaim_b200.so oracle/libaim_oracle.so
+	rm -rf build aim_b200/libaim_b200.so aim_b200/libaim_dpu.so oracle/libaim_oracle.so
 
 .PHONY: all clean

@@ -164,9 +164,13 @@ aim_params normalized(const aim_params *p)
 
 int launch(const KernelArgs &a, Scratch *s, cudaStream_t stream, int *launches)
 {
-    if (a.p.algo == AIM_ALGO_WFA) return launch_wfa(a, s, stream, launches);
-    if (a.p.algo == AIM_ALGO_GENASM_DC || a.p.algo == AIM_ALGO_GENASM_FILTER) return launch_genasm(a, s, stream, launches);
-    return launch_dp(a, s, stream, launches);
+    int rc = scratch_acquire(s, stream);
+    if (rc != AIM_OK) return rc;
+    if (a.p.algo == AIM_ALGO_WFA) rc = launch_wfa(a, s, stream, launches);
+    else if (a.p.algo == AIM_ALGO_GENASM_DC || a.p.algo == AIM_ALGO_GENASM_FILTER) rc = launch_genasm(a, s, stream, launches);
+    else rc = launch_dp(a, s, stream, launches);
+    const int rc2 = scratch_release(s, stream);
+    return rc != AIM_OK ? rc : rc2;
 }
 
 // One GPU's share [first, first + n) of a host batch.
@@ -309,8 +313,8 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
 
 // One GPU's share [first, first + n) of a PACKED host batch (aim_align_packed): per chunk, lengths + packed rows + flag
 // words up, kernels, results + CIGAR rows down; same three-stream pipeline as run_shard.  The chunk's device buffers are
-// reused: d_pat holds the packed rows, d_txt the flag words followed by the CIGAR rows, d_ops the op rows the backtrace
-// writes (they never leave the device).
+// reused: d_pat holds the packed rows, d_cig the flag words followed by the CIGAR rows (sized from cigar_pitch), d_ops the
+// op rows the backtrace writes (they never leave the device).
 int run_shard_packed(const aim_params &p, int device, uint32_t first, uint32_t n, uint32_t idx_base, const int32_t *plen,
                      const int32_t *tlen, const uint32_t *packed, const uint32_t *flags, aim_result *results, char *cigars,
                      int32_t pitch, double phase_ms[3], std::string *err)
@@ -344,9 +348,20 @@ int run_shard_packed(const aim_params &p, int device, uint32_t first, uint32_t n
     const uint32_t nchunks = (uint32_t)ch.size();
     const int nbuf = (int)std::min<uint32_t>(kNumBuf, nchunks);
     const uint32_t cap = std::min(std::max(chunk_pairs, lead), std::max(n, 32u));
+    // flag words (rounded to 256 B) + CIGAR rows live in the chunk's d_cig buffer, sized from the pitch
+    const size_t flag_cap = ((size_t)(cap + 31) / 32 * 4 + 255) / 256 * 256;
     for (int b = 0; b < nbuf; ++b) {
         rc = ensure_chunk(ctx->chunk[b], cap, p.read_size, true, false);
         if (rc != AIM_OK) return fail(rc);
+        ChunkBuf &B = ctx->chunk[b];
+        const size_t need = flag_cap + (size_t)cap * (size_t)pitch;
+        if (B.cig_cap < need) {
+            cudaFree(B.d_cig);
+            B.d_cig = nullptr;
+            B.cig_cap = 0;
+            AIM_CUDA(cudaMalloc(&B.d_cig, need));
+            B.cig_cap = need;
+        }
     }
     double ph[3] = {0, 0, 0};
     auto finish = [&](uint32_t c) -> int {
@@ -377,10 +392,8 @@ int run_shard_packed(const aim_params &p, int device, uint32_t first, uint32_t n
         }
         // flag words of the chunk: the caller's words when the chunk starts on a word boundary, else shifted on the host
         const uint32_t fwords = (m + 31) / 32;
-        uint32_t *d_flags = reinterpret_cast<uint32_t *>(B.d_txt);
-        const size_t flag_bytes = ((size_t)fwords * 4 + 255) / 256 * 256;
-        char *d_cig = B.d_txt + flag_bytes;
-        if (flag_bytes + (size_t)m * (size_t)pitch > (size_t)B.pairs_cap * rs) { set_error("cigar_pitch too large for the chunk buffers"); return fail(AIM_ERR_ARG); }
+        uint32_t *d_flags = reinterpret_cast<uint32_t *>(B.d_cig);
+        char *d_cig = B.d_cig + flag_cap;
         std::vector<uint32_t> shifted;
         const uint32_t *s_flags = flags + (g0 >> 5);
         if (g0 & 31u) {
@@ -444,6 +457,80 @@ int scratch_reserve(Scratch *s, size_t bytes)
     return AIM_OK;
 }
 
+namespace {
+struct PlanEntry { std::vector<unsigned char> host; void *dev; };
+struct PlanCache { std::vector<PlanEntry> e; };
+}  // namespace
+
+const void *cached_plan(Scratch *s, const void *host, size_t bytes)
+{
+    if (!s->plan_cache) s->plan_cache = new PlanCache();
+    PlanCache *pc = static_cast<PlanCache *>(s->plan_cache);
+    for (const PlanEntry &e : pc->e)
+        if (e.host.size() == bytes && memcmp(e.host.data(), host, bytes) == 0) return e.dev;
+    if (pc->e.size() >= 32) {  // a long-lived process cycling through many penalty sets: start over (nothing may still read them)
+        cudaDeviceSynchronize();
+        for (PlanEntry &e : pc->e) cudaFree(e.dev);
+        pc->e.clear();
+    }
+    PlanEntry ne;
+    ne.host.assign(static_cast<const unsigned char *>(host), static_cast<const unsigned char *>(host) + bytes);
+    ne.dev = nullptr;
+    cudaError_t e = cudaMalloc(&ne.dev, std::max<size_t>(bytes, 256));
+    if (e == cudaSuccess) e = cudaMemcpy(ne.dev, host, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error(std::string("plan upload: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        if (ne.dev) cudaFree(ne.dev);
+        return nullptr;
+    }
+    pc->e.push_back(std::move(ne));
+    return pc->e.back().dev;
+}
+
+int scratch_acquire(Scratch *s, void *stream)
+{
+    if (s->busy_valid && s->busy_stream != stream) {
+        cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)s->busy_event, 0);
+        if (e != cudaSuccess) { set_error(std::string("scratch hand-over: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
+    }
+    return AIM_OK;
+}
+
+int scratch_release(Scratch *s, void *stream)
+{
+    cudaError_t e = cudaSuccess;
+    if (!s->busy_event) {
+        cudaEvent_t ev = nullptr;
+        e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        s->busy_event = ev;
+    }
+    if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)s->busy_event, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error(std::string("scratch hand-over: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
+    s->busy_stream = stream;
+    s->busy_valid = true;
+    return AIM_OK;
+}
+
+void scratch_destroy(Scratch *s)
+{
+    cudaFree(s->buf);
+    s->buf = nullptr;
+    s->bytes = 0;
+    if (s->plan_cache) {
+        PlanCache *pc = static_cast<PlanCache *>(s->plan_cache);
+        for (PlanEntry &e : pc->e) cudaFree(e.dev);
+        delete pc;
+        s->plan_cache = nullptr;
+    }
+    if (s->busy_event) cudaEventDestroy((cudaEvent_t)s->busy_event);
+    s->busy_event = nullptr;
+    s->busy_valid = false;
+    if (s->side_stream) cudaStreamDestroy((cudaStream_t)s->side_stream);
+    s->side_stream = nullptr;
+    for (auto &ev : s->side_ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); ev = nullptr; }
+}
+
 }  // namespace aim
 
 using namespace aim;
@@ -476,8 +563,7 @@ extern "C" void aim_shutdown(void)
         cudaDeviceSynchronize();
         for (auto &b : c->chunk) free_chunk(b);
         if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_kernel); cudaStreamDestroy(c->s_d2h); }
-        cudaFree(c->scratch.buf);
-        cudaFree(c->scratch.sched_buf);
+        scratch_destroy(&c->scratch);
         delete c;
     }
     g_ctx.clear();

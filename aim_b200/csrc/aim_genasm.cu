@@ -692,17 +692,21 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
     const size_t hist_bytes = ((size_t)batch * K.hist_stride * 4 + 255) / 256 * 256;
     int rc = scratch_reserve(sc, std::max<size_t>((size_t)halves * (meta_bytes + hist_bytes), 256));
     if (rc != AIM_OK) return rc;
-    static cudaStream_t side[64] = {};
-    static cudaEvent_t ev_fill[64][2] = {}, ev_tb[64][2] = {};
-    const int dev = sc->device & 63;
-    if (overlap && !side[dev]) {
-        cudaError_t e = cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking);
-        for (int h = 0; h < 2 && e == cudaSuccess; ++h) {
-            e = cudaEventCreateWithFlags(&ev_fill[dev][h], cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_tb[dev][h], cudaEventDisableTiming);
+    // traceback side stream + its events live in the device's Scratch (aim_shutdown destroys them)
+    if (overlap && !sc->side_stream) {
+        cudaStream_t st = nullptr;
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        sc->side_stream = st;
+        for (int h = 0; h < 4 && e == cudaSuccess; ++h) {
+            cudaEvent_t ev = nullptr;
+            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            sc->side_ev[h] = ev;
         }
         if (e != cudaSuccess) { set_error(std::string("genasm side stream: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
     }
+    cudaStream_t const side = (cudaStream_t)sc->side_stream;
+    cudaEvent_t const ev_fill[2] = {(cudaEvent_t)sc->side_ev[0], (cudaEvent_t)sc->side_ev[1]};
+    cudaEvent_t const ev_tb[2] = {(cudaEvent_t)sc->side_ev[2], (cudaEvent_t)sc->side_ev[3]};
     // (tuning knob: dummy dynamic shared memory caps the traceback kernel's blocks per SM.  Measured at config 7: 0 KB 293 M pairs/s,
     // 24 KB 157 M, 48 KB 212 M, 100 KB 136 M - the shared-memory carve-out shrinks L1 and the walk needs the threads.)
     size_t tb_smem = 0;
@@ -722,7 +726,7 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
         const uint64_t per_block = (uint64_t)4 * PPW;
         if ((uint64_t)grid * per_block > K.n) grid = (int)std::max<uint64_t>(1, (K.n + per_block - 1) / per_block);
         cudaError_t err = cudaSuccess;
-        if (overlap && nb >= 2) err = cudaStreamWaitEvent(stream, ev_tb[dev][h], 0);  // the traceback that read this half is done
+        if (overlap && nb >= 2) err = cudaStreamWaitEvent(stream, ev_tb[h], 0);  // the traceback that read this half is done
         if (err == cudaSuccess && band) err = launch_band(K, bw, lpl, dc, grid, (size_t)4 * PPW * K.slot_bytes, stream);
         else if (err == cudaSuccess)
             err = W == 2 ? launch_w<2>(K, lpl, dc, grid, smem, stream)
@@ -731,22 +735,22 @@ int launch_genasm(const KernelArgs &a, Scratch *sc, void *stream_v, int *launche
         if (err == cudaSuccess && dc) {
             cudaStream_t ts = stream;
             if (overlap) {
-                ts = side[dev];
-                err = cudaEventRecord(ev_fill[dev][h], stream);
-                if (err == cudaSuccess) err = cudaStreamWaitEvent(ts, ev_fill[dev][h], 0);
+                ts = side;
+                err = cudaEventRecord(ev_fill[h], stream);
+                if (err == cudaSuccess) err = cudaStreamWaitEvent(ts, ev_fill[h], 0);
             }
             if (err == cudaSuccess) {
                 genasm_tb_kernel<<<(K.n + 127) / 128, 128, tb_smem, ts>>>(K);
                 err = cudaGetLastError();
             }
-            if (err == cudaSuccess && overlap) err = cudaEventRecord(ev_tb[dev][h], ts);
+            if (err == cudaSuccess && overlap) err = cudaEventRecord(ev_tb[h], ts);
             if (err == cudaSuccess && launches) ++*launches;
         }
         if (err != cudaSuccess) { set_error(std::string("genasm launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
     }
     if (overlap) {  // the caller's stream continues only after the last tracebacks
         for (int h = 0; h < 2; ++h)
-            if (nb > (uint32_t)h && cudaStreamWaitEvent(stream, ev_tb[dev][h], 0) != cudaSuccess) { set_error("genasm: stream join failed"); return AIM_ERR_CUDA; }
+            if (nb > (uint32_t)h && cudaStreamWaitEvent(stream, ev_tb[h], 0) != cudaSuccess) { set_error("genasm: stream join failed"); return AIM_ERR_CUDA; }
     }
     return AIM_OK;
 }

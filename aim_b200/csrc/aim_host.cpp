@@ -257,6 +257,13 @@ inline size_t put_cigar(char *out, const char *ops, int32_t b, int32_t e)
 // host.c:69-89 edit_cigar_print.
 extern "C" int aim_cigar_rle(const char *ops, int32_t begin_offset, int32_t end_offset, char *out, size_t cap)
 {
+    // a span that starts before the row (an empty pair has begin_offset = -1; the reference then prints the byte before its
+    // buffer, an 'M' of the DPU's memset at best): "1M", as the device-side printer (cigar_rle_kernel) writes it
+    if (begin_offset < 0) {
+        if (cap < 2) return -1;
+        out[0] = '1'; out[1] = 'M';
+        return 2;
+    }
     // edit_cigar_print always emits the op at begin_offset, even for an empty span
     const int32_t e = end_offset > begin_offset ? end_offset : begin_offset + 1;
     if ((size_t)(e - begin_offset) * 11 <= cap) return (int)put_cigar(out, ops, begin_offset, e);
@@ -297,8 +304,9 @@ extern "C" int aim_write_results(const char *path, uint32_t n, int32_t read_size
                 o[pos++] = ','; o[pos++] = ' '; o[pos++] = '\n';
                 if (backtrace) {
                     const int32_t bo = results[i].begin_offset;
-                    const int32_t eo = results[i].end_offset > bo ? results[i].end_offset : bo + 1;
-                    pos += put_cigar(o + pos, ops + i * rs2, bo, eo);
+                    const int32_t eo = std::min<int64_t>(results[i].end_offset > bo ? results[i].end_offset : (int64_t)bo + 1, (int64_t)rs2);
+                    if (bo < 0 || (size_t)bo >= rs2) { o[pos++] = '1'; o[pos++] = 'M'; }  // span outside the row: see aim_cigar_rle
+                    else pos += put_cigar(o + pos, ops + i * rs2, bo, eo);
                     o[pos++] = '\n';
                 }
             }

@@ -44,14 +44,28 @@ struct KernelArgs {
 struct Scratch {
     void *buf = nullptr;        // general scratch (WFA global arena / DP rows+flags)
     size_t bytes = 0;
-    void *sched_buf = nullptr;  // device copy of the static WFA schedule table
-    size_t sched_bytes = 0;
+    void *plan_cache = nullptr; // device copies of static WFA plans, keyed by content (cached_plan)
     int sm_count = 0;
     int device = 0;
+    // the scratch is ONE buffer per device: a launch sequence that uses it records `busy` after its last kernel, and the next
+    // sequence on ANOTHER stream waits for it first (scratch_acquire / scratch_release)
+    void *busy_event = nullptr;   // cudaEvent_t
+    void *busy_stream = nullptr;  // stream the last user ran on
+    bool busy_valid = false;
+    // GenASM-DC: traceback side stream + events (created on first use, destroyed by aim_shutdown)
+    void *side_stream = nullptr;
+    void *side_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 // Ensure scratch->buf holds at least `bytes` (grows, never shrinks).  Returns AIM_OK/AIM_ERR_*.
 int scratch_reserve(Scratch *s, size_t bytes);
+// Device copy of a static plan table: uploaded once per distinct content (synchronously, from the host vector) and reused
+// by every later launch, so no per-chunk pageable cudaMemcpyAsync sits on the kernel stream.  NULL on failure (error set).
+const void *cached_plan(Scratch *s, const void *host, size_t bytes);
+// Order a launch sequence on `stream` after the previous user of the scratch / mark `stream` as its current user.
+int scratch_acquire(Scratch *s, void *stream);
+int scratch_release(Scratch *s, void *stream);
+void scratch_destroy(Scratch *s);
 
 // Launch configuration of the warp-per-pair WFA kernel (aim_wfa.cu), split from the launch so that the
 // long-read kernel can size one scratch for itself plus this kernel serving its leftovers.

@@ -564,7 +564,8 @@ int launch_wfa_long(const KernelArgs &a, Scratch *sc, void *stream_v, int *launc
     unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
     K.work_ctr = reinterpret_cast<uint32_t *>(base);
     K.fail_count = K.work_ctr + 1;
-    K.plan = reinterpret_cast<const uint4 *>(base + off_plan);
+    K.plan = reinterpret_cast<const uint4 *>(cached_plan(sc, plan.data(), plan_bytes));  // uploaded once per penalty set
+    if (!K.plan) return AIM_ERR_CUDA;
     K.dirty = base + off_dirty;
     K.fail_list = reinterpret_cast<uint32_t *>(base + off_fail);
     K.packed = reinterpret_cast<const uint2 *>(base + off_packed);
@@ -574,7 +575,6 @@ int launch_wfa_long(const KernelArgs &a, Scratch *sc, void *stream_v, int *launc
 
     err = cudaMemsetAsync(base, 0, 256, stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(base + off_dirty, 0, a.n, stream);
-    if (err == cudaSuccess) err = cudaMemcpyAsync(base + off_plan, plan.data(), plan_bytes, cudaMemcpyHostToDevice, stream);
     if (err == cudaSuccess) {
         const uint64_t warps = std::min<uint64_t>(2ull * a.n, (uint64_t)sc->sm_count * 64);
         const int pgrid = (int)((warps * 32 + 255) / 256);

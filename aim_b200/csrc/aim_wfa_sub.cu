@@ -768,14 +768,14 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     uint32_t *flags = list_count + 64;
     uint32_t *list = reinterpret_cast<uint32_t *>(base + plan_dev + flags_dev);
     uint32_t *packed = reinterpret_cast<uint32_t *>(base + plan_dev + flags_dev + list_dev);
-    K.plan = reinterpret_cast<const uint32_t *>(base);
+    K.plan = reinterpret_cast<const uint32_t *>(cached_plan(sc, plan.data(), plan_bytes));  // uploaded once per penalty set
+    if (!K.plan) return AIM_ERR_CUDA;
     K.flags = prepacked ? a.pflags : flags;
     K.packed = reinterpret_cast<const uint4 *>(prepacked ? a.packed : packed);
     if (prepacked && aim_packed_row_bytes(p.read_size) != (int32_t)(K.seq_words * 4)) { set_error("packed row pitch mismatch"); return AIM_ERR_ARG; }
     K.arena = reinterpret_cast<uint2 *>(base + plan_dev + flags_dev + list_dev + packed_dev);
     void *warp_scratch = base + plan_dev + flags_dev + list_dev + packed_dev + arena_bytes;
-    cudaError_t err = cudaMemcpyAsync(base, plan.data(), plan_bytes, cudaMemcpyHostToDevice, stream);
-    if (err == cudaSuccess) err = cudaMemsetAsync(list_count, 0, flags_dev, stream);
+    cudaError_t err = cudaMemsetAsync(list_count, 0, flags_dev, stream);
     if (err == cudaSuccess && p.backtrace)  // op rows: 'M' everywhere (wfa.c:499-501); the backtrace overwrites the few edits
         err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * (size_t)p.read_size, stream);
     if (err == cudaSuccess && !prepacked) {

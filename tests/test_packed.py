@@ -190,3 +190,22 @@ def test_packed_writer_blocks_stay_in_order(tmp_path, monkeypatch, threads):
     A.write_results_packed(out, res, cig)
     want = b"".join(b"%d, %d, \n%s\n" % (i, i % 31, rows[i]) for i in range(n))
     assert out.read_bytes() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("length,error,pitch_of", [(150, 0.04, lambda rs: 2 * rs), (50, 0.04, lambda rs: rs), (50, 0.04, lambda rs: 2 * rs)])
+def test_packed_large_pitch_and_small_read_size(length, error, pitch_of):
+    """cigar_pitch up to 2*read_size is accepted as the header says (the CIGAR rows have their own device buffer), and
+    read_size = 64 works with cigar_pitch = 64 (the rows used to share the text buffer)."""
+    ms, rs = A.derive_knobs("wfa", length, error)
+    n = 5000
+    plen, tlen, pats, txts = A.generate_pairs(43, n, length, error, rs)
+    packed, flags = A.pack_pairs(plen, tlen, pats, txts, rs)
+    pitch = pitch_of(rs) // 16 * 16
+    params = A.AlignParams(algo="wfa", max_score=ms, read_size=rs, backtrace=True, reduce=True)
+    res, cig, _ = A.align_packed(params, plen, tlen, packed, flags, cigar_pitch=pitch)
+    exp, eops = O.align("wfa", plen, tlen, pats, txts, max_score=ms, read_size=rs, backtrace=True, reduce=True, nthreads=8)
+    want = A.cigar_strings(oracle_results_to_aim(exp), eops)
+    assert int((res["status"] != 0).sum()) == 0
+    assert np.array_equal(res["score"], exp["score"])
+    assert [bytes(r).split(b"\0", 1)[0].decode() for r in cig] == want
