@@ -12,7 +12,7 @@ CXX_SRCS  := $(CSRC)/aim_host.cpp
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CXX_SRCS))
 HDRS      := include/aim_b200.h $(CSRC)/aim_internal.h $(CSRC)/aim_wfa_common.cuh
 
-all: aim_b200/libaim_b200.so aim_b200/libaim_dpu.so build/host build/aim_genpairs oracle/libaim_oracle.so
+all: aim_b200/libaim_b200.so aim_b200/libaim_dpu.so build/host build/aim_genpairs build/diag_xfer oracle/libaim_oracle.so
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -32,6 +32,11 @@ aim_b200/libaim_dpu.so: $(CSRC)/aim_dpu.cpp include/dpu.h include/aim_b200.h aim
 build/host: tools/host.cpp aim_b200/libaim_b200.so include/aim_b200.h
 	@mkdir -p build
 	$(CXX) -O2 -std=c++17 -Wall -Iinclude tools/host.cpp -o $@ -Laim_b200 -laim_b200 -Wl,-rpath,'$$ORIGIN/../aim_b200' -lpthread -ldl
+
+# copy-only host<->device ceiling for 1..N GPUs
+build/diag_xfer: tools/diag_xfer.cu
+	@mkdir -p build
+	$(NVCC) -O2 -std=c++17 $(ARCH) -cudart static tools/diag_xfer.cu -o $@ -lpthread
 
 # stand-alone pair-file generator for bench.py's reference arm (host-only code, no CUDA, no libaim_b200.so)
 build/aim_genpairs: tools/genpairs.cpp $(CSRC)/aim_host.cpp $(HDRS)

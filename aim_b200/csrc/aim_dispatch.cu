@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -173,9 +174,29 @@ int launch(const KernelArgs &a, Scratch *s, cudaStream_t stream, int *launches)
     return rc != AIM_OK ? rc : rc2;
 }
 
-// One GPU's share [first, first + n) of a host batch.
+// Chunk size (pairs) of the host pipeline: big enough to fill the GPU many times over, small enough that pipeline
+// fill/drain is short (the full-table DP kernels hold one pair per thread for milliseconds: give them several times the
+// resident thread count per chunk so the last, partially filled pass stays short; long reads: a chunk must hold several
+// pairs per resident pair slot, ~6.5 K slots on a B200).  With several GPUs pulling chunks from one queue the batch is cut
+// into at least ~4 chunks per GPU so that variable-cost pairs (long reads) balance.
+uint32_t pick_chunk_pairs(const aim_params &p, uint32_t n, size_t per_pair, int ngpus)
+{
+    size_t chunk_bytes = (p.algo != AIM_ALGO_WFA) ? (384u << 20) : (p.read_size >= 2048 ? (768u << 20) : (96u << 20));
+    if (const char *cm = getenv("AIM_CHUNK_MB")) { const long v = atol(cm); if (v >= 1 && v <= 4096) chunk_bytes = (size_t)v << 20; }
+    uint32_t chunk_pairs = (uint32_t)std::max<size_t>(16384, std::min<size_t>(chunk_bytes / per_pair, 1u << 20));
+    if (ngpus > 1) {
+        const uint32_t floor_pairs = p.read_size >= 2048 ? 4096u : 16384u;
+        chunk_pairs = std::max(floor_pairs, std::min(chunk_pairs, n / (4u * (uint32_t)ngpus)));
+    }
+    return std::max(1u, std::min(chunk_pairs, n));
+}
+
+// One GPU's work on a host batch of n pairs: chunks of chunk_pairs pairs are PULLED from `queue` (shared by the GPUs of an
+// ngpus > 1 call: SURVEY 8e, variable-cost pairs balance themselves; a private counter for a single GPU), each chunk
+// goes through upload / align / download on this GPU's three streams, results land at the chunk's offset of the caller's
+// arrays - already in pair order.
 // cigars != NULL (aim_align_batch_cigars): the op rows stay on the device and pitch-byte CIGAR text rows come back instead.
-int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint32_t idx_base,
+int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uint32_t chunk_pairs, uint32_t n, uint32_t idx_base,
               const int32_t *plen, const int32_t *tlen, const char *patterns, const char *texts,
               aim_result *results, char *ops, double phase_ms[3], std::string *err, char *cigars = nullptr, int32_t pitch = 0)
 {
@@ -189,25 +210,11 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
 
     const size_t rs = (size_t)p.read_size;
     const bool bt = p.backtrace != 0;
-    plen += first; tlen += first;
-    patterns += (size_t)first * rs; texts += (size_t)first * rs;
-    results += first;
-    if (ops) ops += (size_t)first * 2 * rs;
-    if (cigars) cigars += (size_t)first * (size_t)pitch;
     const bool pin_in = is_pinned(plen) && is_pinned(tlen) && is_pinned(patterns) && is_pinned(texts);
     // (CIGAR rows are copied straight into the caller's buffer, pinned or not: no staging copy for them)
     const bool pin_out = cigars ? true : (is_pinned(results) && (!bt || is_pinned(ops)));
     const bool staging = !(pin_in && pin_out);
 
-    const size_t per_pair = 2 * rs + (cigars ? (size_t)pitch : (bt ? 2 * rs : 0)) + sizeof(aim_result) + 8;
-    // chunk: big enough to fill the GPU many times over, small enough that pipeline fill/drain is short
-    // (the full-table DP kernels hold one pair per thread for milliseconds: give them several times the
-    // resident thread count per chunk so the last, partially filled pass stays short)
-    // (long reads: a chunk must hold several pairs per resident pair slot, ~6.5 K slots on a B200)
-    size_t chunk_bytes = (p.algo != AIM_ALGO_WFA) ? (384u << 20) : (p.read_size >= 2048 ? (768u << 20) : (96u << 20));
-    if (const char *cm = getenv("AIM_CHUNK_MB")) { const long v = atol(cm); if (v >= 1 && v <= 4096) chunk_bytes = (size_t)v << 20; }
-    uint32_t chunk_pairs = (uint32_t)std::max<size_t>(16384, std::min<size_t>(chunk_bytes / per_pair, 1u << 20));
-    chunk_pairs = std::min(chunk_pairs, n);
     const uint32_t nchunks = (n + chunk_pairs - 1) / chunk_pairs;
     const int nbuf = (int)std::min<uint32_t>(kNumBuf, nchunks);
     if (!ctx->s_h2d) {
@@ -228,16 +235,16 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
         }
     }
     double ph[3] = {0, 0, 0};
-    std::vector<uint32_t> cn(nchunks);
+    std::vector<uint32_t> mine;  // chunks this GPU pulled, in pull order (the j-th uses buffer j % nbuf)
 
-    auto finish = [&](uint32_t c) -> int {
-        ChunkBuf &B = ctx->chunk[c % (uint32_t)nbuf];
-        const uint32_t off = c * chunk_pairs, m = cn[c];
+    auto finish = [&](uint32_t j) -> int {
+        ChunkBuf &B = ctx->chunk[j % (uint32_t)nbuf];
+        const uint32_t off = mine[j] * chunk_pairs, m = std::min(chunk_pairs, n - off);
         cudaError_t e = cudaEventSynchronize(B.ev[5]);
         if (e != cudaSuccess) { set_error(std::string("chunk sync: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
         if (!pin_out) {
             memcpy(results + off, B.h_res, (size_t)m * sizeof(aim_result));
-            if (bt) memcpy(ops + (size_t)off * 2 * rs, B.h_ops, (size_t)m * 2 * rs);
+            if (bt && !cigars) memcpy(ops + (size_t)off * 2 * rs, B.h_ops, (size_t)m * 2 * rs);
         }
         float t;
         for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&t, B.ev[2 * k], B.ev[2 * k + 1]); ph[k] += t; }
@@ -246,11 +253,14 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
 
     // three-stage pipeline on three streams: all uploads in order on s_h2d, all kernels in order on s_kernel
     // (they share the per-device scratch), all downloads in order on s_d2h; events carry the dependencies.
-    for (uint32_t c = 0; c < nchunks; ++c) {
-        ChunkBuf &B = ctx->chunk[c % (uint32_t)nbuf];
-        if (c >= (uint32_t)nbuf) { rc = finish(c - (uint32_t)nbuf); if (rc != AIM_OK) return fail(rc); }
+    for (;;) {
+        const uint32_t c = queue->fetch_add(1u);
+        if (c >= nchunks) break;
+        const uint32_t j = (uint32_t)mine.size();
+        mine.push_back(c);
+        ChunkBuf &B = ctx->chunk[j % (uint32_t)nbuf];
+        if (j >= (uint32_t)nbuf) { rc = finish(j - (uint32_t)nbuf); if (rc != AIM_OK) return fail(rc); }
         const uint32_t off = c * chunk_pairs, m = std::min(chunk_pairs, n - off);
-        cn[c] = m;
         const int32_t *s_plen = plen + off, *s_tlen = tlen + off;
         {   // host.c:119-123 rejects reads longer than READ_SIZE (there: message + exit)
             int32_t lo = 0, hi = 0;
@@ -259,6 +269,7 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
                 hi = std::max(hi, std::max(s_plen[i], s_tlen[i]));
             }
             if (lo < 0 || hi > p.read_size) {
+                queue->store(nchunks);    // the other GPUs of this call stop pulling
                 cudaDeviceSynchronize();  // drain the chunks in flight before the caller reclaims its buffers
                 if (lo < 0) { set_error("negative sequence length"); return fail(AIM_ERR_ARG); }
                 set_error("READ LENGTH less than length of the input reads");
@@ -280,14 +291,14 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
 
         AIM_CUDA(cudaStreamWaitEvent(ctx->s_kernel, B.ev[1], 0));
         AIM_CUDA(cudaEventRecord(B.ev[2], ctx->s_kernel));
-        KernelArgs a{p, m, idx_base + first + off, B.d_plen, B.d_tlen, B.d_pat, B.d_txt, B.d_res, bt ? B.d_ops : nullptr};
+        KernelArgs a{p, m, idx_base + off, B.d_plen, B.d_tlen, B.d_pat, B.d_txt, B.d_res, bt ? B.d_ops : nullptr};
         rc = launch(a, &ctx->scratch, ctx->s_kernel, nullptr);
-        if (rc != AIM_OK) return fail(rc);
+        if (rc != AIM_OK) { queue->store(nchunks); cudaDeviceSynchronize(); return fail(rc); }
         if (cigars) {
             a.cigars = B.d_cig;
             a.cigar_pitch = pitch;
             rc = launch_cigar_rows(a, ctx->s_kernel, nullptr);
-            if (rc != AIM_OK) return fail(rc);
+            if (rc != AIM_OK) { queue->store(nchunks); cudaDeviceSynchronize(); return fail(rc); }
         }
         AIM_CUDA(cudaEventRecord(B.ev[3], ctx->s_kernel));
 
@@ -303,8 +314,9 @@ int run_shard(const aim_params &p, int device, uint32_t first, uint32_t n, uint3
         }
         AIM_CUDA(cudaEventRecord(B.ev[5], ctx->s_d2h));
     }
-    for (uint32_t c = (nchunks >= (uint32_t)nbuf ? nchunks - (uint32_t)nbuf : 0); c < nchunks; ++c) {
-        rc = finish(c);
+    const uint32_t pulled = (uint32_t)mine.size();
+    for (uint32_t j = (pulled >= (uint32_t)nbuf ? pulled - (uint32_t)nbuf : 0); j < pulled; ++j) {
+        rc = finish(j);
         if (rc != AIM_OK) return fail(rc);
     }
     if (phase_ms) for (int k = 0; k < 3; ++k) phase_ms[k] = ph[k];
@@ -624,18 +636,21 @@ static int align_batch_impl(const aim_params *params, uint32_t n, uint32_t idx_b
     if (ndev == 0) { set_error("no CUDA device (aim_b200 has no CPU fallback)"); return AIM_ERR_NO_DEVICE; }
     int g = params->ngpus <= 1 ? 1 : params->ngpus;
     if (params->device < 0 || params->device + g > ndev) { set_error("device range exceeds visible GPUs"); return AIM_ERR_ARG; }
-    if (g == 1) return run_shard(*params, params->device, 0, n, idx_base, plen, tlen, patterns, texts, results, ops, phase_ms, nullptr, cigars, pitch);
+    const size_t per_pair = 2 * (size_t)params->read_size + (cigars ? (size_t)pitch : (params->backtrace ? 2 * (size_t)params->read_size : 0)) + sizeof(aim_result) + 8;
+    const uint32_t chunk_pairs = pick_chunk_pairs(*params, n, per_pair, g);
+    std::atomic<uint32_t> queue{0};
+    if (n == 0) return AIM_OK;
+    if (g == 1) return run_shard(*params, params->device, &queue, chunk_pairs, n, idx_base, plen, tlen, patterns, texts, results, ops, phase_ms, nullptr, cigars, pitch);
 
-    // contiguous index ranges per GPU, one host thread + stream set each (host.c:201-209 per DPU)
-    const uint32_t per = (n + (uint32_t)g - 1) / (uint32_t)g;
+    // one host thread + stream set per GPU, all pulling chunks from one queue (the reference splits contiguously per DPU,
+    // host.c:201-209; a queue gives the same output - every chunk lands at its own offset - and balances uneven pairs)
     std::vector<std::thread> th;
     std::vector<int> rcs((size_t)g, AIM_OK);
     std::vector<std::string> errs((size_t)g);
     std::vector<double> ph((size_t)g * 3, 0.0);
     for (int d = 0; d < g; ++d) {
-        const uint32_t first = std::min(n, (uint32_t)d * per), cnt = std::min(per, n - first);
-        th.emplace_back([&, d, first, cnt]() {
-            rcs[(size_t)d] = run_shard(*params, params->device + d, first, cnt, idx_base, plen, tlen, patterns, texts,
+        th.emplace_back([&, d]() {
+            rcs[(size_t)d] = run_shard(*params, params->device + d, &queue, chunk_pairs, n, idx_base, plen, tlen, patterns, texts,
                                        results, ops, &ph[(size_t)d * 3], &errs[(size_t)d], cigars, pitch);
             if (rcs[(size_t)d] != AIM_OK && errs[(size_t)d].empty()) errs[(size_t)d] = aim_last_error();
         });

@@ -1,5 +1,6 @@
-"""GPU, needs >= 2 devices (skipped otherwise): in-process sharding (aim_params.ngpus) of aim_align_batch and aim_align_packed -
-contiguous index ranges per GPU, one host thread + stream set each, results in pair order (host.c:201-209 per DPU)."""
+"""GPU, needs >= 2 devices (skipped otherwise): in-process sharding (aim_params.ngpus) of aim_align_batch (chunks pulled from one
+queue by one host thread + stream set per GPU) and aim_align_packed (contiguous index ranges), results in pair order
+(host.c:201-209 per DPU)."""
 import numpy as np
 import pytest
 
@@ -49,3 +50,16 @@ def test_sharded_packed_equals_single_gpu():
         rows1 = [bytes(c1[i]).split(b"\0", 1)[0] for i in np.nonzero(ok)[0][::211]]
         rowsg = [bytes(cg[i]).split(b"\0", 1)[0] for i in np.nonzero(ok)[0][::211]]
         assert rows1 == rowsg
+
+
+def test_chunk_queue_long_reads_equals_single_gpu():
+    """Variable-cost pairs (long reads, adaptive) through the chunk queue: same bytes as one GPU, whatever GPU took which chunk."""
+    _need(2)
+    ms, rs = A.derive_knobs("wfa", 3000, 0.10)
+    n = 20_003
+    arrays = A.generate_pairs(92, n, 3000, 0.10, rs)
+    kw = dict(algo="wfa", max_score=ms, read_size=rs, backtrace=False, reduce=True)
+    one, _, _ = A.align_batch(A.AlignParams(**kw), *arrays, idx_base=11)
+    for g in (2, A.device_count()):
+        many, _, _ = A.align_batch(A.AlignParams(ngpus=g, **kw), *arrays, idx_base=11)
+        assert np.array_equal(one, many), f"results differ with ngpus={g}"
