@@ -7,7 +7,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Iinclude -Iaim_b200/csrc -Xcompiler -fPIC,-Wall,-Wextra -cudart static $(EXTRA_NVFLAGS)
 CSRC      := aim_b200/csrc
 OBJDIR    := build/obj
-CU_SRCS   := $(CSRC)/aim_wfa.cu $(CSRC)/aim_wfa_sub.cu $(CSRC)/aim_wfa_long.cu $(CSRC)/aim_dp.cu $(CSRC)/aim_dp_fast.cu $(CSRC)/aim_genasm.cu $(CSRC)/aim_dispatch.cu $(CSRC)/aim_peak.cu
+CU_SRCS   := $(CSRC)/aim_wfa.cu $(CSRC)/aim_wfa_sub.cu $(CSRC)/aim_wfa_long.cu $(CSRC)/aim_dp.cu $(CSRC)/aim_dp_fast.cu $(CSRC)/aim_genasm.cu $(CSRC)/aim_dispatch.cu $(CSRC)/aim_file.cu $(CSRC)/aim_filepipe.cu $(CSRC)/aim_peak.cu
 CXX_SRCS  := $(CSRC)/aim_host.cpp
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CXX_SRCS))
 HDRS      := include/aim_b200.h $(CSRC)/aim_internal.h $(CSRC)/aim_wfa_common.cuh

@@ -3,10 +3,10 @@ path safaad/aim offloads to UPMEM DPUs.  Thin Python over the C ABI in include/a
 from .api import (align_batch_cigars, align_packed, pack_pairs, packed_row_bytes, write_results_packed,
                   ALGO_GENASM_DC, ALGO_GENASM_FILTER, ALGO_NW, ALGO_SWG, ALGO_WFA, RESULT_DTYPE, STATUS_GENASM_NOALIGN,
                   STATUS_GENASM_UNDEFINED, AimError, AlignParams, PinnedArray, align_batch,
-                  align_device, cigar_strings, count_pairs, derive_knobs, device_count, generate_pairs,
+                  align_device, align_file, cigar_strings, count_pairs, derive_knobs, device_count, generate_pairs,
                   measure_int_peak, pairs_to_process, read_pairs, shutdown, write_pairs, write_results,
                   write_results_genasm)
 
 __all__ = ["align_batch_cigars", "align_packed", "pack_pairs", "packed_row_bytes", "write_results_packed", "ALGO_GENASM_DC", "ALGO_GENASM_FILTER", "STATUS_GENASM_NOALIGN", "STATUS_GENASM_UNDEFINED", "write_results_genasm", "ALGO_NW", "ALGO_SWG", "ALGO_WFA", "RESULT_DTYPE", "AimError", "AlignParams", "PinnedArray",
-           "align_batch", "align_device", "cigar_strings", "count_pairs", "derive_knobs", "device_count",
+           "align_batch", "align_device", "align_file", "cigar_strings", "count_pairs", "derive_knobs", "device_count",
            "generate_pairs", "measure_int_peak", "pairs_to_process", "read_pairs", "shutdown", "write_pairs", "write_results"]

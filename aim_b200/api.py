@@ -166,6 +166,18 @@ def align_batch(params: AlignParams, plen, tlen, patterns, texts, idx_base: int 
     return results, (ops if params.backtrace else None), list(phase)
 
 
+def align_file(params: AlignParams, pairs_path, out_path, n_arg: int, nr_dpus: int = 1):
+    """aim_align_file: `host <pairs> <out> <N>` as one streaming call, parsed and printed on the GPU
+    -> (pairs_done, status_mask, phase_ms[3], launches)."""
+    done, mask, nl = C.c_uint64(0), C.c_uint32(0), C.c_int32(0)
+    phase = (C.c_double * 3)()
+    p = params.to_c()
+    rc = lib.aim_align_file(C.byref(p), os.fsencode(pairs_path), os.fsencode(out_path), n_arg, nr_dpus, C.byref(done), C.byref(mask), phase, C.byref(nl))
+    if rc != 0:
+        raise AimError(rc)
+    return int(done.value), int(mask.value), list(phase), int(nl.value)
+
+
 def align_device(params: AlignParams, n: int, d_plen: int, d_tlen: int, d_patterns: int, d_texts: int,
                  d_results: int, d_ops: int | None, stream: int = 0, device: int = 0, timed: bool = True):
     """aim_align_device on raw device addresses -> (kernel_ms | None, launches)."""

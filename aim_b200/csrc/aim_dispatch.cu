@@ -469,6 +469,20 @@ int scratch_reserve(Scratch *s, size_t bytes)
     return AIM_OK;
 }
 
+int device_state(int device, Scratch **scratch, void **mu)
+{
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(device, &ctx);
+    if (rc != AIM_OK) return rc;
+    *scratch = &ctx->scratch;
+    *mu = &ctx->mu;
+    return AIM_OK;
+}
+
+int launch_algo(const KernelArgs &a, Scratch *s, void *stream, int *launches) { return launch(a, s, (cudaStream_t)stream, launches); }
+
+bool params_valid_for_file(const aim_params *p) { return validate(p, false, nullptr) == AIM_OK; }
+
 namespace {
 struct PlanEntry { std::vector<unsigned char> host; void *dev; };
 struct PlanCache { std::vector<PlanEntry> e; };
@@ -568,6 +582,7 @@ extern "C" void aim_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" void aim_shutdown(void)
 {
+    file_pipeline_shutdown();
     std::lock_guard<std::mutex> lk(g_mu);
     for (DeviceCtx *c : g_ctx) {
         if (!c) continue;

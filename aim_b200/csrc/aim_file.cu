@@ -230,11 +230,13 @@ __global__ void __launch_bounds__(128) fmt_len_kernel(const aim_result *results,
     lens[i] = len;
 }
 
+// (nothing is written when the chunk's text does not fit the buffer: counters[2] = total bytes; the host grows the buffer
+// and runs this kernel again)
 __global__ void __launch_bounds__(128) fmt_write_kernel(const aim_result *results, const char *ops, int RS, int bt, uint32_t m,
-                                                        const uint32_t *offs, char *out)
+                                                        const uint32_t *offs, const uint32_t *counters, size_t out_cap, char *out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+    if (i >= m || (size_t)counters[2] > out_cap) return;
     const aim_result r = results[i];
     char *o = out + offs[i];
     o = put_int(o, (int)r.idx);  // the reference prints the uint32 idx with %d
@@ -320,7 +322,7 @@ int launch_file_parse(const char *d_buf, size_t nbytes, uint32_t lines, int unte
 // Output text of m pairs, densely packed at d_out; d_lens / d_offs: m words each; d_tiles: file_format_scratch_bytes();
 // counters[2] receives the total byte count, counters[3] the OR of (1 << status) over the pairs.
 int launch_file_format(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, uint32_t m, uint32_t *d_lens, uint32_t *d_offs,
-                       uint32_t *d_tiles, uint32_t *d_counters, char *d_out, void *stream_v, int *launches)
+                       uint32_t *d_tiles, uint32_t *d_counters, char *d_out, size_t out_cap, void *stream_v, int *launches)
 {
     cudaStream_t st = (cudaStream_t)stream_v;
     if (m == 0) return AIM_OK;
@@ -329,9 +331,19 @@ int launch_file_format(const aim_result *d_res, const char *d_ops, int read_size
     scan_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(d_lens, m, d_tiles);
     tile_scan_kernel<<<1, 1024, 0, st>>>(d_tiles, ntiles, d_counters + 2);
     scan_local_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(d_lens, m, d_tiles, d_offs);
-    fmt_write_kernel<<<(m + 127) / 128, 128, 0, st>>>(d_res, d_ops, read_size, backtrace, m, d_offs, d_out);
+    fmt_write_kernel<<<(m + 127) / 128, 128, 0, st>>>(d_res, d_ops, read_size, backtrace, m, d_offs, d_counters, out_cap, d_out);
     if (cudaGetLastError() != cudaSuccess) { set_error("file format launch failed"); return AIM_ERR_CUDA; }
     if (launches) *launches += 5;
+    return AIM_OK;
+}
+
+int launch_file_format_write(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, uint32_t m, const uint32_t *d_offs,
+                             const uint32_t *d_counters, char *d_out, size_t out_cap, void *stream_v, int *launches)
+{
+    if (m == 0) return AIM_OK;
+    fmt_write_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(d_res, d_ops, read_size, backtrace, m, d_offs, d_counters, out_cap, d_out);
+    if (cudaGetLastError() != cudaSuccess) { set_error("file format launch failed"); return AIM_ERR_CUDA; }
+    if (launches) ++*launches;
     return AIM_OK;
 }
 

@@ -18,9 +18,44 @@
 #include <thread>
 #include <vector>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 namespace aim {
 thread_local std::string g_last_error;
 void set_error(const std::string &msg) { g_last_error = msg; }
+
+// Number of '\n' bytes in [p, p + n): 32 bytes per step with AVX2 where the CPU has it (the file pipeline counts the
+// newlines of every chunk it reads, at memory speed), 8 bytes per step otherwise.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static size_t count_newlines_avx2(const char *p, size_t n)
+{
+    const __m256i nl = _mm256_set1_epi8('\n');
+    size_t c = 0, i = 0;
+    for (; i + 32 <= n; i += 32)
+        c += (size_t)__builtin_popcount((unsigned)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i *)(p + i)), nl)));
+    for (; i < n; ++i) c += p[i] == '\n';
+    return c;
+}
+#endif
+size_t count_newlines(const char *p, size_t n)
+{
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) return count_newlines_avx2(p, n);
+#endif
+    size_t c = 0, i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        w ^= 0x0a0a0a0a0a0a0a0aull;  // zero bytes where '\n'
+        const uint64_t nz = ((w & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | w;  // high bit of every NON-zero byte
+        c += (size_t)__builtin_popcountll(~nz & 0x8080808080808080ull);
+    }
+    for (; i < n; ++i) c += p[i] == '\n';
+    return c;
+}
 }  // namespace aim
 
 extern "C" const char *aim_last_error(void) { return aim::g_last_error.c_str(); }

@@ -217,6 +217,7 @@ def main() -> None:
                     help="bit-exact check of the step's results against the CPU oracle, outside the timed region "
                          "(auto: every pair for configs 2-4, a bounded sample for long reads / GenASM)")
     ap.add_argument("--parity-pairs", type=int, default=-1, help="pairs per rank to check (0 = all)")
+    ap.add_argument("--no-cli", action="store_true", help="skip the pair-file -> output-file leg (aim_align_file)")
     ap.add_argument("--no-inproc", action="store_true", help="skip the one-process aim_align_batch(ngpus=N) leg at N>1")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -383,6 +384,35 @@ def main() -> None:
                       "d2h_bytes_per_step": int(P * (A.RESULT_DTYPE.itemsize + cpitch)), "ms_per_step": tc_s * 1e3,
                       "api": "aim_align_batch_cigars (C ABI extension): the reference's input buffers, CIGAR text rows out, pinned host buffers"}
 
+    # ---- end-to-end at the PROCESS boundary: pair file (page cache) -> output file, through aim_align_file (what `host <pairs> <out> <N>`
+    # runs): file bytes up, parsed on the GPU, aligned, output text formatted on the GPU, text down, write() ----
+    e2e_cli = None
+    cli_out_path = None
+    if not args.no_e2e and not genasm and not args.no_cli:
+        shm = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path(tempfile.gettempdir())
+        cli_dir = Path(tempfile.mkdtemp(prefix=f"aimcli{rank}_", dir=shm))
+        pairs_path, cli_out_path = cli_dir / "in.pairs", cli_dir / "out"
+        A.write_pairs(pairs_path, h_plen.array, h_tlen.array, h_pat.array, h_txt.array)
+        file_bytes = pairs_path.stat().st_size
+
+        def cli_step():
+            return A.align_file(params, pairs_path, cli_out_path, P, 1)
+        cli_step()
+        barrier()
+        t0 = time.perf_counter()
+        nst = max(2, min(args.steps, 5))
+        for _ in range(nst):
+            done, smask, cph, cl = cli_step()
+        tcli_s = shard.max_over_ranks((time.perf_counter() - t0) / nst, dev)
+        assert done == P and smask == 0, f"bench: aim_align_file aligned {done} of {P} pairs, status mask {smask}"
+        out_bytes = cli_out_path.stat().st_size
+        e2e_cli = {"value": world * P / tcli_s, "unit": "pairs/s", "ms_per_step": tcli_s * 1e3, "pair_file_bytes": file_bytes, "output_file_bytes": out_bytes,
+                   "h2d_bytes_per_step": file_bytes, "d2h_bytes_per_step": out_bytes, "gpu_launches_per_step": cl,
+                   "phase_ms_h2d_kernels_d2h": cph,
+                   "api": "aim_align_file (C ABI; what `host <pairs> <out> <N>` calls): pair file in the page cache -> output file; get_reads and the "
+                          "print loop run as GPU kernels, host threads only read() and write(); buffers allocated and freed inside the call"}
+        pairs_path.unlink()
+
     # ---- parity: this step's results against the CPU oracle, bit-exact, OUTSIDE every timed region ----
     # Checked: the end-to-end arm's output (scores, spans and op bytes as they arrive in the caller's host buffers through
     # the C ABI); the device-resident arm's buffers must then be byte-identical to those.  Every rank checks its own pairs.
@@ -419,13 +449,20 @@ def main() -> None:
             if e2e_packed is not None:
                 assert np.array_equal(h_res2.array["score"], h_res.array["score"]) and np.array_equal(h_res3.array["begin_offset"], h_res.array["begin_offset"])
             cig_checked = len(samp)
+        cli_same = None
+        if e2e_cli is not None and not args.no_e2e:  # the CLI path's output file == the host printer's text of the checked results
+            ref_out = cli_out_path.with_name("expect")
+            A.write_results(ref_out, h_res.array, h_ops.array if bt else None, rs, bt)
+            cli_same = subprocess.run(["cmp", "-s", str(ref_out), str(cli_out_path)]).returncode == 0
+            ref_out.unlink()
+            assert cli_same, "bench: aim_align_file's output file differs from the printed text of the checked results"
         tot = torch.tensor([pr["pairs_checked"], pr["mismatches"], 0 if dev_same else 1], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(tot)
         parity = {"pairs_checked": int(tot[0]), "mismatches": int(tot[1]), "device_arm_differs_on_ranks": int(tot[2]),
                   "against": "oracle/aim_oracle.c (C restatement pinned on the reference's outputs), score + status + begin/end offsets + op bytes of the span",
                   "checked_output": "aim_align_batch host buffers (e2e arm); device-resident buffers byte-compared to them",
-                  "stride": stride, "cigar_text_rows_checked_per_rank": cig_checked, "oracle_threads_per_rank": threads,
+                  "stride": stride, "cigar_text_rows_checked_per_rank": cig_checked, "cli_output_file_identical": cli_same, "oracle_threads_per_rank": threads,
                   "seconds": time.perf_counter() - tpar0, "first_bad_rank0": pr["first_bad"]}
         assert parity["mismatches"] == 0 and parity["device_arm_differs_on_ranks"] == 0, f"bench: PARITY FAILURE {parity}"
 
@@ -520,11 +557,14 @@ def main() -> None:
             "scaling": "weak", "vs_baseline": None, "dtype": "u64" if genasm else "int16", "data": "synthetic",
             "config": config_dict(cfg, P, world), "mean_score": mean_score, "parity": parity, "inproc_ngpus": inproc,
             "gcups_equiv": pl_mean * tl_mean * world * P / (ms_per_step * 1e-3) / 1e9,
-            "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "e2e_cigars": e2e_cigars, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "e2e_cigars": e2e_cigars, "e2e_cli": e2e_cli, "gpu_launches": launches,
             "roofline": roofline, "int_roofline": int_roofline, "cpu_baseline": cpu_baseline,
             "step_ms": step_ms,
         }
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if cli_out_path is not None:
+        import shutil
+        shutil.rmtree(cli_out_path.parent, ignore_errors=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -6,6 +6,9 @@
 //   AIM_ALGO=nw|swg|wfa|genasm_dc|genasm_filter  MAX_SCORE READ_SIZE MATCH MISMATCH GAP_O GAP_E (GAP_I/GAP_D for NW)
 //   BACKTRACE=0|1  REDUCE=0|1  NR_DPUS (only feeds the pairs-to-process rule, host.c:191)
 //   NR_TASKLETS WRAM_SEGMENT (accepted, ignored)  AIM_NGPUS  AIM_DEVICE  AIM_VARIANT=wram|mram
+//   AIM_HOST_PATH=stream|batch  stream (default for NW/SWG/WFA): aim_align_file - the pair file is parsed and the output
+//                               text formatted ON THE GPU, host threads only read() and write();  batch: get_reads on the
+//                               host (aim_read_pairs) + aim_align_batch[_cigars] + the host printer (GenASM always)
 #include <sys/time.h>
 
 #include <algorithm>
@@ -95,6 +98,46 @@ int main(int argc, char *argv[])
     printf("Allocated %d DPU(s)\n", (int)nr_dpus);  // host.c:189
     const uint32_t nb_reads_per_dpu = (uint32_t)(((total_nb_reads / nr_dpus) + 7) / 8 * 8);
     printf("NumReads per dpu = %u\n", nb_reads_per_dpu);  // host.c:192
+
+    const char *path_s = getenv("AIM_HOST_PATH");
+    if (!genasm && !(path_s && std::string(path_s) == "batch")) {
+        // ---- streaming path: host.c:196-353 as one call ----
+        uint64_t done = 0;
+        uint32_t status_mask = 0;
+        double phase[3] = {0, 0, 0};
+        const double t0 = now_s();
+        const int rc = aim_align_file(&p, in, out, total_nb_reads, nr_dpus, &done, &status_mask, phase, nullptr);
+        const double wall_ms = (now_s() - t0) * 1e3;
+        if (rc == AIM_ERR_LENGTH) {  // host.c:119-123
+            printf("READ LENGTH less than length of the input reads");
+            exit(0);
+        }
+        if (rc != AIM_OK) {
+            fprintf(stderr, "aim_b200: %s: %s\n", aim_strerror(rc), aim_last_error());
+            exit(1);
+        }
+        const bool nw = p.algo == AIM_ALGO_NW;
+        printf("Copying data to DPU\n");
+        printf("CPU-DPU: %f ms\n", phase[0]);
+        printf("Run program on DPU(s)\n");
+        printf((nw && variant == "wram") ? "DPU Kernel Time: %f ms\n" : "DPU Kernel: %f ms\n", phase[1]);
+        printf("Retrieve results\n");
+        printf(nw ? "DPU-CPU Time: %f ms\n" : "DPU-CPU: %f ms\n", phase[2]);
+        if (getenv("AIM_VERBOSE")) printf("B200 pipeline wall: %f ms (%llu pairs, %d GPU(s), parsed and printed on the GPU)\n", wall_ms, (unsigned long long)done, p.ngpus);
+        // the reference exits the whole process on a backtrace dead end (swg.c:131-133, wfa_backtracing.c:343-344) or when the
+        // history store runs out of MRAM (dpu_allocator_mram.c:6-10); aim_align_file left the output file empty
+        if (status_mask & (1u << AIM_STATUS_BACKTRACE)) {
+            printf(p.algo == AIM_ALGO_SWG ? "SWG backtrace. No backtrace operation found" : "Backtrace error: No link found during backtrace\n");
+            exit(1);
+        }
+        if (status_mask & (1u << AIM_STATUS_ARENA)) {
+            printf("Out of memory MRAM\n");
+            exit(-1);
+        }
+        if (dpu_file) fclose(dpu_file);
+        aim_shutdown();
+        return 0;
+    }
 
     const uint64_t cap = (uint64_t)nb_reads_per_dpu * nr_dpus;
     int64_t in_file = aim_count_pairs(in);
