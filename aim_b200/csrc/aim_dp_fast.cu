@@ -114,15 +114,17 @@ __device__ __forceinline__ int dp_cell(int upM, int &upI, int leftM, int &leftD,
         ins = min(i1, i2);
         dI = i2 - i1;
         const int d1 = leftM + OE, d2 = leftD + E;
-        del = min(d1, d2);
+        del = __viaddmin_s32(leftM, OE, d2);  // VIADDMNMX: one instruction from leftM to del
         dD = d2 - d1;
         upI = ins;
         leftD = del;
     }
+    // The serial chain of a row runs through leftM: with the DPX forms it is two instructions per cell (leftM -> del -> M:
+    // VIADDMNMX, VIMNMX3) instead of four (add, min, min, min); the differences that carry the predicates hang off it.
     const int m1 = min(del, ins);
     dP = ins - del;
     dQ = mm - m1;
-    return min(m1, mm);
+    return __vimin3_s32(del, ins, mm);
 }
 
 // append the sign bit of d to the accumulator (one SHF.L.W)
@@ -280,6 +282,8 @@ __global__ void __launch_bounds__(128) dp_strip_kernel(const FastK K)
         K.results[i] = res;
     }
 }
+
+#include "aim_dp_pack2.cuh"
 
 // ================= aliased pairs: serial row-major fill, row in shared memory =================
 // Shared memory per thread: (RS+1) row words [column][lane] (NW: M; SWG: M | I << 16).  Pattern bases
@@ -590,19 +594,35 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     const uint32_t wpr = ((uint32_t)RS + 15) / 16;     // records per row (row kernels)
     const int nstrips_max = (RS + KS - 1) / KS;
 
+    // two pairs per thread in s16x2 lanes (aim_dp_pack2.cuh): every value must be a NON-NEGATIVE int16, i.e. MATCH == 0 (NW ignores MATCH)
+    bool pack = nw || p.match == 0;
+    if (const char *e = getenv("AIM_DP_PACK")) pack = pack && atoi(e) != 0;
+    // the packed ROW kernel (aliased pairs) is selectable: at READ_SIZE 272 its shared-memory row holds 3 warps of 64 pairs per
+    // SM against the one-pair-per-thread kernels' 8 warps of 32, and measures slower (54.9 against 39 ms per 420 K pairs)
+    bool pack_row = false;
+    if (const char *e = getenv("AIM_DP_PACK_ROW")) pack_row = atoi(e) != 0;
+    pack_row = pack_row && pack;
     // grids: persistent threads striding over the lists, sized by what is actually resident
     const int strip_block = 128;
     int strip_bps = 0;
     {
         cudaError_t oe;
-        if (nw) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&strip_bps, dp_strip_kernel<AIM_ALGO_NW, true>, strip_block, 0);
+        if (pack) oe = nw ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&strip_bps, dp2_strip_kernel<AIM_ALGO_NW>, strip_block, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&strip_bps, dp2_strip_kernel<AIM_ALGO_SWG>, strip_block, 0);
+        else if (nw) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&strip_bps, dp_strip_kernel<AIM_ALGO_NW, true>, strip_block, 0);
         else if (p.match == 0) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&strip_bps, dp_strip_kernel<AIM_ALGO_SWG, true>, strip_block, 0);
         else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&strip_bps, dp_strip_kernel<AIM_ALGO_SWG, false>, strip_block, 0);
         if (oe != cudaSuccess || strip_bps < 1) { cudaGetLastError(); strip_bps = 4; }
     }
+    if (pack) {  // a thread carries two pairs: half the threads keep the same pairs in flight (and the same scratch)
+        int cap = 4;
+        if (const char *e = getenv("AIM_DP_PACK_BPS")) { const int v = atoi(e); if (v >= 1 && v <= 16) cap = v; }
+        strip_bps = std::min(strip_bps, cap);
+    }
     int strip_grid = sc->sm_count * strip_bps;
-    strip_grid = (int)std::min<uint64_t>((uint64_t)strip_grid, ((uint64_t)a.n + strip_block - 1) / strip_block);
+    strip_grid = (int)std::min<uint64_t>((uint64_t)strip_grid, ((uint64_t)a.n / (pack ? 2 : 1) + strip_block - 1) / strip_block + 1);
     const size_t strip_threads = (size_t)strip_grid * strip_block;
+    const size_t strip_mul = pack ? 2 : 1;  // scratch per thread: boundary words and flag words per record double
 
     // row kernels: launch helper (sets the shared-memory attribute, asks the occupancy, returns the grid)
     struct RowLaunch { void (*fn)(const FastK); size_t smem; int grid; };
@@ -625,20 +645,34 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         out->grid = (int)std::min<uint64_t>((uint64_t)sc->sm_count * (uint64_t)bps, ((uint64_t)a.n + RT - 1) / RT);
         return cudaSuccess;
     };
+    // packed row kernel (two aliased pairs of equal text_len per thread): the row of both pairs in shared memory
+    const size_t row2_smem = ((size_t)RS + 1) * (nw ? 1 : 2) * 4 * RT2;
+    int row2_grid = 0;
+    if (pack_row && row2_smem > kSmemBudget) pack_row = false;
+    if (pack_row) {
+        void (*fn)(const FastK) = nw ? dp2_row_kernel<AIM_ALGO_NW> : dp2_row_kernel<AIM_ALGO_SWG>;
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row2_smem);
+        int bps = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, (int)RT2, row2_smem);
+        if (e != cudaSuccess || bps < 1) { set_error(std::string("dp2_row setup: ") + cudaGetErrorString(e)); cudaGetLastError(); return AIM_ERR_CUDA; }
+        row2_grid = (int)std::min<uint64_t>((uint64_t)sc->sm_count * (uint64_t)bps, ((uint64_t)a.n / 2 + RT2) / RT2 + 1);
+    }
     RowLaunch L0{}, L1{};
     cudaError_t err = prep_row(0, psm0, pt0, bps0, &L0);
     if (err == cudaSuccess && reg_cols > 0) err = prep_row(reg_cols, psm1, pt1, bps1, &L1);
     if (err != cudaSuccess) { set_error(std::string("dp_fast setup: ") + cudaGetErrorString(err)); cudaGetLastError(); return AIM_ERR_CUDA; }
-    const size_t rowk_threads = (size_t)std::max(L0.grid, L1.grid) * row_threads;
+    const size_t rowk_threads = pack_row ? (size_t)row2_grid * RT2 : (size_t)std::max(L0.grid, L1.grid) * row_threads;
 
     // scratch: counters | list | list2 | strip boundary | strip flags | row flags
+    // (packed: list2 = the aliased pairs bucketed by text_len, every bucket starting on an even slot; hist = the buckets)
     const size_t off_list = 256;
     const size_t off_list2 = align_up(off_list + (size_t)a.n * 4, 256);
-    const size_t off_bound = align_up(off_list2 + (size_t)a.n * 4, 256);
-    const size_t off_sflags = align_up(off_bound + strip_threads * (size_t)RS * 4, 256);
-    const size_t sflag_bytes = p.backtrace ? strip_threads * (size_t)nstrips_max * RS * FW * 4 : 0;
+    const size_t off_hist = align_up(off_list2 + ((size_t)a.n + (size_t)RS + 4) * 4, 256);
+    const size_t off_bound = align_up(off_hist + ((size_t)RS + 2) * 4, 256);
+    const size_t off_sflags = align_up(off_bound + strip_threads * (size_t)RS * 4 * strip_mul, 256);
+    const size_t sflag_bytes = p.backtrace ? strip_threads * (size_t)nstrips_max * RS * FW * 4 * strip_mul : 0;
     const size_t off_rflags = align_up(off_sflags + sflag_bytes, 256);
-    const size_t rflag_bytes = p.backtrace ? rowk_threads * (size_t)RS * wpr * FW * 4 : 0;
+    const size_t rflag_bytes = p.backtrace ? rowk_threads * (size_t)RS * wpr * FW * 4 * (pack_row ? 2 : 1) : 0;
     int rc = scratch_reserve(sc, off_rflags + rflag_bytes);
     if (rc != AIM_OK) return rc;
     unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
@@ -654,24 +688,48 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     K.wpr = wpr;
     K.neg1 = -1;
 
+    uint32_t *hist = reinterpret_cast<uint32_t *>(base + off_hist);
     err = cudaMemsetAsync(counters, 0, 16, stream);
     if (err == cudaSuccess && p.backtrace) err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * RS, stream);
-    if (err == cudaSuccess) {
+    int nlaunch = 0;
+    if (err == cudaSuccess && pack_row) {
+        err = cudaMemsetAsync(hist, 0, ((size_t)RS + 2) * 4, stream);
+        if (err == cudaSuccess) err = cudaMemsetAsync(list2, 0xff, ((size_t)a.n + (size_t)RS + 4) * 4, stream);  // kNoPartner in the pad slots
+        if (err == cudaSuccess) {
+            classify2_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(a.plen, a.tlen, a.n, RS, list, counters, hist);
+            bucket_scan_kernel<<<1, 1024, 0, stream>>>(hist, (uint32_t)RS + 1, counters);
+            bucket_scatter_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(a.plen, a.tlen, a.n, RS, hist, list2);
+            err = cudaGetLastError();
+            nlaunch += 3;
+        }
+    } else if (err == cudaSuccess) {
         classify_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(a.plen, a.tlen, a.n, RS, reg_cols, list, list2, counters);
         err = cudaGetLastError();
+        ++nlaunch;
     }
     if (err == cudaSuccess) {
         FastK S = K;
         S.list = list; S.count = counters; S.list_step = 1;
         S.bound = reinterpret_cast<uint32_t *>(base + off_bound);
         S.flags = reinterpret_cast<uint32_t *>(base + off_sflags);
-        if (nw) dp_strip_kernel<AIM_ALGO_NW, true><<<strip_grid, strip_block, 0, stream>>>(S);
+        if (pack && nw) dp2_strip_kernel<AIM_ALGO_NW><<<strip_grid, strip_block, 0, stream>>>(S);
+        else if (pack) dp2_strip_kernel<AIM_ALGO_SWG><<<strip_grid, strip_block, 0, stream>>>(S);
+        else if (nw) dp_strip_kernel<AIM_ALGO_NW, true><<<strip_grid, strip_block, 0, stream>>>(S);
         else if (p.match == 0) dp_strip_kernel<AIM_ALGO_SWG, true><<<strip_grid, strip_block, 0, stream>>>(S);
         else dp_strip_kernel<AIM_ALGO_SWG, false><<<strip_grid, strip_block, 0, stream>>>(S);
         err = cudaGetLastError();
     }
-    int nlaunch = 2;
-    if (err == cudaSuccess && reg_cols > 0) {  // aliased pairs that fit the register-row variant
+    ++nlaunch;
+    if (err == cudaSuccess && pack_row) {  // all aliased pairs, two of equal text_len per thread
+        FastK R2 = K;
+        R2.list = list2; R2.count = counters + 1; R2.list_step = 1;
+        R2.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
+        if (nw) dp2_row_kernel<AIM_ALGO_NW><<<row2_grid, RT2, row2_smem, stream>>>(R2);
+        else dp2_row_kernel<AIM_ALGO_SWG><<<row2_grid, RT2, row2_smem, stream>>>(R2);
+        err = cudaGetLastError();
+        ++nlaunch;
+    }
+    if (err == cudaSuccess && !pack_row && reg_cols > 0) {  // aliased pairs that fit the register-row variant
         FastK Rr = K;
         Rr.list = list + (a.n - 1); Rr.count = counters + 1; Rr.list_step = -1;
         Rr.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
@@ -679,7 +737,7 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         err = cudaGetLastError();
         ++nlaunch;
     }
-    if (err == cudaSuccess) {  // the other aliased pairs (all of them when reg_cols == 0)
+    if (err == cudaSuccess && !pack_row) {  // the other aliased pairs (all of them when reg_cols == 0)
         FastK Rs = K;
         Rs.list = list2; Rs.count = counters + 2; Rs.list_step = 1;
         Rs.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
