@@ -635,7 +635,7 @@ extern "C" int aim_align_device(const aim_params *params, int device, uint32_t n
     return rc;
 }
 
-static int align_batch_impl(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen,
+static int align_batch_once(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen,
                             const int32_t *tlen, const char *patterns, const char *texts,
                             aim_result *results, char *ops, double phase_ms[3], char *cigars, int32_t pitch)
 {
@@ -674,6 +674,47 @@ static int align_batch_impl(const aim_params *params, uint32_t n, uint32_t idx_b
     for (int d = 0; d < g; ++d) {
         if (rcs[(size_t)d] != AIM_OK) { set_error("gpu " + std::to_string(params->device + d) + ": " + errs[(size_t)d]); return rcs[(size_t)d]; }
         if (phase_ms) for (int k = 0; k < 3; ++k) phase_ms[k] = std::max(phase_ms[k], ph[(size_t)d * 3 + k]);
+    }
+    return AIM_OK;
+}
+
+// aim_align_batch + arena-overflow recovery.  Long-read WFA with backtrace keeps a pair's wavefront history in a fixed arena
+// (the reference's per-tasklet MRAM segment; there a pair that outgrows it ends the run: "Out of memory MRAM",
+// dpu_allocator_mram.c:6-10).  Here such pairs come back flagged AIM_STATUS_ARENA and are aligned again, alone, with an arena
+// eight times larger, up to three times; what still does not fit keeps its flag.
+static int align_batch_impl(const aim_params *params, uint32_t n, uint32_t idx_base, const int32_t *plen,
+                            const int32_t *tlen, const char *patterns, const char *texts,
+                            aim_result *results, char *ops, double phase_ms[3], char *cigars, int32_t pitch)
+{
+    int rc = align_batch_once(params, n, idx_base, plen, tlen, patterns, texts, results, ops, phase_ms, cigars, pitch);
+    if (rc != AIM_OK || !params || params->algo != AIM_ALGO_WFA || !params->backtrace || params->read_size < 512 || n == 0) return rc;
+    aim_params q = normalized(params);
+    for (int round = 0; round < 3; ++round) {
+        std::vector<uint32_t> bad;
+        for (uint32_t i = 0; i < n; ++i) if (results[i].status == AIM_STATUS_ARENA) bad.push_back(i);
+        if (bad.empty()) break;
+        q.arena_mb = (q.arena_mb > 0 ? q.arena_mb : 8) * 8;
+        if (q.arena_mb > 4096) break;
+        const size_t rs = (size_t)q.read_size, m = bad.size();
+        std::vector<int32_t> pl(m), tl(m);
+        std::vector<char> pa(m * rs), tx(m * rs), op(cigars ? 0 : m * 2 * rs), cg(cigars ? m * (size_t)pitch : 0);
+        std::vector<aim_result> rr(m);
+        for (size_t k = 0; k < m; ++k) {
+            pl[k] = plen[bad[k]]; tl[k] = tlen[bad[k]];
+            memcpy(&pa[k * rs], patterns + (size_t)bad[k] * rs, rs);
+            memcpy(&tx[k * rs], texts + (size_t)bad[k] * rs, rs);
+        }
+        double ph[3] = {0, 0, 0};
+        rc = align_batch_once(&q, (uint32_t)m, 0, pl.data(), tl.data(), pa.data(), tx.data(), rr.data(), cigars ? nullptr : op.data(), ph,
+                              cigars ? cg.data() : nullptr, pitch);
+        if (rc != AIM_OK) return rc;
+        for (size_t k = 0; k < m; ++k) {
+            rr[k].idx = results[bad[k]].idx;
+            results[bad[k]] = rr[k];
+            if (cigars) memcpy(cigars + (size_t)bad[k] * (size_t)pitch, &cg[k * (size_t)pitch], (size_t)pitch);
+            else memcpy(ops + (size_t)bad[k] * 2 * rs, &op[k * 2 * rs], 2 * rs);
+        }
+        if (phase_ms) for (int k = 0; k < 3; ++k) phase_ms[k] += ph[k];
     }
     return AIM_OK;
 }

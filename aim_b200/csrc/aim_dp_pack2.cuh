@@ -304,6 +304,19 @@ __global__ void __launch_bounds__(RT2) dp2_row_kernel(const FastK K)
         const int nc = tl + 1, plm = max(plA, plB);
         int scoreA = 0, scoreB = 0;
 
+        // Pattern bytes do not change from row to row: record 0's and those of the first two records after the full head records
+        // (remaining head cells + aliased tail) stay in registers for the whole pair; the other records' are fetched one record ahead.
+        auto ld16 = [&](const char *gp, int off, uint2 &a, uint2 &b) {  // 16 bytes at gp + off (off a multiple of 16), zero past the row
+            a = off + 8 <= RS ? __ldg(reinterpret_cast<const uint2 *>(gp + off)) : make_uint2(0u, 0u);
+            b = off + 16 <= RS ? __ldg(reinterpret_cast<const uint2 *>(gp + off) + 1) : make_uint2(0u, 0u);
+        };
+        const int nfull = tl >> 4;       // full head records
+        const bool fast = nc >= 32;      // tail cells read cells at least 32 columns back: never inside the record being computed
+        uint2 p0[4], pg0[4], pg1[4];
+        ld16(gpA, 0, p0[0], p0[1]); ld16(gpB, 0, p0[2], p0[3]);
+        ld16(gpA, 16 * nfull, pg0[0], pg0[1]); ld16(gpB, 16 * nfull, pg0[2], pg0[3]);
+        ld16(gpA, 16 * nfull + 16, pg1[0], pg1[1]); ld16(gpB, 16 * nfull + 16, pg1[2], pg1[3]);
+
         // row 0 (nw.c:119-124 / swg.c:167-175); only the head columns of row 0 are ever read
         st(0, 0u, MS2);
         for (int v = 1; v <= tl; ++v) st(v, pack2::both(SWG ? O + v * E : v * OE), MS2);
@@ -334,8 +347,8 @@ __global__ void __launch_bounds__(RT2) dp2_row_kernel(const FastK K)
             if (tl >= 16) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { curM[j] = ldM(1 + j); curI[j] = ldI(1 + j); }
-                pcur[0] = __ldg(reinterpret_cast<const uint2 *>(gpA)); pcur[1] = __ldg(reinterpret_cast<const uint2 *>(gpA) + 1);
-                pcur[2] = __ldg(reinterpret_cast<const uint2 *>(gpB)); pcur[3] = __ldg(reinterpret_cast<const uint2 *>(gpB) + 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pcur[k] = p0[k];
             }
             for (; v + 15 <= tl; v += 16) {
                 const bool more = v + 31 <= tl;
@@ -373,8 +386,54 @@ __global__ void __launch_bounds__(RT2) dp2_row_kernel(const FastK K)
                     for (int k = 0; k < 4; ++k) pcur[k] = pnxt[k];
                 }
             }
-            // ---- the remaining head cells, then the aliased tail (columns nc..pl: "previous row" = the CURRENT row's head, flat
-            // word nc*(h-1)+v is cell (h, v-nc)); record bits are gathered until a record is complete ----
+            // ---- the remaining head cells, then the aliased tail (columns nc..pl: "previous row" = the CURRENT row's cells nc columns
+            // to the left, flat word nc*(h-1)+v is cell (h, v-nc)).  In flat terms nothing changes at column nc: the left chain runs
+            // on, up = word i-nc, diag = word i-nc-1.  So these columns are records like the others whose sixteen "up" words are
+            // GATHERED from column v (head) or v-nc (tail); the diagonal follows the up sequence one cell behind, as everywhere. ----
+            if (fast) {
+                for (int g = 0; v <= plm; v += 16, ++g) {
+                    uint32_t gM[16], gI[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int vj = v + j;
+                        const int c = vj > plm ? 0 : (vj <= tl ? vj : vj - nc);
+                        gM[j] = ldM(c);
+                        gI[j] = ldI(c);
+                    }
+                    uint2 pq[4];
+                    if (g == 0) { pq[0] = pg0[0]; pq[1] = pg0[1]; pq[2] = pg0[2]; pq[3] = pg0[3]; }
+                    else if (g == 1) { pq[0] = pg1[0]; pq[1] = pg1[1]; pq[2] = pg1[2]; pq[3] = pg1[3]; }
+                    else { ld16(gpA, v - 1, pq[0], pq[1]); ld16(gpB, v - 1, pq[2], pq[3]); }
+                    const uint32_t pcA[4] = {pq[0].x, pq[0].y, pq[1].x, pq[1].y}, pcB[4] = {pq[2].x, pq[2].y, pq[3].x, pq[3].y};
+                    const bool lastrow = h == tl;
+                    uint32_t aP = 0, aQ = 0, aD = 0, aI = 0;
+#define AIM_GCELL2(j)                                                                                                                   \
+    {                                                                                                                                   \
+        const uint32_t um = gM[j];                                                                                                      \
+        const uint32_t mm = pack2::sub2<j>(pcA[(j) >> 2], pcB[(j) >> 2], t2, (uint32_t)X, dg);                                         \
+        const uint32_t m = pack2::cell2<ALGO>(um, gI[j], leftM, leftD, mm, OE2, E2, 1u << (j), 1u << (16 + (j)), aP, aQ, aD, aI);       \
+        dg = um;                                                                                                                        \
+        gM[j] = m;                                                                                                                      \
+        leftM = m;                                                                                                                      \
+        if (v + (j) == nc) { tailM = m; tailI = gI[j]; tailD = leftD; }                                                                 \
+        if (lastrow) {                                                                                                                  \
+            if (v + (j) == plA) scoreA = pack2::lo_half(m);                                                                             \
+            if (v + (j) == plB) scoreB = pack2::hi_half(m);                                                                             \
+        }                                                                                                                               \
+    }
+                    AIM_GCELL2(0) AIM_GCELL2(1) AIM_GCELL2(2) AIM_GCELL2(3) AIM_GCELL2(4) AIM_GCELL2(5) AIM_GCELL2(6) AIM_GCELL2(7)
+                    AIM_GCELL2(8) AIM_GCELL2(9) AIM_GCELL2(10) AIM_GCELL2(11) AIM_GCELL2(12) AIM_GCELL2(13) AIM_GCELL2(14) AIM_GCELL2(15)
+#undef AIM_GCELL2
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (v + j <= plm) st(v + j, gM[j], gI[j]);
+                    if (K.backtrace) {
+                        uint32_t *dst = frow + (size_t)((v - 1) >> 4) * fstep;
+                        if (SWG) *reinterpret_cast<uint4 *>(dst) = make_uint4(aP, aQ, aD, aI);
+                        else *reinterpret_cast<uint2 *>(dst) = make_uint2(aP, aQ);
+                    }
+                }
+            }
+            // (short texts, num_cols < 32: one cell at a time)
             uint32_t aP = 0, aQ = 0, aD = 0, aI = 0;
             for (; v <= plm; ++v) {
                 const bool tail = v >= nc;
@@ -407,60 +466,76 @@ __global__ void __launch_bounds__(RT2) dp2_row_kernel(const FastK K)
             }
         }
 
+        // ---- traceback of both pairs, one step of each per iteration: every step is a dependent load of a flag record from
+        // global memory (L2 latency), and the two walks are independent ----
+        int tb_h[2] = {tl, tl}, tb_v[2] = {plA, plB}, tb_b[2] = {plA + tl - 1, plB + tl - 1}, tb_layer[2] = {0, 0};
+        int tb_status[2] = {AIM_STATUS_OK, AIM_STATUS_OK};
+        bool tb_live[2] = {K.backtrace != 0, K.backtrace != 0 && !single};
+        while (tb_live[0] || tb_live[1]) {
+            uint32_t rec[2][4];
+            int rr[2] = {1, 1}, cc[2] = {1, 1};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                rec[half][0] = rec[half][1] = rec[half][2] = rec[half][3] = 0u;
+                if (tb_live[half] && tb_h[half] > 0 && tb_v[half] > 0) {
+                    const int fi = nc * tb_h[half] + tb_v[half];  // flat word the reference's traceback reads
+                    rr[half] = min(tl, (fi - 1) / nc);            // its last writer (row r, column c)
+                    cc[half] = fi - nc * rr[half];
+                    const uint32_t *src = flg + ((size_t)(rr[half] - 1) * rpr + (size_t)((cc[half] - 1) >> 4)) * fstep;
+                    if (SWG) { const uint4 w = *reinterpret_cast<const uint4 *>(src); rec[half][0] = w.x; rec[half][1] = w.y; rec[half][2] = w.z; rec[half][3] = w.w; }
+                    else { const uint2 w = *reinterpret_cast<const uint2 *>(src); rec[half][0] = w.x; rec[half][1] = w.y; }
+                }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (!tb_live[half]) continue;
+                const uint32_t i = half ? iB : iA;
+                char *ops = K.ops + (size_t)i * 2 * RS;
+                int &h = tb_h[half], &v = tb_v[half], &b = tb_b[half], &layer = tb_layer[half];
+                if (!(h > 0 && v > 0)) {  // the walk left the table: the rest is one gap
+                    while (h > 0) { ops[b--] = 'I'; --h; }
+                    while (v > 0) { ops[b--] = 'D'; --v; }
+                    tb_live[half] = false;
+                    continue;
+                }
+                const char *gp = half ? gpB : gpA, *gt = half ? gtB : gtA;
+                const int r = rr[half], c = cc[half];
+                bool p, q, opD, opI;
+                pack2::decode2(rec[half], (c - 1) & 15, half, SWG, p, q, opD, opI);
+                if (!SWG) {
+                    if (q) {
+                        if (p) { ops[b--] = 'D'; --v; }
+                        else { ops[b--] = 'I'; --h; }
+                    } else {
+                        if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                        --b; --h; --v;
+                    }
+                } else {
+                    if (b < 0) { tb_status[half] = AIM_STATUS_BACKTRACE; tb_live[half] = false; continue; }
+                    if (layer == 2) { ops[b--] = 'D'; if (opD) layer = 0; --v; }
+                    else if (layer == 1) { ops[b--] = 'I'; if (opI) layer = 0; --h; }
+                    else if (q) layer = p ? 2 : 1;
+                    else {
+                        if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                        --b; --h; --v;
+                    }
+                }
+            }
+        }
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             if (half && single) break;
-            const uint32_t i = half ? iB : iA;
             const int pl = half ? plB : plA;
-            const char *gp = half ? gpB : gpA, *gt = half ? gtB : gtA;
             int score = half ? scoreB : scoreA;
             if (pl == 0 || tl == 0) score = 0;
-            int begin_offset = pl + tl - 1;
-            int status = AIM_STATUS_OK;
-            if (K.backtrace) {
-                char *ops = K.ops + (size_t)i * 2 * RS;
-                int b = pl + tl - 1;
-                int h = tl, v = pl;
-                int layer = 0;
-                while (h > 0 && v > 0) {
-                    const int fi = nc * h + v;             // flat word the reference's traceback reads
-                    const int r = min(tl, (fi - 1) / nc);  // its last writer (row r, column c)
-                    const int c = fi - nc * r;
-                    bool p, q, opD, opI;
-                    pack2::decode2(flg + ((size_t)(r - 1) * rpr + (size_t)((c - 1) >> 4)) * fstep, (c - 1) & 15, half, SWG, p, q, opD, opI);
-                    if (!SWG) {
-                        if (q) {
-                            if (p) { ops[b--] = 'D'; --v; }
-                            else { ops[b--] = 'I'; --h; }
-                        } else {
-                            if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
-                            --b; --h; --v;
-                        }
-                    } else {
-                        if (b < 0) { status = AIM_STATUS_BACKTRACE; break; }
-                        if (layer == 2) { ops[b--] = 'D'; if (opD) layer = 0; --v; }
-                        else if (layer == 1) { ops[b--] = 'I'; if (opI) layer = 0; --h; }
-                        else if (q) layer = p ? 2 : 1;
-                        else {
-                            if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
-                            --b; --h; --v;
-                        }
-                    }
-                }
-                if (status == AIM_STATUS_OK) {
-                    while (h > 0) { ops[b--] = 'I'; --h; }
-                    while (v > 0) { ops[b--] = 'D'; --v; }
-                    begin_offset = b + 1;
-                }
-            }
             aim_result res;
             res.max_operations = pl + tl;
-            res.begin_offset = begin_offset;
+            res.begin_offset = (K.backtrace && tb_status[half] == AIM_STATUS_OK) ? tb_b[half] + 1 : pl + tl - 1;
             res.end_offset = pl + tl;
             res.score = score;
-            res.status = status;
-            res.idx = K.idx_base + i;
-            K.results[i] = res;
+            res.status = tb_status[half];
+            res.idx = K.idx_base + (half ? iB : iA);
+            K.results[half ? iB : iA] = res;
         }
     }
 }

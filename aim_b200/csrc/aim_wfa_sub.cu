@@ -598,7 +598,7 @@ cudaError_t launch_g(const SubK &K, bool reduce, bool bt, int grid, int block, s
         if (block <= 128) {                                                                                               \
             e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
             if (e == cudaSuccess) wfa_sub_kernel<G, R, B><<<grid, block, smem, st>>>(K);                                   \
-        } else if constexpr (G == 4) {                                                                                    \
+        } else if constexpr (G <= 4) {                                                                                    \
             e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e == cudaSuccess) wfa_sub_kernel<G, R, B, 768><<<grid, block, smem, st>>>(K);                              \
         } else {                                                                                                          \
@@ -707,7 +707,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     // lanes per pair: wavefronts are about MAX_SCORE diagonals wide on average; a few iterations per score keeps the
     // lanes busy while the per-score bookkeeping is shared by 32/G pairs; env override for tuning
     int G = MS <= 40 ? 4 : MS <= 100 ? 8 : MS <= 300 ? 16 : 32;
-    if (const char *gs = getenv("AIM_WFA_G")) { int g = atoi(gs); if (g == 4 || g == 8 || g == 16 || g == 32) G = g; }
+    if (const char *gs = getenv("AIM_WFA_G")) { int g = atoi(gs); if (g == 2 || g == 4 || g == 8 || g == 16 || g == 32) G = g; }
     const int PPW = 32 / G;
     {   // stagger the pair slots of one warp over the banks with the least padding: a slot stride that is an ODD multiple of
         // 32/PPW words puts the PPW slots on distinct bank groups; slots stay 16-byte aligned
@@ -723,16 +723,16 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     // G = 4 and a large per-pair footprint: ONE block per SM with as many warps as its shared memory holds (20 at config 4
     // against 16 as two-warp blocks) - the per-block plan copy and reserve are paid once, and the kernel, latency-bound at
     // these occupancies, gains ~10 %.  Small footprints keep the two-warp blocks (registers cap those at 32 warps/SM).
-    const int default_wpb = G == 4 ? 2 : 4;
+    const int default_wpb = G <= 4 ? 2 : 4;
     int warps_per_block = default_wpb;
-    if (G == 4) {
+    if (G <= 4) {
         const size_t small_block = fixed_bytes + (size_t)default_wpb * PPW * pair_bytes;
         const int small_warps = (int)std::min<size_t>(32, kSmemPerSm / (small_block + kBlockReserve) * default_wpb);
         int big_warps = (int)std::min<size_t>(24, (kSmemBudget - fixed_bytes) / ((size_t)PPW * pair_bytes));
-        if (big_warps >= 8) big_warps &= ~3;  // the same number of warps on each of the SM's four schedulers (20 beats 21: 300 vs 290 M pairs/s)
+        if (big_warps >= 8 && G == 4) big_warps &= ~3;  // the same number of warps on each of the SM's four schedulers (20 beats 21: 300 vs 290 M pairs/s)
         if (big_warps > small_warps) warps_per_block = big_warps;
     }
-    if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v >= 1 && v <= (G == 4 ? 24 : 4)) warps_per_block = v; }
+    if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v >= 1 && v <= (G <= 4 ? 24 : 4)) warps_per_block = v; }
     if (warps_per_block < 1) return 1;
     size_t smem_block = fixed_bytes + (size_t)warps_per_block * PPW * pair_bytes;
     if (smem_block > kSmemBudget) return 1;
@@ -787,7 +787,8 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     if (err == cudaSuccess) {
         const int block = warps_per_block * 32;
-        if (G == 4) err = launch_g<4>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
+        if (G == 2) err = launch_g<2>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
+        else if (G == 4) err = launch_g<4>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
         else if (G == 8) err = launch_g<8>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
         else if (G == 16) err = launch_g<16>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
         else err = launch_g<32>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);

@@ -359,7 +359,10 @@ def main() -> None:
                       "d2h_bytes_per_step": int(P * (A.RESULT_DTYPE.itemsize + pitch)), "ms_per_step": tp_s * 1e3,
                       "api": "aim_align_packed (C ABI extension): 2-bit packed sequences in, run-length CIGAR rows out, pinned host buffers",
                       "host_pack_pairs_per_s": P / pack_s, "host_pack_threads": threads,
-                      "note": "same scores and CIGAR text; packing happens on the host before the timed region, like the reference's pair-file parse"}
+                      "value_including_host_pack": world * P / (tp_s + shard.max_over_ranks(pack_s, dev)),
+                      "note": "same scores and CIGAR text.  `value` times aim_align_packed on already packed buffers (a caller whose parser emits 2-bit "
+                              "rows, as get_reads could); `value_including_host_pack` adds aim_pack_pairs on this rank's host threads, un-overlapped: "
+                              "from the reference's ASCII buffers e2e_cigars (no host work) is the better route, from a pair FILE e2e_cli (parsed on the GPU)"}
 
     # ---- end-to-end arm with the reference's INPUT layout and CIGAR TEXT rows out (aim_align_batch_cigars) ----
     e2e_cigars = None

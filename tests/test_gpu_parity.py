@@ -164,3 +164,17 @@ def test_errors_are_reported():
     with pytest.raises(A.AimError) as ei:
         A.align_batch(A.AlignParams(algo="wfa", max_score=10, read_size=rs, mismatch=0), plen[:1], tlen[:1], z[:1], z[:1])
     assert ei.value.code == -1  # penalty validation of the run scripts
+
+
+def test_arena_overflow_is_recovered():
+    """Long reads with backtrace and a deliberately small history arena (1 MiB per pair; a 10 kbp pair needs about that much):
+    pairs that outgrow it are re-aligned with a larger arena instead of ending the run (reference: "Out of memory MRAM",
+    dpu_allocator_mram.c:6-10), and the result is the oracle's."""
+    ms, rs = A.derive_knobs("wfa", 10000, 0.10)
+    n = 24
+    plen, tlen, pats, txts = A.generate_pairs(55, n, 10000, 0.10, rs)
+    kw = dict(max_score=ms, read_size=rs, backtrace=True, reduce=True)
+    res, ops, _ = A.align_batch(A.AlignParams(algo="wfa", arena_mb=1, **kw), plen, tlen, pats, txts)
+    assert int((res["status"] != 0).sum()) == 0
+    exp, exp_ops = O.align("wfa", plen, tlen, pats, txts, nthreads=8, **kw)
+    assert_same_alignment(res, ops, exp, exp_ops, True, what="wfa long reads, small arena")
