@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
                     }
                 }
             }
+            __syncwarp();  // the trim scans above read cells of other lanes; the frame below overwrites cells they may have read
             if (!done) {
                 if (sl == 0) sts_u32(aDyn + (offN / M_SLOT_BYTES) * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)newhi << 16));
                 if (BT) {
