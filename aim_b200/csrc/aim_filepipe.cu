@@ -46,7 +46,7 @@ namespace {
         }                                                                                      \
     } while (0)
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 
 struct Slot {
     int device = 0;
@@ -64,6 +64,7 @@ struct Slot {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // h2d start/done, kernels start/done, d2h start/done
     // the chunk in the slot
     uint32_t pairs = 0;
+    size_t text_bytes = 0;
     bool busy = false;
 };
 
@@ -82,12 +83,13 @@ struct Pipe {
     std::vector<Gpu> gpu;
     int fd_out = -1;
     int write_threads = 8;
-    bool out_mappable = true, out_seekable = true;
+    bool out_mappable = true, out_seekable = true, map_populate = false;
     // reader -> writer
     std::mutex m;
     std::condition_variable cv;
-    std::deque<std::pair<int, int>> order;  // (gpu, slot) in chunk order
-    bool reader_done = false;
+    std::deque<std::pair<int, int>> order;   // (gpu, slot) in chunk order: reader -> fetch stage
+    std::deque<std::pair<int, int>> order2;  // fetch stage -> file stage
+    bool reader_done = false, fetch_done = false;
     int rc = AIM_OK;  // first failure (either side)
     std::string err;
     uint32_t status_or = 0;
@@ -245,9 +247,11 @@ void cache_release(FileCache &C)
 }
 
 // The writer: chunks in order -> output file.
-void writer_main(Pipe *P)
+// The writer, in two stages so that fetching chunk c+1's text overlaps copying chunk c's into the file:
+//   fetch_main: chunks in order -> wait for the chunk, check its flags, D2H of the text into the slot's pinned buffer
+//   file_main:  chunks in order -> the text into the output file, slot released
+void fetch_main(Pipe *P)
 {
-    uint64_t file_off = 0;
     for (;;) {
         std::pair<int, int> it;
         {
@@ -265,12 +269,13 @@ void writer_main(Pipe *P)
         const double tw0 = now_s();
         cu(cudaSetDevice(G.device), "cudaSetDevice");
         cu(cudaEventSynchronize(S.ev[5]), "chunk sync");
-        P->t_writer[0] += now_s() - tw0;
+        const double tw1 = now_s();
+        P->t_writer[0] += tw1 - tw0;
         bool failed_before;
         { std::lock_guard<std::mutex> lk(P->m); failed_before = P->rc != AIM_OK; }
+        S.text_bytes = 0;
         if (rc == AIM_OK && !failed_before) {
             const uint32_t lines = 2 * S.pairs;
-            const uint32_t st = S.h_counters[3];
             if (S.h_counters[1]) { rc = AIM_ERR_LENGTH; err = "READ LENGTH less than length of the input reads"; }
             else if (S.h_counters[0] < lines) { rc = AIM_ERR_CUDA; err = "file pipeline: the device found fewer lines than the host"; }
             else {
@@ -284,55 +289,87 @@ void writer_main(Pipe *P)
                     if (rc == AIM_OK && launch_file_format_write(S.d_res, S.d_ops, P->p.read_size, P->p.backtrace, S.pairs, S.d_offs, S.d_counters, S.d_out,
                                                                  S.d_out_cap, G.s_text, nullptr) != AIM_OK) { rc = AIM_ERR_CUDA; err = aim_last_error(); }
                 }
-                const double tw1 = now_s();
                 if (rc == AIM_OK && total) {
                     cu(cudaMemcpyAsync(S.h_out, S.d_out, total, cudaMemcpyDeviceToHost, G.s_text), "text D2H");
                     cu(cudaStreamSynchronize(G.s_text), "text D2H sync");
                 }
-                const double tw2 = now_s();
-                P->t_writer[1] += tw2 - tw1;
-                if (rc == AIM_OK && total) {
-                    // Buffered write()s to one file are serialised by the kernel (about 3 GB/s into fresh page-cache pages whatever
-                    // the thread count), so the text is copied through a shared mapping of the file's next `total` bytes by a few
-                    // threads; files that cannot be mapped (pipes, devices) get plain writes.
-                    bool mapped = false;
-                    if (P->out_mappable && ftruncate(P->fd_out, (off_t)(file_off + total)) == 0) {
-                        const uint64_t page = 4096, map_off = file_off & ~(page - 1);
-                        const size_t len = (size_t)(file_off + total - map_off);
-                        void *m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, P->fd_out, (off_t)map_off);
-                        if (m != MAP_FAILED) {
-                            char *dst = (char *)m + (file_off - map_off);
-                            const int W = (int)std::max<size_t>(1, std::min<size_t>((size_t)P->write_threads, total / ((size_t)1 << 20) + 1));
-                            auto piece = [&](int t) {
-                                const size_t a = total / (size_t)W * (size_t)t, b = t == W - 1 ? total : total / (size_t)W * (size_t)(t + 1);
-                                memcpy(dst + a, S.h_out + a, b - a);
-                            };
-                            std::vector<std::thread> th;
-                            for (int t = 1; t < W; ++t) th.emplace_back(piece, t);
-                            piece(0);
-                            for (auto &x : th) x.join();
-                            munmap(m, len);
-                            mapped = true;
-                        } else {
-                            P->out_mappable = false;
-                        }
-                    }
-                    size_t done = mapped ? total : 0;
-                    while (done < total) {
-                        ssize_t w = P->out_seekable ? pwrite(P->fd_out, S.h_out + done, total - done, (off_t)(file_off + done))
-                                                    : write(P->fd_out, S.h_out + done, total - done);
-                        if (w <= 0) { rc = AIM_ERR_IO; err = "output file: write failed"; break; }
-                        done += (size_t)w;
-                    }
-                    file_off += total;
-                }
-                P->t_writer[2] += now_s() - tw2;
+                if (rc == AIM_OK) S.text_bytes = total;
                 float t;
                 for (int k = 0; k < 3; ++k) { if (cudaEventElapsedTime(&t, S.ev[2 * k], S.ev[2 * k + 1]) == cudaSuccess) P->ph[k] += t; }
                 std::lock_guard<std::mutex> lk(P->m);
-                P->status_or |= st;
+                P->status_or |= S.h_counters[3];
             }
         }
+        P->t_writer[1] += now_s() - tw1;
+        {
+            std::lock_guard<std::mutex> lk(P->m);
+            if (rc != AIM_OK && P->rc == AIM_OK) { P->rc = rc; P->err = err; }
+            P->order2.push_back(it);
+        }
+        P->cv.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(P->m);
+        P->fetch_done = true;
+    }
+    P->cv.notify_all();
+}
+
+void file_main(Pipe *P)
+{
+    uint64_t file_off = 0;
+    for (;;) {
+        std::pair<int, int> it;
+        bool failed;
+        {
+            std::unique_lock<std::mutex> lk(P->m);
+            P->cv.wait(lk, [&] { return !P->order2.empty() || P->fetch_done; });
+            if (P->order2.empty()) break;
+            it = P->order2.front();
+            P->order2.pop_front();
+            failed = P->rc != AIM_OK;
+        }
+        Slot &S = P->gpu[(size_t)it.first].slot[it.second];
+        int rc = AIM_OK;
+        std::string err;
+        const size_t total = failed ? 0 : S.text_bytes;
+        const double tw2 = now_s();
+        if (total) {
+            // Buffered write()s to one file are serialised by the kernel (about 3 GB/s into fresh page-cache pages whatever
+            // the thread count), so the text is copied through a shared mapping of the file's next `total` bytes by a few
+            // threads; files that cannot be mapped (pipes, devices) get plain writes.
+            bool mapped = false;
+            if (P->out_mappable && ftruncate(P->fd_out, (off_t)(file_off + total)) == 0) {
+                const uint64_t page = 4096, map_off = file_off & ~(page - 1);
+                const size_t len = (size_t)(file_off + total - map_off);
+                void *m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED | (P->map_populate ? MAP_POPULATE : 0), P->fd_out, (off_t)map_off);
+                if (m != MAP_FAILED) {
+                    char *dst = (char *)m + (file_off - map_off);
+                    const int W = (int)std::max<size_t>(1, std::min<size_t>((size_t)P->write_threads, total / ((size_t)1 << 20) + 1));
+                    auto piece = [&](int t) {
+                        const size_t a = total / (size_t)W * (size_t)t, b = t == W - 1 ? total : total / (size_t)W * (size_t)(t + 1);
+                        memcpy(dst + a, S.h_out + a, b - a);
+                    };
+                    std::vector<std::thread> th;
+                    for (int t = 1; t < W; ++t) th.emplace_back(piece, t);
+                    piece(0);
+                    for (auto &x : th) x.join();
+                    munmap(m, len);
+                    mapped = true;
+                } else {
+                    P->out_mappable = false;
+                }
+            }
+            size_t done = mapped ? total : 0;
+            while (done < total) {
+                ssize_t w = P->out_seekable ? pwrite(P->fd_out, S.h_out + done, total - done, (off_t)(file_off + done))
+                                            : write(P->fd_out, S.h_out + done, total - done);
+                if (w <= 0) { rc = AIM_ERR_IO; err = "output file: write failed"; break; }
+                done += (size_t)w;
+            }
+            file_off += total;
+        }
+        P->t_writer[2] += now_s() - tw2;
         {
             std::lock_guard<std::mutex> lk(P->m);
             if (rc != AIM_OK && P->rc == AIM_OK) { P->rc = rc; P->err = err; }
@@ -450,10 +487,11 @@ extern "C" int aim_align_file(const aim_params *params, const char *pairs_path, 
     pool.start(io_threads);
     P.write_threads = std::max(1, std::min(8, io_threads / 2));
     if (const char *e = getenv("AIM_WRITE_THREADS")) { const int v = atoi(e); if (v >= 1) P.write_threads = std::min(v, 32); }
+    if (const char *e = getenv("AIM_FILE_POPULATE")) P.map_populate = atoi(e) != 0;
 
     const double t_setup1 = now_s();
-    std::thread writer;
-    if (rc == AIM_OK) writer = std::thread(writer_main, &P);
+    std::thread writer, filer;
+    if (rc == AIM_OK) { writer = std::thread(fetch_main, &P); filer = std::thread(file_main, &P); }
     uint64_t off = 0, pairs_total = 0, chunk_no = 0;
     int nlaunch = 0;
     while (rc == AIM_OK && off < file_size && pairs_total < want) {
@@ -551,6 +589,7 @@ extern "C" int aim_align_file(const aim_params *params, const char *pairs_path, 
     }
     P.cv.notify_all();
     if (writer.joinable()) writer.join();
+    if (filer.joinable()) filer.join();
     const double t_stream1 = now_s();
     rc = P.rc;
     for (Gpu &G : P.gpu) {  // drain, then hand the slots back to the cache

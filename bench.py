@@ -409,9 +409,18 @@ def main() -> None:
         tcli_s = shard.max_over_ranks((time.perf_counter() - t0) / nst, dev)
         assert done == P and smask == 0, f"bench: aim_align_file aligned {done} of {P} pairs, status mask {smask}"
         out_bytes = cli_out_path.stat().st_size
+        # the same call with the output discarded: what remains is reading, parsing, aligning and formatting (populating the pages of
+        # a NEW output file is the operating system's file-write rate, about 4 GB/s on this box whatever the thread count)
+        A.align_file(params, pairs_path, "/dev/null", P, 1)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nst):
+            A.align_file(params, pairs_path, "/dev/null", P, 1)
+        tnull_s = shard.max_over_ranks((time.perf_counter() - t0) / nst, dev)
         e2e_cli = {"value": world * P / tcli_s, "unit": "pairs/s", "ms_per_step": tcli_s * 1e3, "pair_file_bytes": file_bytes, "output_file_bytes": out_bytes,
                    "h2d_bytes_per_step": file_bytes, "d2h_bytes_per_step": out_bytes, "gpu_launches_per_step": cl,
-                   "phase_ms_h2d_kernels_d2h": cph,
+                   "phase_ms_h2d_kernels_d2h": cph, "value_output_discarded": world * P / tnull_s,
+                   "output_file": str(cli_out_path.parent.parent),
                    "api": "aim_align_file (C ABI; what `host <pairs> <out> <N>` calls): pair file in the page cache -> output file; get_reads and the "
                           "print loop run as GPU kernels, host threads only read() and write(); buffers allocated and freed inside the call"}
         pairs_path.unlink()
