@@ -86,6 +86,8 @@ struct SubK {
     uint32_t cw;            // row width in halfwords (multiple of 8)
     uint32_t rows_v4;       // 16-byte units of all rows of a pair
     uint32_t pair_words;    // shared-memory words per pair slot
+    int bias;               // NARROW rows: stored byte = offset + bias; the NULL family (NULL + d) is stored as d
+    int null_max;           // NARROW rows: bytes <= null_max are the NULL family
 };
 
 // ---- shared-memory accessors on 32-bit shared-window addresses ----
@@ -103,6 +105,8 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a)
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ int lds_u8(uint32_t a) { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u8(uint32_t a, int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_v4(uint32_t a, uint4 v)
@@ -193,21 +197,37 @@ __device__ __forceinline__ int hi16s(uint32_t w) { return (int)(short)(w >> 16);
 // lo <= k <= hi
 __device__ __forceinline__ bool in_range(int k, int lo, int hi) { return (unsigned)(k - lo) <= (unsigned)(hi - lo) && lo <= hi; }
 
-template <int G, bool REDUCE, bool BT, int MAXT = 128>
+// NB (narrow rows): the ring rows hold ONE BYTE per offset instead of an int16, which fits 32 warps per SM where the int16 rows fit
+// 20 (config 4: 0.8 KB of shared memory per pair instead of 1.36 KB).  A byte holds offset + bias for every value the reference
+// can produce from -bias up, and d for the NULL family NULL + d (the reference's NULL = -16384 drifts by +1 per wavefront it passes
+// through: wfa.c:249-266); with d <= MAX_SCORE < bias - 10 the two families keep their order and their ties, every max()
+// and +1 of compute_offsets is the same operation on the bytes, and the literal value is recovered wherever a DIFFERENCE to a
+// true offset is taken (adaptive distances, backtrace).  Used when READ_SIZE + 2*MAX_SCORE + 12 <= 255; the history cell shrinks to
+// four bytes {M, I, D}.
+template <int G, bool REDUCE, bool BT, int MAXT = 128, bool NB = false>
 __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
 {
     constexpr int PPW = 32 / G;
+    constexpr uint32_t ES = NB ? 1u : 2u;  // bytes per M cell; an {I,D} cell is 2 * ES bytes (I first)
+    const int BZ = NB ? K.bias : 0;
+    constexpr int NULLV = NB ? 0 : kNull;
+    auto ldM = [](uint32_t a) -> int { return NB ? lds_u8(a) : lds_s16(a); };
+    auto stM = [](uint32_t a, int v) { if (NB) sts_u8(a, v); else sts_u16(a, v); };
+    auto stID_null = [](uint32_t a) { if (NB) sts_u16(a, 0); else sts_u32(a, kNull2); };
+    // literal (reference) value of a stored offset
+    auto lit = [&](int x) -> int { return NB ? (x <= K.null_max ? kNull + x : x - BZ) : x; };
     extern __shared__ __align__(16) uint32_t smem_w[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int sub = lane / G, sl = lane % G;
     const uint32_t wpb = blockDim.x >> 5;
     const int RS = K.read_size, MS = K.max_score;
     const int X = K.x, OE = K.o + K.e, E = K.e;
-    const uint4 null4 = make_uint4(0xc000c000u, 0xc000c000u, 0xc000c000u, 0xc000c000u);  // kNull in every halfword
+    const uint32_t nullw = NB ? 0u : 0xc000c000u;  // NULL in every cell of a word
+    const uint4 null4 = make_uint4(nullw, nullw, nullw, nullw);
 
     // block-wide: the plan and the all-NULL row
     for (uint32_t j = threadIdx.x; j < K.plan_words; j += blockDim.x) smem_w[j] = K.plan[j];
-    for (uint32_t j = threadIdx.x; j < K.cw; j += blockDim.x) smem_w[K.plan_words + j] = 0xc000c000u;  // wide enough for an {I,D} row
+    for (uint32_t j = threadIdx.x; j < K.cw; j += blockDim.x) smem_w[K.plan_words + j] = nullw;  // wide enough for an {I,D} row
     __syncthreads();
 
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_w);
@@ -219,15 +239,16 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
     const uint32_t aRows = aDyn + K.dyn_words * 4u;
     // M rows hold one int16 per diagonal, {I,D} rows one 32-bit cell (I low, D high); diagonal 0 of the row at plan
     // offset `off` is aK0 + off (M rows) / aK0D + off ({I,D} rows); OFF_NULL = the block-wide all-NULL row
-    const uint32_t aK0 = aRows + (uint32_t)(K.koff * 2), aK0D = aRows + (uint32_t)(K.koff * 4);
-    const uint32_t nullrel = (sbase + K.plan_words * 4u + (uint32_t)(K.koff * 2)) - aK0;
-    const uint32_t nullrelD = (sbase + K.plan_words * 4u + (uint32_t)(K.koff * 4)) - aK0D;
+    const uint32_t aK0 = aRows + (uint32_t)K.koff * ES, aK0D = aRows + (uint32_t)K.koff * 2u * ES;
+    const uint32_t nullrel = (sbase + K.plan_words * 4u + (uint32_t)K.koff * ES) - aK0;
+    const uint32_t nullrelD = (sbase + K.plan_words * 4u + (uint32_t)K.koff * 2u * ES) - aK0D;
 #define AIM_ROW(off) (aK0 + ((off) == OFF_NULL ? nullrel : (off)))
 #define AIM_ROWD(off) (aK0D + ((off) == OFF_NULL ? nullrelD : (off)))
 
     const uint32_t slot_global = (blockIdx.x * wpb + wib) * PPW + sub;
     const uint32_t nslots = gridDim.x * wpb * PPW;
-    uint2 *arena = BT ? K.arena + (size_t)slot_global * K.arena_stride : nullptr;
+    uint2 *arena = (BT && !NB) ? K.arena + (size_t)slot_global * K.arena_stride : nullptr;
+    uint32_t *arena1 = (BT && NB) ? reinterpret_cast<uint32_t *>(K.arena) + (size_t)slot_global * K.arena_stride : nullptr;  // {M, I, D} bytes
 
     for (uint32_t base_i = 0; base_i < K.n; base_i += nslots) {  // warp-uniform trip count
         const uint32_t i = base_i + slot_global;
@@ -254,7 +275,8 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
             const uint32_t fl = p0.x;
             if (!(fl & P_PRESENT)) continue;
             const uint4 p1 = lds_v4(aPlan + (uint32_t)s * (PLAN_WORDS * 4) + 16);
-            const int floor_m = hi16s(fl);
+            // the reference's -10 for a missing candidate is a floor under the max (none: -32768, which no stored value is below)
+            const int floor_m = NB ? (hi16s(fl) < -16000 ? 0 : hi16s(fl) + BZ) : hi16s(fl);
             const int lo_s = lo16(p0.y);
 
             // this pair's range (wfa.c:318-343): from the (trimmed) ranges of the source wavefronts; ranges are {lo, -hi}
@@ -286,10 +308,10 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
                     if (left) {
                         const int plo = lo16(pr), phi = -hi16s(pr), qlo = lo16(qr), qhi = -hi16s(qr);
                         // only the (few) cells of the previous range that stick out below lo or above hi are visited
-                        for (int k = plo + sl; k <= min(phi, lo - 1); k += G) sts_u16(aNM + (uint32_t)(k * 2), kNull);
-                        for (int k = max(plo, hi + 1) + sl; k <= phi; k += G) sts_u16(aNM + (uint32_t)(k * 2), kNull);
-                        for (int k = qlo + sl; k <= min(qhi, lo - 1); k += G) sts_u32(aN + (uint32_t)(k * 4), kNull2);
-                        for (int k = max(qlo, hi + 1) + sl; k <= qhi; k += G) sts_u32(aN + (uint32_t)(k * 4), kNull2);
+                        for (int k = plo + sl; k <= min(phi, lo - 1); k += G) stM(aNM + (uint32_t)k * ES, NULLV);
+                        for (int k = max(plo, hi + 1) + sl; k <= phi; k += G) stM(aNM + (uint32_t)k * ES, NULLV);
+                        for (int k = qlo + sl; k <= min(qhi, lo - 1); k += G) stID_null(aN + (uint32_t)k * 2u * ES);
+                        for (int k = max(qlo, hi + 1) + sl; k <= qhi; k += G) stID_null(aN + (uint32_t)k * 2u * ES);
                     }
                 }
             }
@@ -299,16 +321,24 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
             if (!done) {
                 // this lane's cells are k0, k0 + G, ...; row pointers at k0, advanced once per trip
                 const int k0 = lo + sl;
-                uint32_t rB = aBM + (uint32_t)(k0 * 2), rA = aAM + (uint32_t)(k0 * 2), rNM = aNM + (uint32_t)(k0 * 2);
-                uint32_t rE = aE + (uint32_t)(k0 * 4), rN = aN + (uint32_t)(k0 * 4);
-                uint2 *hp = BT ? arena + (p1.y + (uint32_t)(k0 - lo_s)) : nullptr;  // arena cell of (s, k0)
+                uint32_t rB = aBM + (uint32_t)k0 * ES, rA = aAM + (uint32_t)k0 * ES, rNM = aNM + (uint32_t)k0 * ES;
+                uint32_t rE = aE + (uint32_t)k0 * 2u * ES, rN = aN + (uint32_t)k0 * 2u * ES;
+                uint2 *hp = (BT && !NB) ? arena + (p1.y + (uint32_t)(k0 - lo_s)) : nullptr;  // arena cell of (s, k0)
+                uint32_t *hp1 = (BT && NB) ? arena1 + (p1.y + (uint32_t)(k0 - lo_s)) : nullptr;
                 // back half of a cell at j*G past the pointers: finish the extend, store M, history cell, distance for the reduction
                 auto back = [&](const int k, const int j, int m, const uint32_t id, int cnt, const int lim) {
-                    if (cnt == 16 && lim > 16) cnt = extend_more(aP, aT, m - k, m, lim);  // rare
+                    if (cnt == 16 && lim > 16) cnt = extend_more(aP, aT, m - BZ - k, m - BZ, lim);  // rare
                     m += max(min(cnt, lim), 0);
-                    sts_u16(rNM + (uint32_t)(j * 2 * G), m);
-                    if (BT) hp[j * G] = make_uint2((uint32_t)m & 0xffffu, id);
-                    if (REDUCE) md = min(md, max(pl + k, tl) - m);
+                    stM(rNM + (uint32_t)j * ES * G, m);
+                    if (BT) {
+                        if (NB) hp1[j * G] = (uint32_t)m | (id << 8);
+                        else hp[j * G] = make_uint2((uint32_t)m & 0xffffu, id);
+                    }
+                    if (REDUCE) {
+                        // (a NULL-family cell is -16384 + d in the reference: its distance never is the minimum)
+                        if (NB) { if (m > K.null_max) md = min(md, max(pl + k, tl) + BZ - m); }
+                        else md = min(md, max(pl + k, tl) - m);
+                    }
                 };
                 int k = k0;
                 // N cells per trip in PHASES - all source loads, the recurrences, the {I,D} stores, the first extend windows,
@@ -320,27 +350,27 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
                     uint32_t idd[N];
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        const uint32_t o2 = (uint32_t)(j * 2 * G), o4 = (uint32_t)(j * 4 * G);
-                        g1[j] = lds_s16(rB + o2 - 2); g2[j] = lds_s16(rB + o2 + 2);
-                        ii[j] = lds_s16(rE + o4 - 4); dd[j] = lds_s16(rE + o4 + 6);
-                        sb[j] = lds_s16(rA + o2);
+                        const uint32_t o2 = (uint32_t)j * ES * G, o4 = (uint32_t)j * 2u * ES * G;
+                        g1[j] = ldM(rB + o2 - ES); g2[j] = ldM(rB + o2 + ES);
+                        ii[j] = ldM(rE + o4 - 2u * ES); dd[j] = ldM(rE + o4 + 3u * ES);  // I of cell k-1, D of cell k+1
+                        sb[j] = ldM(rA + o2);
                     }
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
                         const int t = max(g1[j], ii[j]) + 1;
-                        const int ins = t == kNull + 1 ? kNull : t;  // both NULL -> NULL (wfa.c:249-252)
+                        const int ins = t == NULLV + 1 ? NULLV : t;  // both NULL -> NULL (wfa.c:249-252)
                         const int del = max(g2[j], dd[j]);
                         mm[j] = max(max(del, sb[j] + 1), max(ins, floor_m));
-                        idd[j] = ((uint32_t)ins & 0xffffu) | ((uint32_t)del << 16);
+                        idd[j] = NB ? ((uint32_t)ins | ((uint32_t)del << 8)) : (((uint32_t)ins & 0xffffu) | ((uint32_t)del << 16));
                     }
 #pragma unroll
-                    for (int j = 0; j < N; ++j) sts_u32(rN + (uint32_t)(j * 4 * G), idd[j]);
+                    for (int j = 0; j < N; ++j) { if (NB) sts_u16(rN + (uint32_t)j * 2u * G, (int)idd[j]); else sts_u32(rN + (uint32_t)(j * 4 * G), idd[j]); }
 #pragma unroll
-                    for (int j = 0; j < N; ++j) cc[j] = extend_first(aP, aT, k + j * G, mm[j], pl, tl, &ll[j]);
+                    for (int j = 0; j < N; ++j) cc[j] = extend_first(aP, aT, k + j * G, mm[j] - BZ, pl, tl, &ll[j]);
 #pragma unroll
                     for (int j = 0; j < N; ++j) back(k + j * G, j, mm[j], idd[j], cc[j], ll[j]);
-                    rB += 2 * N * G; rA += 2 * N * G; rNM += 2 * N * G; rE += 4 * N * G; rN += 4 * N * G;
-                    if (BT) hp += N * G;
+                    rB += ES * N * G; rA += ES * N * G; rNM += ES * N * G; rE += 2 * ES * N * G; rN += 2 * ES * N * G;
+                    if (BT) { if (NB) hp1 += N * G; else hp += N * G; }
                     k += N * G;
                 };
 #ifndef AIM_CPT
@@ -353,7 +383,7 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
             __syncwarp();
             // ---- end reached (wfa.c:217-237).  Trimming never removes diagonal ak, so testing before the
             // reduction is equivalent, and the finishing wavefront's trimmed range is never read again. ----
-            if (!done && in_range(ak, lo, hi) && lds_s16(aNM + (uint32_t)(ak * 2)) >= tl) { done = true; reached = true; fscore = s; }
+            if (!done && in_range(ak, lo, hi) && ldM(aNM + (uint32_t)ak * ES) >= tl + BZ) { done = true; reached = true; fscore = s; }
             if (__all_sync(kFull, done)) break;
 
             // ---- adaptive reduction (wfa.c:70-141) on the pairs still running ----
@@ -370,20 +400,20 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
                     const int kl = hi - ((hi - kf) & (G - 1));  // this lane's last cell (when kf <= hi)
                     int kb = kf;
                     if (wide)
-                        while (kb < top_limit && (max(pl + kb, tl) - lds_s16(aNM + (uint32_t)(kb * 2))) > md) kb += G;
+                        while (kb < top_limit && (max(pl + kb, tl) - lit(ldM(aNM + (uint32_t)kb * ES))) > md) kb += G;
                     kb = group_min<G>(kb);
                     if (wide) newlo = max(lo, min(kb, top_limit));
                     const int bottom_limit = max(ak + 1, newlo);
                     int kt = kf <= hi ? kl : INT_MIN;
                     if (wide)
-                        while (kt > bottom_limit && (max(pl + kt, tl) - lds_s16(aNM + (uint32_t)(kt * 2))) > md) kt -= G;
+                        while (kt > bottom_limit && (max(pl + kt, tl) - lit(ldM(aNM + (uint32_t)kt * ES))) > md) kt -= G;
                     kt = group_max<G>(kt);
                     if (wide) {
                         newhi = min(hi, max(kt, bottom_limit));
                         // keep the frame: the cells the trim cut off read as NULL from now on
-                        for (int k = kf; k < newlo; k += G) { sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u32(aN + (uint32_t)(k * 4), kNull2); }
+                        for (int k = kf; k < newlo; k += G) { stM(aNM + (uint32_t)k * ES, NULLV); stID_null(aN + (uint32_t)k * 2u * ES); }
                         if (kf <= hi)
-                            for (int k = kl; k > newhi; k -= G) { sts_u16(aNM + (uint32_t)(k * 2), kNull); sts_u32(aN + (uint32_t)(k * 4), kNull2); }
+                            for (int k = kl; k > newhi; k -= G) { stM(aNM + (uint32_t)k * ES, NULLV); stID_null(aN + (uint32_t)k * 2u * ES); }
                     }
                 }
                 if (sl == 0 && !done) sts_u32(aDyn + (uint32_t)s * 4u, ((uint32_t)newlo & 0xffffu) | ((uint32_t)(-newhi) << 16));
@@ -396,6 +426,10 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
         const int max_ops = pl + tl;
         int begin_offset = max_ops - 1;
         int status = AIM_STATUS_OK;
+        // history cell c of this pair slot, as the reference's int16 values
+        auto hM = [&](uint32_t c) -> int { return NB ? lit((int)(arena1[c] & 0xffu)) : lo16(arena[c].x); };
+        auto hI = [&](uint32_t c) -> int { return NB ? lit((int)((arena1[c] >> 8) & 0xffu)) : lo16(arena[c].y); };
+        auto hD = [&](uint32_t c) -> int { return NB ? lit((int)((arena1[c] >> 16) & 0xffu)) : hi16s(arena[c].y); };
         if (BT && reached && sl == 0) {
             const int ops_cap = 2 * RS;
             int b = begin_offset;
@@ -404,7 +438,7 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
             {
                 const uint4 q1 = lds_v4(aPlan + (uint32_t)fscore * (PLAN_WORDS * 4) + 16);
                 const uint32_t r = lds_u32(aPlan + (uint32_t)fscore * (PLAN_WORDS * 4) + 4);
-                offset = lo16(arena[q1.y + (uint32_t)(k - lo16(r))].x);
+                offset = hM(q1.y + (uint32_t)(k - lo16(r)));
             }
             int v = offset - k, h = offset;
             bool valid = (v > 0 && v <= pl && h > 0 && h <= tl);
@@ -447,17 +481,17 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
                 int del_ext = kNull, del_open = kNull, ins_ext = kNull, ins_open = kNull, misms = kNull;
                 if (type != 1) {
                     if ((ge_f & P_PRESENT) && (ge_f & P_HAS_D) && ge_lo <= k + 1 && k + 1 <= ge_hi)
-                        del_ext = hi16s(arena[ge_base + (uint32_t)(k + 1 - ge_l0)].y);
-                    if ((go_f & P_PRESENT) && go_lo <= k + 1 && k + 1 <= go_hi) del_open = lo16(arena[go_base + (uint32_t)(k + 1 - go_l0)].x);
+                        del_ext = hD(ge_base + (uint32_t)(k + 1 - ge_l0));
+                    if ((go_f & P_PRESENT) && go_lo <= k + 1 && k + 1 <= go_hi) del_open = hM(go_base + (uint32_t)(k + 1 - go_l0));
                 }
                 if (type != 2) {
                     if ((ge_f & P_PRESENT) && (ge_f & P_HAS_I) && ge_lo <= k - 1 && k - 1 <= ge_hi)
-                        ins_ext = (int16_t)(lo16(arena[ge_base + (uint32_t)(k - 1 - ge_l0)].y) + 1);
+                        ins_ext = (int16_t)(hI(ge_base + (uint32_t)(k - 1 - ge_l0)) + 1);
                     if ((go_f & P_PRESENT) && go_lo <= k - 1 && k - 1 <= go_hi)
-                        ins_open = (int16_t)(lo16(arena[go_base + (uint32_t)(k - 1 - go_l0)].x) + 1);
+                        ins_open = (int16_t)(hM(go_base + (uint32_t)(k - 1 - go_l0)) + 1);
                 }
                 if (type == 0) {
-                    if ((mm_f & P_PRESENT) && mm_lo <= k && k <= mm_hi) misms = (int16_t)(lo16(arena[mm_base + (uint32_t)(k - mm_l0)].x) + 1);
+                    if ((mm_f & P_PRESENT) && mm_lo <= k && k <= mm_hi) misms = (int16_t)(hM(mm_base + (uint32_t)(k - mm_l0)) + 1);
                 }
                 const int max_all = max(misms, max(max(ins_ext, ins_open), max(del_ext, del_open)));
                 if (type == 0) {
@@ -588,14 +622,26 @@ __global__ void __launch_bounds__(128) cigar_rle_kernel(const int32_t *plen, con
 }
 
 template <int G>
-cudaError_t launch_g(const SubK &K, bool reduce, bool bt, int grid, int block, size_t smem, cudaStream_t st)
+cudaError_t launch_g(const SubK &K, bool reduce, bool bt, bool narrow, int grid, int block, size_t smem, cudaStream_t st)
 {
     cudaError_t e;
-    // blocks of more than 4 warps (G = 4 only: one big block fills an SM's shared memory with less per-block overhead)
-    // use a second instantiation whose register budget allows them
+    // blocks of more than 4 warps (G <= 4 only: one big block fills an SM's shared memory with less per-block overhead)
+    // use a second instantiation whose register budget allows them; the narrow-row variant exists for G = 4
 #define AIM_LAUNCH(R, B)                                                                                                  \
     do {                                                                                                                  \
-        if (block <= 128) {                                                                                               \
+        if (narrow) {                                                                                                     \
+            if constexpr (G == 4) {                                                                                       \
+                if (block <= 128) {                                                                                       \
+                    e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                    if (e == cudaSuccess) wfa_sub_kernel<G, R, B, 128, true><<<grid, block, smem, st>>>(K);               \
+                } else {                                                                                                  \
+                    e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                    if (e == cudaSuccess) wfa_sub_kernel<G, R, B, 1024, true><<<grid, block, smem, st>>>(K);              \
+                }                                                                                                         \
+            } else {                                                                                                      \
+                e = cudaErrorInvalidConfiguration;                                                                        \
+            }                                                                                                             \
+        } else if (block <= 128) {                                                                                        \
             e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
             if (e == cudaSuccess) wfa_sub_kernel<G, R, B><<<grid, block, smem, st>>>(K);                                   \
         } else if constexpr (G <= 4) {                                                                                    \
@@ -659,9 +705,15 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     const uint32_t ring_m = (uint32_t)std::max(x, o + e) + 1, ring_e = (uint32_t)e + 1;
     SubK K{};
-    K.cw = round_up((uint32_t)(kmax - kmin + 3), 8);  // one frame cell on both sides; rows are 16-byte multiples
+    // narrow rows (one byte per offset, see the kernel): every offset the reference can produce, plus the bias, fits a byte
+    bool narrow = p.read_size + 2 * MS + 12 <= 255 && MS <= 40 && !getenv("AIM_WFA_G");  // (MS <= 40: G = 4, whose instantiations carry the narrow variant)
+    if (const char *e8 = getenv("AIM_WFA_NARROW")) narrow = narrow && atoi(e8) != 0;
+    K.bias = narrow ? MS + 12 : 0;
+    K.null_max = narrow ? MS : 0;
+    const uint32_t es = narrow ? 1u : 2u;
+    K.cw = round_up((uint32_t)(kmax - kmin + 3), narrow ? 16 : 8);  // one frame cell on both sides; rows are 16-byte multiples
     K.koff = 1 - kmin;
-    const uint32_t row_bytes = K.cw * 2;
+    const uint32_t row_bytes = K.cw * es;
     const uint32_t rows_bytes = (ring_m + 2 * ring_e) * row_bytes;
     if (rows_bytes > 0xfff0u) return 1;
     K.rows_v4 = rows_bytes / 16;
@@ -719,7 +771,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     const uint32_t kSmemBudget = 227u * 1024u, kSmemPerSm = 228u * 1024u, kBlockReserve = 1024u;
     const size_t pair_bytes = (size_t)K.pair_words * 4;
-    const size_t fixed_bytes = (size_t)K.plan_words * 4 + 2 * row_bytes;  // plan + the all-NULL row ({I,D} width)
+    const size_t fixed_bytes = (size_t)K.plan_words * 4 + (size_t)K.cw * 4;  // plan + the all-NULL row (K.cw words: an int16 {I,D} row)
     // G = 4 and a large per-pair footprint: ONE block per SM with as many warps as its shared memory holds (20 at config 4
     // against 16 as two-warp blocks) - the per-block plan copy and reserve are paid once, and the kernel, latency-bound at
     // these occupancies, gains ~10 %.  Small footprints keep the two-warp blocks (registers cap those at 32 warps/SM).
@@ -728,11 +780,11 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     if (G <= 4) {
         const size_t small_block = fixed_bytes + (size_t)default_wpb * PPW * pair_bytes;
         const int small_warps = (int)std::min<size_t>(32, kSmemPerSm / (small_block + kBlockReserve) * default_wpb);
-        int big_warps = (int)std::min<size_t>(24, (kSmemBudget - fixed_bytes) / ((size_t)PPW * pair_bytes));
+        int big_warps = (int)std::min<size_t>(narrow ? 32 : 24, (kSmemBudget - fixed_bytes) / ((size_t)PPW * pair_bytes));
         if (big_warps >= 8 && G == 4) big_warps &= ~3;  // the same number of warps on each of the SM's four schedulers (20 beats 21: 300 vs 290 M pairs/s)
         if (big_warps > small_warps) warps_per_block = big_warps;
     }
-    if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v >= 1 && v <= (G <= 4 ? 24 : 4)) warps_per_block = v; }
+    if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v >= 1 && v <= (G <= 4 ? (narrow ? 32 : 24) : 4)) warps_per_block = v; }
     if (warps_per_block < 1) return 1;
     size_t smem_block = fixed_bytes + (size_t)warps_per_block * PPW * pair_bytes;
     if (smem_block > kSmemBudget) return 1;
@@ -760,7 +812,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     const size_t list_dev = up256((size_t)a.n * 4);
     const size_t packed_dev = up256((size_t)a.n * 2 * K.seq_words * 4);
     K.arena_stride = p.backtrace ? (size_t)round_up((uint32_t)arena_cells, 16) : 0;
-    const size_t arena_bytes = up256((size_t)total_slots * K.arena_stride * 8);
+    const size_t arena_bytes = up256((size_t)total_slots * K.arena_stride * (narrow ? 4 : 8));
     int rc = scratch_reserve(sc, plan_dev + flags_dev + list_dev + packed_dev + arena_bytes + W.scratch_bytes);
     if (rc != AIM_OK) return rc;
     unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
@@ -787,11 +839,11 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     if (err == cudaSuccess) {
         const int block = warps_per_block * 32;
-        if (G == 2) err = launch_g<2>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
-        else if (G == 4) err = launch_g<4>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
-        else if (G == 8) err = launch_g<8>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
-        else if (G == 16) err = launch_g<16>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
-        else err = launch_g<32>(K, p.reduce != 0, p.backtrace != 0, grid, block, smem_block, stream);
+        if (G == 2) err = launch_g<2>(K, p.reduce != 0, p.backtrace != 0, false, grid, block, smem_block, stream);
+        else if (G == 4) err = launch_g<4>(K, p.reduce != 0, p.backtrace != 0, narrow, grid, block, smem_block, stream);
+        else if (G == 8) err = launch_g<8>(K, p.reduce != 0, p.backtrace != 0, false, grid, block, smem_block, stream);
+        else if (G == 16) err = launch_g<16>(K, p.reduce != 0, p.backtrace != 0, false, grid, block, smem_block, stream);
+        else err = launch_g<32>(K, p.reduce != 0, p.backtrace != 0, false, grid, block, smem_block, stream);
     }
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { set_error(std::string("wfa_sub launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
