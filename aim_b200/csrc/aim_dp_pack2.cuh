@@ -46,7 +46,9 @@ __device__ __forceinline__ uint32_t text2(uint32_t ta, uint32_t tb) { return (ta
 // (bitA for pair A, bitB for pair B: compile-time constants inside the unrolled records, where the compiler turns the ORs into
 // selects merged by three-input adds: 1.5 instructions per bit).  Measured against taking the predicates in the data path
 // (bit 15 of b + 0x8000 - a per half, shifted into the accumulators: no predicate registers, VIADDMNMX / VIMNMX3 for the M
-// chain): 24.8 against 30.7 instructions per cell pair in the strip kernel, and faster in both kernels.
+// chain): 24.8 against 30.7 instructions per cell pair in the strip kernel, and faster in both kernels.  Also measured and rejected:
+// the M chain through VIADDMNMX / VIMNMX3 (two dependent instructions per cell) with the predicate-delivering VIMNMX hanging off it:
+// two more instructions per cell pair and 2 ms slower at config 3 in either kernel - the chain depth is not what limits them.
 template <int ALGO>
 __device__ __forceinline__ uint32_t cell2(uint32_t upM, uint32_t &upI, uint32_t leftM, uint32_t &leftD, uint32_t mm, uint32_t OE2, uint32_t E2,
                                           uint32_t bitA, uint32_t bitB, uint32_t &aP, uint32_t &aQ, uint32_t &aD, uint32_t &aI)
