@@ -21,6 +21,13 @@ def main():
     lines = src.splitlines()
     start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
     rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
+    if cubin.endswith(".o"):  # a host object with an embedded cubin: extract it first (nvdisasm reads ELF cubins only)
+        import os, tempfile
+        tmp = tempfile.mkdtemp(prefix="ncu_lines")
+        subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(cubin)], cwd=tmp, capture_output=True)
+        found = [f for f in os.listdir(tmp) if f.endswith(".cubin")]
+        if found:
+            cubin = os.path.join(tmp, found[0])
     dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
     # find the kernel's function body
     infn = False
