@@ -482,6 +482,7 @@ int device_state(int device, Scratch **scratch, void **mu)
 int launch_algo(const KernelArgs &a, Scratch *s, void *stream, int *launches) { return launch(a, s, (cudaStream_t)stream, launches); }
 
 bool params_valid_for_file(const aim_params *p) { return validate(p, false, nullptr) == AIM_OK; }
+aim_params params_normalized(const aim_params *p) { return normalized(p); }
 
 namespace {
 struct PlanEntry { std::vector<unsigned char> host; void *dev; };

@@ -211,14 +211,25 @@ __device__ __forceinline__ void for_each_run(const char *row, int b, int e, F &&
 }
 
 // bytes of pair i's output lines; also ORs the pair's status into *status_or (bit s set = some pair has status s)
-__global__ void __launch_bounds__(128) fmt_len_kernel(const aim_result *results, const char *ops, int RS, int bt, uint32_t m, uint32_t *lens,
+__global__ void __launch_bounds__(128) fmt_len_kernel(const aim_result *results, const char *ops, int RS, int bt, int mode, uint32_t m, uint32_t *lens,
                                                       uint32_t *status_or)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const aim_result r = results[i];
     if (r.status != AIM_STATUS_OK) atomicOr(status_or, 1u << (r.status & 31));
-    uint32_t len = (uint32_t)(ndigits(r.idx) + ndigits_signed(r.score) + 5);  // "%d, %d, \n"
+    if (mode) {  // GenASM: "%d, %d, %s\n" (DC: the CIGAR string of the op row, aim-genasm/GenASM/DPU-WRAM-DC/host/host.c:286-296) / "%d, %d\n" (filter)
+        uint32_t len = (uint32_t)(ndigits_signed((int)r.idx) + ndigits_signed(r.score) + 3);
+        if (mode == 1) {
+            const char *row = ops + (size_t)i * 2 * RS;
+            int sl = 0;
+            while (sl < 2 * RS && row[sl]) ++sl;
+            len += 2u + (uint32_t)sl;
+        }
+        lens[i] = len;
+        return;
+    }
+    uint32_t len = (uint32_t)(ndigits_signed((int)r.idx) + ndigits_signed(r.score) + 5);  // "%d, %d, \n"
     if (bt) {
         // edit_cigar_print always prints the op at begin_offset, even for an empty span; a span that starts before the
         // row (empty pair, begin_offset = -1) prints "1M" (cigar_rle_kernel, aim_cigar_rle)
@@ -232,7 +243,7 @@ __global__ void __launch_bounds__(128) fmt_len_kernel(const aim_result *results,
 
 // (nothing is written when the chunk's text does not fit the buffer: counters[2] = total bytes; the host grows the buffer
 // and runs this kernel again)
-__global__ void __launch_bounds__(128) fmt_write_kernel(const aim_result *results, const char *ops, int RS, int bt, uint32_t m,
+__global__ void __launch_bounds__(128) fmt_write_kernel(const aim_result *results, const char *ops, int RS, int bt, int mode, uint32_t m,
                                                         const uint32_t *offs, const uint32_t *counters, size_t out_cap, char *out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,6 +253,15 @@ __global__ void __launch_bounds__(128) fmt_write_kernel(const aim_result *result
     o = put_int(o, (int)r.idx);  // the reference prints the uint32 idx with %d
     *o++ = ','; *o++ = ' ';
     o = put_int(o, r.score);
+    if (mode) {
+        if (mode == 1) {
+            *o++ = ','; *o++ = ' ';
+            const char *row = ops + (size_t)i * 2 * RS;
+            for (int sl = 0; sl < 2 * RS && row[sl]; ++sl) *o++ = row[sl];
+        }
+        *o++ = '\n';
+        return;
+    }
     *o++ = ','; *o++ = ' '; *o++ = '\n';
     if (bt) {
         const int b = r.begin_offset, e = min(r.end_offset > b ? r.end_offset : b + 1, 2 * RS);
@@ -321,27 +341,27 @@ int launch_file_parse(const char *d_buf, size_t nbytes, uint32_t lines, int unte
 
 // Output text of m pairs, densely packed at d_out; d_lens / d_offs: m words each; d_tiles: file_format_scratch_bytes();
 // counters[2] receives the total byte count, counters[3] the OR of (1 << status) over the pairs.
-int launch_file_format(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, uint32_t m, uint32_t *d_lens, uint32_t *d_offs,
+int launch_file_format(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, int mode, uint32_t m, uint32_t *d_lens, uint32_t *d_offs,
                        uint32_t *d_tiles, uint32_t *d_counters, char *d_out, size_t out_cap, void *stream_v, int *launches)
 {
     cudaStream_t st = (cudaStream_t)stream_v;
     if (m == 0) return AIM_OK;
     const uint32_t ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
-    fmt_len_kernel<<<(m + 127) / 128, 128, 0, st>>>(d_res, d_ops, read_size, backtrace, m, d_lens, d_counters + 3);
+    fmt_len_kernel<<<(m + 127) / 128, 128, 0, st>>>(d_res, d_ops, read_size, backtrace, mode, m, d_lens, d_counters + 3);
     scan_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(d_lens, m, d_tiles);
     tile_scan_kernel<<<1, 1024, 0, st>>>(d_tiles, ntiles, d_counters + 2);
     scan_local_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(d_lens, m, d_tiles, d_offs);
-    fmt_write_kernel<<<(m + 127) / 128, 128, 0, st>>>(d_res, d_ops, read_size, backtrace, m, d_offs, d_counters, out_cap, d_out);
+    fmt_write_kernel<<<(m + 127) / 128, 128, 0, st>>>(d_res, d_ops, read_size, backtrace, mode, m, d_offs, d_counters, out_cap, d_out);
     if (cudaGetLastError() != cudaSuccess) { set_error("file format launch failed"); return AIM_ERR_CUDA; }
     if (launches) *launches += 5;
     return AIM_OK;
 }
 
-int launch_file_format_write(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, uint32_t m, const uint32_t *d_offs,
+int launch_file_format_write(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, int mode, uint32_t m, const uint32_t *d_offs,
                              const uint32_t *d_counters, char *d_out, size_t out_cap, void *stream_v, int *launches)
 {
     if (m == 0) return AIM_OK;
-    fmt_write_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(d_res, d_ops, read_size, backtrace, m, d_offs, d_counters, out_cap, d_out);
+    fmt_write_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(d_res, d_ops, read_size, backtrace, mode, m, d_offs, d_counters, out_cap, d_out);
     if (cudaGetLastError() != cudaSuccess) { set_error("file format launch failed"); return AIM_ERR_CUDA; }
     if (launches) ++*launches;
     return AIM_OK;

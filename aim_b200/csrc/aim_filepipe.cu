@@ -83,6 +83,7 @@ struct Pipe {
     std::vector<Gpu> gpu;
     int fd_out = -1;
     int write_threads = 8;
+    int fmt_mode = 0;  // output line format: 0 NW/SWG/WFA, 1 GenASM-DC, 2 GenASM-filter
     bool out_mappable = true, out_seekable = true, map_populate = false;
     // reader -> writer
     std::mutex m;
@@ -132,7 +133,7 @@ int alloc_slot(Slot &s, int device, const Pipe &P)
     FP_CUDA(cudaMalloc(&s.d_lens, cap * 4));
     FP_CUDA(cudaMalloc(&s.d_offs, cap * 4));
     // text: "%d, %d, \n" is at most 27 bytes; a CIGAR is usually a few runs.  Grown on demand (fmt_write_kernel's guard).
-    s.d_out_cap = s.h_out_cap = cap * (size_t)(P.p.backtrace ? 96 : 32) + 4096;
+    s.d_out_cap = s.h_out_cap = cap * (size_t)(P.p.backtrace ? 96 : 32) + 4096;  // (grown on demand: fmt_write_kernel's guard)
     FP_CUDA(cudaMalloc(&s.d_out, s.d_out_cap));
     FP_CUDA(cudaHostAlloc(&s.h_out, s.h_out_cap, cudaHostAllocPortable));
     for (auto &e : s.ev) FP_CUDA(cudaEventCreate(&e));
@@ -286,7 +287,7 @@ void fetch_main(Pipe *P)
                     S.d_out_cap = S.h_out_cap = total + total / 4 + 4096;
                     cu(cudaMalloc(&S.d_out, S.d_out_cap), "cudaMalloc(text)");
                     cu(cudaHostAlloc(&S.h_out, S.h_out_cap, cudaHostAllocPortable), "cudaHostAlloc(text)");
-                    if (rc == AIM_OK && launch_file_format_write(S.d_res, S.d_ops, P->p.read_size, P->p.backtrace, S.pairs, S.d_offs, S.d_counters, S.d_out,
+                    if (rc == AIM_OK && launch_file_format_write(S.d_res, S.d_ops, P->p.read_size, P->p.backtrace, P->fmt_mode, S.pairs, S.d_offs, S.d_counters, S.d_out,
                                                                  S.d_out_cap, G.s_text, nullptr) != AIM_OK) { rc = AIM_ERR_CUDA; err = aim_last_error(); }
                 }
                 if (rc == AIM_OK && total) {
@@ -400,10 +401,6 @@ extern "C" int aim_align_file(const aim_params *params, const char *pairs_path, 
     if (phase_ms) phase_ms[0] = phase_ms[1] = phase_ms[2] = 0.0;
     if (!params || !pairs_path || !out_path) { set_error("NULL argument"); return AIM_ERR_ARG; }
     if (!params_valid_for_file(params)) return AIM_ERR_ARG;
-    if (params->algo != AIM_ALGO_NW && params->algo != AIM_ALGO_SWG && params->algo != AIM_ALGO_WFA) {
-        set_error("aim_align_file serves NW, SWG and WFA (the GenASM printers differ: aim_write_results_genasm)");
-        return AIM_ERR_ARG;
-    }
     const int ndev = aim_device_count();
     if (ndev == 0) { set_error("no CUDA device (aim_b200 has no CPU fallback)"); return AIM_ERR_NO_DEVICE; }
     const int g = params->ngpus <= 1 ? 1 : params->ngpus;
@@ -421,8 +418,9 @@ extern "C" int aim_align_file(const aim_params *params, const char *pairs_path, 
     if (fd_out < 0) { close(fd); set_error(std::string("Output file '") + out_path + "' couldn't be opened"); return AIM_ERR_IO; }
 
     Pipe P;
-    P.p = *params;
+    P.p = params_normalized(params);
     P.p.ngpus = 1;
+    P.fmt_mode = P.p.algo == AIM_ALGO_GENASM_DC ? 1 : P.p.algo == AIM_ALGO_GENASM_FILTER ? 2 : 0;
     P.fd_out = fd_out;
     {
         struct stat so;
@@ -446,7 +444,7 @@ extern "C" int aim_align_file(const aim_params *params, const char *pairs_path, 
     {   // chunk slots: reuse the cached ones when they fit this call
         FileCache &C = g_cache;
         const bool fits = C.first_device == params->device && (int)C.gpu.size() == g && C.read_size == params->read_size &&
-                          C.backtrace >= (params->backtrace ? 1 : 0) && C.chunk_bytes >= P.chunk_bytes && C.chunk_bytes <= 4 * P.chunk_bytes + ((size_t)8 << 20);
+                          C.backtrace >= (P.p.backtrace ? 1 : 0) && C.chunk_bytes >= P.chunk_bytes && C.chunk_bytes <= 4 * P.chunk_bytes + ((size_t)8 << 20);
         if (fits) {
             P.chunk_bytes = C.chunk_bytes;
             P.cap_pairs = C.cap_pairs;
@@ -471,7 +469,7 @@ extern "C" int aim_align_file(const aim_params *params, const char *pairs_path, 
             if (rc == AIM_OK) {
                 C.first_device = params->device;
                 C.read_size = params->read_size;
-                C.backtrace = params->backtrace ? 1 : 0;
+                C.backtrace = P.p.backtrace ? 1 : 0;
                 C.chunk_bytes = P.chunk_bytes;
                 C.cap_pairs = P.cap_pairs;
             } else {
@@ -561,7 +559,7 @@ extern "C" int aim_align_file(const aim_params *params, const char *pairs_path, 
             KernelArgs a{P.p, (uint32_t)pairs, (uint32_t)pairs_total, S.d_plen, S.d_tlen, S.d_pat, S.d_txt, S.d_res, P.p.backtrace ? S.d_ops : nullptr};
             rc = launch_algo(a, G.scratch, G.s_kernel, &nlaunch);
             if (rc != AIM_OK) break;
-            rc = launch_file_format(S.d_res, S.d_ops, P.p.read_size, P.p.backtrace, (uint32_t)pairs, S.d_lens, S.d_offs, S.d_tiles, S.d_counters, S.d_out,
+            rc = launch_file_format(S.d_res, S.d_ops, P.p.read_size, P.p.backtrace, P.fmt_mode, (uint32_t)pairs, S.d_lens, S.d_offs, S.d_tiles, S.d_counters, S.d_out,
                                     S.d_out_cap, G.s_kernel, &nlaunch);
             if (rc != AIM_OK) break;
             e = cudaEventRecord(S.ev[3], G.s_kernel);

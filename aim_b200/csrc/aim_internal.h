@@ -104,12 +104,13 @@ size_t file_parse_scratch_bytes(size_t chunk_bytes);
 size_t file_format_scratch_bytes(uint32_t max_pairs);
 int launch_file_parse(const char *d_buf, size_t nbytes, uint32_t lines, int unterminated, int read_size, uint32_t *d_tiles, uint32_t *d_nl_pos,
                       uint32_t *d_counters, int32_t *d_plen, int32_t *d_tlen, char *d_pat, char *d_txt, void *stream, int *launches);
-int launch_file_format(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, uint32_t m, uint32_t *d_lens, uint32_t *d_offs,
+int launch_file_format(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, int mode, uint32_t m, uint32_t *d_lens, uint32_t *d_offs,
                        uint32_t *d_tiles, uint32_t *d_counters, char *d_out, size_t out_cap, void *stream, int *launches);
 // second half of launch_file_format alone (after the output buffer was grown)
-int launch_file_format_write(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, uint32_t m, const uint32_t *d_offs,
+int launch_file_format_write(const aim_result *d_res, const char *d_ops, int read_size, int backtrace, int mode, uint32_t m, const uint32_t *d_offs,
                              const uint32_t *d_counters, char *d_out, size_t out_cap, void *stream, int *launches);
 bool params_valid_for_file(const aim_params *p);
+aim_params params_normalized(const aim_params *p);  // GenASM-DC implies the op rows, the filter has none
 size_t count_newlines(const char *p, size_t n);  // aim_host.cpp (AVX2 when available)
 void file_pipeline_shutdown();                   // frees the cached chunk slots of aim_align_file (aim_shutdown)
 

@@ -144,12 +144,13 @@ int aim_align_packed(const aim_params *params, uint32_t n, uint32_t idx_base, co
 /* "%d, %d, \n" + the CIGAR row + "\n" per pair: the reference's output bytes from aim_align_packed's results. */
 int aim_write_results_packed(const char *path, uint32_t n, const aim_result *results, const char *cigars, int32_t cigar_pitch);
 
-/* ---- the process boundary at device rate (extension; NW, SWG, WFA) ----------------------------------------------
+/* ---- the process boundary at device rate (extension; every algorithm) -----------------------------------------
  * `host <pairs-file> <out-file> <N>` (host.c:136-379) as one streaming call: the pair file is read in chunks, PARSED ON THE
  * GPU (get_reads, host.c:91-134: first and last character of every line dropped unchecked, length = line length - 2,
  * a sequence longer than read_size -> AIM_ERR_LENGTH and an empty output file, as the reference exits before printing),
  * aligned, and the output lines ("%d, %d, \n" + run-length CIGAR + "\n", host.c:332-353, 69-89) are FORMATTED ON THE GPU;
- * host threads only read() and write().  Pairs processed = min(pairs in file, nr_dpus * roundup8(n_arg / nr_dpus))
+ * host threads only read() and write().  GenASM: the aim-genasm hosts' lines, "%d, %d, %s\n" with the DPU's CIGAR string (DC) /
+ * "%d, %d\n" (filter) (aim-genasm/GenASM/DPU-WRAM-DC/host/host.c:286-296).  Pairs processed = min(pairs in file, nr_dpus * roundup8(n_arg / nr_dpus))
  * (host.c:191,201-209) -> *pairs_done.  *status_mask = OR of (1 << AIM_STATUS_*) over all pairs: on AIM_STATUS_BACKTRACE /
  * AIM_STATUS_ARENA the output file is left empty (the reference's DPU program exits before anything is printed).
  * params->ngpus > 1: chunk c goes to GPU c % ngpus, the writer keeps pair order. */

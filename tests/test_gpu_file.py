@@ -173,3 +173,21 @@ def test_score_only_and_two_gpus(tmp_path):
         d = _ours(WFA, pairs, tmp_path / "d", n, tmp_path)
         assert c.returncode == 0 and d.returncode == 0, c.stderr + d.stderr
         assert (tmp_path / "c").read_bytes() == (tmp_path / "d").read_bytes()
+
+
+@pytest.mark.parametrize("alg,mem,k,length,rs", [("genasm_dc", "wram", 5, 100, 120), ("genasm_dc", "mram", 8, 150, 168), ("genasm_filter", "wram", 2, 100, 120)])
+def test_genasm_stream_equals_batch_path(alg, mem, k, length, rs, tmp_path):
+    """The GenASM hosts' output lines (`idx, score, CIGAR` / `idx, score`, aim-genasm/GenASM/DPU-WRAM-DC/host/host.c:286-296) formatted
+    on the GPU by aim_align_file = the batch path's host printer (which the golden GenASM cases pin), also over many 1 MiB chunks."""
+    n = 30_000
+    plen, tlen, pats, txts = A.generate_pairs(11, n, length, 0.03, rs)
+    pairs = tmp_path / "in.pairs"
+    A.write_pairs(pairs, plen, tlen, pats, txts)
+    kw = dict(alg=alg, mem=mem, max_score=k, read_size=rs, mismatch=3, gap_o=4, gap_e=1)
+    outs = []
+    for extra in ({"AIM_HOST_PATH": "batch"}, {}, {"AIM_FILE_CHUNK_MB": 1, "AIM_IO_THREADS": 3}):
+        r = _ours(kw, pairs, tmp_path / "o", n + 8, tmp_path, cli=True, **extra)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append((tmp_path / "o").read_bytes())
+    assert outs[0].count(b"\n") == n
+    assert all(o == outs[0] for o in outs[1:])

@@ -6,9 +6,9 @@
 //   AIM_ALGO=nw|swg|wfa|genasm_dc|genasm_filter  MAX_SCORE READ_SIZE MATCH MISMATCH GAP_O GAP_E (GAP_I/GAP_D for NW)
 //   BACKTRACE=0|1  REDUCE=0|1  NR_DPUS (only feeds the pairs-to-process rule, host.c:191)
 //   NR_TASKLETS WRAM_SEGMENT (accepted, ignored)  AIM_NGPUS  AIM_DEVICE  AIM_VARIANT=wram|mram
-//   AIM_HOST_PATH=stream|batch  stream (default for NW/SWG/WFA): aim_align_file - the pair file is parsed and the output
-//                               text formatted ON THE GPU, host threads only read() and write();  batch: get_reads on the
-//                               host (aim_read_pairs) + aim_align_batch[_cigars] + the host printer (GenASM always)
+//   AIM_HOST_PATH=stream|batch  stream (default): aim_align_file - the pair file is parsed and the output text formatted
+//                               ON THE GPU, host threads only read() and write();  batch: get_reads on the host
+//                               (aim_read_pairs) + aim_align_batch[_cigars] + the host printer
 #include <sys/time.h>
 
 #include <algorithm>
@@ -100,7 +100,7 @@ int main(int argc, char *argv[])
     printf("NumReads per dpu = %u\n", nb_reads_per_dpu);  // host.c:192
 
     const char *path_s = getenv("AIM_HOST_PATH");
-    if (!genasm && !(path_s && std::string(path_s) == "batch")) {
+    if (!(path_s && std::string(path_s) == "batch")) {
         // ---- streaming path: host.c:196-353 as one call ----
         uint64_t done = 0;
         uint32_t status_mask = 0;
