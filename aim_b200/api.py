@@ -212,6 +212,25 @@ def align_batch_cigars(params: AlignParams, plen, tlen, patterns, texts, cigar_p
     return results, cigars, list(phase)
 
 
+def op_runs_pitch(read_size: int) -> int:
+    """Bytes of a run row (the form in which aim_align_batch downloads an op row); 0 = rows of this size travel as they are."""
+    return int(lib.aim_op_runs_pitch(read_size))
+
+
+def expand_op_runs(runs: np.ndarray, read_size: int, ops: np.ndarray | None = None):
+    """Host half of aim_align_batch's op-row download: run rows [n, pitch] -> (ops[n, 2*read_size], overflow pair numbers)."""
+    runs = np.ascontiguousarray(runs, np.uint8)
+    n, pitch = runs.shape
+    if ops is None:
+        ops = np.zeros((n, 2 * read_size), np.uint8)
+    ov = np.zeros(max(n, 1), np.uint32)
+    cnt = C.c_uint32(0)
+    rc = lib.aim_expand_op_runs(_ptr(runs), pitch, n, read_size, _ptr(ops), _ptr(ov), len(ov), C.byref(cnt))
+    if rc != 0:
+        raise AimError(rc)
+    return ops, ov[:cnt.value].copy()
+
+
 def packed_row_bytes(read_size: int) -> int:
     return int(lib.aim_packed_row_bytes(read_size))
 

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -44,6 +45,8 @@ struct ChunkBuf {
     int32_t *h_plen = nullptr, *h_tlen = nullptr;
     char *h_pat = nullptr, *h_txt = nullptr, *h_ops = nullptr;
     aim_result *h_res = nullptr;
+    unsigned char *h_runs = nullptr;  // run rows of the chunk as downloaded (op rows are rebuilt from them on the host)
+    size_t h_runs_cap = 0;
     // stage boundaries: [0] h2d start, [1] h2d done, [2] kernel start, [3] kernel done, [4] d2h start, [5] d2h done
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t pairs_cap = 0;
@@ -57,6 +60,7 @@ struct DeviceCtx {
     Scratch scratch;
     ChunkBuf chunk[kNumBuf];
     cudaStream_t s_h2d = nullptr, s_kernel = nullptr, s_d2h = nullptr;  // one stream per pipeline stage
+    cudaStream_t s_fix = nullptr;  // op rows whose runs did not fit their run row, fetched as they are
     std::mutex mu;
 };
 
@@ -98,7 +102,7 @@ void free_chunk(ChunkBuf &b)
 {
     cudaFree(b.d_plen); cudaFree(b.d_tlen); cudaFree(b.d_pat); cudaFree(b.d_txt); cudaFree(b.d_ops); cudaFree(b.d_res); cudaFree(b.d_cig);
     cudaFreeHost(b.h_plen); cudaFreeHost(b.h_tlen); cudaFreeHost(b.h_pat); cudaFreeHost(b.h_txt);
-    cudaFreeHost(b.h_ops); cudaFreeHost(b.h_res);
+    cudaFreeHost(b.h_ops); cudaFreeHost(b.h_res); cudaFreeHost(b.h_runs);
     for (auto &e : b.ev) if (e) cudaEventDestroy(e);
     b = ChunkBuf();
 }
@@ -210,9 +214,18 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
 
     const size_t rs = (size_t)p.read_size;
     const bool bt = p.backtrace != 0;
+    // Op rows come back as RUN rows and are rebuilt by host threads (aim_file.cu op_runs_kernel, aim_host.cpp expand_op_runs):
+    // the device-to-host direction is the scarcer one and an op row is a handful of runs.  AIM_SPARSE_OPS=0: as they are.
+    int32_t runs_pitch = 0;
+    if (bt && !cigars && (p.algo == AIM_ALGO_NW || p.algo == AIM_ALGO_SWG || p.algo == AIM_ALGO_WFA)) {
+        const char *e = getenv("AIM_SPARSE_OPS");
+        if (!(e && atoi(e) == 0)) runs_pitch = op_runs_pitch(p.read_size);
+    }
+    const bool sparse = runs_pitch > 0;
     const bool pin_in = is_pinned(plen) && is_pinned(tlen) && is_pinned(patterns) && is_pinned(texts);
-    // (CIGAR rows are copied straight into the caller's buffer, pinned or not: no staging copy for them)
-    const bool pin_out = cigars ? true : (is_pinned(results) && (!bt || is_pinned(ops)));
+    // (CIGAR rows are copied straight into the caller's buffer, pinned or not: no staging copy for them; rebuilt op rows are
+    // written by host threads)
+    const bool pin_out = cigars ? true : (is_pinned(results) && (!bt || sparse || is_pinned(ops)));
     const bool staging = !(pin_in && pin_out);
 
     const uint32_t nchunks = (n + chunk_pairs - 1) / chunk_pairs;
@@ -226,16 +239,26 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
         rc = ensure_chunk(ctx->chunk[b], chunk_pairs, p.read_size, bt, staging);
         if (rc != AIM_OK) return fail(rc);
         ChunkBuf &B = ctx->chunk[b];
-        if (cigars && B.cig_cap < (size_t)chunk_pairs * (size_t)pitch) {
+        const size_t cig_need = (size_t)chunk_pairs * (size_t)(sparse ? runs_pitch : cigars ? pitch : 0);
+        if (B.cig_cap < cig_need) {
             cudaFree(B.d_cig);
             B.d_cig = nullptr;
             B.cig_cap = 0;
-            AIM_CUDA(cudaMalloc(&B.d_cig, (size_t)chunk_pairs * (size_t)pitch));
-            B.cig_cap = (size_t)chunk_pairs * (size_t)pitch;
+            AIM_CUDA(cudaMalloc(&B.d_cig, cig_need));
+            B.cig_cap = cig_need;
+        }
+        if (sparse && B.h_runs_cap < cig_need) {
+            cudaFreeHost(B.h_runs);
+            B.h_runs = nullptr;
+            B.h_runs_cap = 0;
+            AIM_CUDA(cudaHostAlloc(&B.h_runs, cig_need, cudaHostAllocDefault));
+            B.h_runs_cap = cig_need;
         }
     }
+    if (sparse && !ctx->s_fix) AIM_CUDA(cudaStreamCreateWithFlags(&ctx->s_fix, cudaStreamNonBlocking));
     double ph[3] = {0, 0, 0};
     std::vector<uint32_t> mine;  // chunks this GPU pulled, in pull order (the j-th uses buffer j % nbuf)
+    mine.reserve(nchunks);       // (the coordinator thread reads entries while later ones are appended)
 
     auto finish = [&](uint32_t j) -> int {
         ChunkBuf &B = ctx->chunk[j % (uint32_t)nbuf];
@@ -244,10 +267,71 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
         if (e != cudaSuccess) { set_error(std::string("chunk sync: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
         if (!pin_out) {
             memcpy(results + off, B.h_res, (size_t)m * sizeof(aim_result));
-            if (bt && !cigars) memcpy(ops + (size_t)off * 2 * rs, B.h_ops, (size_t)m * 2 * rs);
+            if (bt && !cigars && !sparse) memcpy(ops + (size_t)off * 2 * rs, B.h_ops, (size_t)m * 2 * rs);
+        }
+        if (sparse) {
+            std::vector<uint32_t> ov;
+            char *o_ops = ops + (size_t)off * 2 * rs;
+            expand_op_runs(B.h_runs, runs_pitch, m, p.read_size, o_ops, &ov);
+            if (!ov.empty()) {  // rows with more runs than a run row holds: fetched as they are (a few: one by one; many: the chunk's rows)
+                if (ov.size() <= 64) {
+                    for (uint32_t i : ov) {
+                        e = cudaMemcpyAsync(o_ops + (size_t)i * 2 * rs, B.d_ops + (size_t)i * 2 * rs, 2 * rs, cudaMemcpyDeviceToHost, ctx->s_fix);
+                        if (e != cudaSuccess) break;
+                    }
+                } else {
+                    e = cudaMemcpyAsync(o_ops, B.d_ops, (size_t)m * 2 * rs, cudaMemcpyDeviceToHost, ctx->s_fix);
+                }
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_fix);
+                if (e != cudaSuccess) { set_error(std::string("op row fetch: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
+            }
         }
         float t;
         for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&t, B.ev[2 * k], B.ev[2 * k + 1]); ph[k] += t; }
+        return AIM_OK;
+    };
+
+    // sparse: a coordinator thread completes the chunks in submission order (event wait, row rebuild on the host pool) while
+    // this thread keeps submitting; a chunk buffer is reused once its chunk is complete
+    struct Coord {
+        std::mutex m;
+        std::condition_variable cv;
+        uint32_t submitted = 0, done = 0;
+        bool closing = false;
+        int rc = AIM_OK;
+        std::string err;
+        std::thread th;
+        void close()
+        {
+            if (!th.joinable()) return;
+            { std::lock_guard<std::mutex> lk(m); closing = true; }
+            cv.notify_all();
+            th.join();
+        }
+        ~Coord() { close(); }
+    } co;
+    if (sparse)
+        co.th = std::thread([&]() {
+            cudaSetDevice(device);
+            for (uint32_t j = 0;; ++j) {
+                {
+                    std::unique_lock<std::mutex> lk(co.m);
+                    co.cv.wait(lk, [&] { return co.submitted > j || co.closing; });
+                    if (co.submitted <= j) break;
+                }
+                const int r = finish(j);
+                {
+                    std::lock_guard<std::mutex> lk(co.m);
+                    if (r != AIM_OK && co.rc == AIM_OK) { co.rc = r; co.err = aim_last_error(); }
+                    co.done = j + 1;
+                }
+                co.cv.notify_all();
+            }
+        });
+    auto wait_done = [&](uint32_t j) -> int {  // chunk j complete (sparse)
+        std::unique_lock<std::mutex> lk(co.m);
+        co.cv.wait(lk, [&] { return co.done > j; });
+        if (co.rc != AIM_OK) { set_error(co.err); return co.rc; }
         return AIM_OK;
     };
 
@@ -259,7 +343,10 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
         const uint32_t j = (uint32_t)mine.size();
         mine.push_back(c);
         ChunkBuf &B = ctx->chunk[j % (uint32_t)nbuf];
-        if (j >= (uint32_t)nbuf) { rc = finish(j - (uint32_t)nbuf); if (rc != AIM_OK) return fail(rc); }
+        if (j >= (uint32_t)nbuf) {
+            rc = sparse ? wait_done(j - (uint32_t)nbuf) : finish(j - (uint32_t)nbuf);
+            if (rc != AIM_OK) { if (sparse) { queue->store(nchunks); cudaDeviceSynchronize(); } return fail(rc); }
+        }
         const uint32_t off = c * chunk_pairs, m = std::min(chunk_pairs, n - off);
         const int32_t *s_plen = plen + off, *s_tlen = tlen + off;
         {   // host.c:119-123 rejects reads longer than READ_SIZE (there: message + exit)
@@ -300,6 +387,10 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
             rc = launch_cigar_rows(a, ctx->s_kernel, nullptr);
             if (rc != AIM_OK) { queue->store(nchunks); cudaDeviceSynchronize(); return fail(rc); }
         }
+        if (sparse) {
+            rc = launch_op_runs(B.d_ops, p.read_size, m, reinterpret_cast<unsigned char *>(B.d_cig), runs_pitch, ctx->s_kernel, nullptr);
+            if (rc != AIM_OK) { queue->store(nchunks); cudaDeviceSynchronize(); return fail(rc); }
+        }
         AIM_CUDA(cudaEventRecord(B.ev[3], ctx->s_kernel));
 
         AIM_CUDA(cudaStreamWaitEvent(ctx->s_d2h, B.ev[3], 0));
@@ -308,16 +399,27 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
         AIM_CUDA(cudaMemcpyAsync(o_res, B.d_res, (size_t)m * sizeof(aim_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
         if (cigars) {
             AIM_CUDA(cudaMemcpyAsync(cigars + (size_t)off * (size_t)pitch, B.d_cig, (size_t)m * (size_t)pitch, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        } else if (sparse) {
+            AIM_CUDA(cudaMemcpyAsync(B.h_runs, B.d_cig, (size_t)m * (size_t)runs_pitch, cudaMemcpyDeviceToHost, ctx->s_d2h));
         } else if (bt) {
             char *o_ops = pin_out ? ops + (size_t)off * 2 * rs : B.h_ops;
             AIM_CUDA(cudaMemcpyAsync(o_ops, B.d_ops, (size_t)m * 2 * rs, cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
         AIM_CUDA(cudaEventRecord(B.ev[5], ctx->s_d2h));
+        if (sparse) {
+            { std::lock_guard<std::mutex> lk(co.m); co.submitted = j + 1; }
+            co.cv.notify_all();
+        }
     }
     const uint32_t pulled = (uint32_t)mine.size();
-    for (uint32_t j = (pulled >= (uint32_t)nbuf ? pulled - (uint32_t)nbuf : 0); j < pulled; ++j) {
-        rc = finish(j);
-        if (rc != AIM_OK) return fail(rc);
+    if (sparse) {
+        co.close();
+        if (co.rc != AIM_OK) { set_error(co.err); return fail(co.rc); }
+    } else {
+        for (uint32_t j = (pulled >= (uint32_t)nbuf ? pulled - (uint32_t)nbuf : 0); j < pulled; ++j) {
+            rc = finish(j);
+            if (rc != AIM_OK) return fail(rc);
+        }
     }
     if (phase_ms) for (int k = 0; k < 3; ++k) phase_ms[k] = ph[k];
     return AIM_OK;
@@ -584,6 +686,7 @@ extern "C" void aim_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" void aim_shutdown(void)
 {
     file_pipeline_shutdown();
+    host_pool_shutdown();
     std::lock_guard<std::mutex> lk(g_mu);
     for (DeviceCtx *c : g_ctx) {
         if (!c) continue;
@@ -591,6 +694,7 @@ extern "C" void aim_shutdown(void)
         cudaDeviceSynchronize();
         for (auto &b : c->chunk) free_chunk(b);
         if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_kernel); cudaStreamDestroy(c->s_d2h); }
+        if (c->s_fix) cudaStreamDestroy(c->s_fix);
         scratch_destroy(&c->scratch);
         delete c;
     }

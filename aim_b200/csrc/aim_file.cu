@@ -367,4 +367,59 @@ int launch_file_format_write(const aim_result *d_res, const char *d_ops, int rea
     return AIM_OK;
 }
 
+
+// ---- op rows as RUN rows (aim_align_batch's download) ----
+// The op row the reference pulls back per pair is 2 * READ_SIZE bytes (host.c:316-326), 'M' but for a handful of runs; the
+// device-to-host direction is the scarcer one of the platform, so the row crosses PCIe as its non-'M' runs and
+// the host writes the row out again (expand_op_runs, aim_host.cpp).  A run row = `pitch` bytes = 32-bit words: the number of
+// runs, then one word per run of bytes other than 'M' over the WHOLE row: position | length (1..255) << 16 | op << 24 (so
+// the rebuilt row is the device row byte for byte); 0xffffffff in the first word = more runs than the row holds, the op row
+// is then fetched as it is.  One pair per thread, eight ops per step, all-'M' words skipped.
+namespace {
+__global__ void __launch_bounds__(128) op_runs_kernel(const char *ops, int row_bytes, unsigned char *runs, int pitch, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long *row = reinterpret_cast<const unsigned long long *>(ops + (size_t)i * row_bytes);
+    uint32_t *out = reinterpret_cast<uint32_t *>(runs + (size_t)i * pitch);
+    const int nw = row_bytes >> 3;
+    const uint32_t cap = (uint32_t)(pitch >> 2) - 1u;
+    const unsigned long long M8 = 0x4d4d4d4d4d4d4d4dull;
+    uint32_t cnt = 0;
+    int start = -1;  // first byte of the open non-'M' run
+    uint32_t op = 0;
+    auto close = [&](int end) {
+        for (int s = start; s < end; s += 255) {
+            if (cnt < cap) out[1 + cnt] = (uint32_t)s | ((uint32_t)min(end - s, 255) << 16) | (op << 24);
+            ++cnt;
+        }
+        start = -1;
+    };
+    for (int w = 0; w < nw; ++w) {
+        const unsigned long long x = row[w];
+        if (x == M8) {
+            if (start >= 0) close(8 * w);
+            continue;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t c = (uint32_t)(x >> (8 * k)) & 0xffu;
+            if (start >= 0 && c != op) close(8 * w + k);
+            if (c != 'M' && start < 0) { start = 8 * w + k; op = c; }
+        }
+    }
+    if (start >= 0) close(row_bytes);
+    out[0] = cnt <= cap ? cnt : 0xffffffffu;
+}
+}  // namespace
+
+int launch_op_runs(const char *d_ops, int read_size, uint32_t m, unsigned char *d_runs, int pitch, void *stream_v, int *launches)
+{
+    if (m == 0) return AIM_OK;
+    op_runs_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(d_ops, 2 * read_size, d_runs, pitch, m);
+    if (cudaGetLastError() != cudaSuccess) { set_error("op runs launch failed"); return AIM_ERR_CUDA; }
+    if (launches) ++*launches;
+    return AIM_OK;
+}
+
 }  // namespace aim

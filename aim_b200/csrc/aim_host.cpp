@@ -10,10 +10,14 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -56,7 +60,197 @@ size_t count_newlines(const char *p, size_t n)
     for (; i < n; ++i) c += p[i] == '\n';
     return c;
 }
+
+// ---- host pool: a few long-lived threads for the byte work that has to happen on the host beside the DMA ----
+namespace {
+class HostPool {
+  public:
+    ~HostPool() { shutdown(); }
+    // fn(b) for every b in [0, nblocks), on the pool's threads and the caller's; returns when all are done
+    void run(uint32_t nblocks, const std::function<void(uint32_t)> &fn)
+    {
+        std::lock_guard<std::mutex> call(call_mu_);  // one job at a time (several GPUs' coordinators share the pool)
+        if (nblocks <= 1 || threads() == 0) { for (uint32_t b = 0; b < nblocks; ++b) fn(b); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            start_threads();
+            fn_ = &fn;
+            nblocks_ = nblocks;
+            next_.store(0);
+            active_ = (int)th_.size();
+            ++gen_;
+        }
+        cv_work_.notify_all();
+        for (uint32_t b; (b = next_.fetch_add(1)) < nblocks;) fn(b);
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return active_ == 0; });
+        fn_ = nullptr;
+    }
+    void shutdown()
+    {
+        std::lock_guard<std::mutex> call(call_mu_);
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_work_.notify_all();
+        for (auto &t : th_) t.join();
+        th_.clear();
+        stop_ = false;
+    }
+    // helper threads beside the caller's: AIM_HOST_THREADS - 1, else half of this process's share of the cores (torchrun:
+    // LOCAL_WORLD_SIZE ranks) - 1; more than that fight the DMA-feeding and CUDA threads for the cores (measured)
+    static int threads()
+    {
+        static const int n = [] {
+            if (const char *e = getenv("AIM_HOST_THREADS")) return std::max(0, std::min(atoi(e), 64) - 1);
+            int hw = (int)std::thread::hardware_concurrency(), ranks = 1;
+            if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+            return std::max(1, std::min(hw / ranks / 2, 16) - 1);
+        }();
+        return n;
+    }
+
+  private:
+    void start_threads()
+    {
+        if (!th_.empty()) return;
+        const int n = threads();
+        for (int t = 0; t < n; ++t) th_.emplace_back([this] { worker(); });
+    }
+    void worker()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(uint32_t)> *fn;
+            uint32_t nb;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                fn = fn_;
+                nb = nblocks_;
+            }
+            for (uint32_t b; (b = next_.fetch_add(1)) < nb;) (*fn)(b);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--active_ == 0) cv_done_.notify_all();
+        }
+    }
+    std::mutex call_mu_, m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> th_;
+    const std::function<void(uint32_t)> *fn_ = nullptr;
+    uint32_t nblocks_ = 0;
+    std::atomic<uint32_t> next_{0};
+    uint64_t gen_ = 0;
+    int active_ = 0;
+    bool stop_ = false;
+};
+HostPool g_pool;
+
+// dst <- src with stores that bypass the cache (the rows are written once, at memory speed, and read by nobody on this
+// core).  dst and src are 16-byte aligned and congruent modulo 32, n is a multiple of 16.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void stream_block_avx2(char *dst, const char *src, size_t n)
+{
+    size_t k = 0;
+    if (((uintptr_t)dst & 31u) && n) { _mm_stream_si128((__m128i *)dst, _mm_load_si128((const __m128i *)src)); k = 16; }
+    for (; k + 32 <= n; k += 32) _mm256_stream_si256((__m256i *)(dst + k), _mm256_load_si256((const __m256i *)(src + k)));
+    if (k < n) _mm_stream_si128((__m128i *)(dst + k), _mm_load_si128((const __m128i *)(src + k)));
+}
+void stream_block_sse2(char *dst, const char *src, size_t n)
+{
+    for (size_t k = 0; k < n; k += 16) _mm_stream_si128((__m128i *)(dst + k), _mm_load_si128((const __m128i *)(src + k)));
+}
+#endif
+}  // namespace
+
+// Inverse of op_runs_kernel (aim_file.cu): every pair's 2 * read_size op row from its run row (run count, then position |
+// length << 16 | op << 24 per run of bytes other than 'M').  Sixteen rows at a time are put together in a cache-resident
+// buffer - 'M' fill, then the few runs as byte stores - and streamed out.
+void expand_op_runs(const unsigned char *runs, int pitch, uint32_t m, int read_size, char *ops, std::vector<uint32_t> *overflow)
+{
+    const size_t row = 2 * (size_t)read_size;
+    const uint32_t cap = (uint32_t)(pitch >> 2) - 1u;
+    constexpr uint32_t BLK = 2048, GRP = 16;
+    std::mutex ov_mu;
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    const bool aligned16 = ((uintptr_t)ops & 15u) == 0;  // (row is a multiple of 16)
+#endif
+    g_pool.run((m + BLK - 1) / BLK, [&](uint32_t b) {
+        alignas(64) char store[GRP * 2048 + 64];
+        std::vector<uint32_t> ov;
+        const uint32_t i1 = std::min(m, (b + 1) * BLK);
+        for (uint32_t g0 = b * BLK; g0 < i1; g0 += GRP) {
+            const uint32_t g1 = std::min(i1, g0 + GRP);
+            char *dst0 = ops + (size_t)g0 * row;
+            char *buf = store + ((uintptr_t)dst0 & 31u);  // the group's rows, laid out as at dst0 modulo 32
+            memset(buf, 'M', (size_t)(g1 - g0) * row);
+            uint32_t bad = 0;  // bit per row of the group that is not rebuilt
+            for (uint32_t i = g0; i < g1; ++i) {
+                const uint32_t *rp = reinterpret_cast<const uint32_t *>(runs + (size_t)i * (size_t)pitch);
+                char *rb = buf + (size_t)(i - g0) * row;
+                const uint32_t c = rp[0];
+                bool ok = c <= cap;  // 0xffffffff = more runs than the run row holds (op_runs_kernel)
+                for (uint32_t j = 0; ok && j < c; ++j) {
+                    const uint32_t e = rp[1 + j];
+                    const size_t pos = e & 0xffffu, len = (e >> 16) & 0xffu;
+                    const char op = (char)(e >> 24);
+                    if (pos + len > row) { ok = false; break; }  // (cannot happen with rows op_runs_kernel wrote)
+                    rb[pos] = op;
+                    for (size_t q = 1; q < len; ++q) rb[pos + q] = op;
+                }
+                if (!ok) { ov.push_back(i); bad |= 1u << (i - g0); }
+            }
+            if (bad == 0) {
+#if defined(__x86_64__)
+                if (aligned16) {
+                    if (avx2) stream_block_avx2(dst0, buf, (size_t)(g1 - g0) * row);
+                    else stream_block_sse2(dst0, buf, (size_t)(g1 - g0) * row);
+                    continue;
+                }
+#endif
+                memcpy(dst0, buf, (size_t)(g1 - g0) * row);
+            } else {  // rows that are not rebuilt stay untouched
+                for (uint32_t i = g0; i < g1; ++i)
+                    if (!((bad >> (i - g0)) & 1u)) memcpy(ops + (size_t)i * row, buf + (size_t)(i - g0) * row, row);
+            }
+        }
+#if defined(__x86_64__)
+        _mm_sfence();
+#endif
+        if (!ov.empty()) { std::lock_guard<std::mutex> lk(ov_mu); overflow->insert(overflow->end(), ov.begin(), ov.end()); }
+    });
+}
+
+void host_pool_shutdown() { g_pool.shutdown(); }
+
+// bytes of a run row for READ_SIZE-wide pairs: room for ~3/32 * READ_SIZE runs of ops other than 'M' (a 4 % error rate makes
+// ~0.04 per base); 0 = rows of this size are downloaded as they are
+int32_t op_runs_pitch(int32_t read_size)
+{
+    if (read_size < 32 || read_size > 1024) return 0;
+    return std::max(32, (read_size * 3 / 8 + 15) / 16 * 16);
+}
 }  // namespace aim
+
+extern "C" int32_t aim_op_runs_pitch(int32_t read_size) { return aim::op_runs_pitch(read_size); }
+
+extern "C" int aim_expand_op_runs(const unsigned char *runs, int32_t pitch, uint32_t n, int32_t read_size, char *ops,
+                                  uint32_t *overflow, uint32_t overflow_cap, uint32_t *overflow_count)
+{
+    if (overflow_count) *overflow_count = 0;
+    if (n == 0) return AIM_OK;
+    if (!runs || !ops || pitch < 8 || (pitch % 4) != 0 || ((uintptr_t)runs & 3u) != 0 || read_size <= 0 || (read_size % 8) != 0 || read_size > 1024) {
+        aim::set_error("aim_expand_op_runs: runs (4-byte aligned) and ops required, pitch a multiple of 4, read_size a multiple of 8 in 8..1024");
+        return AIM_ERR_ARG;
+    }
+    std::vector<uint32_t> ov;
+    aim::expand_op_runs(runs, pitch, n, read_size, ops, &ov);
+    std::sort(ov.begin(), ov.end());
+    if (overflow_count) *overflow_count = (uint32_t)ov.size();
+    if (overflow) for (size_t k = 0; k < ov.size() && k < overflow_cap; ++k) overflow[k] = ov[k];
+    return AIM_OK;
+}
 
 extern "C" const char *aim_last_error(void) { return aim::g_last_error.c_str(); }
 extern "C" int aim_abi_version(void) { return AIM_B200_ABI_VERSION; }

@@ -4,6 +4,7 @@
 
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "aim_b200.h"
 
@@ -113,6 +114,15 @@ bool params_valid_for_file(const aim_params *p);
 aim_params params_normalized(const aim_params *p);  // GenASM-DC implies the op rows, the filter has none
 size_t count_newlines(const char *p, size_t n);  // aim_host.cpp (AVX2 when available)
 void file_pipeline_shutdown();                   // frees the cached chunk slots of aim_align_file (aim_shutdown)
+
+
+// ---- op rows as run rows across PCIe (kernel: aim_file.cu; expansion and its thread pool: aim_host.cpp) ----
+int32_t op_runs_pitch(int32_t read_size);  // bytes per pair, 0 = not served (the rows are downloaded as they are)
+int launch_op_runs(const char *d_ops, int read_size, uint32_t m, unsigned char *d_runs, int pitch, void *stream, int *launches);
+// Rebuilds the 2 * read_size op rows of m pairs at `ops` from their run rows on the host pool's threads; *overflow receives
+// the pairs whose run row carries the "did not fit" mark (their rows are left untouched).
+void expand_op_runs(const unsigned char *runs, int pitch, uint32_t m, int read_size, char *ops, std::vector<uint32_t> *overflow);
+void host_pool_shutdown();
 
 }  // namespace aim
 

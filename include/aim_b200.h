@@ -115,6 +115,20 @@ int aim_align_device(const aim_params *params, int device, uint32_t n, uint32_t 
                      aim_result *d_results, char *d_ops,
                      void *stream, float *kernel_ms, int32_t *launches);
 
+/* ---- how aim_align_batch brings the op rows back (NW, SWG, WFA; read_size 32..1024) --------------------------------
+ * The caller's `ops` buffer is filled exactly as documented above, but the rows do not cross PCIe as they are: the device-to-
+ * host direction is the scarcer one of a multi-GPU host (all GPUs together: 72-94 GB/s against 110-187 GB/s host-to-device,
+ * DESIGN.md 6.2) and a 2*read_size row is 'M' but for a handful of runs.  A kernel turns every op row into a RUN ROW of
+ * aim_op_runs_pitch(read_size) bytes - 32-bit words: the number of runs, then per run of bytes other than 'M' over the whole
+ * row: position | length (1..255) << 16 | op << 24; first word 0xffffffff = more runs than the row holds - and host threads
+ * (AIM_HOST_THREADS, default half of the cores) rebuild the rows into `ops` with cache-bypassing stores while later chunks
+ * are in flight; rows that did not fit are fetched as they are.  AIM_SPARSE_OPS=0 moves the rows as they are.
+ * aim_expand_op_runs is that host half (exported for tests and for callers that keep run rows): rebuilds n rows, lists the
+ * pairs whose run row carries the mark (ascending, at most overflow_cap of *overflow_count). */
+int32_t aim_op_runs_pitch(int32_t read_size);
+int aim_expand_op_runs(const unsigned char *runs, int32_t pitch, uint32_t n, int32_t read_size, char *ops,
+                       uint32_t *overflow, uint32_t overflow_cap, uint32_t *overflow_count);
+
 /* ---- compact transfers (extension; WFA short reads) -------------------------------------------------
  * aim_align_batch moves the reference host's own buffers: 2*READ_SIZE ASCII bytes in and the 2*READ_SIZE op row out per
  * pair (696 B at READ_SIZE 168), which is what bounds it: one PCIe Gen5 x16 link carries ~1.2e8 pairs/s of that layout and
