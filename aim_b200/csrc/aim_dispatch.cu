@@ -112,7 +112,9 @@ int ensure_chunk(ChunkBuf &b, uint32_t pairs, int32_t read_size, bool ops, bool 
     if (b.pairs_cap >= pairs && b.read_size == read_size && (b.has_ops || !ops) && (b.has_staging || !staging)) return AIM_OK;
     free_chunk(b);
     const size_t rs = (size_t)read_size;
-    for (auto &e : b.ev) AIM_CUDA(cudaEventCreate(&e));
+    // (blocking sync: a host thread that waits for a chunk sleeps instead of spinning - the cores are needed by the threads
+    // that rebuild op rows, and by the other ranks of a multi-GPU job)
+    for (auto &e : b.ev) AIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventBlockingSync));
     AIM_CUDA(cudaMalloc(&b.d_plen, pairs * sizeof(int32_t)));
     AIM_CUDA(cudaMalloc(&b.d_tlen, pairs * sizeof(int32_t)));
     AIM_CUDA(cudaMalloc(&b.d_pat, pairs * rs));
@@ -764,6 +766,9 @@ static int align_batch_once(const aim_params *params, uint32_t n, uint32_t idx_b
 
     // one host thread + stream set per GPU, all pulling chunks from one queue (the reference splits contiguously per DPU,
     // host.c:201-209; a queue gives the same output - every chunk lands at its own offset - and balances uneven pairs)
+    // the host threads that rebuild the op rows serve g GPUs now: 3/4 of the cores, less the g submitters (one process drives
+    // the box's GPUs here, so the cores are not shared with other ranks)
+    host_pool_want((int)std::thread::hardware_concurrency() * 3 / 4 - g);
     std::vector<std::thread> th;
     std::vector<int> rcs((size_t)g, AIM_OK);
     std::vector<std::string> errs((size_t)g);

@@ -95,29 +95,38 @@ class HostPool {
         th_.clear();
         stop_ = false;
     }
-    // helper threads beside the caller's: AIM_HOST_THREADS - 1, else half of this process's share of the cores (torchrun:
-    // LOCAL_WORLD_SIZE ranks) - 1; more than that fight the DMA-feeding and CUDA threads for the cores (measured)
+    // helper threads beside the caller's: AIM_HOST_THREADS - 1, else this process's share of the cores (torchrun:
+    // LOCAL_WORLD_SIZE ranks) less one for the submitting thread, at most 8 threads in all: more fight the DMA-feeding and
+    // CUDA threads for the cores and add nothing (measured)
+    // more helpers for a caller that drives several GPUs from one process (never fewer)
+    void want(int helpers)
+    {
+        std::lock_guard<std::mutex> call(call_mu_);
+        std::lock_guard<std::mutex> lk(m_);
+        if (getenv("AIM_HOST_THREADS")) return;
+        extra_ = std::max(extra_, std::min(helpers, 63) - threads());
+        if (!th_.empty()) grow();
+    }
     static int threads()
     {
         static const int n = [] {
             if (const char *e = getenv("AIM_HOST_THREADS")) return std::max(0, std::min(atoi(e), 64) - 1);
             int hw = (int)std::thread::hardware_concurrency(), ranks = 1;
             if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
-            return std::max(1, std::min(hw / ranks / 2, 16) - 1);
+            return std::max(1, std::min(hw / ranks - 1, 8) - 1);
         }();
         return n;
     }
 
   private:
-    void start_threads()
+    void start_threads() { grow(); }
+    void grow()  // (m_ held; a thread that starts now has seen no generation yet and joins the next job)
     {
-        if (!th_.empty()) return;
-        const int n = threads();
-        for (int t = 0; t < n; ++t) th_.emplace_back([this] { worker(); });
+        const int n = threads() + std::max(0, extra_);
+        while ((int)th_.size() < n) { const uint64_t g = gen_; th_.emplace_back([this, g] { worker(g); }); }
     }
-    void worker()
+    void worker(uint64_t seen)
     {
-        uint64_t seen = 0;
         for (;;) {
             const std::function<void(uint32_t)> *fn;
             uint32_t nb;
@@ -141,7 +150,7 @@ class HostPool {
     uint32_t nblocks_ = 0;
     std::atomic<uint32_t> next_{0};
     uint64_t gen_ = 0;
-    int active_ = 0;
+    int active_ = 0, extra_ = 0;
     bool stop_ = false;
 };
 HostPool g_pool;
@@ -223,6 +232,7 @@ void expand_op_runs(const unsigned char *runs, int pitch, uint32_t m, int read_s
 }
 
 void host_pool_shutdown() { g_pool.shutdown(); }
+void host_pool_want(int helpers) { g_pool.want(helpers); }
 
 // bytes of a run row for READ_SIZE-wide pairs: room for ~3/32 * READ_SIZE runs of ops other than 'M' (a 4 % error rate makes
 // ~0.04 per base); 0 = rows of this size are downloaded as they are

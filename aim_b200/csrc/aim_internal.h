@@ -123,6 +123,7 @@ int launch_op_runs(const char *d_ops, int read_size, uint32_t m, unsigned char *
 // the pairs whose run row carries the "did not fit" mark (their rows are left untouched).
 void expand_op_runs(const unsigned char *runs, int pitch, uint32_t m, int read_size, char *ops, std::vector<uint32_t> *overflow);
 void host_pool_shutdown();
+void host_pool_want(int helpers);  // at least this many helper threads from now on (one process driving several GPUs)
 
 }  // namespace aim
 

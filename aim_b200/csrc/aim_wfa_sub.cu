@@ -114,38 +114,47 @@ __device__ __forceinline__ void sts_v4(uint32_t a, uint4 v)
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// 16 bases starting at base b of an ASCII row -> one 32-bit word, first base in the two most significant bits;
-// bases at or beyond len (or the row) read as 'A'.  *ok is cleared by a byte outside {A,C,G,T} below len.
-__device__ __forceinline__ uint32_t pack16(const char *row, int b, int len, int RS, bool *ok)
-{
-    uint32_t w = 0;
-#pragma unroll
-    for (int hlf = 0; hlf < 2; ++hlf) {
-        const int bb = b + 8 * hlf;
-        uint32_t h16 = 0;
-        if (bb < len && bb < RS) h16 = pack8(__ldg(reinterpret_cast<const uint2 *>(row + bb)), len - bb, ok);
-        w = (w << 16) | h16;
-    }
-    return w;
-}
-
-// One thread per (pair, sequence, 16-base word): word j = bases 16j..16j+15, first base in the top two bits.  HBM-bound.
+// One thread per (pair, sequence, 16-base word): word j = bases 16j..16j+15, first base in the top two bits.  HBM-bound:
+// a block covers 256 / SW consecutive rows per step (a thread keeps its word index j, so there is no division in the loop)
+// and every thread has two rows' loads in flight.
 // A pair holding a byte outside {A,C,G,T} (the reference compares raw bytes, wfa.c:209) cannot be 2-bit packed: it is
 // flagged and listed once for the warp-per-pair kernel of aim_wfa.cu, which compares bytes.
 __global__ void __launch_bounds__(256) wfa_prep_kernel(const char *patterns, const char *texts, const int32_t *plen, const int32_t *tlen,
                                                        uint32_t n, int RS, uint32_t SW, uint32_t *packed, uint32_t *flags,
                                                        uint32_t *list, uint32_t *list_count)
 {
-    const uint64_t total = (uint64_t)n * 2u * SW;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t j = (uint32_t)(t % SW);
-        const uint64_t r = t / SW;
-        const uint32_t q = (uint32_t)(r & 1u), i = (uint32_t)(r >> 1);
-        const int len = min(max(q ? tlen[i] : plen[i], 0), RS);
+    const uint32_t rpb = 256u / SW;  // rows (sequences) per block and step
+    const uint32_t jr = threadIdx.x / SW, j = threadIdx.x - jr * SW;
+    if (jr >= rpb) return;
+    const uint64_t rows = 2ull * n, step = (uint64_t)gridDim.x * rpb;
+    const int b = (int)j * 16;
+    struct Raw { uint2 lo, hi; int len; };
+    auto fetch = [&](uint64_t r) {
+        Raw w{make_uint2(0, 0), make_uint2(0, 0), 0};
+        const uint32_t i = (uint32_t)(r >> 1);
+        const bool q = r & 1u;
+        w.len = min(max(q ? tlen[i] : plen[i], 0), RS);
         const char *row = (q ? texts : patterns) + (size_t)i * RS;
+        if (b < w.len && b < RS) w.lo = __ldg(reinterpret_cast<const uint2 *>(row + b));
+        if (b + 8 < w.len && b + 8 < RS) w.hi = __ldg(reinterpret_cast<const uint2 *>(row + b + 8));
+        return w;
+    };
+    auto finish = [&](uint64_t r, const Raw &w) {
         bool ok = true;
-        packed[t] = pack16(row, (int)j * 16, len, RS, &ok);
+        uint32_t h0 = 0, h1 = 0;
+        if (b < w.len && b < RS) h0 = pack8(w.lo, w.len - b, &ok);
+        if (b + 8 < w.len && b + 8 < RS) h1 = pack8(w.hi, w.len - b - 8, &ok);
+        packed[r * SW + j] = (h0 << 16) | h1;
+        const uint32_t i = (uint32_t)(r >> 1);
         if (!ok && !(atomicOr(&flags[i >> 5], 1u << (i & 31)) & (1u << (i & 31)))) list[atomicAdd(list_count, 1u)] = i;  // first to flag it
+    };
+    for (uint64_t r = (uint64_t)blockIdx.x * rpb + jr; r < rows; r += 2 * step) {
+        const bool two = r + step < rows;
+        const Raw w0 = fetch(r);
+        Raw w1{make_uint2(0, 0), make_uint2(0, 0), 0};
+        if (two) w1 = fetch(r + step);
+        finish(r, w0);
+        if (two) finish(r + step, w1);
     }
 }
 
@@ -753,6 +762,7 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     K.results = a.results; K.ops = a.ops; K.n = a.n; K.idx_base = a.idx_base;
     K.x = x; K.o = o; K.e = e; K.max_score = MS; K.read_size = p.read_size;
     K.seq_words = round_up((uint32_t)p.read_size / 16 + 2, 4);
+    if (K.seq_words > 256) return 1;  // (wfa_prep_kernel: a block covers whole rows; such reads are the long-read kernel's anyway)
     K.dyn_words = p.reduce ? round_up((uint32_t)MS + 1, 4) : 0;
     const uint32_t pair_words_raw = 2 * K.seq_words + K.dyn_words + rows_bytes / 4;
 
@@ -831,8 +841,8 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     if (err == cudaSuccess && p.backtrace)  // op rows: 'M' everywhere (wfa.c:499-501); the backtrace overwrites the few edits
         err = cudaMemsetAsync(a.ops, 'M', (size_t)a.n * 2 * (size_t)p.read_size, stream);
     if (err == cudaSuccess && !prepacked) {
-        const uint64_t total = (uint64_t)a.n * 2 * K.seq_words;
-        const int pgrid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sc->sm_count * 64);
+        const uint64_t rpb = 256u / K.seq_words;  // (seq_words <= 72: read_size is below the long-read threshold here)
+        const int pgrid = (int)std::min<uint64_t>((2ull * a.n + 2 * rpb - 1) / (2 * rpb), (uint64_t)sc->sm_count * 64);
         wfa_prep_kernel<<<pgrid, 256, 0, stream>>>(a.patterns, a.texts, a.plen, a.tlen, a.n, p.read_size, K.seq_words, packed, flags, list, list_count);
         err = cudaGetLastError();
         if (launches) ++*launches;

@@ -121,8 +121,9 @@ int aim_align_device(const aim_params *params, int device, uint32_t n, uint32_t 
  * DESIGN.md 6.2) and a 2*read_size row is 'M' but for a handful of runs.  A kernel turns every op row into a RUN ROW of
  * aim_op_runs_pitch(read_size) bytes - 32-bit words: the number of runs, then per run of bytes other than 'M' over the whole
  * row: position | length (1..255) << 16 | op << 24; first word 0xffffffff = more runs than the row holds - and host threads
- * (AIM_HOST_THREADS, default half of the cores) rebuild the rows into `ops` with cache-bypassing stores while later chunks
- * are in flight; rows that did not fit are fetched as they are.  AIM_SPARSE_OPS=0 moves the rows as they are.
+ * (AIM_HOST_THREADS; default: the process's share of the cores, at most 8) rebuild the rows into `ops` with cache-bypassing
+ * stores while later chunks are in flight; rows that did not fit are fetched as they are.  AIM_SPARSE_OPS=0 moves the rows
+ * as they are.
  * aim_expand_op_runs is that host half (exported for tests and for callers that keep run rows): rebuilds n rows, lists the
  * pairs whose run row carries the mark (ascending, at most overflow_cap of *overflow_count). */
 int32_t aim_op_runs_pitch(int32_t read_size);
