@@ -12,7 +12,7 @@ CXX_SRCS  := $(CSRC)/aim_host.cpp
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CXX_SRCS))
 HDRS      := include/aim_b200.h $(CSRC)/aim_internal.h $(CSRC)/aim_wfa_common.cuh $(CSRC)/aim_dp_pack2.cuh
 
-all: aim_b200/libaim_b200.so aim_b200/libaim_dpu.so build/host build/aim_genpairs build/diag_xfer oracle/libaim_oracle.so
+all: aim_b200/libaim_b200.so aim_b200/libaim_dpu.so build/host build/aim_genpairs build/diag_xfer build/diag_hostfill oracle/libaim_oracle.so
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -37,6 +37,11 @@ build/host: tools/host.cpp aim_b200/libaim_b200.so include/aim_b200.h
 build/diag_xfer: tools/diag_xfer.cu
 	@mkdir -p build
 	$(NVCC) -O2 -std=c++17 $(ARCH) -cudart static tools/diag_xfer.cu -o $@ -lpthread
+
+# how fast host threads rebuild op rows beside a saturating H2D copy
+build/diag_hostfill: tools/diag_hostfill.cu
+	@mkdir -p build
+	$(NVCC) -O2 -std=c++17 $(ARCH) -cudart static tools/diag_hostfill.cu -o $@ -lpthread
 
 # stand-alone pair-file generator for bench.py's reference arm (host-only code, no CUDA, no libaim_b200.so)
 build/aim_genpairs: tools/genpairs.cpp $(CSRC)/aim_host.cpp $(HDRS)
