@@ -190,6 +190,9 @@ uint32_t pick_chunk_pairs(const aim_params &p, uint32_t n, size_t per_pair, int 
     size_t chunk_bytes = (p.algo != AIM_ALGO_WFA) ? (384u << 20) : (p.read_size >= 2048 ? (768u << 20) : (96u << 20));
     if (const char *cm = getenv("AIM_CHUNK_MB")) { const long v = atol(cm); if (v >= 1 && v <= 4096) chunk_bytes = (size_t)v << 20; }
     uint32_t chunk_pairs = (uint32_t)std::max<size_t>(16384, std::min<size_t>(chunk_bytes / per_pair, 1u << 20));
+    // a batch of a few such chunks (config 2: 2 M pairs = 3) spends as long filling and draining the pipeline as in it: at least
+    // ~8 chunks per call, none below 256 K pairs (a DP kernel wave is ~150 K pairs)
+    if (p.algo != AIM_ALGO_WFA && !getenv("AIM_CHUNK_MB")) chunk_pairs = std::min(chunk_pairs, std::max(1u << 18, n / 8u));
     if (ngpus > 1) {
         const uint32_t floor_pairs = p.read_size >= 2048 ? 4096u : 16384u;
         chunk_pairs = std::max(floor_pairs, std::min(chunk_pairs, n / (4u * (uint32_t)ngpus)));
@@ -312,7 +315,7 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
         }
         ~Coord() { close(); }
     } co;
-    if (sparse)
+    if (sparse) try {
         co.th = std::thread([&]() {
             cudaSetDevice(device);
             for (uint32_t j = 0;; ++j) {
@@ -330,6 +333,10 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
                 co.cv.notify_all();
             }
         });
+    } catch (...) {
+        set_error("cannot start the chunk coordinator thread");
+        return fail(AIM_ERR_NOMEM);
+    }
     auto wait_done = [&](uint32_t j) -> int {  // chunk j complete (sparse)
         std::unique_lock<std::mutex> lk(co.m);
         co.cv.wait(lk, [&] { return co.done > j; });

@@ -74,6 +74,7 @@ class HostPool {
         {
             std::lock_guard<std::mutex> lk(m_);
             start_threads();
+            if (th_.empty()) { for (uint32_t b = 0; b < nblocks; ++b) fn(b); return; }
             fn_ = &fn;
             nblocks_ = nblocks;
             next_.store(0);
@@ -123,7 +124,10 @@ class HostPool {
     void grow()  // (m_ held; a thread that starts now has seen no generation yet and joins the next job)
     {
         const int n = threads() + std::max(0, extra_);
-        while ((int)th_.size() < n) { const uint64_t g = gen_; th_.emplace_back([this, g] { worker(g); }); }
+        try {
+            while ((int)th_.size() < n) { const uint64_t g = gen_; th_.emplace_back([this, g] { worker(g); }); }
+        } catch (...) {  // no more threads to be had: the ones there are (or the caller alone) do the work
+        }
     }
     void worker(uint64_t seen)
     {

@@ -88,6 +88,7 @@ struct SubK {
     uint32_t pair_words;    // shared-memory words per pair slot
     int bias;               // NARROW rows: stored byte = offset + bias; the NULL family (NULL + d) is stored as d
     int null_max;           // NARROW rows: bytes <= null_max are the NULL family
+    uint32_t own_bytes;     // POOL: bytes of a warp's cell table (16-bit entries, PPW * cw of them), after the pair slots
 };
 
 // ---- shared-memory accessors on 32-bit shared-window addresses ----
@@ -105,6 +106,8 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a)
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ int lds_u16(uint32_t a) { int v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_u16s(uint32_t a) { return lds_u16(a); }
 __device__ __forceinline__ int lds_u8(uint32_t a) { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u8(uint32_t a, int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory"); }
@@ -213,9 +216,17 @@ __device__ __forceinline__ bool in_range(int k, int lo, int hi) { return (unsign
 // and +1 of compute_offsets is the same operation on the bytes, and the literal value is recovered wherever a DIFFERENCE to a
 // true offset is taken (adaptive distances, backtrace).  Used when READ_SIZE + 2*MAX_SCORE + 12 <= 255; the history cell shrinks to
 // four bytes {M, I, D}.
-template <int G, bool REDUCE, bool BT, int MAXT = 128, bool NB = false>
+// POOL (narrow rows, G = 4): the cells of a wavefront are dealt to the 32 lanes of the WARP instead of the four lanes of their pair.
+// The pairs of a warp walk the scores together, but adaptive trimming gives them different widths and they finish at different
+// scores, so with four fixed lanes per pair the warp runs the widest pair's trips (18 of 32 lanes busy, ncu).  Per score the
+// sub-warps write their pair's cells (pair, diagonal) into a warp-wide table in shared memory, in pair order; lane l then takes
+// cells l, l + 32, ... whatever pair they belong to (row addresses from the pair number, lengths by shuffle from the pair's
+// lanes) and leaves each cell's distance to the end in the cell's table entry, from which the pair's lanes take the minimum the
+// reduction needs.  Range computation, frame clean-up, end test, reduction and backtrace stay with the pair's own lanes.
+template <int G, bool REDUCE, bool BT, int MAXT = 128, bool NB = false, bool POOL = false>
 __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
 {
+    static_assert(!POOL || (NB && G == 4), "the pooled cell loop is written for narrow rows with four lanes per pair");
     constexpr int PPW = 32 / G;
     constexpr uint32_t ES = NB ? 1u : 2u;  // bytes per M cell; an {I,D} cell is 2 * ES bytes (I first)
     const int BZ = NB ? K.bias : 0;
@@ -254,6 +265,8 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
 #define AIM_ROW(off) (aK0 + ((off) == OFF_NULL ? nullrel : (off)))
 #define AIM_ROWD(off) (aK0D + ((off) == OFF_NULL ? nullrelD : (off)))
 
+    const uint32_t aOwn = sbase + (K.plan_words + K.cw + wpb * PPW * K.pair_words) * 4u + (uint32_t)wib * K.own_bytes;  // POOL
+    const uint32_t aSlot0 = aSlot - (uint32_t)sub * K.pair_words * 4u;                                                // slot of the warp's first pair
     const uint32_t slot_global = (blockIdx.x * wpb + wib) * PPW + sub;
     const uint32_t nslots = gridDim.x * wpb * PPW;
     uint2 *arena = (BT && !NB) ? K.arena + (size_t)slot_global * K.arena_stride : nullptr;
@@ -327,7 +340,96 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
 
             // ---- compute_offsets (wfa.c:238-273) fused with extend (wfa.c:193-215); no range tests: see the header ----
             int md = max(pl, tl);
-            if (!done) {
+            bool pooled = false;
+            if constexpr (POOL) {
+                if (!(fl & P_NULL_ROW)) {  // (early scores read the block-wide NULL row for a missing source: they keep the per-pair loop)
+                    pooled = true;
+                    // ---- the warp's cell table: pair p's cells at [pre_p, pre_p + w_p) ----
+                    const int w = (!done && hi >= lo) ? hi - lo + 1 : 0;
+                    int incl = w;
+                    {
+                        int t = __shfl_up_sync(kFull, incl, G);
+                        if (lane >= G) incl += t;
+                        t = __shfl_up_sync(kFull, incl, 2 * G);
+                        if (lane >= 2 * G) incl += t;
+                        t = __shfl_up_sync(kFull, incl, 4 * G);
+                        if (lane >= 4 * G) incl += t;
+                    }
+                    const int pre = incl - w;
+                    const int W = __shfl_sync(kFull, incl, 31);
+                    for (int j = sl; j < w; j += G) sts_u16(aOwn + 2u * (uint32_t)(pre + j), (sub << 8) | (lo + j + 128));
+                    __syncwarp();
+                    // row offsets from a pair's slot (the layout is the same for every pair)
+                    const uint32_t uNM = aNM - aSlot, uAM = aAM - aSlot, uBM = aBM - aSlot, uE = aE - aSlot, uN = aN - aSlot;
+                    const uint32_t pairb = K.pair_words * 4u, seqb = K.seq_words * 4u;
+                    const uint32_t mypt = (uint32_t)pl | ((uint32_t)tl << 16);
+                    const uint32_t hist0 = p1.y - (uint32_t)lo_s;  // arena cell of diagonal k: hist0 + k
+                    uint32_t *arena_w0 = BT ? arena1 - (size_t)sub * K.arena_stride : nullptr;
+                    const uint32_t astride = (uint32_t)K.arena_stride;
+                    for (int c0 = 0; c0 < W; c0 += 64) {  // warp-uniform trips, two cells per lane
+                        constexpr int N = 2;
+                        bool ok[N];
+                        int kk[N], cpl[N], ctl[N], g1[N] = {}, g2[N] = {}, ii[N] = {}, dd[N] = {}, sb[N] = {}, mm[N], cc[N], ll[N];
+                        uint32_t ps[N], slot[N], idd[N];
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            const int c = c0 + 32 * j + lane;
+                            ok[j] = c < W;
+                            const uint32_t en = ok[j] ? (uint32_t)lds_u16(aOwn + 2u * (uint32_t)c) : 128u;
+                            ps[j] = en >> 8;
+                            kk[j] = (int)(en & 0xffu) - 128;
+                            const uint32_t pt = __shfl_sync(kFull, mypt, (int)ps[j] * G);
+                            cpl[j] = (int)(pt & 0xffffu);
+                            ctl[j] = (int)(pt >> 16);
+                            slot[j] = aSlot0 + ps[j] * pairb;
+                        }
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            if (ok[j]) {
+                                const uint32_t a1 = slot[j] + (uint32_t)kk[j], a2 = a1 + (uint32_t)kk[j];
+                                g1[j] = lds_u8(a1 + uBM - 1u); g2[j] = lds_u8(a1 + uBM + 1u);
+                                ii[j] = lds_u8(a2 + uE - 2u); dd[j] = lds_u8(a2 + uE + 3u);  // I of cell k-1, D of cell k+1
+                                sb[j] = lds_u8(a1 + uAM);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            const int t = max(g1[j], ii[j]) + 1;
+                            const int ins = t == 1 ? 0 : t;  // both NULL -> NULL (wfa.c:249-252)
+                            const int del = max(g2[j], dd[j]);
+                            mm[j] = max(max(del, sb[j] + 1), max(ins, floor_m));
+                            idd[j] = (uint32_t)ins | ((uint32_t)del << 8);
+                        }
+#pragma unroll
+                        for (int j = 0; j < N; ++j)
+                            if (ok[j]) sts_u16(slot[j] + 2u * (uint32_t)kk[j] + uN, (int)idd[j]);
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            cc[j] = 0; ll[j] = 0;
+                            if (ok[j]) cc[j] = extend_first(slot[j], slot[j] + seqb, kk[j], mm[j] - BZ, cpl[j], ctl[j], &ll[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            if (ok[j]) {
+                                int m = mm[j], cnt = cc[j];
+                                if (cnt == 16 && ll[j] > 16) cnt = extend_more(slot[j], slot[j] + seqb, m - BZ - kk[j], m - BZ, ll[j]);  // rare
+                                m += max(min(cnt, ll[j]), 0);
+                                sts_u8(slot[j] + (uint32_t)kk[j] + uNM, m);
+                                if (BT) arena_w0[ps[j] * astride + (hist0 + (uint32_t)kk[j])] = (uint32_t)m | (idd[j] << 8);
+                                if (REDUCE) {
+                                    // the cell's distance to the end (a NULL-family cell is -16384 + d in the reference: never the minimum)
+                                    const int d = m > K.null_max ? max(cpl[j] + kk[j], ctl[j]) + BZ - m : 0x7fff;
+                                    sts_u16(aOwn + 2u * (uint32_t)(c0 + 32 * j + lane), d);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (REDUCE)
+                        for (int j = sl; j < w; j += G) md = min(md, lds_u16s(aOwn + 2u * (uint32_t)(pre + j)));
+                }
+            }
+            if (!done && !pooled) {
                 // this lane's cells are k0, k0 + G, ...; row pointers at k0, advanced once per trip
                 const int k0 = lo + sl;
                 uint32_t rB = aBM + (uint32_t)k0 * ES, rA = aAM + (uint32_t)k0 * ES, rNM = aNM + (uint32_t)k0 * ES;
@@ -385,6 +487,9 @@ __global__ void __launch_bounds__(MAXT) wfa_sub_kernel(const SubK K)
 #ifndef AIM_CPT
 #define AIM_CPT 2
 #endif
+                // (measured and rejected, round 2: warp-wide two-cell trips with the cell a lane does not have masked off, so that lanes
+                // with an odd count do not cost the warp an extra one-cell trip - the votes, selects and predicates cost more than the
+                // trips they save: 3.41e8 against 3.48e8 pairs/s)
                 while (k + (AIM_CPT - 1) * G <= hi) trip(std::integral_constant<int, AIM_CPT>{});
                 if (AIM_CPT > 2 && k + G <= hi) trip(std::integral_constant<int, 2>{});
                 if (k <= hi) trip(std::integral_constant<int, 1>{});
@@ -631,7 +736,7 @@ __global__ void __launch_bounds__(128) cigar_rle_kernel(const int32_t *plen, con
 }
 
 template <int G>
-cudaError_t launch_g(const SubK &K, bool reduce, bool bt, bool narrow, int grid, int block, size_t smem, cudaStream_t st)
+cudaError_t launch_g(const SubK &K, bool reduce, bool bt, bool narrow, bool pool, int grid, int block, size_t smem, cudaStream_t st)
 {
     cudaError_t e;
     // blocks of more than 4 warps (G <= 4 only: one big block fills an SM's shared memory with less per-block overhead)
@@ -640,7 +745,10 @@ cudaError_t launch_g(const SubK &K, bool reduce, bool bt, bool narrow, int grid,
     do {                                                                                                                  \
         if (narrow) {                                                                                                     \
             if constexpr (G == 4) {                                                                                       \
-                if (block <= 128) {                                                                                       \
+                if (pool) {                                                                                               \
+                    e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B, 896, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                    if (e == cudaSuccess) wfa_sub_kernel<G, R, B, 896, true, true><<<grid, block, smem, st>>>(K);         \
+                } else if (block <= 128) {                                                                                       \
                     e = cudaFuncSetAttribute(wfa_sub_kernel<G, R, B, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
                     if (e == cudaSuccess) wfa_sub_kernel<G, R, B, 128, true><<<grid, block, smem, st>>>(K);               \
                 } else {                                                                                                  \
@@ -787,18 +895,26 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     // these occupancies, gains ~10 %.  Small footprints keep the two-warp blocks (registers cap those at 32 warps/SM).
     const int default_wpb = G <= 4 ? 2 : 4;
     int warps_per_block = default_wpb;
+    // POOL (see the kernel): a warp's cells dealt to all its lanes; one table of PPW * cw 16-bit entries per warp.  Bit-exact, but
+    // measured SLOWER at config 4 (2.83e8 against 3.48e8 pairs/s: 23 instead of 18 lanes busy, but 25 % more warp instructions -
+    // with balanced widths the warp runs as many trips as before and every cell pays ~13 more instructions): off
+    // unless AIM_WFA_POOL=1
+    bool pool = false;
+    if (const char *ps = getenv("AIM_WFA_POOL")) pool = narrow && G == 4 && atoi(ps) != 0;
+    K.own_bytes = pool ? round_up((uint32_t)PPW * K.cw * 2u, 16) : 0u;
+    const size_t warp_bytes = (size_t)PPW * pair_bytes + K.own_bytes;
     if (G <= 4) {
-        const size_t small_block = fixed_bytes + (size_t)default_wpb * PPW * pair_bytes;
+        const size_t small_block = fixed_bytes + (size_t)default_wpb * warp_bytes;
         const int small_warps = (int)std::min<size_t>(32, kSmemPerSm / (small_block + kBlockReserve) * default_wpb);
-        int big_warps = (int)std::min<size_t>(narrow ? 32 : 24, (kSmemBudget - fixed_bytes) / ((size_t)PPW * pair_bytes));
+        int big_warps = (int)std::min<size_t>(pool ? 28 : narrow ? 32 : 24, (kSmemBudget - fixed_bytes) / warp_bytes);
         if (big_warps >= 8 && G == 4) big_warps &= ~3;  // the same number of warps on each of the SM's four schedulers (20 beats 21: 300 vs 290 M pairs/s)
-        if (big_warps > small_warps) warps_per_block = big_warps;
+        if (big_warps > small_warps || pool) warps_per_block = big_warps;
     }
-    if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v >= 1 && v <= (G <= 4 ? (narrow ? 32 : 24) : 4)) warps_per_block = v; }
+    if (const char *ws = getenv("AIM_WFA_WPB")) { int v = atoi(ws); if (v >= 1 && v <= (G <= 4 ? (pool ? 28 : narrow ? 32 : 24) : 4)) warps_per_block = v; }
     if (warps_per_block < 1) return 1;
-    size_t smem_block = fixed_bytes + (size_t)warps_per_block * PPW * pair_bytes;
+    size_t smem_block = fixed_bytes + (size_t)warps_per_block * warp_bytes;
     if (smem_block > kSmemBudget) return 1;
-    if (fixed_bytes + (size_t)default_wpb * PPW * pair_bytes > kSmemBudget / 3) return 1;  // too few warps/SM would fit: leave it to the long-read kernel
+    if (fixed_bytes + (size_t)default_wpb * warp_bytes > kSmemBudget / 3) return 1;  // too few warps/SM would fit: leave it to the long-read kernel
     int blocks_per_sm = (int)std::min<uint32_t>(kSmemPerSm / ((uint32_t)smem_block + kBlockReserve), 32u);
     int max_warps = 48;
     if (const char *ws = getenv("AIM_WFA_MAXWARPS")) { int v = atoi(ws); if (v >= 4 && v <= 64) max_warps = v; }
@@ -849,11 +965,11 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     if (err == cudaSuccess) {
         const int block = warps_per_block * 32;
-        if (G == 2) err = launch_g<2>(K, p.reduce != 0, p.backtrace != 0, false, grid, block, smem_block, stream);
-        else if (G == 4) err = launch_g<4>(K, p.reduce != 0, p.backtrace != 0, narrow, grid, block, smem_block, stream);
-        else if (G == 8) err = launch_g<8>(K, p.reduce != 0, p.backtrace != 0, false, grid, block, smem_block, stream);
-        else if (G == 16) err = launch_g<16>(K, p.reduce != 0, p.backtrace != 0, false, grid, block, smem_block, stream);
-        else err = launch_g<32>(K, p.reduce != 0, p.backtrace != 0, false, grid, block, smem_block, stream);
+        if (G == 2) err = launch_g<2>(K, p.reduce != 0, p.backtrace != 0, false, false, grid, block, smem_block, stream);
+        else if (G == 4) err = launch_g<4>(K, p.reduce != 0, p.backtrace != 0, narrow, pool, grid, block, smem_block, stream);
+        else if (G == 8) err = launch_g<8>(K, p.reduce != 0, p.backtrace != 0, false, false, grid, block, smem_block, stream);
+        else if (G == 16) err = launch_g<16>(K, p.reduce != 0, p.backtrace != 0, false, false, grid, block, smem_block, stream);
+        else err = launch_g<32>(K, p.reduce != 0, p.backtrace != 0, false, false, grid, block, smem_block, stream);
     }
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { set_error(std::string("wfa_sub launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
