@@ -896,9 +896,9 @@ int launch_wfa_sub(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     const int default_wpb = G <= 4 ? 2 : 4;
     int warps_per_block = default_wpb;
     // POOL (see the kernel): a warp's cells dealt to all its lanes; one table of PPW * cw 16-bit entries per warp.  Bit-exact, but
-    // measured SLOWER at config 4 (2.83e8 against 3.48e8 pairs/s: 23 instead of 18 lanes busy, but 25 % more warp instructions -
-    // with balanced widths the warp runs as many trips as before and every cell pays ~13 more instructions): off
-    // unless AIM_WFA_POOL=1
+    // measured SLOWER at config 4 (2.83e8 against 3.48e8 pairs/s: 23 instead of 18 lanes busy and 37 % fewer cell rounds, but a
+    // round costs ~108 warp instructions instead of ~50 - the per-pair loop's running pointers and register-resident pair state
+    // are rebuilt per cell): off unless AIM_WFA_POOL=1
     bool pool = false;
     if (const char *ps = getenv("AIM_WFA_POOL")) pool = narrow && G == 4 && atoi(ps) != 0;
     K.own_bytes = pool ? round_up((uint32_t)PPW * K.cw * 2u, 16) : 0u;
