@@ -46,11 +46,15 @@ namespace aim {
 namespace {
 
 constexpr uint32_t L_PRESENT = 1, L_SUB_NULL = 2, L_O_NULL = 4, L_IE_NULL = 8, L_DE_NULL = 16, L_HAS_I = 32, L_HAS_D = 64;
-constexpr int WC = 256;                        // cells (diagonals) per ring slot, power of two
-constexpr int PAD = 16;                        // NULL cells kept on both sides of every stored wavefront
-constexpr int W_CAP = WC - 2 * PAD;            // widest wavefront served here
-constexpr uint32_t M_SLOT_BYTES = WC * 2;      // one int16 array
-constexpr uint32_t ID_SLOT_BYTES = 2 * WC * 2; // I array then D array
+// Window geometry (template parameters of the kernel): WC cells (diagonals) per ring slot, a power of two; PAD NULL cells kept on
+// both sides of every stored wavefront; W_CAP = WC - 2 * PAD = the widest wavefront a window serves; an M slot is WC int16, an
+// I/D slot the I array then the D array.  Two geometries are instantiated: 128 / 8 (2.6 KB of shared memory per pair: 36 instead
+// of 20 resident warps per SM) for the first pass and 256 / 16 for the pairs that outgrow it - at l = 10 K, e = 10 % the widest
+// wavefront of a pair is 91 diagonals in the median, 111 at the 99th percentile and 118 at most (1 500 pairs, counted with an
+// instrumented copy of the oracle), so 112 serves all but ~1 % of them.
+__host__ __device__ constexpr uint32_t m_slot_bytes(int wc) { return (uint32_t)wc * 2u; }
+__host__ __device__ constexpr uint32_t id_slot_bytes(int wc) { return (uint32_t)wc * 4u; }
+__host__ __device__ constexpr int w_cap(int wc, int pad) { return wc - 2 * pad; }
 // per-score plan (4 words): w0 flags
 //                           w1 M slot offset of s   | M slot offset of s-x << 16      (bytes)
 //                           w2 M slot offset of s-o-e | I/D slot offset of s-e << 16
@@ -66,6 +70,8 @@ struct LongK {
     uint32_t *work_ctr;
     uint32_t *fail_list;
     uint32_t *fail_count;
+    const uint32_t *in_list;   // second pass: the pairs the first pass handed back (NULL: pairs 0 .. n-1)
+    const uint32_t *in_count;
     uint32_t n, idx_base;
     int x, o, e;
     int max_score, read_size;
@@ -119,9 +125,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volati
 __device__ __forceinline__ void sts_u16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-// byte offset of diagonal k inside a ring array
-__device__ __forceinline__ uint32_t cell(int k) { return ((uint32_t)k & (uint32_t)(WC - 1)) << 1; }
-
 // equal bases from pattern[v], text[h], at most lim (> 0); duplicated packed words through L1
 __device__ __forceinline__ int match_packed_g(const uint2 *P2, const uint2 *T2, int v, int h, int lim)
 {
@@ -151,9 +154,12 @@ __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffff
 __device__ __forceinline__ int hi16s(uint32_t w) { return (int)(short)(w >> 16); }
 __device__ __forceinline__ bool in_range(int k, int lo, int hi) { return (unsigned)(k - lo) <= (unsigned)(hi - lo) && lo <= hi; }
 
-template <int G, bool REDUCE, bool BT>
+template <int G, bool REDUCE, bool BT, int WC, int PAD>
 __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
 {
+    constexpr int W_CAP = w_cap(WC, PAD);
+    constexpr uint32_t M_SLOT_BYTES = m_slot_bytes(WC);
+    auto cell = [](int k) -> uint32_t { return ((uint32_t)k & (uint32_t)(WC - 1)) << 1; };  // byte offset of diagonal k inside a ring array
     constexpr int PPW = 32 / G;
     constexpr uint32_t GM = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
     extern __shared__ __align__(16) uint32_t smem_w[];
@@ -170,13 +176,15 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
     uint4 *meta = BT ? K.meta + (size_t)slot_global * (size_t)(MS + 1) : nullptr;
     const int X = K.x, OE = K.o + K.e, E = K.e;
 
+    const uint32_t n_work = K.in_count ? min(__ldg(K.in_count), K.n) : K.n;
     for (;;) {
         uint32_t base_i = 0;
         if (lane == 0) base_i = atomicAdd(K.work_ctr, (uint32_t)PPW);
         base_i = __shfl_sync(kFull, base_i, 0);
-        if (base_i >= K.n) break;  // warp-uniform
-        const uint32_t i = base_i + (uint32_t)sub;
-        bool active = i < K.n;
+        if (base_i >= n_work) break;  // warp-uniform
+        const uint32_t wi = base_i + (uint32_t)sub;
+        bool active = wi < n_work;
+        const uint32_t i = active ? (K.in_list ? K.in_list[wi] : wi) : 0u;
         bool failed = false;
         if (active && K.dirty[i]) { failed = true; active = false; }
         const int pl = active ? min(max(K.plen[i], 0), RS) : 0;
@@ -463,11 +471,16 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 // Picks the instantiation, sets its shared-memory attribute and returns its resident grid.
 typedef void (*LongKernel)(const LongK);
-template <int G>
+template <int G, int WC, int PAD>
 LongKernel pick_g(bool reduce, bool bt)
 {
-    if (reduce) return bt ? wfa_long_kernel<G, true, true> : wfa_long_kernel<G, true, false>;
-    return bt ? wfa_long_kernel<G, false, true> : wfa_long_kernel<G, false, false>;
+    if (reduce) return bt ? wfa_long_kernel<G, true, true, WC, PAD> : wfa_long_kernel<G, true, false, WC, PAD>;
+    return bt ? wfa_long_kernel<G, false, true, WC, PAD> : wfa_long_kernel<G, false, false, WC, PAD>;
+}
+LongKernel pick(int G, int wc, bool reduce, bool bt)
+{
+    if (wc == 128) return G == 8 ? pick_g<8, 128, 8>(reduce, bt) : G == 16 ? pick_g<16, 128, 8>(reduce, bt) : pick_g<32, 128, 8>(reduce, bt);
+    return G == 8 ? pick_g<8, 256, 16>(reduce, bt) : G == 16 ? pick_g<16, 256, 16>(reduce, bt) : pick_g<32, 256, 16>(reduce, bt);
 }
 
 }  // namespace
@@ -479,118 +492,143 @@ int launch_wfa_long(const KernelArgs &a, Scratch *sc, void *stream_v, int *launc
     const aim_params &p = a.p;
     if (const char *mode = getenv("AIM_WFA_MODE")) { if (std::string(mode) == "warp") return 1; }
     const int MS = p.max_score, x = p.mismatch, o = p.gap_open, e = p.gap_ext;
-    if (!p.reduce && MS > 2 * W_CAP) return 1;  // untrimmed wavefronts (2s+1 wide) would mostly outgrow the window
+    if (!p.reduce && MS > 2 * w_cap(256, 16)) return 1;  // untrimmed wavefronts (2s+1 wide) would mostly outgrow the window
     const uint32_t ring_m = (uint32_t)std::max(x, o + e) + 1, ring_e = (uint32_t)e + 1;
-    if (ring_m * M_SLOT_BYTES > 0xffffu || ring_e * ID_SLOT_BYTES > 0xffffu) return 1;
+    if (ring_m * m_slot_bytes(256) > 0xffffu || ring_e * id_slot_bytes(256) > 0xffffu) return 1;
+    // first pass in the narrow window when trimming keeps the wavefronts inside it (see the geometry note above); AIM_WFA_LONG_WC=256: one pass
+    int wc1 = p.reduce ? 128 : 256;
+    if (const char *ws = getenv("AIM_WFA_LONG_WC")) { const int v = atoi(ws); if (v == 128 || v == 256) wc1 = v; }
+    const int npass = wc1 == 128 ? 2 : 1;
 
-    // ---- static schedule (presence and components only; ranges are dynamic here) ----
+    // ---- static schedule (presence and components only; ranges are dynamic here); slot offsets depend on the window ----
     struct S { bool present, has_i, has_d; };
     std::vector<S> w((size_t)MS + 1);
-    std::vector<uint4> plan((size_t)MS + 1, make_uint4(0, 0, 0, 0));
     w[0] = {true, false, false};
-    auto m_off = [&](int s) -> uint32_t { return s < 0 ? 0u : ((uint32_t)s % ring_m) * M_SLOT_BYTES; };
-    auto id_off = [&](int s) -> uint32_t { return s < 0 ? 0u : ((uint32_t)s % ring_e) * ID_SLOT_BYTES; };
-    for (int s = 0; s <= MS; ++s) {
+    for (int s = 1; s <= MS; ++s) {
         const bool A = s - x >= 0 && w[s - x].present, B = s - o - e >= 0 && w[s - o - e].present, E = s - e >= 0 && w[s - e].present;
         const bool ie_null = !(E && w[s - e].has_i), de_null = !(E && w[s - e].has_d);
-        if (s > 0) {
-            const bool i_out_null = !B && ie_null, d_out_null = !B && de_null;
-            if (!A && i_out_null && d_out_null) { w[s] = {false, false, false}; continue; }
-            w[s] = {true, !i_out_null, !d_out_null};
-        }
-        uint4 q;
-        q.x = L_PRESENT | (A ? 0u : L_SUB_NULL) | (B ? 0u : L_O_NULL) | (ie_null ? L_IE_NULL : 0u) | (de_null ? L_DE_NULL : 0u) |
-              (w[s].has_i ? L_HAS_I : 0u) | (w[s].has_d ? L_HAS_D : 0u);
-        q.y = m_off(s) | (m_off(s - x) << 16);
-        q.z = m_off(s - o - e) | (id_off(s - e) << 16);
-        q.w = id_off(s) | ((s - e < 0 ? 0u : (uint32_t)(s - e) % ring_m) << 16);
-        plan[(size_t)s] = q;
+        const bool i_out_null = !B && ie_null, d_out_null = !B && de_null;
+        if (!A && i_out_null && d_out_null) { w[s] = {false, false, false}; continue; }
+        w[s] = {true, !i_out_null, !d_out_null};
     }
+    auto make_plan = [&](int wc) {
+        std::vector<uint4> plan((size_t)MS + 1, make_uint4(0, 0, 0, 0));
+        auto m_off = [&](int s) -> uint32_t { return s < 0 ? 0u : ((uint32_t)s % ring_m) * m_slot_bytes(wc); };
+        auto id_off = [&](int s) -> uint32_t { return s < 0 ? 0u : ((uint32_t)s % ring_e) * id_slot_bytes(wc); };
+        for (int s = 0; s <= MS; ++s) {
+            if (!w[s].present) continue;
+            const bool A = s - x >= 0 && w[s - x].present, B = s - o - e >= 0 && w[s - o - e].present, E = s - e >= 0 && w[s - e].present;
+            const bool ie_null = !(E && w[s - e].has_i), de_null = !(E && w[s - e].has_d);
+            uint4 q;
+            q.x = L_PRESENT | (A ? 0u : L_SUB_NULL) | (B ? 0u : L_O_NULL) | (ie_null ? L_IE_NULL : 0u) | (de_null ? L_DE_NULL : 0u) |
+                  (w[s].has_i ? L_HAS_I : 0u) | (w[s].has_d ? L_HAS_D : 0u);
+            q.y = m_off(s) | (m_off(s - x) << 16);
+            q.z = m_off(s - o - e) | (id_off(s - e) << 16);
+            q.w = id_off(s) | ((s - e < 0 ? 0u : (uint32_t)(s - e) % ring_m) << 16);
+            plan[(size_t)s] = q;
+        }
+        return plan;
+    };
 
-    LongK K{};
-    K.plen = a.plen; K.tlen = a.tlen; K.results = a.results; K.n = a.n; K.idx_base = a.idx_base;
-    K.x = x; K.o = o; K.e = e; K.max_score = MS; K.read_size = p.read_size;
-    K.pk_words = (uint32_t)p.read_size / 16 + 1;
-    K.dyn_words = round_up(ring_m, 4);
-    K.mring_bytes = ring_m * M_SLOT_BYTES;
     int G = 16;
     if (const char *gs = getenv("AIM_WFA_LONG_G")) { int g = atoi(gs); if (g == 8 || g == 16 || g == 32) G = g; }
     const uint32_t PPW = 32u / (uint32_t)G;
-    {   // stagger the pair slots of one warp over the banks
-        const uint32_t raw = K.dyn_words + (K.mring_bytes + ring_e * ID_SLOT_BYTES) / 4;
-        const uint32_t want = PPW > 1 ? std::max(4u, 32u / PPW) : 0u;
-        K.pair_words = raw + ((want + 32u - raw % 32u) % 32u);
-    }
-    const size_t pair_bytes = (size_t)K.pair_words * 4;
-    if (pair_bytes * 4 * PPW > 227u * 1024u / 2) return 1;  // fewer than two blocks per SM: not worth it
+    const bool bt = p.backtrace != 0;
+    const int block = 128;
 
-    // the warp-per-pair kernel serves what this one hands back (rare: a few resident warps are enough)
+    // per pass: kernel arguments that depend on the window, the instantiation and its resident grid
+    struct Pass { LongK K; LongKernel fn; size_t smem; int grid; std::vector<uint4> plan; };
+    Pass ps[2];
+    size_t slots = 0;
+    for (int q = 0; q < npass; ++q) {
+        const int wc = q == 0 ? wc1 : 256;
+        LongK &K = ps[q].K;
+        K = LongK{};
+        K.plen = a.plen; K.tlen = a.tlen; K.results = a.results; K.n = a.n; K.idx_base = a.idx_base;
+        K.x = x; K.o = o; K.e = e; K.max_score = MS; K.read_size = p.read_size;
+        K.pk_words = (uint32_t)p.read_size / 16 + 1;
+        K.dyn_words = round_up(ring_m, 4);
+        K.mring_bytes = ring_m * m_slot_bytes(wc);
+        {   // stagger the pair slots of one warp over the banks
+            const uint32_t raw = K.dyn_words + (K.mring_bytes + ring_e * id_slot_bytes(wc)) / 4;
+            const uint32_t want = PPW > 1 ? std::max(4u, 32u / PPW) : 0u;
+            K.pair_words = raw + ((want + 32u - raw % 32u) % 32u);
+        }
+        const size_t pair_bytes = (size_t)K.pair_words * 4;
+        if (pair_bytes * 4 * PPW > 227u * 1024u / 2) return 1;  // fewer than two blocks per SM: not worth it
+        ps[q].fn = pick(G, wc, p.reduce != 0, bt);
+        ps[q].smem = (size_t)(block / 32) * PPW * pair_bytes;
+        int bps = 0;
+        cudaError_t err = cudaFuncSetAttribute(ps[q].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps[q].smem);
+        if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ps[q].fn, block, ps[q].smem);
+        if (err != cudaSuccess) { set_error(std::string("wfa_long setup: ") + cudaGetErrorString(err)); cudaGetLastError(); return AIM_ERR_CUDA; }
+        int grid = sc->sm_count * std::max(1, bps);
+        const uint64_t per_block = (uint64_t)(block / 32) * PPW;
+        grid = (int)std::min<uint64_t>((uint64_t)grid, (a.n + per_block - 1) / per_block);
+        ps[q].grid = grid;
+        slots = std::max(slots, (size_t)grid * (block / 32) * PPW);
+        ps[q].plan = make_plan(wc);
+    }
+
+    // the warp-per-pair kernel serves what the last pass hands back (rare: a few resident warps are enough)
     // (without trimming the window is outgrown at score ~W_CAP/2: hand-overs are then common, keep the full grid)
     const WarpPlan W = wfa_warp_plan(a, sc->sm_count, p.reduce ? std::min<uint32_t>(a.n, (uint32_t)sc->sm_count * 4u) : a.n);
     if (W.rc != AIM_OK) { set_error("READ_SIZE too large for the shared-memory sequence stage"); return W.rc; }
 
-    // kernel instantiation and its resident grid
-    const bool bt = p.backtrace != 0;
-    LongKernel fn = G == 8 ? pick_g<8>(p.reduce != 0, bt) : G == 16 ? pick_g<16>(p.reduce != 0, bt) : pick_g<32>(p.reduce != 0, bt);
-    const int block = 128;
-    const size_t smem = (size_t)(block / 32) * PPW * pair_bytes;
-    int bps = 0;
-    cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, block, smem);
-    if (err != cudaSuccess) { set_error(std::string("wfa_long setup: ") + cudaGetErrorString(err)); cudaGetLastError(); return AIM_ERR_CUDA; }
-    int grid = sc->sm_count * std::max(1, bps);
-    {
-        const uint64_t per_block = (uint64_t)(block / 32) * PPW;
-        grid = (int)std::min<uint64_t>((uint64_t)grid, (a.n + per_block - 1) / per_block);
-    }
-    const size_t slots = (size_t)grid * (block / 32) * PPW;
     // history arena per resident pair slot (backtrace): 4 MiB by default = 512 K cells, ~3x what a 10 Kbp / 10 % pair
     // writes; a pair that needs more is handed to the warp-per-pair kernel with its own (arena_mb) arena
-    K.arena_cells = bt ? (uint32_t)(((size_t)(p.arena_mb > 0 ? p.arena_mb : 4) << 20) / sizeof(uint2)) : 0;
+    const uint32_t arena_cells = bt ? (uint32_t)(((size_t)(p.arena_mb > 0 ? p.arena_mb : 4) << 20) / sizeof(uint2)) : 0;
 
-    // scratch: counters | plan | dirty | fail list | packed sequences | meta | arena | warp-per-pair scratch
-    const size_t plan_bytes = plan.size() * sizeof(uint4);
-    const size_t off_plan = 256;
-    const size_t off_dirty = align256(off_plan + plan_bytes);
+    // scratch: counters | dirty | fail lists (one per pass) | packed sequences | meta | arena | warp-per-pair scratch
+    const size_t off_dirty = 256;
     const size_t off_fail = align256(off_dirty + a.n);
-    const size_t off_packed = align256(off_fail + (size_t)a.n * 4);
-    const size_t packed_bytes = (size_t)a.n * 2 * K.pk_words * sizeof(uint2);
+    const size_t fail_bytes = align256((size_t)a.n * 4);
+    const size_t off_packed = off_fail + 2 * fail_bytes;
+    const size_t packed_bytes = (size_t)a.n * 2 * ps[0].K.pk_words * sizeof(uint2);
     const size_t off_meta = align256(off_packed + packed_bytes);
     const size_t meta_bytes = bt ? slots * ((size_t)MS + 1) * sizeof(uint4) : 0;
     const size_t off_arena = align256(off_meta + meta_bytes);
-    const size_t arena_bytes = bt ? slots * (size_t)K.arena_cells * sizeof(uint2) : 0;
+    const size_t arena_bytes = bt ? slots * (size_t)arena_cells * sizeof(uint2) : 0;
     const size_t off_warp = align256(off_arena + arena_bytes);
     int rc = scratch_reserve(sc, off_warp + W.scratch_bytes);
     if (rc != AIM_OK) return rc;
     unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
-    K.work_ctr = reinterpret_cast<uint32_t *>(base);
-    K.fail_count = K.work_ctr + 1;
-    K.plan = reinterpret_cast<const uint4 *>(cached_plan(sc, plan.data(), plan_bytes));  // uploaded once per penalty set
-    if (!K.plan) return AIM_ERR_CUDA;
-    K.dirty = base + off_dirty;
-    K.fail_list = reinterpret_cast<uint32_t *>(base + off_fail);
-    K.packed = reinterpret_cast<const uint2 *>(base + off_packed);
-    K.ops = a.ops;
-    K.meta = reinterpret_cast<uint4 *>(base + off_meta);
-    K.arena = reinterpret_cast<uint2 *>(base + off_arena);
+    uint32_t *ctr = reinterpret_cast<uint32_t *>(base);  // per pass: work counter, fail count
+    for (int q = 0; q < npass; ++q) {
+        LongK &K = ps[q].K;
+        K.work_ctr = ctr + 2 * q;
+        K.fail_count = ctr + 2 * q + 1;
+        K.fail_list = reinterpret_cast<uint32_t *>(base + off_fail + (size_t)q * fail_bytes);
+        K.in_list = q == 0 ? nullptr : ps[q - 1].K.fail_list;
+        K.in_count = q == 0 ? nullptr : ps[q - 1].K.fail_count;
+        K.plan = reinterpret_cast<const uint4 *>(cached_plan(sc, ps[q].plan.data(), ps[q].plan.size() * sizeof(uint4)));  // uploaded once per penalty set
+        if (!K.plan) return AIM_ERR_CUDA;
+        K.dirty = base + off_dirty;
+        K.packed = reinterpret_cast<const uint2 *>(base + off_packed);
+        K.ops = a.ops;
+        K.meta = reinterpret_cast<uint4 *>(base + off_meta);
+        K.arena = reinterpret_cast<uint2 *>(base + off_arena);
+        K.arena_cells = arena_cells;
+    }
 
-    err = cudaMemsetAsync(base, 0, 256, stream);
+    cudaError_t err = cudaMemsetAsync(base, 0, 256, stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(base + off_dirty, 0, a.n, stream);
     if (err == cudaSuccess) {
         const uint64_t warps = std::min<uint64_t>(2ull * a.n, (uint64_t)sc->sm_count * 64);
         const int pgrid = (int)((warps * 32 + 255) / 256);
-        pack_kernel<<<pgrid, 256, 0, stream>>>(a.plen, a.tlen, a.patterns, a.texts, a.n, p.read_size, K.pk_words,
+        pack_kernel<<<pgrid, 256, 0, stream>>>(a.plen, a.tlen, a.patterns, a.texts, a.n, p.read_size, ps[0].K.pk_words,
                                                reinterpret_cast<uint2 *>(base + off_packed), base + off_dirty);
         err = cudaGetLastError();
+        if (launches) ++*launches;
     }
-    if (err == cudaSuccess) {
-        fn<<<grid, block, smem, stream>>>(K);
+    for (int q = 0; q < npass && err == cudaSuccess; ++q) {
+        ps[q].fn<<<ps[q].grid, block, ps[q].smem, stream>>>(ps[q].K);
         err = cudaGetLastError();
+        if (launches) ++*launches;
     }
     if (err != cudaSuccess) { set_error(std::string("wfa_long launch: ") + cudaGetErrorString(err)); return AIM_ERR_CUDA; }
-    if (launches) *launches += 2;
     // leftovers (window or history outgrown, non-ACGT bytes)
-    return wfa_warp_launch(W, base + off_warp, K.fail_list, K.fail_count, stream_v, launches);
+    return wfa_warp_launch(W, base + off_warp, ps[npass - 1].K.fail_list, ps[npass - 1].K.fail_count, stream_v, launches);
 }
 
 }  // namespace aim

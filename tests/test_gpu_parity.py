@@ -109,6 +109,37 @@ def test_long_read_kernel_lane_groups(g, monkeypatch):
     _vs_oracle_ragged("wfa", dict(max_score=2500, read_size=3008, backtrace=False, reduce=True), (23, 200, 2000, 3000), True)
 
 
+@pytest.mark.parametrize("backtrace", [False, True])
+def test_long_read_second_pass_window(backtrace, monkeypatch):
+    """Long reads run in a 128-diagonal window first; a pair whose wavefront outgrows it (112 diagonals) is handed to a second
+    pass in the 256-diagonal window, and from there (224) to the warp-per-pair kernel.  A block of 120-260 inserted bases
+    forces the wavefront to span that many diagonals (trimming never cuts diagonal tlen - plen): all three routes are taken."""
+    rng = np.random.default_rng(77)
+    n, rs = 40, 3008
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    plen, tlen = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    pats, txts = np.zeros((n, rs), np.uint8), np.zeros((n, rs), np.uint8)
+    for i in range(n):
+        pl = int(rng.integers(2200, 2600))
+        ins = 0 if i % 4 == 0 else int(rng.integers(120, 261))
+        p = alpha[rng.integers(0, 4, pl)]
+        at = int(rng.integers(200, pl - 200))
+        t = np.concatenate([p[:at], alpha[rng.integers(0, 4, ins)], p[at:]])
+        flips = rng.random(len(t)) < 0.03
+        t[flips] = alpha[rng.integers(0, 4, int(flips.sum()))]
+        plen[i], tlen[i] = pl, len(t)
+        pats[i, :pl], txts[i, :len(t)] = p, t
+    kw = dict(max_score=2500, read_size=rs, backtrace=backtrace, reduce=True)
+    exp, exp_ops = O.align("wfa", plen, tlen, pats, txts, nthreads=8, **kw)
+    got = {}
+    for wc in ("128", "256"):
+        monkeypatch.setenv("AIM_WFA_LONG_WC", wc)
+        res, ops, _ = A.align_batch(A.AlignParams(algo="wfa", **kw), plen, tlen, pats, txts)
+        assert_same_alignment(res, ops, exp, exp_ops, backtrace, what=f"long reads, first window {wc}")
+        got[wc] = (res.tobytes(), None if ops is None else ops.tobytes())
+    assert got["128"] == got["256"]
+
+
 def test_dp_long_rows_fall_back_to_literal_kernel():
     """(2*READ_SIZE+2)*max penalty >= 32767: int16 truncation is possible, the literal kernel must serve."""
     kw = dict(max_score=50, read_size=2304, mismatch=6, gap_open=7, backtrace=True)
