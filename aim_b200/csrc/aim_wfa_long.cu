@@ -50,8 +50,8 @@ constexpr uint32_t L_PRESENT = 1, L_SUB_NULL = 2, L_O_NULL = 4, L_IE_NULL = 8, L
 // both sides of every stored wavefront; W_CAP = WC - 2 * PAD = the widest wavefront a window serves; an M slot is WC int16, an
 // I/D slot the I array then the D array.  Two geometries are instantiated: 128 / 8 (2.6 KB of shared memory per pair: 36 instead
 // of 20 resident warps per SM) for the first pass and 256 / 16 for the pairs that outgrow it - at l = 10 K, e = 10 % the widest
-// wavefront of a pair is 91 diagonals in the median, 111 at the 99th percentile and 118 at most (1 500 pairs, counted with an
-// instrumented copy of the oracle), so 112 serves all but ~1 % of them.
+// wavefront of a pair is 91 diagonals in the median, 111 at the 99th percentile and 118 at most (1 500 pairs, counted on
+// the CPU), so 112 serves all but ~1 % of them.
 __host__ __device__ constexpr uint32_t m_slot_bytes(int wc) { return (uint32_t)wc * 2u; }
 __host__ __device__ constexpr uint32_t id_slot_bytes(int wc) { return (uint32_t)wc * 4u; }
 __host__ __device__ constexpr int w_cap(int wc, int pad) { return wc - 2 * pad; }
