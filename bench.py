@@ -60,9 +60,9 @@ CONFIGS = {
             mismatch=3, gap_open=4, gap_ext=1, reduce=False, backtrace=True, pairs=2_000_000, seed=4),
 }
 # dominant kernel of each config (the one `roofline` describes; one step = all kernels of the launch)
-KERNELS = {2: "dp_strip_kernel<NW> + dp_row_kernel<NW> (aim_dp_fast.cu)", 3: "dp_strip_kernel<SWG> + dp_row_kernel<SWG> (aim_dp_fast.cu)",
+KERNELS = {2: "dp2_strip_kernel<NW> (two pairs per thread) + dp_row_kernel<NW> (aim_dp_fast.cu, aim_dp_pack2.cuh)", 3: "dp2_strip_kernel<SWG> (two pairs per thread) + dp_row_kernel<SWG> (aim_dp_fast.cu, aim_dp_pack2.cuh)",
            4: "wfa_sub_kernel<4, reduce, backtrace, narrow rows> (aim_wfa_sub.cu)", 5: "wfa_long_kernel<16, reduce, 128- then 256-diagonal window> (aim_wfa_long.cu)",
-           6: "wfa_kernel<true> (aim_wfa.cu)", 7: "genasm_band_kernel<1 word, DC> + genasm_tb_kernel (aim_genasm.cu)",
+           6: "wfa_long_kernel<16, reduce, backtrace, 128- then 256-diagonal window> (aim_wfa_long.cu)", 7: "genasm_band_kernel<1 word, DC> + genasm_tb_kernel (aim_genasm.cu)",
            8: "genasm_band_kernel<1 word, filter> (aim_genasm.cu)", 9: "genasm_band_kernel<4 words, DC> + genasm_tb_kernel (aim_genasm.cu)"}
 INT_OPS_PER_GENASM_WORD = 14  # one (text step, level, 64-bit word): 3 shifts with carry, 1 or, 3 and = 7 64-bit ops = 14 int32 ops
 
