@@ -217,6 +217,11 @@ def op_runs_pitch(read_size: int) -> int:
     return int(lib.aim_op_runs_pitch(read_size))
 
 
+def str_rows_pitch(read_size: int, max_score: int) -> int:
+    """GenASM-DC: bytes of every op row (the head holding its CIGAR string) that aim_align_batch downloads; 0 = whole rows."""
+    return int(lib.aim_str_rows_pitch(read_size, max_score))
+
+
 def expand_op_runs(runs: np.ndarray, read_size: int, ops: np.ndarray | None = None):
     """Host half of aim_align_batch's op-row download: run rows [n, pitch] -> (ops[n, 2*read_size], overflow pair numbers)."""
     runs = np.ascontiguousarray(runs, np.uint8)

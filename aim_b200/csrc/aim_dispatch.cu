@@ -222,9 +222,13 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
     // Op rows come back as RUN rows and are rebuilt by host threads (aim_file.cu op_runs_kernel, aim_host.cpp expand_op_runs):
     // the device-to-host direction is the scarcer one and an op row is a handful of runs.  AIM_SPARSE_OPS=0: as they are.
     int32_t runs_pitch = 0;
-    if (bt && !cigars && (p.algo == AIM_ALGO_NW || p.algo == AIM_ALGO_SWG || p.algo == AIM_ALGO_WFA)) {
+    bool strings = false;  // GenASM-DC: the rows hold CIGAR strings; their heads come back instead of run rows
+    if (bt && !cigars) {
         const char *e = getenv("AIM_SPARSE_OPS");
-        if (!(e && atoi(e) == 0)) runs_pitch = op_runs_pitch(p.read_size);
+        if (!(e && atoi(e) == 0)) {
+            if (p.algo == AIM_ALGO_NW || p.algo == AIM_ALGO_SWG || p.algo == AIM_ALGO_WFA) runs_pitch = op_runs_pitch(p.read_size);
+            else if (p.algo == AIM_ALGO_GENASM_DC) { runs_pitch = str_rows_pitch(p.read_size, p.max_score); strings = runs_pitch > 0; }
+        }
     }
     const bool sparse = runs_pitch > 0;
     const bool pin_in = is_pinned(plen) && is_pinned(tlen) && is_pinned(patterns) && is_pinned(texts);
@@ -277,7 +281,8 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
         if (sparse) {
             std::vector<uint32_t> ov;
             char *o_ops = ops + (size_t)off * 2 * rs;
-            expand_op_runs(B.h_runs, runs_pitch, m, p.read_size, o_ops, &ov);
+            if (strings) expand_str_rows(B.h_runs, runs_pitch, m, p.read_size, o_ops, &ov);
+            else expand_op_runs(B.h_runs, runs_pitch, m, p.read_size, o_ops, &ov);
             if (!ov.empty()) {  // rows with more runs than a run row holds: fetched as they are (a few: one by one; many: the chunk's rows)
                 if (ov.size() <= 64) {
                     for (uint32_t i : ov) {
@@ -397,7 +402,8 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
             if (rc != AIM_OK) { queue->store(nchunks); cudaDeviceSynchronize(); return fail(rc); }
         }
         if (sparse) {
-            rc = launch_op_runs(B.d_ops, p.read_size, m, reinterpret_cast<unsigned char *>(B.d_cig), runs_pitch, ctx->s_kernel, nullptr);
+            rc = strings ? launch_str_rows(B.d_ops, p.read_size, m, reinterpret_cast<unsigned char *>(B.d_cig), runs_pitch, ctx->s_kernel, nullptr)
+                         : launch_op_runs(B.d_ops, p.read_size, m, reinterpret_cast<unsigned char *>(B.d_cig), runs_pitch, ctx->s_kernel, nullptr);
             if (rc != AIM_OK) { queue->store(nchunks); cudaDeviceSynchronize(); return fail(rc); }
         }
         AIM_CUDA(cudaEventRecord(B.ev[3], ctx->s_kernel));

@@ -413,6 +413,29 @@ __global__ void __launch_bounds__(128) op_runs_kernel(const char *ops, int row_b
 }
 }  // namespace
 
+// GenASM-DC: the op row holds the DPU's CIGAR string (NUL-terminated, a few dozen bytes of 2 * READ_SIZE): its first `pitch` bytes
+// are what crosses PCIe (one 16-byte piece per thread); a string that does not end inside them is fetched with its whole row.
+namespace {
+__global__ void __launch_bounds__(256) str_rows_kernel(const char *ops, int row_bytes, unsigned char *rows, int pitch, uint32_t n)
+{
+    const uint32_t per = (uint32_t)pitch >> 4;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n * per) return;
+    const uint32_t i = (uint32_t)(t / per), c = (uint32_t)(t % per);
+    reinterpret_cast<uint4 *>(rows + (size_t)i * pitch)[c] = reinterpret_cast<const uint4 *>(ops + (size_t)i * row_bytes)[c];
+}
+}  // namespace
+
+int launch_str_rows(const char *d_ops, int read_size, uint32_t m, unsigned char *d_rows, int pitch, void *stream_v, int *launches)
+{
+    if (m == 0) return AIM_OK;
+    const uint64_t total = (uint64_t)m * (uint64_t)(pitch >> 4);
+    str_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_v>>>(d_ops, 2 * read_size, d_rows, pitch, m);
+    if (cudaGetLastError() != cudaSuccess) { set_error("string rows launch failed"); return AIM_ERR_CUDA; }
+    if (launches) ++*launches;
+    return AIM_OK;
+}
+
 int launch_op_runs(const char *d_ops, int read_size, uint32_t m, unsigned char *d_runs, int pitch, void *stream_v, int *launches)
 {
     if (m == 0) return AIM_OK;

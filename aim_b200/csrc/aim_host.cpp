@@ -235,6 +235,32 @@ void expand_op_runs(const unsigned char *runs, int pitch, uint32_t m, int read_s
     });
 }
 
+// GenASM-DC strings: k error levels make at most 2k + 1 runs of at most 5 characters ("1000M"); pieces of up to half a row
+int32_t str_rows_pitch(int32_t read_size, int32_t max_score)
+{
+    const int64_t need = (2 * (int64_t)std::max(max_score, 0) + 1) * 5 + 1;
+    const int32_t pitch = (int32_t)std::min<int64_t>((need + 15) / 16 * 16, 1 << 20);
+    return (read_size >= 32 && pitch <= read_size) ? pitch : 0;
+}
+
+void expand_str_rows(const unsigned char *rows, int pitch, uint32_t m, int read_size, char *ops, std::vector<uint32_t> *overflow)
+{
+    const size_t row = 2 * (size_t)read_size;
+    constexpr uint32_t BLK = 4096;
+    std::mutex ov_mu;
+    g_pool.run((m + BLK - 1) / BLK, [&](uint32_t b) {
+        std::vector<uint32_t> ov;
+        const uint32_t i1 = std::min(m, (b + 1) * BLK);
+        for (uint32_t i = b * BLK; i < i1; ++i) {
+            const unsigned char *r = rows + (size_t)i * (size_t)pitch;
+            const size_t len = strnlen(reinterpret_cast<const char *>(r), (size_t)pitch);
+            if (len == (size_t)pitch) { ov.push_back(i); continue; }
+            memcpy(ops + (size_t)i * row, r, len + 1);
+        }
+        if (!ov.empty()) { std::lock_guard<std::mutex> lk(ov_mu); overflow->insert(overflow->end(), ov.begin(), ov.end()); }
+    });
+}
+
 void host_pool_shutdown() { g_pool.shutdown(); }
 void host_pool_want(int helpers) { g_pool.want(helpers); }
 
@@ -248,6 +274,7 @@ int32_t op_runs_pitch(int32_t read_size)
 }  // namespace aim
 
 extern "C" int32_t aim_op_runs_pitch(int32_t read_size) { return aim::op_runs_pitch(read_size); }
+extern "C" int32_t aim_str_rows_pitch(int32_t read_size, int32_t max_score) { return aim::str_rows_pitch(read_size, max_score); }
 
 extern "C" int aim_expand_op_runs(const unsigned char *runs, int32_t pitch, uint32_t n, int32_t read_size, char *ops,
                                   uint32_t *overflow, uint32_t overflow_cap, uint32_t *overflow_count)

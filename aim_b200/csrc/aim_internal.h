@@ -122,6 +122,11 @@ int launch_op_runs(const char *d_ops, int read_size, uint32_t m, unsigned char *
 // Rebuilds the 2 * read_size op rows of m pairs at `ops` from their run rows on the host pool's threads; *overflow receives
 // the pairs whose run row carries the "did not fit" mark (their rows are left untouched).
 void expand_op_runs(const unsigned char *runs, int pitch, uint32_t m, int read_size, char *ops, std::vector<uint32_t> *overflow);
+// GenASM-DC: the same for the CIGAR strings its op rows hold - the first str_rows_pitch() bytes of every row cross PCIe, the host
+// copies each string (with its NUL) to the head of the caller's row; *overflow: strings that do not end inside their piece.
+int32_t str_rows_pitch(int32_t read_size, int32_t max_score);  // 0 = not worth it
+int launch_str_rows(const char *d_ops, int read_size, uint32_t m, unsigned char *d_rows, int pitch, void *stream, int *launches);
+void expand_str_rows(const unsigned char *rows, int pitch, uint32_t m, int read_size, char *ops, std::vector<uint32_t> *overflow);
 void host_pool_shutdown();
 void host_pool_want(int helpers);  // at least this many helper threads from now on (one process driving several GPUs)
 

@@ -326,15 +326,19 @@ def main() -> None:
         te_s = shard.max_over_ranks((time.perf_counter() - t0) / args.steps, dev)
         assert np.array_equal(h_res.array["score"], res_dev["score"]), "bench: e2e and device-resident scores differ"
         # op rows cross PCIe as run rows and are rebuilt into the caller's buffer by host threads inside the call (include/aim_b200.h)
-        runs_pitch = A.op_runs_pitch(rs) if (bt and not genasm and os.environ.get("AIM_SPARSE_OPS", "1") != "0") else 0
+        runs_pitch = 0
+        if bt and os.environ.get("AIM_SPARSE_OPS", "1") != "0":
+            runs_pitch = A.str_rows_pitch(rs, ms) if cfg["algo"] == "genasm_dc" else (0 if genasm else A.op_runs_pitch(rs))
         e2e = {"value": world * P / te_s, "unit": "pairs/s",
                "h2d_bytes_per_step": int(P * (2 * rs + 8)),
                "d2h_bytes_per_step": int(P * (A.RESULT_DTYPE.itemsize + (runs_pitch if runs_pitch else (2 * rs if bt else 0)))),
                "ms_per_step": te_s * 1e3,
                "api": "aim_align_batch (C ABI), pinned host buffers, H2D+kernel+D2H double-buffered inside"}
         if runs_pitch:
-            e2e["op_rows"] = {"download": f"run rows of {runs_pitch} B per pair (op_runs_kernel), rebuilt into the caller's {2 * rs}-byte rows by host "
-                                          "threads inside the timed call (AIM_SPARSE_OPS=0: the rows themselves cross PCIe)",
+            e2e["op_rows"] = {"download": (f"the first {runs_pitch} B of every row (its CIGAR string), copied to the head of the caller's {2 * rs}-byte rows by host "
+                                           "threads inside the timed call (AIM_SPARSE_OPS=0: the rows themselves cross PCIe)") if genasm else
+                                          (f"run rows of {runs_pitch} B per pair (op_runs_kernel), rebuilt into the caller's {2 * rs}-byte rows by host "
+                                           "threads inside the timed call (AIM_SPARSE_OPS=0: the rows themselves cross PCIe)"),
                               "bytes_delivered_to_caller_per_step": int(P * (A.RESULT_DTYPE.itemsize + 2 * rs))}
 
     # ---- end-to-end arm with COMPACT transfers (aim_align_packed: 2-bit sequences in, run-length CIGAR rows out) ----

@@ -115,7 +115,7 @@ int aim_align_device(const aim_params *params, int device, uint32_t n, uint32_t 
                      aim_result *d_results, char *d_ops,
                      void *stream, float *kernel_ms, int32_t *launches);
 
-/* ---- how aim_align_batch brings the op rows back (NW, SWG, WFA; read_size 32..1024) --------------------------------
+/* ---- how aim_align_batch brings the op rows back (NW, SWG, WFA: read_size 32..1024; GenASM-DC: see below) ----------
  * The caller's `ops` buffer is filled exactly as documented above, but the rows do not cross PCIe as they are: the device-to-
  * host direction is the scarcer one of a multi-GPU host (all GPUs together: 72-94 GB/s against 110-187 GB/s host-to-device,
  * DESIGN.md 6.2) and a 2*read_size row is 'M' but for a handful of runs.  A kernel turns every op row into a RUN ROW of
@@ -127,6 +127,10 @@ int aim_align_device(const aim_params *params, int device, uint32_t n, uint32_t 
  * aim_expand_op_runs is that host half (exported for tests and for callers that keep run rows): rebuilds n rows, lists the
  * pairs whose run row carries the mark (ascending, at most overflow_cap of *overflow_count). */
 int32_t aim_op_runs_pitch(int32_t read_size);
+/* GenASM-DC rows hold the DPU's CIGAR string: the first aim_str_rows_pitch(read_size, max_score) bytes of every row - room for
+ * the longest string max_score error levels can make - cross PCIe and each string is copied, with its NUL, to the head of the
+ * caller's row (bytes behind the NUL are not written); 0 = the rows move as they are (the heads would exceed half a row). */
+int32_t aim_str_rows_pitch(int32_t read_size, int32_t max_score);
 int aim_expand_op_runs(const unsigned char *runs, int32_t pitch, uint32_t n, int32_t read_size, char *ops,
                        uint32_t *overflow, uint32_t overflow_cap, uint32_t *overflow_count);
 

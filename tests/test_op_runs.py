@@ -130,3 +130,26 @@ def test_two_gpus_share_the_host_pool():
     params2 = A.AlignParams(**{**params.__dict__, "ngpus": 2})
     res2, ops2, _ = A.align_batch(params2, *arrays)
     assert res1.tobytes() == res2.tobytes() and (ops1 == ops2).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,rs,chunk_mb", [(5, 120, None), (5, 120, 1), (11, 128, 1)])
+def test_genasm_dc_strings_identical_with_and_without_string_heads(k, rs, chunk_mb, monkeypatch):
+    """GenASM-DC: the op rows hold the DPU's CIGAR strings; only the head of every row (room for the longest string k error levels can
+    make) crosses PCIe and the host copies each string with its NUL into the caller's row.  k = 11 at READ_SIZE 128 leaves no room
+    (the heads would be as long as the rows): that case moves the rows as they are."""
+    n = 60_000
+    arrays = A.generate_pairs(9, n, 100, 0.03, rs)
+    params = A.AlignParams(algo="genasm_dc", max_score=k, read_size=rs)
+    if chunk_mb:
+        monkeypatch.setenv("AIM_CHUNK_MB", str(chunk_mb))
+    monkeypatch.setenv("AIM_SPARSE_OPS", "0")
+    res0, ops0, _ = A.align_batch(params, *arrays)
+    monkeypatch.delenv("AIM_SPARSE_OPS")
+    res1, ops1, _ = A.align_batch(params, *arrays)
+    assert res0.tobytes() == res1.tobytes()
+    ends = res0["end_offset"]
+    assert ends.max() > 0
+    for i in range(0, n, 7):
+        e = int(ends[i])
+        assert bytes(ops0[i, :e + 1]) == bytes(ops1[i, :e + 1]) and ops1[i, e] == 0, i
