@@ -665,6 +665,67 @@ inline __attribute__((always_inline)) bool pack_range(const PackJob &J, uint32_t
 }
 bool pack_range_swar(const PackJob &J, uint32_t w0, uint32_t w1) { return pack_range(J, w0, w1, [](uint64_t c) { return gather_swar(c); }); }
 #if defined(__x86_64__) && defined(__GNUC__)
+// 32 bases per step: codes (c >> 1) & 3, the validity test as a table look-up of the letter each code stands for, four codes to
+// a byte with two multiply-adds (64 16 4 1, then pairs of 16-bit sums), the four bytes of a word gathered most significant first.
+__attribute__((target("avx2"))) bool pack_row_avx2(const unsigned char *row, int32_t len, int32_t row_bytes, uint32_t words, uint32_t *out)
+{
+    const __m256i three = _mm256_set1_epi8(3), ones16 = _mm256_set1_epi16(1);
+    const __m256i lut = _mm256_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 'A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i wts = _mm256_setr_epi8(64, 16, 4, 1, 64, 16, 4, 1, 64, 16, 4, 1, 64, 16, 4, 1, 64, 16, 4, 1, 64, 16, 4, 1, 64, 16, 4, 1, 64, 16, 4, 1);
+    const __m256i gat = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    uint32_t w = 0, bad = 0;
+    int32_t pos = 0;
+    auto chunk = [&](__m256i x, uint32_t counts) __attribute__((target("avx2"))) {
+        const __m256i c = _mm256_and_si256(_mm256_srli_epi16(x, 1), three);
+        bad |= ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, c), x)) & counts;
+        const __m256i g = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(c, wts), ones16), gat);
+        if (w < words) out[w] = (uint32_t)_mm256_extract_epi32(g, 0);
+        if (w + 1 < words) out[w + 1] = (uint32_t)_mm256_extract_epi32(g, 4);
+        w += 2;
+    };
+    for (; pos + 32 <= len; pos += 32) chunk(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(row + pos)), 0xffffffffu);
+    if (pos < len) {  // last, partial step: 'A' past the end, and never a byte read past the row
+        alignas(32) static const unsigned char ramp[64] = {0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff,
+                                                           0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff};
+        const int32_t rem = len - pos;
+        __m256i x;
+        if (pos + 32 <= row_bytes) {
+            x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(row + pos));
+        } else {
+            alignas(32) unsigned char tmp[32] = {};
+            memcpy(tmp, row + pos, (size_t)rem);
+            x = _mm256_load_si256(reinterpret_cast<const __m256i *>(tmp));
+        }
+        const __m256i keep = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(ramp + 32 - rem));  // 0xff for the rem bytes that count
+        x = _mm256_blendv_epi8(_mm256_set1_epi8('A'), x, keep);
+        chunk(x, (1u << rem) - 1u);
+    }
+    for (; w < words; ++w) out[w] = 0u;
+    return bad == 0;
+}
+__attribute__((target("avx2"))) bool pack_range_avx2(const PackJob &J, uint32_t w0, uint32_t w1)
+{
+    const size_t rs = (size_t)J.read_size;
+    bool lengths_ok = true;
+    for (uint32_t fw = w0; fw < w1; ++fw) {
+        uint32_t fbits = 0;
+        const uint32_t hi = std::min(J.n, (fw + 1) * 32);
+        for (uint32_t i = fw * 32; i < hi; ++i) {
+            bool ok = true;
+            for (int q = 0; q < 2; ++q) {
+                const int32_t len = q ? J.tlen[i] : J.plen[i];
+                if (len < 0 || len > J.read_size) { lengths_ok = false; continue; }
+                const unsigned char *row = reinterpret_cast<const unsigned char *>((q ? J.texts : J.patterns) + (size_t)i * rs);
+                ok &= pack_row_avx2(row, len, J.read_size, J.words, J.packed + ((size_t)i * 2 + (size_t)q) * J.words);
+            }
+            if (!ok) fbits |= 1u << (i & 31);
+        }
+        J.flags[fw] = fbits;
+    }
+    return lengths_ok;
+}
+#endif
+#if defined(__x86_64__) && defined(__GNUC__)
 __attribute__((target("bmi2"))) bool pack_range_bmi2(const PackJob &J, uint32_t w0, uint32_t w1)
 {
     return pack_range(J, w0, w1, [](uint64_t c) __attribute__((target("bmi2"))) { return (uint32_t)__builtin_ia32_pext_di(__builtin_bswap64(c), 0x0303030303030303ull); });
@@ -689,6 +750,7 @@ extern "C" int aim_pack_pairs(uint32_t n, int32_t read_size, const int32_t *plen
     bool (*range)(const PackJob &, uint32_t, uint32_t) = pack_range_swar;
 #if defined(__x86_64__) && defined(__GNUC__)
     if (__builtin_cpu_supports("bmi2") && !getenv("AIM_NO_BMI2")) range = pack_range_bmi2;
+    if (__builtin_cpu_supports("avx2") && !getenv("AIM_NO_AVX2")) range = pack_range_avx2;
 #endif
     int T = nthreads > 0 ? nthreads : io_threads((size_t)n * rs * 2);
     T = std::max(1, std::min<int>(T, (int)std::max<uint32_t>(1, fwords)));

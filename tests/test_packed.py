@@ -43,6 +43,40 @@ def test_pack_pairs_matches_restatement_and_flags_non_acgt():
         assert set_bits == [5, 64]
 
 
+@pytest.mark.parametrize("variant", ["avx2", "bmi2", "swar"])
+@pytest.mark.parametrize("rs", [168, 40, 256])
+def test_pack_pairs_variants_on_ragged_rows(variant, rs, monkeypatch):
+    """Every packer variant (AVX2 32 bases per step / BMI2 pext / plain 64-bit) against the restatement: every length 0..READ_SIZE (full
+    and partial 32-base steps, READ_SIZE not a multiple of 32), a byte outside ACGT at every position class (first, last counted, first
+    uncounted), lower case, and rows whose bytes beyond the sequence are not bases."""
+    if variant != "avx2":
+        monkeypatch.setenv("AIM_NO_AVX2", "1")
+    if variant == "swar":
+        monkeypatch.setenv("AIM_NO_BMI2", "1")
+    rng = np.random.default_rng(rs)
+    n = rs + 1 + 64
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    plen = np.concatenate([np.arange(rs + 1), rng.integers(0, rs + 1, 64)]).astype(np.int32)
+    tlen = plen[::-1].copy()
+    pats = alpha[rng.integers(0, 4, (n, rs))]
+    txts = alpha[rng.integers(0, 4, (n, rs))]
+    want_flag = set()
+    for i in range(n):
+        pats[i, plen[i]:] = rng.integers(0, 256, rs - plen[i])   # bytes beyond the sequence do not count
+        k = i % 7
+        if k == 1 and plen[i] > 0: pats[i, 0] = ord("N"); want_flag.add(i)
+        if k == 2 and plen[i] > 0: pats[i, plen[i] - 1] = ord("a"); want_flag.add(i)
+        if k == 3 and tlen[i] > 33: txts[i, 33] = 0; want_flag.add(i)
+        if k == 4 and tlen[i] < rs: txts[i, tlen[i]] = ord("N")  # first uncounted byte: not flagged
+    words = A.packed_row_bytes(rs) // 4
+    packed, flags = A.pack_pairs(plen, tlen, pats, txts, rs, nthreads=2)
+    for i in range(n):
+        assert list(packed[i, 0]) == py_pack(bytes(pats[i]), plen[i], words) or i in want_flag, (variant, i)
+        assert list(packed[i, 1]) == py_pack(bytes(txts[i]), tlen[i], words) or i in want_flag, (variant, i)
+    got_flag = {i for i in range(n) if (flags[i >> 5] >> (i & 31)) & 1}
+    assert got_flag == want_flag
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("reduce", [True, False])
 def test_packed_path_equals_oracle(reduce, monkeypatch):
