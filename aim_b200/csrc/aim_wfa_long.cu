@@ -132,8 +132,8 @@ __device__ __forceinline__ int match_packed_g(const uint2 *P2, const uint2 *T2, 
     for (;;) {
         const int pv = v + cnt, ph = h + cnt;
         const uint2 a2 = __ldg(P2 + ((uint32_t)pv >> 4)), b2 = __ldg(T2 + ((uint32_t)ph >> 4));
-        const uint32_t a = __funnelshift_l(a2.y, a2.x, (pv & 15) * 2);
-        const uint32_t b = __funnelshift_l(b2.y, b2.x, (ph & 15) * 2);
+        const uint32_t a = __funnelshift_l(a2.y, a2.x, 2 * pv);  // (the funnel shift takes its amount modulo 32)
+        const uint32_t b = __funnelshift_l(b2.y, b2.x, 2 * ph);
         const uint32_t d = a ^ b;
         if (d) { cnt += __clz(d) >> 1; break; }
         cnt += 16;
@@ -530,9 +530,8 @@ int launch_wfa_long(const KernelArgs &a, Scratch *sc, void *stream_v, int *launc
         return plan;
     };
 
-    int G = 16;
-    if (const char *gs = getenv("AIM_WFA_LONG_G")) { int g = atoi(gs); if (g == 8 || g == 16 || g == 32) G = g; }
-    const uint32_t PPW = 32u / (uint32_t)G;
+    int G1 = 16;
+    if (const char *gs = getenv("AIM_WFA_LONG_G")) { int g = atoi(gs); if (g == 8 || g == 16 || g == 32) G1 = g; }
     const bool bt = p.backtrace != 0;
     const int block = 128;
 
@@ -542,6 +541,9 @@ int launch_wfa_long(const KernelArgs &a, Scratch *sc, void *stream_v, int *launc
     size_t slots = 0;
     for (int q = 0; q < npass; ++q) {
         const int wc = q == 0 ? wc1 : 256;
+        // the second pass is a tail - a few hundred pairs of milliseconds each on an otherwise empty GPU - so every pair gets a whole warp
+        const int G = q == 0 ? G1 : 32;
+        const uint32_t PPW = 32u / (uint32_t)G;
         LongK &K = ps[q].K;
         K = LongK{};
         K.plen = a.plen; K.tlen = a.tlen; K.results = a.results; K.n = a.n; K.idx_base = a.idx_base;
