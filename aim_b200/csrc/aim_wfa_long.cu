@@ -231,7 +231,6 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
 
             // ---- compute_offsets (wfa.c:238-273) fused with extend (wfa.c:193-215) ----
             int md = max(pl, tl);
-            bool hit_end = false;
             // frame-based loop: all components present and the source ranges nearly aligned, for every running pair of the warp
             bool framed = (fl & (L_SUB_NULL | L_O_NULL | L_IE_NULL | L_DE_NULL | L_HAS_I | L_HAS_D)) == (L_HAS_I | L_HAS_D);
             if (framed) {
@@ -241,14 +240,16 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
             }
             if (!done && framed) {
                 const uint32_t a_w = (uint32_t)(a_hi - a_lo);
-                for (int k = lo + sl; k <= hi; k += G) {
+                int plk = pl + lo + sl;                      // pl + k
+                uint32_t ka = (uint32_t)(lo + sl - a_lo);    // k - a_lo
+                for (int k = lo + sl; k <= hi; k += G, plk += G, ka += G) {
                     const uint32_t k2 = (uint32_t)k << 1;
                     const uint32_t ck = k2 & (2 * WC - 2), ckm = (k2 - 2u) & (2 * WC - 2), ckp = (k2 + 2u) & (2 * WC - 2);
                     const int mx = max(lds_s16(aBM + ckm), lds_s16(aEI + ckm));
                     const int ins = (mx == kNull) ? kNull : mx + 1;
                     const int del = max(lds_s16(aBM + ckp), lds_s16(aED + ckp));
                     const int sa = lds_s16(aAM + ck) + 1;
-                    const int sb = ((uint32_t)(k - a_lo) <= a_w) ? sa : kNull;
+                    const int sb = (ka <= a_w) ? sa : kNull;
                     sts_u16(aNI + ck, ins);
                     sts_u16(aND + ck, del);
                     int m = max(del, max(sb, ins));
@@ -259,8 +260,7 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
                     }
                     sts_u16(aNM + ck, m);
                     if (BT) hC[k] = make_uint2(((uint32_t)m & 0xffffu) | ((uint32_t)ins << 16), (uint32_t)del & 0xffffu);
-                    if (REDUCE) md = min(md, max(pl - (m - k), tl - m));
-                    if (k == ak && m >= tl) hit_end = true;
+                    if (REDUCE) md = min(md, max(plk, tl) - m);  // max(pl - (m - k), tl - m)
                 }
             } else if (!done) {
                 for (int k = lo + sl; k <= hi; k += G) {
@@ -291,13 +291,13 @@ __global__ void __launch_bounds__(128) wfa_long_kernel(const LongK K)
                     sts_u16(aNM + ck, m);
                     if (BT) hC[k] = make_uint2(((uint32_t)m & 0xffffu) | ((uint32_t)ins << 16), (uint32_t)del & 0xffffu);
                     if (REDUCE) md = min(md, max(pl - (m - k), tl - m));
-                    if (k == ak && m >= tl) hit_end = true;
                 }
             }
             // ---- end reached (wfa.c:217-237); trimming never removes diagonal ak, so testing before the
-            // reduction is equivalent and the finishing wavefront's trimmed range is never read again ----
-            const uint32_t eb = __ballot_sync(kFull, hit_end);
-            if (!done && ((eb >> subshift) & GM)) { done = true; reached = true; fscore = s; }
+            // reduction is equivalent and the finishing wavefront's trimmed range is never read again.  The offset of
+            // diagonal ak is read back from the row (one broadcast load per score instead of a test per cell) ----
+            __syncwarp();
+            if (!done && in_range(ak, lo, hi) && lds_s16(aNM + cell(ak)) >= tl) { done = true; reached = true; fscore = s; }
             if (BT && ran && sl == 0 && done) meta[s] = make_uint4(((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16), (uint32_t)lo, abase, 0u);
             if (__all_sync(kFull, done)) break;
 
