@@ -129,8 +129,7 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("
 __device__ __forceinline__ int match_packed_g(const uint2 *P2, const uint2 *T2, int v, int h, int lim)
 {
     int cnt = 0;
-    for (;;) {
-        const int pv = v + cnt, ph = h + cnt;
+    for (int pv = v, ph = h;; pv += 16, ph += 16) {
         const uint2 a2 = __ldg(P2 + ((uint32_t)pv >> 4)), b2 = __ldg(T2 + ((uint32_t)ph >> 4));
         const uint32_t a = __funnelshift_l(a2.y, a2.x, 2 * pv);  // (the funnel shift takes its amount modulo 32)
         const uint32_t b = __funnelshift_l(b2.y, b2.x, 2 * ph);

@@ -11,7 +11,7 @@ mkdir -p $out
 timeout 300 python bench.py > $out/${tag}_bench_cfg4.json 2> $out/${tag}_bench_cfg4.err
 AIM_SPARSE_OPS=0 timeout 300 python bench.py --no-cli --no-cpu-baseline --parity off > $out/${tag}_bench_cfg4_direct_rows.json 2>> $out/${tag}_bench_cfg4.err
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref_cfg4.json 2>/dev/null
-for c in 2 3 5; do timeout 300 python bench.py --config $c > $out/${tag}_bench_cfg$c.json 2> $out/${tag}_bench_cfg$c.err; done
+for c in 2 3 5 6 7; do timeout 300 python bench.py --config $c > $out/${tag}_bench_cfg$c.json 2> $out/${tag}_bench_cfg$c.err; done
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/${tag}_launches_cfg4.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-cli --parity off > /dev/null 2>&1
 cat > /tmp/e2e_small.py <<'PY'
