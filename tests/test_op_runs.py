@@ -153,3 +153,35 @@ def test_genasm_dc_strings_identical_with_and_without_string_heads(k, rs, chunk_
     for i in range(0, n, 7):
         e = int(ends[i])
         assert bytes(ops0[i, :e + 1]) == bytes(ops1[i, :e + 1]) and ops1[i, e] == 0, i
+
+
+def test_expand_from_several_threads_at_once():
+    """One process driving several GPUs has one coordinator thread per GPU calling into the same host pool: jobs are serialised, every
+    caller gets its own rows back."""
+    import threading
+    rs, n = 168, 20_000
+    pitch = A.op_runs_pitch(rs)
+    rng = np.random.default_rng(3)
+    jobs = []
+    for t in range(4):
+        rows = np.full((n, 2 * rs), ord("M"), np.uint8)
+        pos = rng.integers(0, 2 * rs, size=(n, 5))
+        for j in range(5):
+            rows[np.arange(n), pos[:, j]] = ord("XIDX"[(t + j) % 4])
+        runs = np.frombuffer(b"".join(_encode(bytes(r), pitch) for r in rows[:2000]), np.uint8).reshape(2000, pitch)
+        jobs.append((rows[:2000], runs))
+    errs = []
+
+    def work(rows, runs):
+        try:
+            for _ in range(10):
+                got, ov = A.expand_op_runs(runs, rs)
+                assert len(ov) == 0 and (got == rows).all()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
