@@ -42,6 +42,7 @@ def _load() -> C.CDLL:
         "aim_packed_row_bytes": (C.c_int32, [C.c_int32]),
         "aim_op_runs_pitch": (C.c_int32, [C.c_int32]),
         "aim_str_rows_pitch": (C.c_int32, [C.c_int32, C.c_int32]),
+        "aim_op_rows_download_bytes": (C.c_int32, [P(AimParams)]),
         "aim_expand_op_runs": (C.c_int, [vp, C.c_int32, C.c_uint32, C.c_int32, vp, vp, C.c_uint32, P(C.c_uint32)]),
         "aim_write_results_packed": (C.c_int, [cp, C.c_uint32, vp, vp, C.c_int32]),
         "aim_align_file": (C.c_int, [P(AimParams), cp, cp, C.c_uint32, C.c_uint32, P(C.c_uint64), P(C.c_uint32), P(C.c_double), P(C.c_int32)]),
@@ -75,4 +76,4 @@ lib = _load()
 EXPORTED = ["aim_align_file", "aim_align_batch", "aim_align_device", "aim_align_batch_cigars", "aim_align_packed", "aim_pack_pairs", "aim_packed_row_bytes", "aim_write_results_packed", "aim_host_alloc", "aim_host_free", "aim_shutdown",
             "aim_device_count", "aim_measure_int_peak", "aim_last_error", "aim_strerror", "aim_abi_version", "aim_derive_knobs",
             "aim_pairs_to_process", "aim_read_pairs", "aim_count_pairs", "aim_write_results", "aim_write_results_genasm", "aim_cigar_rle",
-            "aim_generate_pairs", "aim_write_pairs", "aim_op_runs_pitch", "aim_str_rows_pitch", "aim_expand_op_runs"]
+            "aim_generate_pairs", "aim_write_pairs", "aim_op_runs_pitch", "aim_str_rows_pitch", "aim_op_rows_download_bytes", "aim_expand_op_runs"]

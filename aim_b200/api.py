@@ -222,6 +222,12 @@ def str_rows_pitch(read_size: int, max_score: int) -> int:
     return int(lib.aim_str_rows_pitch(read_size, max_score))
 
 
+def op_rows_download_bytes(params: "AlignParams") -> int:
+    """Bytes per pair that cross PCIe for the op row under these parameters (0 = the 2*read_size row itself)."""
+    p = params.to_c()
+    return int(lib.aim_op_rows_download_bytes(C.byref(p)))
+
+
 def expand_op_runs(runs: np.ndarray, read_size: int, ops: np.ndarray | None = None):
     """Host half of aim_align_batch's op-row download: run rows [n, pitch] -> (ops[n, 2*read_size], overflow pair numbers)."""
     runs = np.ascontiguousarray(runs, np.uint8)

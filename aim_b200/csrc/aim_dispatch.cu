@@ -226,8 +226,8 @@ int run_shard(const aim_params &p, int device, std::atomic<uint32_t> *queue, uin
     if (bt && !cigars) {
         const char *e = getenv("AIM_SPARSE_OPS");
         if (!(e && atoi(e) == 0)) {
-            if (p.algo == AIM_ALGO_NW || p.algo == AIM_ALGO_SWG || p.algo == AIM_ALGO_WFA) runs_pitch = op_runs_pitch(p.read_size);
-            else if (p.algo == AIM_ALGO_GENASM_DC) { runs_pitch = str_rows_pitch(p.read_size, p.max_score); strings = runs_pitch > 0; }
+            runs_pitch = op_rows_download_bytes(p);
+            strings = runs_pitch > 0 && p.algo == AIM_ALGO_GENASM_DC;
         }
     }
     const bool sparse = runs_pitch > 0;

@@ -235,6 +235,23 @@ void expand_op_runs(const unsigned char *runs, int pitch, uint32_t m, int read_s
     });
 }
 
+// What crosses PCIe per pair for the op row of this parameter set (0 = the row itself).  WFA: an alignment of score s has at most
+// s / min(x, o + e) runs of ops other than 'M' (each costs at least a mismatch or a gap of one), and MAX_SCORE bounds s, so the
+// run row needs no more words than that (config 4: 11 words = 44 bytes instead of 64); a row with more runs is fetched as it is anyway.
+int32_t op_rows_download_bytes(const aim_params &p)
+{
+    if (!p.backtrace && p.algo != AIM_ALGO_GENASM_DC) return 0;
+    if (p.algo == AIM_ALGO_GENASM_DC) return str_rows_pitch(p.read_size, p.max_score);
+    if (p.algo != AIM_ALGO_NW && p.algo != AIM_ALGO_SWG && p.algo != AIM_ALGO_WFA) return 0;
+    int32_t pitch = op_runs_pitch(p.read_size);
+    if (pitch > 0 && p.algo == AIM_ALGO_WFA && p.max_score >= 0) {
+        const int32_t unit = std::max(1, std::min(p.mismatch, p.gap_open + p.gap_ext));
+        const int64_t by_score = 4 * (1 + (int64_t)p.max_score / unit);
+        if (by_score >= 16 && by_score < pitch) pitch = (int32_t)by_score;
+    }
+    return pitch;
+}
+
 // GenASM-DC strings: k error levels make at most 2k + 1 runs of at most 5 characters ("1000M"); pieces of up to half a row
 int32_t str_rows_pitch(int32_t read_size, int32_t max_score)
 {
@@ -275,6 +292,7 @@ int32_t op_runs_pitch(int32_t read_size)
 
 extern "C" int32_t aim_op_runs_pitch(int32_t read_size) { return aim::op_runs_pitch(read_size); }
 extern "C" int32_t aim_str_rows_pitch(int32_t read_size, int32_t max_score) { return aim::str_rows_pitch(read_size, max_score); }
+extern "C" int32_t aim_op_rows_download_bytes(const aim_params *params) { return params ? aim::op_rows_download_bytes(*params) : 0; }
 
 extern "C" int aim_expand_op_runs(const unsigned char *runs, int32_t pitch, uint32_t n, int32_t read_size, char *ops,
                                   uint32_t *overflow, uint32_t overflow_cap, uint32_t *overflow_count)

@@ -125,6 +125,7 @@ void expand_op_runs(const unsigned char *runs, int pitch, uint32_t m, int read_s
 // GenASM-DC: the same for the CIGAR strings its op rows hold - the first str_rows_pitch() bytes of every row cross PCIe, the host
 // copies each string (with its NUL) to the head of the caller's row; *overflow: strings that do not end inside their piece.
 int32_t str_rows_pitch(int32_t read_size, int32_t max_score);  // 0 = not worth it
+int32_t op_rows_download_bytes(const aim_params &p);           // run row / string head bytes of this parameter set (0 = whole rows)
 int launch_str_rows(const char *d_ops, int read_size, uint32_t m, unsigned char *d_rows, int pitch, void *stream, int *launches);
 void expand_str_rows(const unsigned char *rows, int pitch, uint32_t m, int read_size, char *ops, std::vector<uint32_t> *overflow);
 void host_pool_shutdown();

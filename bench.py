@@ -328,7 +328,7 @@ def main() -> None:
         # op rows cross PCIe as run rows and are rebuilt into the caller's buffer by host threads inside the call (include/aim_b200.h)
         runs_pitch = 0
         if bt and os.environ.get("AIM_SPARSE_OPS", "1") != "0":
-            runs_pitch = A.str_rows_pitch(rs, ms) if cfg["algo"] == "genasm_dc" else (0 if genasm else A.op_runs_pitch(rs))
+            runs_pitch = A.op_rows_download_bytes(params)
         e2e = {"value": world * P / te_s, "unit": "pairs/s",
                "h2d_bytes_per_step": int(P * (2 * rs + 8)),
                "d2h_bytes_per_step": int(P * (A.RESULT_DTYPE.itemsize + (runs_pitch if runs_pitch else (2 * rs if bt else 0)))),

@@ -131,6 +131,10 @@ int32_t aim_op_runs_pitch(int32_t read_size);
  * the longest string max_score error levels can make - cross PCIe and each string is copied, with its NUL, to the head of the
  * caller's row (bytes behind the NUL are not written); 0 = the rows move as they are (the heads would exceed half a row). */
 int32_t aim_str_rows_pitch(int32_t read_size, int32_t max_score);
+/* Bytes per pair that cross PCIe for the op row under these parameters (0 = the row itself): aim_op_runs_pitch(read_size), for
+ * WFA cut down to the 4 * (1 + max_score / min(mismatch, gap_open + gap_ext)) bytes an alignment within max_score can need, or
+ * aim_str_rows_pitch for GenASM-DC. */
+int32_t aim_op_rows_download_bytes(const aim_params *params);
 int aim_expand_op_runs(const unsigned char *runs, int32_t pitch, uint32_t n, int32_t read_size, char *ops,
                        uint32_t *overflow, uint32_t overflow_cap, uint32_t *overflow_count);
 

@@ -36,6 +36,17 @@ def test_pitch_rule():
     assert A.op_runs_pitch(32) == 32 and A.op_runs_pitch(24) == 0 and A.op_runs_pitch(1024) == 384 and A.op_runs_pitch(1032) == 0
 
 
+def test_download_bytes_rule():
+    wfa = dict(algo="wfa", mismatch=3, gap_open=4, gap_ext=1, read_size=168, reduce=True)
+    assert A.op_rows_download_bytes(A.AlignParams(max_score=30, backtrace=True, **wfa)) == 44   # 1 + 30 / 3 words
+    assert A.op_rows_download_bytes(A.AlignParams(max_score=400, backtrace=True, **wfa)) == 64  # the READ_SIZE rule is the smaller one
+    assert A.op_rows_download_bytes(A.AlignParams(max_score=30, backtrace=False, **wfa)) == 0   # no op rows at all
+    assert A.op_rows_download_bytes(A.AlignParams(algo="nw", max_score=4, read_size=112, backtrace=True)) == 48
+    assert A.op_rows_download_bytes(A.AlignParams(algo="genasm_dc", max_score=5, read_size=120)) == 64
+    assert A.op_rows_download_bytes(A.AlignParams(algo="genasm_dc", max_score=30, read_size=168)) == 0
+    assert A.op_rows_download_bytes(A.AlignParams(algo="genasm_filter", max_score=2, read_size=120)) == 0
+
+
 @pytest.mark.parametrize("rs,n", [(168, 5000), (32, 300), (1024, 100), (112, 1)])
 def test_expand_restores_rows_and_lists_overflows(rs, n):
     rng = np.random.default_rng(rs)
@@ -92,6 +103,8 @@ def _mixed_pairs(n, length, rs, noisy_every, seed):
 @pytest.mark.gpu
 @pytest.mark.parametrize("algo,length,rs,max_score,noisy_every,chunk_mb", [
     ("wfa", 150, 168, 400, 0, None),       # no overflow
+    ("wfa", 150, 168, 30, 0, None),        # config 4: the run row is cut down to what a score of 30 can need (44 bytes)
+    ("wfa", 150, 168, 30, 3000, 1),        # ... and unrelated pairs give up with untouched rows
     ("wfa", 150, 168, 400, 3000, 1),       # a few overflowing rows per chunk, many chunks: fetched one by one
     ("wfa", 150, 168, 400, 2, 1),          # half the rows overflow: the chunk's rows are fetched as they are
     ("nw", 100, 112, 40, 97, None),
@@ -114,7 +127,7 @@ def test_batch_rows_identical_with_and_without_run_rows(algo, length, rs, max_sc
     po.array[:] = 0
     res2, ops2, _ = A.align_batch(params, *arrays, results=pr.array, ops=po.array)  # pinned output buffers
     assert res0.tobytes() == res2.tobytes() and (ops0 == ops2).all()
-    if noisy_every:
+    if noisy_every and max_score > 100:
         pitch = A.op_runs_pitch(rs)
         spans_long = sum(_encode(bytes(ops0[i]), pitch)[:4] == b"\xff\xff\xff\xff" for i in range(0, n, noisy_every))
         assert spans_long > 0, "the case was meant to overflow some run rows"
