@@ -139,9 +139,10 @@ int aim_expand_op_runs(const unsigned char *runs, int32_t pitch, uint32_t n, int
                        uint32_t *overflow, uint32_t overflow_cap, uint32_t *overflow_count);
 
 /* ---- compact transfers (extension; WFA short reads) -------------------------------------------------
- * aim_align_batch moves the reference host's own buffers: 2*READ_SIZE ASCII bytes in and the 2*READ_SIZE op row out per
- * pair (696 B at READ_SIZE 168), which is what bounds it: one PCIe Gen5 x16 link carries ~1.2e8 pairs/s of that layout and
- * the host's memory ~1.9e8 pairs/s for all GPUs of a box together, while one B200 aligns 3e8 pairs/s.  This entry moves the
+ * aim_align_batch serves the reference host's own buffers: 2*READ_SIZE ASCII bytes in and the 2*READ_SIZE op row out per
+ * pair (680 B at READ_SIZE 168; the ASCII rows cross PCIe, the op rows are rebuilt on the host), which is what bounds it: one
+ * PCIe Gen5 x16 link carries 1.2-1.3e8 pairs/s of that layout and the host's memory ~2.3e8 pairs/s for all GPUs of a box
+ * together, while one B200 aligns 3.5e8 pairs/s.  This entry moves the
  * information instead: sequences 2 bits per base (aim_pack_pairs: what get_reads would produce, host.c:91-134), and per
  * pair the CIGAR TEXT the reference prints (edit_cigar_print, host.c:69-89: "40M1D59M", NUL-terminated) in a row of
  * cigar_pitch bytes, i.e. what the print loop (host.c:340-350) needs, ready to write.  Same scores, same CIGARs.
