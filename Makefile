@@ -10,7 +10,7 @@ OBJDIR    := build/obj
 CU_SRCS   := $(CSRC)/aim_wfa.cu $(CSRC)/aim_wfa_sub.cu $(CSRC)/aim_wfa_long.cu $(CSRC)/aim_dp.cu $(CSRC)/aim_dp_fast.cu $(CSRC)/aim_genasm.cu $(CSRC)/aim_dispatch.cu $(CSRC)/aim_file.cu $(CSRC)/aim_filepipe.cu $(CSRC)/aim_peak.cu
 CXX_SRCS  := $(CSRC)/aim_host.cpp
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CXX_SRCS))
-HDRS      := include/aim_b200.h $(CSRC)/aim_internal.h $(CSRC)/aim_wfa_common.cuh $(CSRC)/aim_dp_pack2.cuh
+HDRS      := include/aim_b200.h $(CSRC)/aim_internal.h $(CSRC)/aim_wfa_common.cuh $(CSRC)/aim_dp_pack2.cuh $(CSRC)/aim_dp_scan.cuh
 
 all: aim_b200/libaim_b200.so aim_b200/libaim_dpu.so build/host build/aim_genpairs build/diag_xfer build/diag_hostfill oracle/libaim_oracle.so
 

@@ -56,13 +56,15 @@ struct FastK {
     uint32_t *bound;        // strip kernel: boundary column, [row][thread]
     uint32_t *flags;        // predicate bits
     uint32_t wpr;           // row kernel: flag records per row
+    uint2 *tflags;          // scan kernel: the tail cells' predicate nibbles, one 64-bit word per (row, pair)
     int neg1;               // -1, kept opaque to the compiler (see dp_cell)
 };
 
 // ---- classification: non-aliased pairs to the front of `list`, aliased ones that fit the register-row
 // kernel (tlen >= reg_cols, plen - tlen <= 16) to its back, the other aliased ones to `list2` ----
-__global__ void classify_kernel(const int32_t *plen, const int32_t *tlen, uint32_t n, int RS, int reg_cols, uint32_t *list, uint32_t *list2,
-                                uint32_t *counters)
+// (scan_cols > 0: the back of `list` takes the aliased pairs dp_scan_kernel serves instead: tlen <= scan_cols, plen - tlen <= min(scan_d, tlen): the tail reads head columns only)
+__global__ void classify_kernel(const int32_t *plen, const int32_t *tlen, uint32_t n, int RS, int reg_cols, int scan_cols, int scan_d,
+                                uint32_t *list, uint32_t *list2, uint32_t *counters)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -70,7 +72,8 @@ __global__ void classify_kernel(const int32_t *plen, const int32_t *tlen, uint32
     if (valid) {
         const int pl = min(max(plen[i], 0), RS), tl = min(max(tlen[i], 0), RS);
         alias = pl > tl;
-        regrow = alias && reg_cols > 0 && tl >= reg_cols && pl - tl <= 16;
+        regrow = scan_cols > 0 ? (alias && tl <= scan_cols && pl - tl <= min(scan_d, tl))
+                               : (alias && reg_cols > 0 && tl >= reg_cols && pl - tl <= 16);
     }
     const uint32_t m0 = __ballot_sync(0xffffffffu, valid && !alias), m1 = __ballot_sync(0xffffffffu, regrow),
                    m2 = __ballot_sync(0xffffffffu, valid && alias && !regrow);
@@ -549,6 +552,220 @@ __global__ void __launch_bounds__(RT) __maxnreg__(R > 0 ? 224 : 128) dp_row_kern
     }
 }
 
+#include "aim_dp_scan.cuh"
+
+// ================= aliased pairs: the row spread over G lanes, min-plus scan of the horizontal gap =================
+// See aim_dp_scan.cuh for the algorithm.  32 / G pairs per warp walk their rows in lockstep (rows 1 .. the largest text_len of
+// the warp; a pair that is through keeps computing rows nobody reads).  No shared memory: the row lives in 4*C (NW) / 5*C
+// registers per lane, so the register file, not the row, bounds the resident pairs.  Predicates: per (row, lane) one record
+// {P, Q[, opD, opI]} with bit (column - 1) % 2C, written as one coalesced store per warp and row, + one 64-bit word per
+// (row, pair) for the tail cells; the traceback walks them on the sub-warp's first lane.
+// Preconditions (classify_kernel / launcher): text_len < pattern_len, text_len <= 2*C*G, pattern_len - text_len <= min(C, text_len),
+// o >= 0, e >= 0, MATCH == 0, every value + the scan's "infinity" inside int16.
+template <int C, bool SWG>
+struct ScanFlags {
+    static constexpr int FW = SWG ? (C == 16 ? 4 : 2) : (C == 16 ? 2 : 1);
+    __device__ __forceinline__ static void store(uint32_t *d, uint32_t aP, uint32_t aQ, uint32_t aD, uint32_t aI)
+    {
+        if (SWG && C == 16) *reinterpret_cast<uint4 *>(d) = make_uint4(aP, aQ, aD, aI);
+        else if (SWG) *reinterpret_cast<uint2 *>(d) = make_uint2(aP | (aQ << 16), aD | (aI << 16));
+        else if (C == 16) *reinterpret_cast<uint2 *>(d) = make_uint2(aP, aQ);
+        else d[0] = aP | (aQ << 16);
+    }
+    __device__ __forceinline__ static void load(const uint32_t *d, int bit, bool &p, bool &q, bool &opD, bool &opI)
+    {
+        opD = opI = false;
+        if (SWG && C == 16) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(d);
+            p = (w.x >> bit) & 1u; q = (w.y >> bit) & 1u; opD = (w.z >> bit) & 1u; opI = (w.w >> bit) & 1u;
+        } else if (SWG) {
+            const uint2 w = *reinterpret_cast<const uint2 *>(d);
+            p = (w.x >> bit) & 1u; q = (w.x >> (16 + bit)) & 1u; opD = (w.y >> bit) & 1u; opI = (w.y >> (16 + bit)) & 1u;
+        } else if (C == 16) {
+            const uint2 w = *reinterpret_cast<const uint2 *>(d);
+            p = (w.x >> bit) & 1u; q = (w.y >> bit) & 1u;
+        } else {
+            const uint32_t w = d[0];
+            p = (w >> bit) & 1u; q = (w >> (16 + bit)) & 1u;
+        }
+    }
+};
+
+template <int ALGO, int C, int G, int MINB>
+__global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
+{
+    constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
+    constexpr int PPW = 32 / G;  // pairs per warp
+    constexpr int FW = ScanFlags<C, SWG>::FW;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, sl = lane & (G - 1), sub = lane / G;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t count = *K.count;
+    const int RS = K.read_size;
+    scan::Pen P;
+    P.O = K.o; P.X = K.x; P.MS = K.max_score;
+    P.OE = SWG ? K.o + K.e : K.o;
+    P.E = SWG ? K.e : K.o;
+    P.INF = 32767 - P.E * C - P.OE - 8;
+    P.OE2 = scan::both(P.OE); P.E2 = scan::both(P.E); P.INF2 = scan::both(P.INF);
+    const int EC = P.E * C;
+    uint32_t *fl = K.flags + ((size_t)warp * RS * 32 + lane) * FW;  // + (row - 1) * 32 * FW
+    uint2 *tf = K.tflags + (size_t)warp * RS * PPW + sub;           // + (row - 1) * PPW
+
+    for (uint32_t g = warp; (uint64_t)g * PPW < count; g += nwarps) {
+        const uint32_t li = g * PPW + sub;
+        const bool have = li < count;  // a sub-warp without a pair shadows the warp's first pair and writes nothing
+        const uint32_t i = K.list[(int64_t)K.list_step * (int64_t)(have ? li : g * PPW)];
+        const int pl = min(max(K.plen[i], 0), RS), tl = min(max(K.tlen[i], 0), RS);
+        const char *gp = K.patterns + (size_t)i * RS;
+        const char *gt = K.texts + (size_t)i * RS;
+        const int nc = tl + 1, d = pl - tl;
+        const int tlmax = __reduce_max_sync(FULL, tl), dmax = __reduce_max_sync(FULL, d);
+
+        scan::Lane<C> L;
+        uint32_t tp[C / 4];  // pattern bytes of the tail cells
+        {
+            uint32_t wlo[C / 4], whi[C / 4];
+#pragma unroll
+            for (int w = 0; w < C / 4; ++w) {
+                const int oa = 2 * C * sl + 4 * w, ob = oa + C;
+                wlo[w] = oa < RS ? __ldg(reinterpret_cast<const uint32_t *>(gp + oa)) : 0u;
+                whi[w] = ob < RS ? __ldg(reinterpret_cast<const uint32_t *>(gp + ob)) : 0u;
+                uint32_t t = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int o = tl + 4 * w + b;
+                    t |= (o < RS ? (uint32_t)(unsigned char)__ldg(gp + o) : 0u) << (8 * b);
+                }
+                tp[w] = t;
+            }
+            scan::init_lane<C, SWG>(L, sl, P, wlo, whi);
+        }
+        // where column text_len lives
+        const int pt = tl - 1, ot = pt / (2 * C), ht = (pt / C) & 1, rt = pt % C;
+        scan::Edge ed;
+        ed.bM = ed.bI = ed.bD = 0;
+        ed.c0prev = 0;                                    // M(0, 0)
+        ed.dgt = SWG ? P.O + tl * P.E : tl * P.OE;        // M(0, text_len)
+        int tM = 0, tI = 0, tD = 0, score = 0;
+
+        uint32_t tw = 0, twn = __ldg(reinterpret_cast<const uint32_t *>(gt));
+        for (int h = 1; h <= tlmax; ++h) {
+            if (((h - 1) & 3) == 0) {  // four text bytes per load, the next four fetched now
+                tw = twn;
+                if (h + 3 < RS) twn = __ldg(reinterpret_cast<const uint32_t *>(gt) + ((h + 3) >> 2));
+            }
+            const uint32_t tc = tw & 0xffu, t4 = tc * 0x01010101u;
+            tw >>= 8;
+            // column 0 of this row (nw.c:114-118 / swg.c:158-166; aliased from row 2 on: cell (h-1, num_cols))
+            if (h >= 2) { ed.bM = tM; ed.bI = tI; ed.bD = tD; }
+            else if (SWG) { ed.bD = P.MS; ed.bI = P.O + P.E; ed.bM = ed.bI; }
+            else { ed.bM = P.OE; ed.bI = 0; ed.bD = 0; }
+
+            // phase 1 + 2
+            const uint32_t nb = __shfl_up_sync(FULL, L.uM[C - 1], 1, G);
+            const uint32_t dg0 = scan::pack16(sl == 0 ? ed.c0prev : scan::hi16(nb), scan::lo16(L.uM[C - 1]));
+            uint32_t aP = 0, aQ = 0, aD = 0, aI = 0;
+            const uint32_t dl = scan::phase12<C, SWG>(L, dg0, t4, P, aI);
+            // phase 3: the true D at the first column of every block
+            const int a_lo = scan::lo16(dl), a_hi = scan::hi16(dl);
+            int val = min(a_hi, a_lo + EC);
+#pragma unroll
+            for (int dlt = 1; dlt < G; dlt <<= 1) {
+                const int t = __shfl_up_sync(FULL, val, dlt, G);
+                if (sl >= dlt) val = min(val, t + 2 * EC * dlt);
+            }
+            const int din0_own = SWG ? min(ed.bM + P.OE, ed.bD + P.E) : ed.bM + P.OE;
+            const int din0 = __shfl_sync(FULL, din0_own, 0, G);
+            const int S = min(val, din0 + 2 * EC * (sl + 1));
+            const int sp = __shfl_up_sync(FULL, S, 1, G);
+            const int in_lo = sl == 0 ? din0 : sp;
+            const int in_hi = min(a_lo, in_lo + EC);
+            const uint32_t din = scan::pack16(in_lo, in_hi);
+            // phase 4
+            scan::phase4<C, SWG>(L, din, P, aP, aQ, aD);
+            if (SWG) {
+                const uint32_t nbn = __shfl_up_sync(FULL, L.uM[C - 1], 1, G);
+                const uint32_t mleft = scan::pack16(sl == 0 ? ed.bM : scan::hi16(nbn), scan::lo16(L.uM[C - 1]));
+                scan::opd_first<C>(mleft, din, P, aD);
+            }
+            if (K.backtrace)
+                ScanFlags<C, SWG>::store(fl + (size_t)(h - 1) * 32 * FW, scan::compact<C>(aP), scan::compact<C>(aQ), scan::compact<C>(aD), scan::compact<C>(aI));
+            // M and del of column text_len, then the tail cells on the first lane
+            const uint32_t sm = __shfl_sync(FULL, scan::pick<C>(L.uM, rt), ot, G);
+            const uint32_t sd = __shfl_sync(FULL, scan::pick<C>(L.dn, rt), ot, G);
+            int lm = ht ? scan::hi16(sm) : scan::lo16(sm);
+            const int ld = ht ? scan::hi16(sd) : scan::lo16(sd);
+            const int mtl = lm;
+            const int dlim = __any_sync(FULL, h == tl) ? dmax : 1;
+            const uint64_t tword = scan::tail_cells<C, SWG>(L, ed, lm, ld, tp, tc, d, dlim, P, tM, tI, tD);
+            if (K.backtrace && sl == 0) tf[(size_t)(h - 1) * PPW] = make_uint2((uint32_t)tword, (uint32_t)(tword >> 32));
+            if (h == tl) score = lm;
+            ed.c0prev = ed.bM;
+            ed.dgt = mtl;
+        }
+
+        if (have && sl == 0) {
+            int begin_offset = pl + tl - 1;
+            int status = AIM_STATUS_OK;
+            if (K.backtrace) {
+                char *ops = K.ops + (size_t)i * 2 * RS;  // pre-filled with 'M' by the launcher
+                const uint32_t *flw = K.flags + (size_t)warp * RS * 32 * FW;
+                int b = pl + tl - 1;
+                int h = tl, v = pl;
+                int layer = 0;  // SWG: 0 M, 1 I, 2 D
+                while (h > 0 && v > 0) {
+                    int r, c;
+                    scan::last_writer(nc, tl, h, v, r, c);
+                    bool p, q, opD, opI;
+                    if (c >= nc) {
+                        const uint2 t2 = tf[(size_t)(r - 1) * PPW];
+                        const uint64_t t = (uint64_t)t2.x | ((uint64_t)t2.y << 32);
+                        const uint32_t nib = (uint32_t)(t >> (4 * (c - nc))) & 15u;
+                        p = nib & 1u; q = nib & 2u; opD = nib & 4u; opI = nib & 8u;
+                    } else {
+                        const int pos = c - 1;
+                        ScanFlags<C, SWG>::load(flw + ((size_t)(r - 1) * 32 + (size_t)(sub * G + pos / (2 * C))) * FW, pos % (2 * C), p, q, opD, opI);
+                    }
+                    if (!SWG) {
+                        if (q) {
+                            if (p) { ops[b--] = 'D'; --v; }
+                            else { ops[b--] = 'I'; --h; }
+                        } else {
+                            if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                            --b; --h; --v;
+                        }
+                    } else {
+                        if (b < 0) { status = AIM_STATUS_BACKTRACE; break; }
+                        if (layer == 2) { ops[b--] = 'D'; if (opD) layer = 0; --v; }
+                        else if (layer == 1) { ops[b--] = 'I'; if (opI) layer = 0; --h; }
+                        else if (q) layer = p ? 2 : 1;
+                        else {
+                            if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                            --b; --h; --v;
+                        }
+                    }
+                }
+                if (status == AIM_STATUS_OK) {
+                    while (h > 0) { ops[b--] = 'I'; --h; }
+                    while (v > 0) { ops[b--] = 'D'; --v; }
+                    begin_offset = b + 1;
+                }
+            }
+            aim_result res;
+            res.max_operations = pl + tl;
+            res.begin_offset = begin_offset;
+            res.end_offset = pl + tl;
+            res.score = score;
+            res.status = status;
+            res.idx = K.idx_base + i;
+            K.results[i] = res;
+        }
+        __syncwarp();  // the next pairs' rows overwrite the records this traceback reads
+    }
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -589,6 +806,47 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     if (const char *rc_s = getenv("AIM_DP_REGCOLS")) { const int v = atoi(rc_s); if (v == 0 || v == 96 || v == 112) reg_cols = v; }
     if (reg_cols > 0 && !row_cfg(reg_cols, &pt1, &psm1, &bps1)) reg_cols = 0;
     const int row_threads = (int)RT;
+
+    // aliased pairs with the row spread over the lanes of a sub-warp (dp_scan_kernel): geometry by READ_SIZE
+    struct ScanCfg { int C, G; void (*fn)(const FastK); };
+    ScanCfg scn{0, 0, nullptr};
+    {
+        int mode = 0;  // 0 off, 1 default geometry, 2 the narrower blocks
+        if (const char *e = getenv("AIM_DP_SCAN")) mode = atoi(e);
+        const bool pen_ok = p.gap_open >= 0 && p.mismatch >= 0 && (nw || (p.gap_ext >= 0 && p.match == 0));
+        if (mode > 0 && pen_ok && RS >= 16 && RS <= 528) {
+            // resident blocks per SM the register allocation aims at: 8 (128 registers) or 10 (96; 16-column blocks spill there)
+            int minb = 0;
+            if (const char *e = getenv("AIM_DP_SCAN_MINB")) minb = atoi(e);
+#define AIM_SCAN_FN(C, G, B) (nw ? (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_NW, C, G, B> : (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_SWG, C, G, B>)
+#define AIM_SCAN_CFG(C, G, BDEF) ((minb ? minb : BDEF) >= 10 ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 10)} : ScanCfg{C, G, AIM_SCAN_FN(C, G, 8)})
+            if (RS <= 144) scn = mode == 2 ? AIM_SCAN_CFG(4, 16, 10) : AIM_SCAN_CFG(8, 8, 10);
+            else if (RS <= 288) scn = mode == 2 ? AIM_SCAN_CFG(8, 16, 10) : AIM_SCAN_CFG(16, 8, 8);
+            else scn = AIM_SCAN_CFG(16, 16, 8);
+#undef AIM_SCAN_CFG
+#undef AIM_SCAN_FN
+            const int64_t oe = nw ? p.gap_open : p.gap_open + p.gap_ext, ee = nw ? p.gap_open : p.gap_ext;
+            const int64_t pen = std::max<int64_t>(p.mismatch, oe);
+            const int64_t top = (2 * (int64_t)RS + 2 + 2 * scn.C * scn.G) * pen + (nw ? 0 : (int64_t)p.max_score) + oe + ee * scn.C + 16;
+            if (top >= 32767) scn = ScanCfg{0, 0, nullptr};
+        }
+    }
+    int scan_grid = 0;
+    size_t scan_flag_bytes = 0, scan_tail_off = 0;
+    if (scn.fn) {
+        int bps = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, scn.fn, 64, 0);
+        if (e != cudaSuccess || bps < 1) { cudaGetLastError(); scn = ScanCfg{0, 0, nullptr}; }
+        else {
+            const int ppw = 32 / scn.G;
+            scan_grid = (int)std::min<uint64_t>((uint64_t)sc->sm_count * (uint64_t)bps, ((uint64_t)a.n / ppw + 2) / 2 + 1);
+            const size_t warps = (size_t)scan_grid * 2;
+            const int fw = nw ? (scn.C == 16 ? 2 : 1) : (scn.C == 16 ? 4 : 2);
+            scan_tail_off = align_up(p.backtrace ? warps * (size_t)RS * 32 * fw * 4 : 0, 256);
+            scan_flag_bytes = scan_tail_off + (p.backtrace ? warps * (size_t)RS * ppw * 8 : 0);
+            reg_cols = 0;  // its class of the list is the scan kernel's
+        }
+    }
 
     const int FW = nw ? 1 : 2;                         // flag words per 16-cell record
     const uint32_t wpr = ((uint32_t)RS + 15) / 16;     // records per row (row kernels)
@@ -672,7 +930,7 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     const size_t off_sflags = align_up(off_bound + strip_threads * (size_t)RS * 4 * strip_mul, 256);
     const size_t sflag_bytes = p.backtrace ? strip_threads * (size_t)nstrips_max * RS * FW * 4 * strip_mul : 0;
     const size_t off_rflags = align_up(off_sflags + sflag_bytes, 256);
-    const size_t rflag_bytes = p.backtrace ? rowk_threads * (size_t)RS * wpr * FW * 4 * (pack_row ? 2 : 1) : 0;
+    const size_t rflag_bytes = std::max(p.backtrace ? rowk_threads * (size_t)RS * wpr * FW * 4 * (pack_row ? 2 : 1) : 0, scan_flag_bytes);
     int rc = scratch_reserve(sc, off_rflags + rflag_bytes);
     if (rc != AIM_OK) return rc;
     unsigned char *base = reinterpret_cast<unsigned char *>(sc->buf);
@@ -703,7 +961,8 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
             nlaunch += 3;
         }
     } else if (err == cudaSuccess) {
-        classify_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(a.plen, a.tlen, a.n, RS, reg_cols, list, list2, counters);
+        classify_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(a.plen, a.tlen, a.n, RS, reg_cols, scn.fn ? 2 * scn.C * scn.G : 0, scn.C, list, list2,
+                                                               counters);
         err = cudaGetLastError();
         ++nlaunch;
     }
@@ -726,6 +985,15 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         R2.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
         if (nw) dp2_row_kernel<AIM_ALGO_NW><<<row2_grid, RT2, row2_smem, stream>>>(R2);
         else dp2_row_kernel<AIM_ALGO_SWG><<<row2_grid, RT2, row2_smem, stream>>>(R2);
+        err = cudaGetLastError();
+        ++nlaunch;
+    }
+    if (err == cudaSuccess && !pack_row && scn.fn) {  // aliased pairs: the row over the lanes of a sub-warp
+        FastK Sc = K;
+        Sc.list = list + (a.n - 1); Sc.count = counters + 1; Sc.list_step = -1;
+        Sc.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
+        Sc.tflags = reinterpret_cast<uint2 *>(base + off_rflags + scan_tail_off);
+        scn.fn<<<scan_grid, 64, 0, stream>>>(Sc);
         err = cudaGetLastError();
         ++nlaunch;
     }

@@ -102,6 +102,27 @@ def test_vs_oracle_ragged_literal_dp_kernel(algo, kw, gen, monkeypatch):
     _vs_oracle_ragged(algo, kw, gen, True)
 
 
+SCAN_CASES = DP_CASES + [
+    ("swg", dict(max_score=80, read_size=272, mismatch=4, gap_open=6, gap_ext=2, backtrace=True), (24, 800, 225, 262)),   # config 3's geometry
+    ("swg", dict(max_score=80, read_size=272, mismatch=4, gap_open=6, gap_ext=2, backtrace=False), (25, 400, 200, 260)),
+    ("swg", dict(max_score=30, read_size=160, mismatch=1, gap_open=0, gap_ext=1, backtrace=True), (26, 800, 100, 150)),  # o = 0
+    ("nw", dict(max_score=0, read_size=112, mismatch=3, gap_open=4, backtrace=True), (27, 2000, 80, 104)),                # config 2's
+    ("nw", dict(max_score=0, read_size=528, mismatch=2, gap_open=3, backtrace=True), (28, 200, 380, 520)),
+]
+
+
+@pytest.mark.parametrize("mode,minb", [("0", "0"), ("1", "0"), ("2", "0"), ("1", "10"), ("2", "8")])
+@pytest.mark.parametrize("algo,kw,gen", SCAN_CASES, ids=[f"{c[0]}-{c[2][0]}" for c in SCAN_CASES])
+def test_vs_oracle_ragged_scan_kernel(algo, kw, gen, mode, minb, monkeypatch):
+    """Aliased pairs (pattern longer than text) through dp_scan_kernel - the row spread over the lanes of a sub-warp, the
+    horizontal gap as a min-plus scan (aim_dp_scan.cuh) - in both block geometries and both register budgets, and with it
+    switched off (dp_row_kernel).  Lengths differ by up to 12, so each batch also holds pairs the scan kernel must leave to
+    dp_row_kernel (more tail cells than a block has columns) and non-aliased ones (dp2_strip_kernel)."""
+    monkeypatch.setenv("AIM_DP_SCAN", mode)
+    monkeypatch.setenv("AIM_DP_SCAN_MINB", minb)
+    _vs_oracle_ragged(algo, kw, gen, True)
+
+
 @pytest.mark.parametrize("g", ["8", "32"])
 def test_long_read_kernel_lane_groups(g, monkeypatch):
     """The windowed-ring long-read kernel with 8 and 32 lanes per pair (default 16)."""
