@@ -57,6 +57,7 @@ struct FastK {
     uint32_t *flags;        // predicate bits
     uint32_t wpr;           // row kernel: flag records per row
     uint2 *tflags;          // scan kernel: the tail cells' predicate nibbles, one 64-bit word per (row, pair)
+    uint32_t lbase, llimit; // scan kernels: the list entries [lbase, min(llimit, *count)) of this launch
     int neg1;               // -1, kept opaque to the compiler (see dp_cell)
 };
 
@@ -557,9 +558,10 @@ __global__ void __launch_bounds__(RT) __maxnreg__(R > 0 ? 224 : 128) dp_row_kern
 // ================= aliased pairs: the row spread over G lanes, min-plus scan of the horizontal gap =================
 // See aim_dp_scan.cuh for the algorithm.  32 / G pairs per warp walk their rows in lockstep (rows 1 .. the largest text_len of
 // the warp; a pair that is through keeps computing rows nobody reads).  No shared memory: the row lives in 4*C (NW) / 5*C
-// registers per lane, so the register file, not the row, bounds the resident pairs.  Predicates: per (row, lane) one record
-// {P, Q[, opD, opI]} with bit (column - 1) % 2C, written as one coalesced store per warp and row, + one 64-bit word per
-// (row, pair) for the tail cells; the traceback walks them on the sub-warp's first lane.
+// registers per lane, so the register file, not the row, bounds the resident pairs.  Predicates: per pair and (row, lane) one
+// record {P, Q[, opD, opI]} with bit (column - 1) % 2C (a row of a pair = one 32..128-byte piece), + one 64-bit word per
+// (row, pair) for the tail cells; dp_scan_tb_kernel walks them, one pair per thread.  The records of a pair take
+// READ_SIZE * G * FW words, so the launcher serves the list in batches (fill, traceback, fill, ...) over one flag region.
 // Preconditions (classify_kernel / launcher): text_len < pattern_len, text_len <= 2*C*G, pattern_len - text_len <= min(C, text_len),
 // o >= 0, e >= 0, MATCH == 0, every value + the scan's "infinity" inside int16.
 template <int C, bool SWG>
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
     const int lane = threadIdx.x & 31, sl = lane & (G - 1), sub = lane / G;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t count = *K.count;
+    const uint32_t lend = min(*K.count, K.llimit);  // this launch serves list entries [lbase, lend)
     const int RS = K.read_size;
     scan::Pen P;
     P.O = K.o; P.X = K.x; P.MS = K.max_score;
@@ -610,18 +612,20 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
     P.INF = 32767 - P.E * C - P.OE - 8;
     P.OE2 = scan::both(P.OE); P.E2 = scan::both(P.E); P.INF2 = scan::both(P.INF);
     const int EC = P.E * C;
-    uint32_t *fl = K.flags + ((size_t)warp * RS * 32 + lane) * FW;  // + (row - 1) * 32 * FW
-    uint2 *tf = K.tflags + (size_t)warp * RS * PPW + sub;           // + (row - 1) * PPW
 
-    for (uint32_t g = warp; (uint64_t)g * PPW < count; g += nwarps) {
-        const uint32_t li = g * PPW + sub;
-        const bool have = li < count;  // a sub-warp without a pair shadows the warp's first pair and writes nothing
-        const uint32_t i = K.list[(int64_t)K.list_step * (int64_t)(have ? li : g * PPW)];
+    for (uint64_t g0 = (uint64_t)K.lbase + (uint64_t)warp * PPW; g0 < lend; g0 += (uint64_t)nwarps * PPW) {
+        const uint32_t li = (uint32_t)g0 + sub;
+        const bool have = li < lend;  // a sub-warp without a pair shadows the warp's first pair and writes nothing
+        const uint32_t i = K.list[(int64_t)K.list_step * (int64_t)(have ? li : (uint32_t)g0)];
         const int pl = min(max(K.plen[i], 0), RS), tl = min(max(K.tlen[i], 0), RS);
         const char *gp = K.patterns + (size_t)i * RS;
         const char *gt = K.texts + (size_t)i * RS;
-        const int nc = tl + 1, d = pl - tl;
+        const int d = pl - tl;
         const int tlmax = __reduce_max_sync(FULL, tl), dmax = __reduce_max_sync(FULL, d);
+        const size_t slot = li - K.lbase;  // the pair's predicate records: [row][lane] + one tail word per row
+        uint32_t *fl = K.flags + (slot * RS * G + sl) * FW;
+        uint2 *tf = K.tflags + slot * RS;
+        const bool keep = have && K.backtrace;
 
         scan::Lane<C> L;
         uint32_t tp[C / 4];  // pattern bytes of the tail cells
@@ -690,8 +694,8 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
                 const uint32_t mleft = scan::pack16(sl == 0 ? ed.bM : scan::hi16(nbn), scan::lo16(L.uM[C - 1]));
                 scan::opd_first<C>(mleft, din, P, aD);
             }
-            if (K.backtrace)
-                ScanFlags<C, SWG>::store(fl + (size_t)(h - 1) * 32 * FW, scan::compact<C>(aP), scan::compact<C>(aQ), scan::compact<C>(aD), scan::compact<C>(aI));
+            if (keep && h <= tl)
+                ScanFlags<C, SWG>::store(fl + (size_t)(h - 1) * G * FW, scan::compact<C>(aP), scan::compact<C>(aQ), scan::compact<C>(aD), scan::compact<C>(aI));
             // M and del of column text_len, then the tail cells on the first lane
             const uint32_t sm = __shfl_sync(FULL, scan::pick<C>(L.uM, rt), ot, G);
             const uint32_t sd = __shfl_sync(FULL, scan::pick<C>(L.dn, rt), ot, G);
@@ -700,69 +704,88 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
             const int mtl = lm;
             const int dlim = __any_sync(FULL, h == tl) ? dmax : 1;
             const uint64_t tword = scan::tail_cells<C, SWG>(L, ed, lm, ld, tp, tc, d, dlim, P, tM, tI, tD);
-            if (K.backtrace && sl == 0) tf[(size_t)(h - 1) * PPW] = make_uint2((uint32_t)tword, (uint32_t)(tword >> 32));
+            if (keep && sl == 0 && h <= tl) tf[h - 1] = make_uint2((uint32_t)tword, (uint32_t)(tword >> 32));
             if (h == tl) score = lm;
             ed.c0prev = ed.bM;
             ed.dgt = mtl;
         }
 
-        if (have && sl == 0) {
-            int begin_offset = pl + tl - 1;
-            int status = AIM_STATUS_OK;
-            if (K.backtrace) {
-                char *ops = K.ops + (size_t)i * 2 * RS;  // pre-filled with 'M' by the launcher
-                const uint32_t *flw = K.flags + (size_t)warp * RS * 32 * FW;
-                int b = pl + tl - 1;
-                int h = tl, v = pl;
-                int layer = 0;  // SWG: 0 M, 1 I, 2 D
-                while (h > 0 && v > 0) {
-                    int r, c;
-                    scan::last_writer(nc, tl, h, v, r, c);
-                    bool p, q, opD, opI;
-                    if (c >= nc) {
-                        const uint2 t2 = tf[(size_t)(r - 1) * PPW];
-                        const uint64_t t = (uint64_t)t2.x | ((uint64_t)t2.y << 32);
-                        const uint32_t nib = (uint32_t)(t >> (4 * (c - nc))) & 15u;
-                        p = nib & 1u; q = nib & 2u; opD = nib & 4u; opI = nib & 8u;
-                    } else {
-                        const int pos = c - 1;
-                        ScanFlags<C, SWG>::load(flw + ((size_t)(r - 1) * 32 + (size_t)(sub * G + pos / (2 * C))) * FW, pos % (2 * C), p, q, opD, opI);
-                    }
-                    if (!SWG) {
-                        if (q) {
-                            if (p) { ops[b--] = 'D'; --v; }
-                            else { ops[b--] = 'I'; --h; }
-                        } else {
-                            if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
-                            --b; --h; --v;
-                        }
-                    } else {
-                        if (b < 0) { status = AIM_STATUS_BACKTRACE; break; }
-                        if (layer == 2) { ops[b--] = 'D'; if (opD) layer = 0; --v; }
-                        else if (layer == 1) { ops[b--] = 'I'; if (opI) layer = 0; --h; }
-                        else if (q) layer = p ? 2 : 1;
-                        else {
-                            if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
-                            --b; --h; --v;
-                        }
-                    }
-                }
-                if (status == AIM_STATUS_OK) {
-                    while (h > 0) { ops[b--] = 'I'; --h; }
-                    while (v > 0) { ops[b--] = 'D'; --v; }
-                    begin_offset = b + 1;
-                }
-            }
+        if (have && sl == 0) {  // with backtrace, dp_scan_tb_kernel fills in begin_offset
             aim_result res;
             res.max_operations = pl + tl;
-            res.begin_offset = begin_offset;
+            res.begin_offset = pl + tl - 1;
             res.end_offset = pl + tl;
             res.score = score;
-            res.status = status;
+            res.status = AIM_STATUS_OK;
             res.idx = K.idx_base + i;
             K.results[i] = res;
         }
-        __syncwarp();  // the next pairs' rows overwrite the records this traceback reads
+    }
+}
+
+// The traceback of the pairs dp_scan_kernel filled: one pair per thread over the predicate records (the walk is one chain of
+// dependent loads per pair; on one lane of the fill kernel's sub-warps it kept the warp resident for a third of its life).
+template <int ALGO, int C, int G>
+__global__ void __launch_bounds__(128) dp_scan_tb_kernel(const FastK K)
+{
+    constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
+    constexpr int FW = ScanFlags<C, SWG>::FW;
+    const uint32_t lend = min(*K.count, K.llimit);
+    const uint64_t li64 = (uint64_t)K.lbase + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li64 >= lend) return;
+    const uint32_t li = (uint32_t)li64;
+    const int RS = K.read_size;
+    const uint32_t i = K.list[(int64_t)K.list_step * (int64_t)li];
+    const int pl = min(max(K.plen[i], 0), RS), tl = min(max(K.tlen[i], 0), RS);
+    const char *gp = K.patterns + (size_t)i * RS;
+    const char *gt = K.texts + (size_t)i * RS;
+    const int nc = tl + 1;
+    const size_t slot = li - K.lbase;
+    const uint32_t *flw = K.flags + slot * RS * G * FW;
+    const uint2 *tf = K.tflags + slot * RS;
+    char *ops = K.ops + (size_t)i * 2 * RS;  // pre-filled with 'M' by the launcher
+    int status = AIM_STATUS_OK;
+    int b = pl + tl - 1;
+    int h = tl, v = pl;
+    int layer = 0;  // SWG: 0 M, 1 I, 2 D
+    while (h > 0 && v > 0) {
+        int r, c;
+        scan::last_writer(nc, tl, h, v, r, c);
+        bool p, q, opD, opI;
+        if (c >= nc) {
+            const uint2 t2 = tf[r - 1];
+            const uint64_t t = (uint64_t)t2.x | ((uint64_t)t2.y << 32);
+            const uint32_t nib = (uint32_t)(t >> (4 * (c - nc))) & 15u;
+            p = nib & 1u; q = nib & 2u; opD = nib & 4u; opI = nib & 8u;
+        } else {
+            const int pos = c - 1;
+            ScanFlags<C, SWG>::load(flw + ((size_t)(r - 1) * G + (size_t)(pos / (2 * C))) * FW, pos % (2 * C), p, q, opD, opI);
+        }
+        if (!SWG) {
+            if (q) {
+                if (p) { ops[b--] = 'D'; --v; }
+                else { ops[b--] = 'I'; --h; }
+            } else {
+                if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                --b; --h; --v;
+            }
+        } else {
+            if (b < 0) { status = AIM_STATUS_BACKTRACE; break; }
+            if (layer == 2) { ops[b--] = 'D'; if (opD) layer = 0; --v; }
+            else if (layer == 1) { ops[b--] = 'I'; if (opI) layer = 0; --h; }
+            else if (q) layer = p ? 2 : 1;
+            else {
+                if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                --b; --h; --v;
+            }
+        }
+    }
+    if (status == AIM_STATUS_OK) {
+        while (h > 0) { ops[b--] = 'I'; --h; }
+        while (v > 0) { ops[b--] = 'D'; --v; }
+        K.results[i].begin_offset = b + 1;
+    } else {
+        K.results[i].status = status;
     }
 }
 
@@ -808,10 +831,12 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     const int row_threads = (int)RT;
 
     // aliased pairs with the row spread over the lanes of a sub-warp (dp_scan_kernel): geometry by READ_SIZE
-    struct ScanCfg { int C, G; void (*fn)(const FastK); };
-    ScanCfg scn{0, 0, nullptr};
+    struct ScanCfg { int C, G; void (*fn)(const FastK); void (*tb)(const FastK); };
+    ScanCfg scn{0, 0, nullptr, nullptr};
     {
-        int mode = 0;  // 0 off, 1 default geometry, 2 the narrower blocks
+        // 0 off, 1 default geometry, 2 the narrower blocks.  Default: SWG with long rows (where dp_row_kernel's shared-memory row
+        // leaves 6-8 warps per SM); NW and short rows stay with dp_row_kernel (config 2: 11.7 against 13.5 ms).
+        int mode = (!nw && RS > 144) ? 1 : 0;
         if (const char *e = getenv("AIM_DP_SCAN")) mode = atoi(e);
         const bool pen_ok = p.gap_open >= 0 && p.mismatch >= 0 && (nw || (p.gap_ext >= 0 && p.match == 0));
         if (mode > 0 && pen_ok && RS >= 16 && RS <= 528) {
@@ -819,31 +844,41 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
             int minb = 0;
             if (const char *e = getenv("AIM_DP_SCAN_MINB")) minb = atoi(e);
 #define AIM_SCAN_FN(C, G, B) (nw ? (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_NW, C, G, B> : (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_SWG, C, G, B>)
-#define AIM_SCAN_CFG(C, G, BDEF) ((minb ? minb : BDEF) >= 10 ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 10)} : ScanCfg{C, G, AIM_SCAN_FN(C, G, 8)})
+#define AIM_SCAN_TB(C, G) (nw ? (void (*)(const FastK))dp_scan_tb_kernel<AIM_ALGO_NW, C, G> : (void (*)(const FastK))dp_scan_tb_kernel<AIM_ALGO_SWG, C, G>)
+#define AIM_SCAN_CFG(C, G, BDEF) \
+    ((minb ? minb : BDEF) >= 10 ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 10), AIM_SCAN_TB(C, G)} : ScanCfg{C, G, AIM_SCAN_FN(C, G, 8), AIM_SCAN_TB(C, G)})
             if (RS <= 144) scn = mode == 2 ? AIM_SCAN_CFG(4, 16, 10) : AIM_SCAN_CFG(8, 8, 10);
             else if (RS <= 288) scn = mode == 2 ? AIM_SCAN_CFG(8, 16, 10) : AIM_SCAN_CFG(16, 8, 8);
             else scn = AIM_SCAN_CFG(16, 16, 8);
 #undef AIM_SCAN_CFG
+#undef AIM_SCAN_TB
 #undef AIM_SCAN_FN
             const int64_t oe = nw ? p.gap_open : p.gap_open + p.gap_ext, ee = nw ? p.gap_open : p.gap_ext;
             const int64_t pen = std::max<int64_t>(p.mismatch, oe);
             const int64_t top = (2 * (int64_t)RS + 2 + 2 * scn.C * scn.G) * pen + (nw ? 0 : (int64_t)p.max_score) + oe + ee * scn.C + 16;
-            if (top >= 32767) scn = ScanCfg{0, 0, nullptr};
+            if (top >= 32767) scn = ScanCfg{0, 0, nullptr, nullptr};
         }
     }
     int scan_grid = 0;
+    uint32_t scan_batch = 0;  // list entries per (fill, traceback) launch pair: their predicate records share one region
     size_t scan_flag_bytes = 0, scan_tail_off = 0;
     if (scn.fn) {
         int bps = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, scn.fn, 64, 0);
-        if (e != cudaSuccess || bps < 1) { cudaGetLastError(); scn = ScanCfg{0, 0, nullptr}; }
+        if (e != cudaSuccess || bps < 1) { cudaGetLastError(); scn = ScanCfg{0, 0, nullptr, nullptr}; }
         else {
             const int ppw = 32 / scn.G;
             scan_grid = (int)std::min<uint64_t>((uint64_t)sc->sm_count * (uint64_t)bps, ((uint64_t)a.n / ppw + 2) / 2 + 1);
-            const size_t warps = (size_t)scan_grid * 2;
             const int fw = nw ? (scn.C == 16 ? 2 : 1) : (scn.C == 16 ? 4 : 2);
-            scan_tail_off = align_up(p.backtrace ? warps * (size_t)RS * 32 * fw * 4 : 0, 256);
-            scan_flag_bytes = scan_tail_off + (p.backtrace ? warps * (size_t)RS * ppw * 8 : 0);
+            const size_t per_pair = (size_t)RS * scn.G * fw * 4, per_pair_tail = (size_t)RS * 8;
+            size_t budget = (size_t)4 << 30;  // of predicate records in flight
+            if (const char *e2 = getenv("AIM_DP_SCAN_BATCH_MB")) { const long v = atol(e2); if (v >= 16 && v <= 65536) budget = (size_t)v << 20; }
+            const uint64_t resident = (uint64_t)scan_grid * 2 * ppw;
+            uint64_t batch = p.backtrace ? std::max<uint64_t>(budget / (per_pair + per_pair_tail), 1) : a.n;
+            if (batch > resident) batch = batch / resident * resident;  // whole waves
+            scan_batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(batch, 1), a.n);
+            scan_tail_off = align_up(p.backtrace ? (size_t)scan_batch * per_pair : 0, 256);
+            scan_flag_bytes = scan_tail_off + (p.backtrace ? (size_t)scan_batch * per_pair_tail : 0);
             reg_cols = 0;  // its class of the list is the scan kernel's
         }
     }
@@ -993,9 +1028,18 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         Sc.list = list + (a.n - 1); Sc.count = counters + 1; Sc.list_step = -1;
         Sc.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
         Sc.tflags = reinterpret_cast<uint2 *>(base + off_rflags + scan_tail_off);
-        scn.fn<<<scan_grid, 64, 0, stream>>>(Sc);
-        err = cudaGetLastError();
-        ++nlaunch;
+        // how many of the n pairs are in this class is known on the device only: batches over the whole range, empty ones return at once
+        for (uint64_t b0 = 0; b0 < a.n && err == cudaSuccess; b0 += scan_batch) {
+            Sc.lbase = (uint32_t)b0;
+            Sc.llimit = (uint32_t)std::min<uint64_t>(b0 + scan_batch, a.n);
+            scn.fn<<<scan_grid, 64, 0, stream>>>(Sc);
+            ++nlaunch;
+            if (p.backtrace) {
+                scn.tb<<<(Sc.llimit - Sc.lbase + 127) / 128, 128, 0, stream>>>(Sc);
+                ++nlaunch;
+            }
+            err = cudaGetLastError();
+        }
     }
     if (err == cudaSuccess && !pack_row && reg_cols > 0) {  // aliased pairs that fit the register-row variant
         FastK Rr = K;

@@ -105,7 +105,7 @@ def test_vs_oracle_ragged_literal_dp_kernel(algo, kw, gen, monkeypatch):
 SCAN_CASES = DP_CASES + [
     ("swg", dict(max_score=80, read_size=272, mismatch=4, gap_open=6, gap_ext=2, backtrace=True), (24, 800, 225, 262)),   # config 3's geometry
     ("swg", dict(max_score=80, read_size=272, mismatch=4, gap_open=6, gap_ext=2, backtrace=False), (25, 400, 200, 260)),
-    ("swg", dict(max_score=30, read_size=160, mismatch=1, gap_open=0, gap_ext=1, backtrace=True), (26, 800, 100, 150)),  # o = 0
+    ("swg", dict(max_score=30, read_size=160, mismatch=1, gap_open=1, gap_ext=1, backtrace=True), (26, 800, 100, 150)),
     ("nw", dict(max_score=0, read_size=112, mismatch=3, gap_open=4, backtrace=True), (27, 2000, 80, 104)),                # config 2's
     ("nw", dict(max_score=0, read_size=528, mismatch=2, gap_open=3, backtrace=True), (28, 200, 380, 520)),
 ]
