@@ -611,6 +611,7 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
     P.E = SWG ? K.e : K.o;
     P.INF = 32767 - P.E * C - P.OE - 8;
     P.OE2 = scan::both(P.OE); P.E2 = scan::both(P.E); P.INF2 = scan::both(P.INF);
+    P.E2K = P.E2 + 0x80008000u;
     const int EC = P.E * C;
 
     for (uint64_t g0 = (uint64_t)K.lbase + (uint64_t)warp * PPW; g0 < lend; g0 += (uint64_t)nwarps * PPW) {
@@ -728,6 +729,7 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
 template <int ALGO, int C, int G>
 __global__ void __launch_bounds__(128) dp_scan_tb_kernel(const FastK K)
 {
+    constexpr int TB_AHEAD = 6;  // rows between the record read and the record prefetched
     constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
     constexpr int FW = ScanFlags<C, SWG>::FW;
     const uint32_t lend = min(*K.count, K.llimit);
@@ -759,7 +761,11 @@ __global__ void __launch_bounds__(128) dp_scan_tb_kernel(const FastK K)
             p = nib & 1u; q = nib & 2u; opD = nib & 4u; opI = nib & 8u;
         } else {
             const int pos = c - 1;
-            ScanFlags<C, SWG>::load(flw + ((size_t)(r - 1) * G + (size_t)(pos / (2 * C))) * FW, pos % (2 * C), p, q, opD, opI);
+            const uint32_t *rec = flw + ((size_t)(r - 1) * G + (size_t)(pos / (2 * C))) * FW;
+            // the walk is one chain of dependent loads; the path climbs a row per step or two and rarely leaves its lane's record,
+            // so the record a few rows up is asked for now (L2) and the chain runs on L2 hits instead of DRAM misses
+            if (r > TB_AHEAD) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec - (size_t)TB_AHEAD * G * FW));
+            ScanFlags<C, SWG>::load(rec, pos % (2 * C), p, q, opD, opI);
         }
         if (!SWG) {
             if (q) {
@@ -840,13 +846,16 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         if (const char *e = getenv("AIM_DP_SCAN")) mode = atoi(e);
         const bool pen_ok = p.gap_open >= 0 && p.mismatch >= 0 && (nw || (p.gap_ext >= 0 && p.match == 0));
         if (mode > 0 && pen_ok && RS >= 16 && RS <= 528) {
-            // resident blocks per SM the register allocation aims at: 8 (128 registers) or 10 (96; 16-column blocks spill there)
+            // resident blocks per SM the register allocation aims at: 6 (168 registers), 7 (144), 8 (128) or 10 (96; 16-column blocks spill there)
             int minb = 0;
             if (const char *e = getenv("AIM_DP_SCAN_MINB")) minb = atoi(e);
 #define AIM_SCAN_FN(C, G, B) (nw ? (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_NW, C, G, B> : (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_SWG, C, G, B>)
 #define AIM_SCAN_TB(C, G) (nw ? (void (*)(const FastK))dp_scan_tb_kernel<AIM_ALGO_NW, C, G> : (void (*)(const FastK))dp_scan_tb_kernel<AIM_ALGO_SWG, C, G>)
-#define AIM_SCAN_CFG(C, G, BDEF) \
-    ((minb ? minb : BDEF) >= 10 ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 10), AIM_SCAN_TB(C, G)} : ScanCfg{C, G, AIM_SCAN_FN(C, G, 8), AIM_SCAN_TB(C, G)})
+#define AIM_SCAN_CFG(C, G, BDEF)                                                                     \
+    ((minb ? minb : BDEF) >= 10  ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 10), AIM_SCAN_TB(C, G)}           \
+     : (minb ? minb : BDEF) >= 8 ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 8), AIM_SCAN_TB(C, G)}            \
+     : (minb ? minb : BDEF) == 7 ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 7), AIM_SCAN_TB(C, G)}            \
+                                 : ScanCfg{C, G, AIM_SCAN_FN(C, G, 6), AIM_SCAN_TB(C, G)})
             if (RS <= 144) scn = mode == 2 ? AIM_SCAN_CFG(4, 16, 10) : AIM_SCAN_CFG(8, 8, 10);
             else if (RS <= 288) scn = mode == 2 ? AIM_SCAN_CFG(8, 16, 10) : AIM_SCAN_CFG(16, 8, 8);
             else scn = AIM_SCAN_CFG(16, 16, 8);

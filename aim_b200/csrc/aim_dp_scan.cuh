@@ -37,7 +37,7 @@ static inline uint32_t vminu(uint32_t a, uint32_t b)
     return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
 }
 static inline uint32_t vadd(uint32_t a, uint32_t b) { return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16); }
-static inline uint32_t viaddmin(uint32_t a, uint32_t b, uint32_t c) { return vmin(vadd(a, b), c); }
+static inline uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return vmin(vmin(a, b), c); }
 static inline uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s)
 {
     const uint64_t v = ((uint64_t)y << 32) | x;
@@ -51,22 +51,32 @@ static inline uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s)
 namespace scanx {
 AIM_SD uint32_t vmin(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 AIM_SD uint32_t vminu(uint32_t a, uint32_t b) { return __vminu2(a, b); }
-AIM_SD uint32_t viaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
+AIM_SD uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 AIM_SD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }
 }  // namespace scanx
 #endif
 
 namespace scanx {
-// min of both halves, and the two predicates (a <= b) pushed into acc: acc moves one bit to the right and takes them at bits 15
-// and 31.  In the DATA path (both halves are non-negative int16, so (b | 0x8000) - a never borrows from the neighbour and bit 15
-// of each half is "b >= a"): VIMNMX + IADD3 + SHF + LOP3.  The predicate outputs of VIMNMX.S16x2 would save one instruction, but the
-// columns of a block are independent, ptxas issues their minima back to back, runs out of predicate registers, parks the
-// predicates in general registers (P2R) and re-tests them at the end of the row: 1100 instead of 480 instructions per row.
-AIM_SD uint32_t vmin_push(uint32_t a, uint32_t b, uint32_t &acc)
+// The two predicates (a <= b) of a packed comparison as bits R and 16 + R of acc, in the DATA path: both halves are non-negative
+// int16, so (b + 0x8000) - a never borrows from the neighbour and bit 15 of each half is "b >= a".  bk = b + 0x80008000 is
+// passed in (the caller folds the constant into an addition it makes anyway).  The kernel is bound by the alu pipe (min/max,
+// logic, shifts, three-input adds: 85 % busy at 66 % issue), so everything that can runs on the fma pipe: the subtraction as a
+// two-input add (IMAD.IADD), the shift to bit R as a multiply-high (IMAD.HI), and only the merge is a LOP3.
+// (The predicate outputs of VIMNMX.S16x2 would be cheaper still, but the columns of a block are independent, ptxas issues their
+// minima back to back, runs out of predicate registers, parks them in general registers (P2R) and re-tests them at the end
+// of the row: 1100 instead of 500 instructions per row.)
+AIM_SD void push_le(uint32_t a, uint32_t bk, uint32_t &acc, const int R)  // R: a compile-time constant once the loops are unrolled
 {
-    const uint32_t t = (b + 0x80008000u) - a;
-    acc = (acc >> 1) | (t & 0x80008000u);
-    return vmin(a, b);
+#ifdef AIM_SCAN_HOST_MODEL
+    const uint32_t t = bk - a;
+    const uint32_t sh = R == 15 ? t : (uint32_t)(((uint64_t)t << (17 + R)) >> 32);
+#else
+    uint32_t t, sh;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(a), "r"(0xffffffffu), "r"(bk));  // bk - a on the fma pipe
+    if (R == 15) sh = t;
+    else asm("mul.hi.u32 %0, %1, %2;" : "=r"(sh) : "r"(t), "r"(1u << ((17 + R) & 31)));
+#endif
+    acc |= sh & (0x00010001u << R);
 }
 }  // namespace scanx
 
@@ -83,6 +93,7 @@ struct Pen {
     int O, E, OE, X, MS;       // E: SWG gap_ext, NW the gap (so that E * C is the carry of a block in both); MATCH == 0 (launcher)
     int INF;                   // "no carry-in": above every table value, INF + E * C still an int16
     uint32_t OE2, E2, INF2;
+    uint32_t E2K;              // E2 + 0x80008000 (see push_le)
 };
 
 // The lane's share of one row: C packed registers, block A (columns base+1 .. base+C) in the low halves, block B
@@ -115,7 +126,7 @@ AIM_SD void init_lane(Lane<C> &L, int lane, const Pen &P, const uint32_t *wlo, c
 // Phase 1 + 2: I and diag + sub of every column, X = min(I, diag + sub), and the blocks' local scans.
 // dg0 = M of the previous row at the column left of each block; t4 = this row's text byte in all four bytes.
 // Returns, per half, D at the first column AFTER the block if nothing came in from the left.
-// Predicate bits (vmin_push): column r of block A ends at bit 16 - C + r, of block B at bit 32 - C + r; compact() closes the gap.
+// Predicate bits (push_le): column r of block A -> bit r, of block B -> bit 16 + r; compact() closes the gap when C < 16.
 template <int C, bool SWG>
 AIM_SD uint32_t phase12(Lane<C> &L, uint32_t dg0, uint32_t t4, const Pen &P, uint32_t &aI)
 {
@@ -125,7 +136,9 @@ AIM_SD uint32_t phase12(Lane<C> &L, uint32_t dg0, uint32_t t4, const Pen &P, uin
         const uint32_t um = L.uM[r];
         uint32_t ins;
         if (SWG) {
-            ins = scanx::vmin_push(um + P.OE2, L.uI[r] + P.E2, aI);  // opI = (upM+o+e <= upI+e)  (swg.c:97)
+            const uint32_t i1 = um + P.OE2;
+            scanx::push_le(i1, L.uI[r] + P.E2K, aI, r);  // opI = (upM+o+e <= upI+e)  (swg.c:97)
+            ins = scanx::vmin(i1, L.uI[r] + P.E2);
         } else {
             ins = um + P.OE2;  // GAP_I
         }
@@ -133,8 +146,7 @@ AIM_SD uint32_t phase12(Lane<C> &L, uint32_t dg0, uint32_t t4, const Pen &P, uin
         const uint32_t mm = scanx::vminu(L.pat[r] ^ t4, 0x00010001u) * (uint32_t)P.X + dg;
         L.mm[r] = mm;
         dg = um;
-        const uint32_t x = scanx::vmin(ins, mm);
-        dl = scanx::viaddmin(dl, P.E2, x + P.OE2);  // D[v+1] = min(D[v] + e, X[v] + o + e)
+        dl = scanx::vmin3(dl + P.E2, ins + P.OE2, mm + P.OE2);  // D[v+1] = min(D[v] + e, X[v] + o + e), X = min(ins, diag + sub): one VIMNMX3
     }
     return dl;
 }
@@ -150,12 +162,16 @@ AIM_SD void phase4(Lane<C> &L, uint32_t din, const Pen &P, uint32_t &aP, uint32_
         uint32_t del;
         if (r == 0) del = din;
         else if (SWG) {
-            del = scanx::vmin_push(mprev + P.OE2, dprev + P.E2, aD);  // opD = (leftM+o+e <= leftD+e)  (swg.c:88)
+            const uint32_t d1 = mprev + P.OE2;
+            scanx::push_le(d1, dprev + P.E2K, aD, r);  // opD = (leftM+o+e <= leftD+e)  (swg.c:88)
+            del = scanx::vmin(d1, dprev + P.E2);
         } else {
             del = mprev + P.OE2;  // GAP_D
         }
-        const uint32_t m1 = scanx::vmin_push(del, L.uI[r], aP);  // p = (del <= ins)
-        const uint32_t m = scanx::vmin_push(m1, L.mm[r], aQ);    // q = (min(del, ins) <= diag + sub)
+        scanx::push_le(del, L.uI[r] + 0x80008000u, aP, r);  // p = (del <= ins)
+        const uint32_t m1 = scanx::vmin(del, L.uI[r]);
+        scanx::push_le(m1, L.mm[r] + 0x80008000u, aQ, r);   // q = (min(del, ins) <= diag + sub)
+        const uint32_t m = scanx::vmin(m1, L.mm[r]);
         L.uM[r] = m;
         L.dn[r] = del;
         mprev = m;
@@ -168,8 +184,7 @@ AIM_SD void phase4(Lane<C> &L, uint32_t din, const Pen &P, uint32_t &aP, uint32_
 template <int C>
 AIM_SD void opd_first(uint32_t mleft, uint32_t din, const Pen &P, uint32_t &aD)
 {
-    const uint32_t t = (din + 0x80008000u) - (mleft + P.OE2);
-    aD |= (t & 0x80008000u) >> (C - 1);
+    scanx::push_le(mleft + P.OE2, din + 0x80008000u, aD, 0);
 }
 
 // The 2*C predicate bits of an accumulator as bits 0 .. 2C-1 (block A, then block B)
@@ -177,8 +192,8 @@ template <int C>
 AIM_SD uint32_t compact(uint32_t acc)
 {
     if (C == 16) return acc;
-    if (C == 8) return scanx::byte_perm(acc, 0u, 0x4431u);  // bytes 1 and 3
-    return ((acc >> (16 - C)) & ((1u << C) - 1u)) | (((acc >> (32 - C)) & ((1u << C) - 1u)) << C);
+    if (C == 8) return scanx::byte_perm(acc, 0u, 0x4420u);  // bytes 0 and 2
+    return (acc & ((1u << C) - 1u)) | (((acc >> 16) & ((1u << C) - 1u)) << C);
 }
 
 // a[r] for a run-time r (the registers cannot be indexed): a binary tree of selects

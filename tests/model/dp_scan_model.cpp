@@ -46,6 +46,7 @@ void model_pair(int X, int O, int E_, int MS, int RS, int backtrace, int pl, int
     P.E = SWG ? E_ : O;
     P.INF = 32767 - P.E * C - P.OE - 8;
     P.OE2 = scan::both(P.OE); P.E2 = scan::both(P.E); P.INF2 = scan::both(P.INF);
+    P.E2K = P.E2 + 0x80008000u;
     const int EC = P.E * C;
     const int nc = tl + 1, d = pl - tl;
     const int tlmax = std::min(RS, tl + tlmax_extra), dmax = std::min(C, d + (tlmax_extra ? 1 : 0));  // as if a longer pair shared the warp

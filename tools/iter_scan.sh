@@ -21,6 +21,7 @@ for kv in "AIM_DP_SCAN=1"; do
     python bench.py --config 3 --no-cpu-baseline --no-e2e --no-cli --parity off --steps 1 --warmup 1 > /dev/null 2>&1
 done
 python tools/launch_table.py gpurun_out/${tag}_launches_cfg3_AIM_DP_SCAN_1.csv 2>/dev/null | tail -12
+if [ -n "$NO_FULL" ]; then exit 0; fi
 # one --set full capture of the fill kernel (200 K pairs)
 AIM_DP_SCAN=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:dp_scan_kernel -c 1 -f -o gpurun_out/${tag}_dp_scan_cfg3 \
     python bench.py --config 3 --steps 1 --warmup 1 --pairs 200000 --no-cpu-baseline --no-e2e --no-cli --parity off > /dev/null 2>&1
