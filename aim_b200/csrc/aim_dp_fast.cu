@@ -729,7 +729,6 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
 template <int ALGO, int C, int G>
 __global__ void __launch_bounds__(128) dp_scan_tb_kernel(const FastK K)
 {
-    constexpr int TB_AHEAD = 6;  // rows between the record read and the record prefetched
     constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
     constexpr int FW = ScanFlags<C, SWG>::FW;
     const uint32_t lend = min(*K.count, K.llimit);
@@ -762,9 +761,6 @@ __global__ void __launch_bounds__(128) dp_scan_tb_kernel(const FastK K)
         } else {
             const int pos = c - 1;
             const uint32_t *rec = flw + ((size_t)(r - 1) * G + (size_t)(pos / (2 * C))) * FW;
-            // the walk is one chain of dependent loads; the path climbs a row per step or two and rarely leaves its lane's record,
-            // so the record a few rows up is asked for now (L2) and the chain runs on L2 hits instead of DRAM misses
-            if (r > TB_AHEAD) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec - (size_t)TB_AHEAD * G * FW));
             ScanFlags<C, SWG>::load(rec, pos % (2 * C), p, q, opD, opI);
         }
         if (!SWG) {
@@ -870,26 +866,43 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     int scan_grid = 0;
     uint32_t scan_batch = 0;  // list entries per (fill, traceback) launch pair: their predicate records share one region
-    size_t scan_flag_bytes = 0, scan_tail_off = 0;
+    size_t scan_flag_bytes = 0, scan_tail_off = 0, scan_half_bytes = 0;
+    // two halves of the record region: the traceback of batch b (latency-bound, one pair per thread, 32 registers) runs on a side
+    // stream under the fill of batch b + 1 (alu-bound), which leaves it one block's worth of registers per SM
+    bool scan_overlap = false;
     if (scn.fn) {
         int bps = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, scn.fn, 64, 0);
         if (e != cudaSuccess || bps < 1) { cudaGetLastError(); scn = ScanCfg{0, 0, nullptr, nullptr}; }
         else {
             const int ppw = 32 / scn.G;
-            scan_grid = (int)std::min<uint64_t>((uint64_t)sc->sm_count * (uint64_t)bps, ((uint64_t)a.n / ppw + 2) / 2 + 1);
             const int fw = nw ? (scn.C == 16 ? 2 : 1) : (scn.C == 16 ? 4 : 2);
             const size_t per_pair = (size_t)RS * scn.G * fw * 4, per_pair_tail = (size_t)RS * 8;
             size_t budget = (size_t)4 << 30;  // of predicate records in flight
             if (const char *e2 = getenv("AIM_DP_SCAN_BATCH_MB")) { const long v = atol(e2); if (v >= 16 && v <= 65536) budget = (size_t)v << 20; }
+            scan_overlap = p.backtrace && bps >= 4 && (uint64_t)a.n * (per_pair + per_pair_tail) > budget && !getenv("AIM_DP_SCAN_NO_OVERLAP");
+            if (scan_overlap) { --bps; budget /= 2; }
+            scan_grid = (int)std::min<uint64_t>((uint64_t)sc->sm_count * (uint64_t)bps, ((uint64_t)a.n / ppw + 2) / 2 + 1);
             const uint64_t resident = (uint64_t)scan_grid * 2 * ppw;
             uint64_t batch = p.backtrace ? std::max<uint64_t>(budget / (per_pair + per_pair_tail), 1) : a.n;
             if (batch > resident) batch = batch / resident * resident;  // whole waves
             scan_batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(batch, 1), a.n);
             scan_tail_off = align_up(p.backtrace ? (size_t)scan_batch * per_pair : 0, 256);
-            scan_flag_bytes = scan_tail_off + (p.backtrace ? (size_t)scan_batch * per_pair_tail : 0);
+            scan_half_bytes = align_up(scan_tail_off + (p.backtrace ? (size_t)scan_batch * per_pair_tail : 0), 256);
+            scan_flag_bytes = scan_half_bytes * (scan_overlap ? 2 : 1);
             reg_cols = 0;  // its class of the list is the scan kernel's
         }
+    }
+    if (scan_overlap && !sc->side_stream) {  // side stream + events live in the device's Scratch (shared with GenASM; aim_shutdown destroys them)
+        cudaStream_t st = nullptr;
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        sc->side_stream = st;
+        for (int h = 0; h < 4 && e == cudaSuccess; ++h) {
+            cudaEvent_t ev = nullptr;
+            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            sc->side_ev[h] = ev;
+        }
+        if (e != cudaSuccess) { set_error(std::string("dp_scan side stream: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
     }
 
     const int FW = nw ? 1 : 2;                         // flag words per 16-cell record
@@ -1038,16 +1051,37 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         Sc.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
         Sc.tflags = reinterpret_cast<uint2 *>(base + off_rflags + scan_tail_off);
         // how many of the n pairs are in this class is known on the device only: batches over the whole range, empty ones return at once
-        for (uint64_t b0 = 0; b0 < a.n && err == cudaSuccess; b0 += scan_batch) {
+        cudaStream_t const side = (cudaStream_t)sc->side_stream;
+        cudaEvent_t const ev_fill[2] = {(cudaEvent_t)sc->side_ev[0], (cudaEvent_t)sc->side_ev[1]};
+        cudaEvent_t const ev_tb[2] = {(cudaEvent_t)sc->side_ev[2], (cudaEvent_t)sc->side_ev[3]};
+        uint32_t nb = 0;
+        for (uint64_t b0 = 0; b0 < a.n && err == cudaSuccess; b0 += scan_batch, ++nb) {
+            const int h = scan_overlap ? (int)(nb & 1u) : 0;
+            Sc.flags = reinterpret_cast<uint32_t *>(base + off_rflags + (size_t)h * scan_half_bytes);
+            Sc.tflags = reinterpret_cast<uint2 *>(base + off_rflags + (size_t)h * scan_half_bytes + scan_tail_off);
             Sc.lbase = (uint32_t)b0;
             Sc.llimit = (uint32_t)std::min<uint64_t>(b0 + scan_batch, a.n);
+            if (scan_overlap && nb >= 2) err = cudaStreamWaitEvent(stream, ev_tb[h], 0);  // the traceback that read this half is done
+            if (err != cudaSuccess) break;
             scn.fn<<<scan_grid, 64, 0, stream>>>(Sc);
             ++nlaunch;
             if (p.backtrace) {
-                scn.tb<<<(Sc.llimit - Sc.lbase + 127) / 128, 128, 0, stream>>>(Sc);
+                cudaStream_t ts = stream;
+                if (scan_overlap) {
+                    ts = side;
+                    err = cudaEventRecord(ev_fill[h], stream);
+                    if (err == cudaSuccess) err = cudaStreamWaitEvent(ts, ev_fill[h], 0);
+                    if (err != cudaSuccess) break;
+                }
+                scn.tb<<<(Sc.llimit - Sc.lbase + 127) / 128, 128, 0, ts>>>(Sc);
                 ++nlaunch;
+                if (scan_overlap) err = cudaEventRecord(ev_tb[h], ts);
             }
-            err = cudaGetLastError();
+            if (err == cudaSuccess) err = cudaGetLastError();
+        }
+        if (scan_overlap) {  // the stream continues (dp_row_kernel reuses the region) only after the last tracebacks
+            for (int h = 0; h < 2 && err == cudaSuccess; ++h)
+                if (nb > (uint32_t)h) err = cudaStreamWaitEvent(stream, ev_tb[h], 0);
         }
     }
     if (err == cudaSuccess && !pack_row && reg_cols > 0) {  // aliased pairs that fit the register-row variant

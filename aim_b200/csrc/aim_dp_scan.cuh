@@ -21,6 +21,14 @@
 #ifndef AIM_DP_SCAN_CUH
 #define AIM_DP_SCAN_CUH
 
+// build-time variants (measured on config 3)
+#ifndef AIM_SCAN_PUSH_FMA
+#define AIM_SCAN_PUSH_FMA 0   // 1: the predicate's shift as IMAD.HI on the fma pipe instead of SHF
+#endif
+#ifndef AIM_SCAN_MIN3
+#define AIM_SCAN_MIN3 0       // 1: the block's local scan as one VIMNMX3 per column, 0: VIMNMX + VIADDMNMX (config 3: 43.7 against 43.6 ms)
+#endif
+
 #include <stdint.h>
 
 #ifdef AIM_SCAN_HOST_MODEL
@@ -38,6 +46,7 @@ static inline uint32_t vminu(uint32_t a, uint32_t b)
 }
 static inline uint32_t vadd(uint32_t a, uint32_t b) { return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16); }
 static inline uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return vmin(vmin(a, b), c); }
+static inline uint32_t viaddmin(uint32_t a, uint32_t b, uint32_t c) { return vmin(vadd(a, b), c); }
 static inline uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s)
 {
     const uint64_t v = ((uint64_t)y << 32) | x;
@@ -52,6 +61,7 @@ namespace scanx {
 AIM_SD uint32_t vmin(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 AIM_SD uint32_t vminu(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 AIM_SD uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
+AIM_SD uint32_t viaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
 AIM_SD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }
 }  // namespace scanx
 #endif
@@ -67,14 +77,17 @@ namespace scanx {
 // of the row: 1100 instead of 500 instructions per row.)
 AIM_SD void push_le(uint32_t a, uint32_t bk, uint32_t &acc, const int R)  // R: a compile-time constant once the loops are unrolled
 {
-#ifdef AIM_SCAN_HOST_MODEL
     const uint32_t t = bk - a;
+#if AIM_SCAN_PUSH_FMA
+#ifdef AIM_SCAN_HOST_MODEL
     const uint32_t sh = R == 15 ? t : (uint32_t)(((uint64_t)t << (17 + R)) >> 32);
 #else
-    uint32_t t, sh;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(a), "r"(0xffffffffu), "r"(bk));  // bk - a on the fma pipe
+    uint32_t sh;
     if (R == 15) sh = t;
     else asm("mul.hi.u32 %0, %1, %2;" : "=r"(sh) : "r"(t), "r"(1u << ((17 + R) & 31)));
+#endif
+#else
+    const uint32_t sh = t >> (15 - R);
 #endif
     acc |= sh & (0x00010001u << R);
 }
@@ -146,7 +159,12 @@ AIM_SD uint32_t phase12(Lane<C> &L, uint32_t dg0, uint32_t t4, const Pen &P, uin
         const uint32_t mm = scanx::vminu(L.pat[r] ^ t4, 0x00010001u) * (uint32_t)P.X + dg;
         L.mm[r] = mm;
         dg = um;
-        dl = scanx::vmin3(dl + P.E2, ins + P.OE2, mm + P.OE2);  // D[v+1] = min(D[v] + e, X[v] + o + e), X = min(ins, diag + sub): one VIMNMX3
+        // D[v+1] = min(D[v] + e, X[v] + o + e), X = min(ins, diag + sub)
+#if AIM_SCAN_MIN3
+        dl = scanx::vmin3(dl + P.E2, ins + P.OE2, mm + P.OE2);
+#else
+        dl = scanx::viaddmin(dl, P.E2, scanx::vmin(ins, mm) + P.OE2);
+#endif
     }
     return dl;
 }
