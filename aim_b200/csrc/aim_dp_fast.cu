@@ -842,7 +842,8 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         if (const char *e = getenv("AIM_DP_SCAN")) mode = atoi(e);
         const bool pen_ok = p.gap_open >= 0 && p.mismatch >= 0 && (nw || (p.gap_ext >= 0 && p.match == 0));
         if (mode > 0 && pen_ok && RS >= 16 && RS <= 528) {
-            // resident blocks per SM the register allocation aims at: 6 (168 registers), 7 (144), 8 (128) or 10 (96; 16-column blocks spill there)
+            // resident blocks per SM the register allocation aims at: 6 (168 registers), 8 (128) or 10 (96; 16-column blocks spill there).
+            // Config 3, 16-column blocks: 43.6 / 43.7 / 44.1 ms with 6 / 8 / 10 (the kernel is bound by the alu pipe, not by resident warps).
             int minb = 0;
             if (const char *e = getenv("AIM_DP_SCAN_MINB")) minb = atoi(e);
 #define AIM_SCAN_FN(C, G, B) (nw ? (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_NW, C, G, B> : (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_SWG, C, G, B>)
@@ -850,7 +851,6 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
 #define AIM_SCAN_CFG(C, G, BDEF)                                                                     \
     ((minb ? minb : BDEF) >= 10  ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 10), AIM_SCAN_TB(C, G)}           \
      : (minb ? minb : BDEF) >= 8 ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 8), AIM_SCAN_TB(C, G)}            \
-     : (minb ? minb : BDEF) == 7 ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 7), AIM_SCAN_TB(C, G)}            \
                                  : ScanCfg{C, G, AIM_SCAN_FN(C, G, 6), AIM_SCAN_TB(C, G)})
             if (RS <= 144) scn = mode == 2 ? AIM_SCAN_CFG(4, 16, 10) : AIM_SCAN_CFG(8, 8, 10);
             else if (RS <= 288) scn = mode == 2 ? AIM_SCAN_CFG(8, 16, 10) : AIM_SCAN_CFG(16, 8, 8);
@@ -866,10 +866,7 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     }
     int scan_grid = 0;
     uint32_t scan_batch = 0;  // list entries per (fill, traceback) launch pair: their predicate records share one region
-    size_t scan_flag_bytes = 0, scan_tail_off = 0, scan_half_bytes = 0;
-    // two halves of the record region: the traceback of batch b (latency-bound, one pair per thread, 32 registers) runs on a side
-    // stream under the fill of batch b + 1 (alu-bound), which leaves it one block's worth of registers per SM
-    bool scan_overlap = false;
+    size_t scan_flag_bytes = 0, scan_tail_off = 0;
     if (scn.fn) {
         int bps = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, scn.fn, 64, 0);
@@ -880,29 +877,15 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
             const size_t per_pair = (size_t)RS * scn.G * fw * 4, per_pair_tail = (size_t)RS * 8;
             size_t budget = (size_t)4 << 30;  // of predicate records in flight
             if (const char *e2 = getenv("AIM_DP_SCAN_BATCH_MB")) { const long v = atol(e2); if (v >= 16 && v <= 65536) budget = (size_t)v << 20; }
-            scan_overlap = p.backtrace && bps >= 4 && (uint64_t)a.n * (per_pair + per_pair_tail) > budget && !getenv("AIM_DP_SCAN_NO_OVERLAP");
-            if (scan_overlap) { --bps; budget /= 2; }
             scan_grid = (int)std::min<uint64_t>((uint64_t)sc->sm_count * (uint64_t)bps, ((uint64_t)a.n / ppw + 2) / 2 + 1);
             const uint64_t resident = (uint64_t)scan_grid * 2 * ppw;
             uint64_t batch = p.backtrace ? std::max<uint64_t>(budget / (per_pair + per_pair_tail), 1) : a.n;
             if (batch > resident) batch = batch / resident * resident;  // whole waves
             scan_batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(batch, 1), a.n);
             scan_tail_off = align_up(p.backtrace ? (size_t)scan_batch * per_pair : 0, 256);
-            scan_half_bytes = align_up(scan_tail_off + (p.backtrace ? (size_t)scan_batch * per_pair_tail : 0), 256);
-            scan_flag_bytes = scan_half_bytes * (scan_overlap ? 2 : 1);
+            scan_flag_bytes = scan_tail_off + (p.backtrace ? (size_t)scan_batch * per_pair_tail : 0);
             reg_cols = 0;  // its class of the list is the scan kernel's
         }
-    }
-    if (scan_overlap && !sc->side_stream) {  // side stream + events live in the device's Scratch (shared with GenASM; aim_shutdown destroys them)
-        cudaStream_t st = nullptr;
-        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-        sc->side_stream = st;
-        for (int h = 0; h < 4 && e == cudaSuccess; ++h) {
-            cudaEvent_t ev = nullptr;
-            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-            sc->side_ev[h] = ev;
-        }
-        if (e != cudaSuccess) { set_error(std::string("dp_scan side stream: ") + cudaGetErrorString(e)); return AIM_ERR_CUDA; }
     }
 
     const int FW = nw ? 1 : 2;                         // flag words per 16-cell record
@@ -1050,38 +1033,20 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         Sc.list = list + (a.n - 1); Sc.count = counters + 1; Sc.list_step = -1;
         Sc.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
         Sc.tflags = reinterpret_cast<uint2 *>(base + off_rflags + scan_tail_off);
-        // how many of the n pairs are in this class is known on the device only: batches over the whole range, empty ones return at once
-        cudaStream_t const side = (cudaStream_t)sc->side_stream;
-        cudaEvent_t const ev_fill[2] = {(cudaEvent_t)sc->side_ev[0], (cudaEvent_t)sc->side_ev[1]};
-        cudaEvent_t const ev_tb[2] = {(cudaEvent_t)sc->side_ev[2], (cudaEvent_t)sc->side_ev[3]};
-        uint32_t nb = 0;
-        for (uint64_t b0 = 0; b0 < a.n && err == cudaSuccess; b0 += scan_batch, ++nb) {
-            const int h = scan_overlap ? (int)(nb & 1u) : 0;
-            Sc.flags = reinterpret_cast<uint32_t *>(base + off_rflags + (size_t)h * scan_half_bytes);
-            Sc.tflags = reinterpret_cast<uint2 *>(base + off_rflags + (size_t)h * scan_half_bytes + scan_tail_off);
+        // How many of the n pairs are in this class is known on the device only: batches over the whole range, empty ones return at
+        // once.  Fill and traceback alternate on the one stream.  Measured and rejected: the traceback of batch b on a side stream
+        // under the fill of batch b + 1 (two halves of the record region, the fill kernel one block per SM short so that the traceback
+        // blocks fit): 44.6 against 43.7 ms at config 3 - the fill kernel loses more with 14 warps per SM than the 2.9 ms it hides.
+        for (uint64_t b0 = 0; b0 < a.n && err == cudaSuccess; b0 += scan_batch) {
             Sc.lbase = (uint32_t)b0;
             Sc.llimit = (uint32_t)std::min<uint64_t>(b0 + scan_batch, a.n);
-            if (scan_overlap && nb >= 2) err = cudaStreamWaitEvent(stream, ev_tb[h], 0);  // the traceback that read this half is done
-            if (err != cudaSuccess) break;
             scn.fn<<<scan_grid, 64, 0, stream>>>(Sc);
             ++nlaunch;
             if (p.backtrace) {
-                cudaStream_t ts = stream;
-                if (scan_overlap) {
-                    ts = side;
-                    err = cudaEventRecord(ev_fill[h], stream);
-                    if (err == cudaSuccess) err = cudaStreamWaitEvent(ts, ev_fill[h], 0);
-                    if (err != cudaSuccess) break;
-                }
-                scn.tb<<<(Sc.llimit - Sc.lbase + 127) / 128, 128, 0, ts>>>(Sc);
+                scn.tb<<<(Sc.llimit - Sc.lbase + 127) / 128, 128, 0, stream>>>(Sc);
                 ++nlaunch;
-                if (scan_overlap) err = cudaEventRecord(ev_tb[h], ts);
             }
-            if (err == cudaSuccess) err = cudaGetLastError();
-        }
-        if (scan_overlap) {  // the stream continues (dp_row_kernel reuses the region) only after the last tracebacks
-            for (int h = 0; h < 2 && err == cudaSuccess; ++h)
-                if (nb > (uint32_t)h) err = cudaStreamWaitEvent(stream, ev_tb[h], 0);
+            err = cudaGetLastError();
         }
     }
     if (err == cudaSuccess && !pack_row && reg_cols > 0) {  // aliased pairs that fit the register-row variant

@@ -111,7 +111,7 @@ SCAN_CASES = DP_CASES + [
 ]
 
 
-@pytest.mark.parametrize("mode,minb", [("0", "0"), ("1", "0"), ("2", "0"), ("1", "10"), ("2", "8")])
+@pytest.mark.parametrize("mode,minb", [("0", "0"), ("1", "0"), ("2", "0"), ("1", "10"), ("1", "6"), ("2", "8")])
 @pytest.mark.parametrize("algo,kw,gen", SCAN_CASES, ids=[f"{c[0]}-{c[2][0]}" for c in SCAN_CASES])
 def test_vs_oracle_ragged_scan_kernel(algo, kw, gen, mode, minb, monkeypatch):
     """Aliased pairs (pattern longer than text) through dp_scan_kernel - the row spread over the lanes of a sub-warp, the
