@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(RT) __maxnreg__(R > 0 ? 224 : 128) dp_row_kern
 // See aim_dp_scan.cuh for the algorithm.  32 / G pairs per warp walk their rows in lockstep (rows 1 .. the largest text_len of
 // the warp; a pair that is through keeps computing rows nobody reads).  No shared memory: the row lives in 4*C (NW) / 5*C
 // registers per lane, so the register file, not the row, bounds the resident pairs.  Predicates: per pair and (row, lane) one
-// record {P, Q[, opD, opI]} with bit (column - 1) % 2C (a row of a pair = one 32..128-byte piece), + one 64-bit word per
+// record {P, Q[, opD, opI]} (complements, bit scan::flag_bit(column - 1); a row of a pair = one 32..128-byte piece), + one 64-bit word per
 // (row, pair) for the tail cells; dp_scan_tb_kernel walks them, one pair per thread.  The records of a pair take
 // READ_SIZE * G * FW words, so the launcher serves the list in batches (fill, traceback, fill, ...) over one flag region.
 // Preconditions (classify_kernel / launcher): text_len < pattern_len, text_len <= 2*C*G, pattern_len - text_len <= min(C, text_len),
@@ -574,21 +574,22 @@ struct ScanFlags {
         else if (C == 16) *reinterpret_cast<uint2 *>(d) = make_uint2(aP, aQ);
         else d[0] = aP | (aQ << 16);
     }
+    // the records hold the predicates' complements (scanx::push_gt); bit = scan::flag_bit<C>(column - 1)
     __device__ __forceinline__ static void load(const uint32_t *d, int bit, bool &p, bool &q, bool &opD, bool &opI)
     {
         opD = opI = false;
         if (SWG && C == 16) {
             const uint4 w = *reinterpret_cast<const uint4 *>(d);
-            p = (w.x >> bit) & 1u; q = (w.y >> bit) & 1u; opD = (w.z >> bit) & 1u; opI = (w.w >> bit) & 1u;
+            p = !((w.x >> bit) & 1u); q = !((w.y >> bit) & 1u); opD = !((w.z >> bit) & 1u); opI = !((w.w >> bit) & 1u);
         } else if (SWG) {
             const uint2 w = *reinterpret_cast<const uint2 *>(d);
-            p = (w.x >> bit) & 1u; q = (w.x >> (16 + bit)) & 1u; opD = (w.y >> bit) & 1u; opI = (w.y >> (16 + bit)) & 1u;
+            p = !((w.x >> bit) & 1u); q = !((w.x >> (16 + bit)) & 1u); opD = !((w.y >> bit) & 1u); opI = !((w.y >> (16 + bit)) & 1u);
         } else if (C == 16) {
             const uint2 w = *reinterpret_cast<const uint2 *>(d);
-            p = (w.x >> bit) & 1u; q = (w.y >> bit) & 1u;
+            p = !((w.x >> bit) & 1u); q = !((w.y >> bit) & 1u);
         } else {
             const uint32_t w = d[0];
-            p = (w >> bit) & 1u; q = (w >> (16 + bit)) & 1u;
+            p = !((w >> bit) & 1u); q = !((w >> (16 + bit)) & 1u);
         }
     }
 };
@@ -611,7 +612,6 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
     P.E = SWG ? K.e : K.o;
     P.INF = 32767 - P.E * C - P.OE - 8;
     P.OE2 = scan::both(P.OE); P.E2 = scan::both(P.E); P.INF2 = scan::both(P.INF);
-    P.E2K = P.E2 + 0x80008000u;
     const int EC = P.E * C;
 
     for (uint64_t g0 = (uint64_t)K.lbase + (uint64_t)warp * PPW; g0 < lend; g0 += (uint64_t)nwarps * PPW) {
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(128) dp_scan_tb_kernel(const FastK K)
         } else {
             const int pos = c - 1;
             const uint32_t *rec = flw + ((size_t)(r - 1) * G + (size_t)(pos / (2 * C))) * FW;
-            ScanFlags<C, SWG>::load(rec, pos % (2 * C), p, q, opD, opI);
+            ScanFlags<C, SWG>::load(rec, scan::flag_bit<C>(pos), p, q, opD, opI);
         }
         if (!SWG) {
             if (q) {

@@ -22,9 +22,6 @@
 #define AIM_DP_SCAN_CUH
 
 // build-time variants (measured on config 3)
-#ifndef AIM_SCAN_PUSH_FMA
-#define AIM_SCAN_PUSH_FMA 0   // 1: the predicate's shift as IMAD.HI on the fma pipe instead of SHF
-#endif
 #ifndef AIM_SCAN_MIN3
 #define AIM_SCAN_MIN3 0       // 1: the block's local scan as one VIMNMX3 per column, 0: VIMNMX + VIADDMNMX (config 3: 43.7 against 43.6 ms)
 #endif
@@ -47,6 +44,12 @@ static inline uint32_t vminu(uint32_t a, uint32_t b)
 static inline uint32_t vadd(uint32_t a, uint32_t b) { return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16); }
 static inline uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return vmin(vmin(a, b), c); }
 static inline uint32_t viaddmin(uint32_t a, uint32_t b, uint32_t c) { return vmin(vadd(a, b), c); }
+static inline uint32_t vmin_relu(uint32_t a, uint32_t b)
+{   // per-half max(min(a, b), 0), signed (VIMNMX.S16x2.RELU)
+    const uint32_t m = vmin(a, b);
+    const int16_t ml = (int16_t)(m & 0xffffu), mh = (int16_t)(m >> 16);
+    return (uint32_t)(uint16_t)(ml < 0 ? 0 : ml) | ((uint32_t)(uint16_t)(mh < 0 ? 0 : mh) << 16);
+}
 static inline uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s)
 {
     const uint64_t v = ((uint64_t)y << 32) | x;
@@ -62,34 +65,25 @@ AIM_SD uint32_t vmin(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 AIM_SD uint32_t vminu(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 AIM_SD uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 AIM_SD uint32_t viaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
+AIM_SD uint32_t vmin_relu(uint32_t a, uint32_t b) { return __vimin_s16x2_relu(a, b); }
 AIM_SD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }
 }  // namespace scanx
 #endif
 
 namespace scanx {
-// The two predicates (a <= b) of a packed comparison as bits R and 16 + R of acc, in the DATA path: both halves are non-negative
-// int16, so (b + 0x8000) - a never borrows from the neighbour and bit 15 of each half is "b >= a".  bk = b + 0x80008000 is
-// passed in (the caller folds the constant into an addition it makes anyway).  The kernel is bound by the alu pipe (min/max,
-// logic, shifts, three-input adds: 85 % busy at 66 % issue), so everything that can runs on the fma pipe: the subtraction as a
-// two-input add (IMAD.IADD), the shift to bit R as a multiply-high (IMAD.HI), and only the merge is a LOP3.
-// (The predicate outputs of VIMNMX.S16x2 would be cheaper still, but the columns of a block are independent, ptxas issues their
-// minima back to back, runs out of predicate registers, parks them in general registers (P2R) and re-tests them at the end
-// of the row: 1100 instead of 500 instructions per row.)
-AIM_SD void push_le(uint32_t a, uint32_t bk, uint32_t &acc, const int R)  // R: a compile-time constant once the loops are unrolled
+// The two predicates of a packed comparison pushed into acc, in the DATA path: acc = 2 * acc + [a > b] per half, i.e. the
+// COMPLEMENT of the traceback's "a <= b", the first push ending highest (C pushes: column r at bit C-1-r, block B 16 higher).
+// Both halves are non-negative int16, so (b + 0x8000) - a never borrows from the neighbour and, read as a signed half, is
+// positive exactly where a > b; VIMNMX.S16x2.RELU clamps it to {0, 1}, one IMAD appends it: two alu-pipe instructions (the
+// three-input add, the clamp) and one on the fma pipe.  The kernel is bound by the alu pipe (85 % busy at 66 % issue), and a
+// third of its instructions push predicates.  Measured against this: shift + and-or merge (SHF, LOP3: three alu instructions per
+// push, 43.7 ms at config 3); the shift as IMAD.HI (more instructions, 48.5 ms); the predicate outputs of VIMNMX.S16x2 with
+// predicated adds (the columns of a block are independent, ptxas issues their minima back to back, runs out of predicate
+// registers, parks them in general registers (P2R) and re-tests them at the end of the row: 1100 instead of 500 instructions).
+AIM_SD void push_gt(uint32_t a, uint32_t b, uint32_t &acc)
 {
-    const uint32_t t = bk - a;
-#if AIM_SCAN_PUSH_FMA
-#ifdef AIM_SCAN_HOST_MODEL
-    const uint32_t sh = R == 15 ? t : (uint32_t)(((uint64_t)t << (17 + R)) >> 32);
-#else
-    uint32_t sh;
-    if (R == 15) sh = t;
-    else asm("mul.hi.u32 %0, %1, %2;" : "=r"(sh) : "r"(t), "r"(1u << ((17 + R) & 31)));
-#endif
-#else
-    const uint32_t sh = t >> (15 - R);
-#endif
-    acc |= sh & (0x00010001u << R);
+    const uint32_t t = (b + 0x80008000u) - a;  // per half b - a + 0x8000, in [1, 0xffff]: 1..0x7fff (a positive int16) where a > b
+    acc = acc * 2u + vmin_relu(t, 0x00010001u);
 }
 }  // namespace scanx
 
@@ -106,7 +100,6 @@ struct Pen {
     int O, E, OE, X, MS;       // E: SWG gap_ext, NW the gap (so that E * C is the carry of a block in both); MATCH == 0 (launcher)
     int INF;                   // "no carry-in": above every table value, INF + E * C still an int16
     uint32_t OE2, E2, INF2;
-    uint32_t E2K;              // E2 + 0x80008000 (see push_le)
 };
 
 // The lane's share of one row: C packed registers, block A (columns base+1 .. base+C) in the low halves, block B
@@ -139,7 +132,7 @@ AIM_SD void init_lane(Lane<C> &L, int lane, const Pen &P, const uint32_t *wlo, c
 // Phase 1 + 2: I and diag + sub of every column, X = min(I, diag + sub), and the blocks' local scans.
 // dg0 = M of the previous row at the column left of each block; t4 = this row's text byte in all four bytes.
 // Returns, per half, D at the first column AFTER the block if nothing came in from the left.
-// Predicate bits (push_le): column r of block A -> bit r, of block B -> bit 16 + r; compact() closes the gap when C < 16.
+// Predicate bits (push_gt: complements): column r of block A -> bit C-1-r, of block B -> bit 16+C-1-r; compact() closes the gap when C < 16.
 template <int C, bool SWG>
 AIM_SD uint32_t phase12(Lane<C> &L, uint32_t dg0, uint32_t t4, const Pen &P, uint32_t &aI)
 {
@@ -150,8 +143,9 @@ AIM_SD uint32_t phase12(Lane<C> &L, uint32_t dg0, uint32_t t4, const Pen &P, uin
         uint32_t ins;
         if (SWG) {
             const uint32_t i1 = um + P.OE2;
-            scanx::push_le(i1, L.uI[r] + P.E2K, aI, r);  // opI = (upM+o+e <= upI+e)  (swg.c:97)
-            ins = scanx::vmin(i1, L.uI[r] + P.E2);
+            const uint32_t i2 = L.uI[r] + P.E2;
+            scanx::push_gt(i1, i2, aI);  // opI = (upM+o+e <= upI+e)  (swg.c:97)
+            ins = scanx::vmin(i1, i2);
         } else {
             ins = um + P.OE2;  // GAP_I
         }
@@ -181,14 +175,15 @@ AIM_SD void phase4(Lane<C> &L, uint32_t din, const Pen &P, uint32_t &aP, uint32_
         if (r == 0) del = din;
         else if (SWG) {
             const uint32_t d1 = mprev + P.OE2;
-            scanx::push_le(d1, dprev + P.E2K, aD, r);  // opD = (leftM+o+e <= leftD+e)  (swg.c:88)
-            del = scanx::vmin(d1, dprev + P.E2);
+            const uint32_t d2 = dprev + P.E2;
+            scanx::push_gt(d1, d2, aD);  // opD = (leftM+o+e <= leftD+e)  (swg.c:88)
+            del = scanx::vmin(d1, d2);
         } else {
             del = mprev + P.OE2;  // GAP_D
         }
-        scanx::push_le(del, L.uI[r] + 0x80008000u, aP, r);  // p = (del <= ins)
+        scanx::push_gt(del, L.uI[r], aP);  // p = (del <= ins)
         const uint32_t m1 = scanx::vmin(del, L.uI[r]);
-        scanx::push_le(m1, L.mm[r] + 0x80008000u, aQ, r);   // q = (min(del, ins) <= diag + sub)
+        scanx::push_gt(m1, L.mm[r], aQ);   // q = (min(del, ins) <= diag + sub)
         const uint32_t m = scanx::vmin(m1, L.mm[r]);
         L.uM[r] = m;
         L.dn[r] = del;
@@ -202,7 +197,16 @@ AIM_SD void phase4(Lane<C> &L, uint32_t din, const Pen &P, uint32_t &aP, uint32_
 template <int C>
 AIM_SD void opd_first(uint32_t mleft, uint32_t din, const Pen &P, uint32_t &aD)
 {
-    scanx::push_le(mleft + P.OE2, din + 0x80008000u, aD, 0);
+    const uint32_t t = (din + 0x80008000u) - (mleft + P.OE2);  // (as push_gt)
+    aD |= scanx::vmin_relu(t, 0x00010001u) << (C - 1);
+}
+
+// Bit of column position pos (= column - 1) in a compacted accumulator; the stored bit is the predicate's complement
+template <int C>
+AIM_SD int flag_bit(int pos)
+{
+    const int b = pos % (2 * C);
+    return (b / C) * C + (C - 1 - b % C);
 }
 
 // The 2*C predicate bits of an accumulator as bits 0 .. 2C-1 (block A, then block B)

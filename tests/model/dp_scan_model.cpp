@@ -24,12 +24,12 @@ struct Flags {  // ScanFlags of the kernel
         else d[0] = aP | (aQ << 16);
     }
     static void load(const uint32_t *d, int bit, bool &p, bool &q, bool &opD, bool &opI)
-    {
+    {   // complements
         opD = opI = false;
-        if (SWG && C == 16) { p = (d[0] >> bit) & 1u; q = (d[1] >> bit) & 1u; opD = (d[2] >> bit) & 1u; opI = (d[3] >> bit) & 1u; }
-        else if (SWG) { p = (d[0] >> bit) & 1u; q = (d[0] >> (16 + bit)) & 1u; opD = (d[1] >> bit) & 1u; opI = (d[1] >> (16 + bit)) & 1u; }
-        else if (C == 16) { p = (d[0] >> bit) & 1u; q = (d[1] >> bit) & 1u; }
-        else { p = (d[0] >> bit) & 1u; q = (d[0] >> (16 + bit)) & 1u; }
+        if (SWG && C == 16) { p = !((d[0] >> bit) & 1u); q = !((d[1] >> bit) & 1u); opD = !((d[2] >> bit) & 1u); opI = !((d[3] >> bit) & 1u); }
+        else if (SWG) { p = !((d[0] >> bit) & 1u); q = !((d[0] >> (16 + bit)) & 1u); opD = !((d[1] >> bit) & 1u); opI = !((d[1] >> (16 + bit)) & 1u); }
+        else if (C == 16) { p = !((d[0] >> bit) & 1u); q = !((d[1] >> bit) & 1u); }
+        else { p = !((d[0] >> bit) & 1u); q = !((d[0] >> (16 + bit)) & 1u); }
     }
 };
 
@@ -46,7 +46,6 @@ void model_pair(int X, int O, int E_, int MS, int RS, int backtrace, int pl, int
     P.E = SWG ? E_ : O;
     P.INF = 32767 - P.E * C - P.OE - 8;
     P.OE2 = scan::both(P.OE); P.E2 = scan::both(P.E); P.INF2 = scan::both(P.INF);
-    P.E2K = P.E2 + 0x80008000u;
     const int EC = P.E * C;
     const int nc = tl + 1, d = pl - tl;
     const int tlmax = std::min(RS, tl + tlmax_extra), dmax = std::min(C, d + (tlmax_extra ? 1 : 0));  // as if a longer pair shared the warp
@@ -148,7 +147,7 @@ void model_pair(int X, int O, int E_, int MS, int RS, int backtrace, int pl, int
                 p = nib & 1u; q = nib & 2u; opD = nib & 4u; opI = nib & 8u;
             } else {
                 const int pos = c - 1;
-                Flags<C, SWG>::load(&fl[((size_t)(r - 1) * G + pos / (2 * C)) * FW], pos % (2 * C), p, q, opD, opI);
+                Flags<C, SWG>::load(&fl[((size_t)(r - 1) * G + pos / (2 * C)) * FW], scan::flag_bit<C>(pos), p, q, opD, opI);
             }
             if (!SWG) {
                 if (q) {
