@@ -10,8 +10,10 @@ mkdir -p $out
 cat $out/${tag}_tests.log
 timeout 300 python bench.py --config 3 > $out/${tag}_bench_cfg3.json 2> $out/${tag}_bench_cfg3.err
 AIM_DP_SCAN=0 timeout 300 python bench.py --config 3 --no-cli --no-cpu-baseline --parity-pairs 200000 > $out/${tag}_bench_cfg3_scan_off.json 2>> $out/${tag}_bench_cfg3.err
+if [ -z "$ONLY_CFG3" ]; then
 timeout 300 python bench.py --config 2 > $out/${tag}_bench_cfg2.json 2> $out/${tag}_bench_cfg2.err
 timeout 300 python bench.py > $out/${tag}_bench_cfg4.json 2> $out/${tag}_bench_cfg4.err
+fi
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/${tag}_launches_cfg3.csv \
     python bench.py --config 3 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-cli --parity off > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:dp_scan_kernel -c 1 -f -o $out/${tag}_dp_scan_cfg3 \
