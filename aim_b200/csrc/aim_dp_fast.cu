@@ -594,7 +594,83 @@ struct ScanFlags {
     }
 };
 
-template <int ALGO, int C, int G, int MINB>
+// The traceback of one pair dp_scan_kernel filled, over its predicate records (slot = where they are).  One chain of dependent
+// loads per pair: always one pair per THREAD (on one lane of the fill kernel's sub-warps it kept the warp resident for a third
+// of its life).
+template <int ALGO, int C, int G>
+__device__ __forceinline__ void scan_traceback(const FastK &K, uint32_t li, size_t slot)
+{
+    constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
+    constexpr int FW = ScanFlags<C, SWG>::FW;
+    const int RS = K.read_size;
+    const uint32_t i = K.list[(int64_t)K.list_step * (int64_t)li];
+    const int pl = min(max(K.plen[i], 0), RS), tl = min(max(K.tlen[i], 0), RS);
+    const char *gp = K.patterns + (size_t)i * RS;
+    const char *gt = K.texts + (size_t)i * RS;
+    const int nc = tl + 1;
+    const uint32_t *flw = K.flags + slot * RS * G * FW;
+    const uint2 *tf = K.tflags + slot * RS;
+    char *ops = K.ops + (size_t)i * 2 * RS;  // pre-filled with 'M' by the launcher
+    int status = AIM_STATUS_OK;
+    int b = pl + tl - 1;
+    int h = tl, v = pl;
+    int layer = 0;  // SWG: 0 M, 1 I, 2 D
+    while (h > 0 && v > 0) {
+        int r, c;
+        scan::last_writer(nc, tl, h, v, r, c);
+        bool p, q, opD, opI;
+        if (c >= nc) {
+            const uint2 t2 = tf[r - 1];
+            const uint64_t t = (uint64_t)t2.x | ((uint64_t)t2.y << 32);
+            const uint32_t nib = (uint32_t)(t >> (4 * (c - nc))) & 15u;
+            p = nib & 1u; q = nib & 2u; opD = nib & 4u; opI = nib & 8u;
+        } else {
+            const int pos = c - 1;
+            const uint32_t *rec = flw + ((size_t)(r - 1) * G + (size_t)(pos / (2 * C))) * FW;
+            ScanFlags<C, SWG>::load(rec, scan::flag_bit<C>(pos), p, q, opD, opI);
+        }
+        if (!SWG) {
+            if (q) {
+                if (p) { ops[b--] = 'D'; --v; }
+                else { ops[b--] = 'I'; --h; }
+            } else {
+                if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                --b; --h; --v;
+            }
+        } else {
+            if (b < 0) { status = AIM_STATUS_BACKTRACE; break; }
+            if (layer == 2) { ops[b--] = 'D'; if (opD) layer = 0; --v; }
+            else if (layer == 1) { ops[b--] = 'I'; if (opI) layer = 0; --h; }
+            else if (q) layer = p ? 2 : 1;
+            else {
+                if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
+                --b; --h; --v;
+            }
+        }
+    }
+    if (status == AIM_STATUS_OK) {
+        while (h > 0) { ops[b--] = 'I'; --h; }
+        while (v > 0) { ops[b--] = 'D'; --v; }
+        K.results[i].begin_offset = b + 1;
+    } else {
+        K.results[i].status = status;
+    }
+}
+
+// TBIN = false: the traceback as a kernel of its own after every batch of fills.
+template <int ALGO, int C, int G>
+__global__ void __launch_bounds__(128) dp_scan_tb_kernel(const FastK K)
+{
+    const uint32_t lend = min(*K.count, K.llimit);
+    const uint64_t li64 = (uint64_t)K.lbase + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li64 >= lend) return;
+    scan_traceback<ALGO, C, G>(K, (uint32_t)li64, (size_t)(li64 - K.lbase));
+}
+
+// TBIN = true: the warp keeps the records of its last 32 pairs (32 / PPW groups) and then walks them itself, one pair per LANE,
+// while the SM's other warps fill: the walk is latency-bound and costs the alu-bound fill next to nothing, there is no second
+// kernel, no batching, and the record region is resident warps x 32 pairs (2.8 GB at config 3).
+template <int ALGO, int C, int G, int MINB, bool TBIN>
 __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
 {
     constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
@@ -614,6 +690,9 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
     P.OE2 = scan::both(P.OE); P.E2 = scan::both(P.E); P.INF2 = scan::both(P.INF);
     const int EC = P.E * C;
 
+    constexpr uint32_t KG = 32 / PPW;  // groups per traceback round (TBIN)
+    uint32_t it = 0;                   // groups this warp has filled
+    uint64_t round_g0 = (uint64_t)K.lbase + (uint64_t)warp * PPW;  // first group of the round under way
     for (uint64_t g0 = (uint64_t)K.lbase + (uint64_t)warp * PPW; g0 < lend; g0 += (uint64_t)nwarps * PPW) {
         const uint32_t li = (uint32_t)g0 + sub;
         const bool have = li < lend;  // a sub-warp without a pair shadows the warp's first pair and writes nothing
@@ -623,7 +702,8 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
         const char *gt = K.texts + (size_t)i * RS;
         const int d = pl - tl;
         const int tlmax = __reduce_max_sync(FULL, tl), dmax = __reduce_max_sync(FULL, d);
-        const size_t slot = li - K.lbase;  // the pair's predicate records: [row][lane] + one tail word per row
+        // the pair's predicate records: [row][lane] + one tail word per row
+        const size_t slot = TBIN ? (size_t)warp * 32 + (it % KG) * PPW + sub : (size_t)(li - K.lbase);
         uint32_t *fl = K.flags + (slot * RS * G + sl) * FW;
         uint2 *tf = K.tflags + slot * RS;
         const bool keep = have && K.backtrace;
@@ -711,7 +791,7 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
             ed.dgt = mtl;
         }
 
-        if (have && sl == 0) {  // with backtrace, dp_scan_tb_kernel fills in begin_offset
+        if (have && sl == 0) {  // with backtrace, the traceback fills in begin_offset
             aim_result res;
             res.max_operations = pl + tl;
             res.begin_offset = pl + tl - 1;
@@ -721,75 +801,21 @@ __global__ void __launch_bounds__(64, MINB) dp_scan_kernel(const FastK K)
             res.idx = K.idx_base + i;
             K.results[i] = res;
         }
+        ++it;
+        if (TBIN && K.backtrace) {
+            const bool last = g0 + (uint64_t)nwarps * PPW >= lend;
+            if (it % KG == 0 || last) {  // lane t walks the pair of group t / PPW, sub-warp t % PPW of this round: slot warp * 32 + t
+                __syncwarp();
+                const uint32_t filled = (it - 1) % KG + 1;
+                const uint64_t li_t = round_g0 + (uint64_t)(lane / PPW) * nwarps * PPW + (uint32_t)(lane % PPW);
+                if ((uint32_t)(lane / PPW) < filled && li_t < lend) scan_traceback<ALGO, C, G>(K, (uint32_t)li_t, (size_t)warp * 32 + lane);
+                __syncwarp();  // the next round's rows overwrite the records
+                round_g0 = g0 + (uint64_t)nwarps * PPW;
+            }
+        }
     }
 }
 
-// The traceback of the pairs dp_scan_kernel filled: one pair per thread over the predicate records (the walk is one chain of
-// dependent loads per pair; on one lane of the fill kernel's sub-warps it kept the warp resident for a third of its life).
-template <int ALGO, int C, int G>
-__global__ void __launch_bounds__(128) dp_scan_tb_kernel(const FastK K)
-{
-    constexpr bool SWG = (ALGO == AIM_ALGO_SWG);
-    constexpr int FW = ScanFlags<C, SWG>::FW;
-    const uint32_t lend = min(*K.count, K.llimit);
-    const uint64_t li64 = (uint64_t)K.lbase + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (li64 >= lend) return;
-    const uint32_t li = (uint32_t)li64;
-    const int RS = K.read_size;
-    const uint32_t i = K.list[(int64_t)K.list_step * (int64_t)li];
-    const int pl = min(max(K.plen[i], 0), RS), tl = min(max(K.tlen[i], 0), RS);
-    const char *gp = K.patterns + (size_t)i * RS;
-    const char *gt = K.texts + (size_t)i * RS;
-    const int nc = tl + 1;
-    const size_t slot = li - K.lbase;
-    const uint32_t *flw = K.flags + slot * RS * G * FW;
-    const uint2 *tf = K.tflags + slot * RS;
-    char *ops = K.ops + (size_t)i * 2 * RS;  // pre-filled with 'M' by the launcher
-    int status = AIM_STATUS_OK;
-    int b = pl + tl - 1;
-    int h = tl, v = pl;
-    int layer = 0;  // SWG: 0 M, 1 I, 2 D
-    while (h > 0 && v > 0) {
-        int r, c;
-        scan::last_writer(nc, tl, h, v, r, c);
-        bool p, q, opD, opI;
-        if (c >= nc) {
-            const uint2 t2 = tf[r - 1];
-            const uint64_t t = (uint64_t)t2.x | ((uint64_t)t2.y << 32);
-            const uint32_t nib = (uint32_t)(t >> (4 * (c - nc))) & 15u;
-            p = nib & 1u; q = nib & 2u; opD = nib & 4u; opI = nib & 8u;
-        } else {
-            const int pos = c - 1;
-            const uint32_t *rec = flw + ((size_t)(r - 1) * G + (size_t)(pos / (2 * C))) * FW;
-            ScanFlags<C, SWG>::load(rec, scan::flag_bit<C>(pos), p, q, opD, opI);
-        }
-        if (!SWG) {
-            if (q) {
-                if (p) { ops[b--] = 'D'; --v; }
-                else { ops[b--] = 'I'; --h; }
-            } else {
-                if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
-                --b; --h; --v;
-            }
-        } else {
-            if (b < 0) { status = AIM_STATUS_BACKTRACE; break; }
-            if (layer == 2) { ops[b--] = 'D'; if (opD) layer = 0; --v; }
-            else if (layer == 1) { ops[b--] = 'I'; if (opI) layer = 0; --h; }
-            else if (q) layer = p ? 2 : 1;
-            else {
-                if (gp[c - 1] != gt[r - 1]) ops[b] = 'X';
-                --b; --h; --v;
-            }
-        }
-    }
-    if (status == AIM_STATUS_OK) {
-        while (h > 0) { ops[b--] = 'I'; --h; }
-        while (v > 0) { ops[b--] = 'D'; --v; }
-        K.results[i].begin_offset = b + 1;
-    } else {
-        K.results[i].status = status;
-    }
-}
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -835,6 +861,9 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
     // aliased pairs with the row spread over the lanes of a sub-warp (dp_scan_kernel): geometry by READ_SIZE
     struct ScanCfg { int C, G; void (*fn)(const FastK); void (*tb)(const FastK); };
     ScanCfg scn{0, 0, nullptr, nullptr};
+    // the traceback inside the fill kernel (one pair per lane every 32 pairs of a warp) or as a kernel of its own after every batch
+    bool tbin = true;
+    if (const char *e = getenv("AIM_DP_SCAN_TB")) tbin = std::string(e) != "kernel";
     {
         // 0 off, 1 default geometry, 2 the narrower blocks.  Default: SWG with long rows (where dp_row_kernel's shared-memory row
         // leaves 6-8 warps per SM); NW and short rows stay with dp_row_kernel (config 2: 11.7 against 13.5 ms).
@@ -846,7 +875,9 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
             // Config 3, 16-column blocks: 43.6 / 43.7 / 44.1 ms with 6 / 8 / 10 (the kernel is bound by the alu pipe, not by resident warps).
             int minb = 0;
             if (const char *e = getenv("AIM_DP_SCAN_MINB")) minb = atoi(e);
-#define AIM_SCAN_FN(C, G, B) (nw ? (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_NW, C, G, B> : (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_SWG, C, G, B>)
+#define AIM_SCAN_FN(C, G, B)                                                                                                        \
+    (tbin ? (nw ? (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_NW, C, G, B, true> : (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_SWG, C, G, B, true>) \
+          : (nw ? (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_NW, C, G, B, false> : (void (*)(const FastK))dp_scan_kernel<AIM_ALGO_SWG, C, G, B, false>))
 #define AIM_SCAN_TB(C, G) (nw ? (void (*)(const FastK))dp_scan_tb_kernel<AIM_ALGO_NW, C, G> : (void (*)(const FastK))dp_scan_tb_kernel<AIM_ALGO_SWG, C, G>)
 #define AIM_SCAN_CFG(C, G, BDEF)                                                                     \
     ((minb ? minb : BDEF) >= 10  ? ScanCfg{C, G, AIM_SCAN_FN(C, G, 10), AIM_SCAN_TB(C, G)}           \
@@ -878,12 +909,15 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
             size_t budget = (size_t)4 << 30;  // of predicate records in flight
             if (const char *e2 = getenv("AIM_DP_SCAN_BATCH_MB")) { const long v = atol(e2); if (v >= 16 && v <= 65536) budget = (size_t)v << 20; }
             scan_grid = (int)std::min<uint64_t>((uint64_t)sc->sm_count * (uint64_t)bps, ((uint64_t)a.n / ppw + 2) / 2 + 1);
+            if (const char *e3 = getenv("AIM_DP_SCAN_GRID")) { const int v = atoi(e3); if (v >= 1 && v < scan_grid) scan_grid = v; }  // (tests: many groups per warp)
             const uint64_t resident = (uint64_t)scan_grid * 2 * ppw;
             uint64_t batch = p.backtrace ? std::max<uint64_t>(budget / (per_pair + per_pair_tail), 1) : a.n;
             if (batch > resident) batch = batch / resident * resident;  // whole waves
             scan_batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(batch, 1), a.n);
-            scan_tail_off = align_up(p.backtrace ? (size_t)scan_batch * per_pair : 0, 256);
-            scan_flag_bytes = scan_tail_off + (p.backtrace ? (size_t)scan_batch * per_pair_tail : 0);
+            size_t slots = scan_batch;
+            if (tbin) { scan_batch = a.n; slots = (size_t)scan_grid * 2 * 32; }  // one launch; every warp owns 32 record slots
+            scan_tail_off = align_up(p.backtrace ? slots * per_pair : 0, 256);
+            scan_flag_bytes = scan_tail_off + (p.backtrace ? slots * per_pair_tail : 0);
             reg_cols = 0;  // its class of the list is the scan kernel's
         }
     }
@@ -1033,8 +1067,8 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
         Sc.list = list + (a.n - 1); Sc.count = counters + 1; Sc.list_step = -1;
         Sc.flags = reinterpret_cast<uint32_t *>(base + off_rflags);
         Sc.tflags = reinterpret_cast<uint2 *>(base + off_rflags + scan_tail_off);
-        // How many of the n pairs are in this class is known on the device only: batches over the whole range, empty ones return at
-        // once.  Fill and traceback alternate on the one stream.  Measured and rejected: the traceback of batch b on a side stream
+        // Traceback inside the kernel: one launch.  Otherwise: how many of the n pairs are in this class is known on the device only:
+        // batches over the whole range, empty ones return at once; fill and traceback alternate on the one stream.  Measured and rejected: the traceback of batch b on a side stream
         // under the fill of batch b + 1 (two halves of the record region, the fill kernel one block per SM short so that the traceback
         // blocks fit): 44.6 against 43.7 ms at config 3 - the fill kernel loses more with 14 warps per SM than the 2.9 ms it hides.
         for (uint64_t b0 = 0; b0 < a.n && err == cudaSuccess; b0 += scan_batch) {
@@ -1042,7 +1076,7 @@ int launch_dp_fast(const KernelArgs &a, Scratch *sc, void *stream_v, int *launch
             Sc.llimit = (uint32_t)std::min<uint64_t>(b0 + scan_batch, a.n);
             scn.fn<<<scan_grid, 64, 0, stream>>>(Sc);
             ++nlaunch;
-            if (p.backtrace) {
+            if (p.backtrace && !tbin) {
                 scn.tb<<<(Sc.llimit - Sc.lbase + 127) / 128, 128, 0, stream>>>(Sc);
                 ++nlaunch;
             }

@@ -111,15 +111,20 @@ SCAN_CASES = DP_CASES + [
 ]
 
 
-@pytest.mark.parametrize("mode,minb", [("0", "0"), ("1", "0"), ("2", "0"), ("1", "10"), ("1", "6"), ("2", "8")])
+@pytest.mark.parametrize("mode,minb,tb,grid", [("0", "0", "fused", "0"), ("1", "0", "fused", "0"), ("2", "0", "fused", "0"), ("1", "10", "fused", "3"),
+                                               ("1", "6", "kernel", "0"), ("2", "8", "fused", "2"), ("1", "0", "kernel", "5"), ("2", "0", "kernel", "0")])
 @pytest.mark.parametrize("algo,kw,gen", SCAN_CASES, ids=[f"{c[0]}-{c[2][0]}" for c in SCAN_CASES])
-def test_vs_oracle_ragged_scan_kernel(algo, kw, gen, mode, minb, monkeypatch):
+def test_vs_oracle_ragged_scan_kernel(algo, kw, gen, mode, minb, tb, grid, monkeypatch):
     """Aliased pairs (pattern longer than text) through dp_scan_kernel - the row spread over the lanes of a sub-warp, the
-    horizontal gap as a min-plus scan (aim_dp_scan.cuh) - in both block geometries and both register budgets, and with it
-    switched off (dp_row_kernel).  Lengths differ by up to 12, so each batch also holds pairs the scan kernel must leave to
-    dp_row_kernel (more tail cells than a block has columns) and non-aliased ones (dp2_strip_kernel)."""
+    horizontal gap as a min-plus scan (aim_dp_scan.cuh) - in both block geometries and all register budgets, with the traceback
+    inside the fill kernel (every warp walks its last 32 pairs, one per lane) and as a kernel of its own, with a grid of a few
+    blocks (every warp then serves many rounds of 32 pairs), and with the kernel switched off (dp_row_kernel).  Lengths differ by
+    up to 12, so each batch also holds pairs the scan kernel must leave to dp_row_kernel (more tail cells than a block has
+    columns) and non-aliased ones (dp2_strip_kernel)."""
     monkeypatch.setenv("AIM_DP_SCAN", mode)
     monkeypatch.setenv("AIM_DP_SCAN_MINB", minb)
+    monkeypatch.setenv("AIM_DP_SCAN_TB", tb)
+    monkeypatch.setenv("AIM_DP_SCAN_GRID", grid)
     _vs_oracle_ragged(algo, kw, gen, True)
 
 
