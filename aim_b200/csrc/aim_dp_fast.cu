@@ -560,8 +560,9 @@ __global__ void __launch_bounds__(RT) __maxnreg__(R > 0 ? 224 : 128) dp_row_kern
 // the warp; a pair that is through keeps computing rows nobody reads).  No shared memory: the row lives in 4*C (NW) / 5*C
 // registers per lane, so the register file, not the row, bounds the resident pairs.  Predicates: per pair and (row, lane) one
 // record {P, Q[, opD, opI]} (complements, bit scan::flag_bit(column - 1); a row of a pair = one 32..128-byte piece), + one 64-bit word per
-// (row, pair) for the tail cells; dp_scan_tb_kernel walks them, one pair per thread.  The records of a pair take
-// READ_SIZE * G * FW words, so the launcher serves the list in batches (fill, traceback, fill, ...) over one flag region.
+// (row, pair) for the tail cells; the traceback walks them one pair per thread - the lanes of the warp that filled them (TBIN,
+// the default) or dp_scan_tb_kernel.  The records of a pair take READ_SIZE * G * FW words: every warp owns 32 pairs' worth (TBIN),
+// or the launcher serves the list in batches (fill, traceback, fill, ...) over one flag region.
 // Preconditions (classify_kernel / launcher): text_len < pattern_len, text_len <= 2*C*G, pattern_len - text_len <= min(C, text_len),
 // o >= 0, e >= 0, MATCH == 0, every value + the scan's "infinity" inside int16.
 template <int C, bool SWG>

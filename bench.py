@@ -60,7 +60,7 @@ CONFIGS = {
             mismatch=3, gap_open=4, gap_ext=1, reduce=False, backtrace=True, pairs=2_000_000, seed=4),
 }
 # dominant kernel of each config (the one `roofline` describes; one step = all kernels of the launch)
-KERNELS = {2: "dp2_strip_kernel<NW> (two pairs per thread) + dp_row_kernel<NW> (aim_dp_fast.cu, aim_dp_pack2.cuh)", 3: "dp2_strip_kernel<SWG> (two pairs per thread) + dp_scan_kernel<SWG, 16 columns x 2 per lane, 8 lanes per pair> / dp_scan_tb_kernel for the aliased pairs (aim_dp_fast.cu, aim_dp_pack2.cuh, aim_dp_scan.cuh)",
+KERNELS = {2: "dp2_strip_kernel<NW> (two pairs per thread) + dp_row_kernel<NW> (aim_dp_fast.cu, aim_dp_pack2.cuh)", 3: "dp2_strip_kernel<SWG> (two pairs per thread) + dp_scan_kernel<SWG, 16 columns x 2 per lane, 8 lanes per pair, traceback by the warp's lanes> for the aliased pairs (aim_dp_fast.cu, aim_dp_pack2.cuh, aim_dp_scan.cuh)",
            4: "wfa_sub_kernel<4, reduce, backtrace, narrow rows> (aim_wfa_sub.cu)", 5: "wfa_long_kernel<16, reduce, 128- then 256-diagonal window> (aim_wfa_long.cu)",
            6: "wfa_long_kernel<16, reduce, backtrace, 128- then 256-diagonal window> (aim_wfa_long.cu)", 7: "genasm_band_kernel<1 word, DC> + genasm_tb_kernel (aim_genasm.cu)",
            8: "genasm_band_kernel<1 word, filter> (aim_genasm.cu)", 9: "genasm_band_kernel<4 words, DC> + genasm_tb_kernel (aim_genasm.cu)"}
