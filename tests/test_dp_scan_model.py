@@ -113,3 +113,35 @@ def test_model_other_penalties(model):
         plen, tlen, pats, txts = ragged(x * 100 + o, 200, 160, 1, 128, 8, True)
         res, ops, served = run_model(model, "swg", 8, 8, x, o, e, ms, 160, plen, tlen, pats, txts)
         compare("swg", res, ops, served, plen, tlen, pats, txts, x, o, e, ms, 160)
+
+
+def test_model_random_sweep(model):
+    """Many small random cases over penalties, geometries and length ranges (the corners a fixed case list misses: text_len of a few
+    bases, text_len at the last column a geometry holds, d = C, equal / unrelated sequences, non-ACGT bytes)."""
+    rng = np.random.default_rng(2024)
+    geos = [(4, 16), (8, 8), (8, 16), (16, 8), (16, 16)]
+    checked = 0
+    for it in range(40):
+        c, g = geos[it % len(geos)]
+        algo = "swg" if it % 3 else "nw"
+        cols = 2 * c * g
+        rs = int(min(528, (cols + 8 * int(rng.integers(0, 5)) + 7) // 8 * 8))
+        x = int(rng.integers(1, 7))
+        o = int(rng.integers(1, 9))
+        e = int(rng.integers(1, 5))
+        ms = int(rng.integers(1, 120))
+        lo = int(rng.choice([1, 2, max(1, cols - 20)]))
+        hi = min(cols, rs - 1)
+        plen, tlen, pats, txts = ragged(1000 + it, 60, rs, lo, hi, c + 1, related=bool(it % 2))
+        if it % 5 == 0:  # bytes outside ACGT are compared as bytes (swg.c:206, nw.c:143)
+            for i in range(0, 60, 7):
+                pats[i, rng.integers(0, plen[i])] = ord("N")
+                txts[i, rng.integers(0, tlen[i])] = ord("n")
+        if it % 7 == 0:  # a few identical-prefix pairs: text = pattern cut at the end
+            for i in range(1, 60, 9):
+                txts[i, :tlen[i]] = pats[i, :tlen[i]]
+        res, ops, served = run_model(model, algo, c, g, x, o, e, ms, rs, plen, tlen, pats, txts, extra=it % 3)
+        if served.sum() == 0:
+            continue
+        checked += compare(algo, res, ops, served, plen, tlen, pats, txts, x, o, e, ms, rs)
+    assert checked > 1000
