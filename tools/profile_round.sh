@@ -14,7 +14,7 @@ full() {  # cfg kernel-regex name pairs
 }
 full 4 wfa_sub_kernel wfa_sub 2000000
 full 3 dp2_strip_kernel dp2_strip 200000
-full 3 dp_row_kernel dp_row 200000
+full 3 dp_scan_kernel dp_scan 200000
 full 2 dp2_strip_kernel dp2_strip 400000
 full 5 wfa_long_kernel wfa_long 20000
 full 6 wfa_long_kernel wfa_long_bt 8000
